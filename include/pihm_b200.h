@@ -1,0 +1,259 @@
+/*
+ * pihm_b200.h -- C ABI of the B200-native MM-PIHM hot path (libpihm_b200.so).
+ *
+ * Everything here is plain C: pointers, sizes and opaque handles.  No torch,
+ * no C++ types.  A PIHM driver written in C links this library and keeps its
+ * own elem_struct/river_struct arrays; the packing stub that turns those AoS
+ * arrays into the column tables below is shown in INTEGRATION.md (and is what
+ * oracle/ref_shim.c does for the tests).
+ *
+ * Each entry point cites the reference interface it replaces
+ * (paths relative to the MM-PIHM tree).
+ */
+#ifndef PIHM_B200_H
+#define PIHM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIHM_B200_ABI_VERSION 1
+
+/* ------------------------------------------------------------------------
+ * Column tables.  Every table is a dense row-major array [NCOL][n]; column c
+ * of entity i lives at table[c * n + i].  Values are exactly the fields the
+ * reference RHS reads after Initialize() (src/initialize.c:5-205).
+ * ---------------------------------------------------------------------- */
+
+/* element, static double columns (src/include/elem_struct.h:28-111,136,240) */
+enum pihm_b200_elem_col {
+    PB_E_AREA = 0, PB_E_ZMIN, PB_E_ZMAX, PB_E_ZBED,
+    PB_E_EDGE0, PB_E_EDGE1, PB_E_EDGE2,
+    PB_E_NABRDIST0, PB_E_NABRDIST1, PB_E_NABRDIST2,
+    PB_E_NABRX0, PB_E_NABRX1, PB_E_NABRX2,
+    PB_E_NABRY0, PB_E_NABRY1, PB_E_NABRY2,
+    PB_E_DEPTH, PB_E_KSATH, PB_E_KSATV, PB_E_KINFV, PB_E_DINF,
+    PB_E_ALPHA, PB_E_BETA, PB_E_POROSITY, PB_E_DMAC, PB_E_KMACH,
+    PB_E_KMACV, PB_E_AREAFV, PB_E_AREAFH,
+    PB_E_ROUGH, PB_E_RZD,
+    /* fractured bedrock (geol_struct), only read when fbr != 0 */
+    PB_E_GDEPTH, PB_E_GKSATH, PB_E_GKSATV, PB_E_GALPHA, PB_E_GBETA,
+    PB_E_GPOROSITY,
+    PB_E_NCOL
+};
+
+/* element, static int32 columns (elem_struct.h:1560, attrib_struct :5-25).
+ * NABRj: >0 neighbour element (1-based), <0 -(river index, 1-based), 0 boundary */
+enum pihm_b200_elem_icol {
+    PB_EI_NABR0 = 0, PB_EI_NABR1, PB_EI_NABR2,
+    PB_EI_BC0, PB_EI_BC1, PB_EI_BC2,
+    PB_EI_FBRBC0, PB_EI_FBRBC1, PB_EI_FBRBC2,
+    PB_EI_NCOL
+};
+
+/* element, per-step forcing columns (wf.pcpdrp/edir/ett written by
+ * IntcpSnowEt, src/is_sm_et.c:126-223; ws0.surf written by Summary,
+ * src/update.c:47; bc/fbr_bc written by ApplyBc, src/forcing.c:55-86) */
+enum pihm_b200_elem_forc_col {
+    PB_F_PCPDRP = 0, PB_F_EDIR, PB_F_ETT, PB_F_WS0SURF,
+    PB_F_BC0, PB_F_BC1, PB_F_BC2,
+    PB_F_FBRBC0, PB_F_FBRBC1, PB_F_FBRBC2,
+    PB_F_NCOL
+};
+
+/* river, static double columns (src/include/river_struct.h:11-60) */
+enum pihm_b200_riv_col {
+    PB_R_AREA = 0, PB_R_ZMIN, PB_R_ZMAX, PB_R_ZBED, PB_R_NODE_ZMAX,
+    PB_R_DIST_LEFT, PB_R_DIST_RIGHT,
+    PB_R_SHP_DEPTH, PB_R_SHP_COEFF, PB_R_SHP_LENGTH, PB_R_SHP_WIDTH,
+    PB_R_ROUGH, PB_R_CWR, PB_R_KSATH, PB_R_KSATV, PB_R_BEDTHICK,
+    PB_R_POROSITY,
+    PB_R_NCOL
+};
+
+/* river, static int32 columns (river_struct.h:137-146, :41) */
+enum pihm_b200_riv_icol {
+    PB_RI_LEFTELE = 0, PB_RI_RIGHTELE, PB_RI_DOWN, PB_RI_BCTYPE,
+    PB_RI_INTRPL_ORD,
+    PB_RI_NCOL
+};
+
+/* per-element flux diagnostics returned by pihm_b200_get_elem_fluxes
+ * (wflux_struct, elem_struct.h:407-477) */
+enum pihm_b200_elem_flux_col {
+    PB_X_OVL0 = 0, PB_X_OVL1, PB_X_OVL2,
+    PB_X_SUB0, PB_X_SUB1, PB_X_SUB2,
+    PB_X_INFIL, PB_X_RECHG,
+    PB_X_EDIR_SURF, PB_X_EDIR_UNSAT, PB_X_EDIR_GW, PB_X_ETT_UNSAT, PB_X_ETT_GW,
+    PB_X_FBR_INFIL, PB_X_FBR_RECHG, PB_X_FBRFLOW0, PB_X_FBRFLOW1, PB_X_FBRFLOW2,
+    PB_X_NCOL
+};
+
+#define PIHM_B200_NUM_RIVFLX 11   /* src/include/pihm_const.h:71,130-140 */
+
+typedef struct pihm_b200_mesh {
+    int32_t         nelem;
+    int32_t         nriver;
+    int32_t         fbr;        /* 0: pihm (3 states/elem); 1: pihm-fbr (5) */
+    int32_t         surf_mode;  /* 1 kinematic, 2 diffusion wave (ctrl_struct) */
+    int32_t         riv_mode;
+    int32_t         reserved;
+    double          stepsize;   /* ctrl.stepsize: dt of Infil(), hydrol.c:22 */
+    const double   *elem_f64;   /* [PB_E_NCOL ][nelem]  */
+    const int32_t  *elem_i32;   /* [PB_EI_NCOL][nelem]  */
+    const double   *riv_f64;    /* [PB_R_NCOL ][nriver] */
+    const int32_t  *riv_i32;    /* [PB_RI_NCOL][nriver] */
+} pihm_b200_mesh;
+
+typedef struct pihm_b200_ctx pihm_b200_ctx;    /* opaque device context */
+typedef struct pihm_b200_vec pihm_b200_vec;    /* opaque device vector   */
+
+/* Error handling: every int-returning call gives 0 on success, <0 on failure;
+ * the message of the last failure on the calling thread is kept here. */
+const char     *pihm_b200_last_error(void);
+int             pihm_b200_abi_version(void);
+int             pihm_b200_device_count(void);
+
+/* ------------------------------------------------------------------------
+ * Context: device mirror of pihm->elem / pihm->river.
+ *   replaces: nothing in the reference (it computes in place on the AoS);
+ *   call after Initialize() (src/main.c:77) with the packed tables.
+ * `reorder`: 0 keep reference order on the device, 1 locality reordering
+ * (patch ordering of elements; the permutation is internal -- every host
+ * buffer crossing this ABI is in reference order).
+ * ---------------------------------------------------------------------- */
+pihm_b200_ctx  *pihm_b200_create(const pihm_b200_mesh *mesh, int device,
+                                 int reorder);
+void            pihm_b200_destroy(pihm_b200_ctx *ctx);
+/* number of ODE unknowns, NumStateVar() (src/ode.c:313-339) */
+int64_t         pihm_b200_num_state_var(const pihm_b200_ctx *ctx);
+/* run all work of this context on `stream` (a cudaStream_t); NULL = default */
+int             pihm_b200_set_stream(pihm_b200_ctx *ctx, void *stream);
+void           *pihm_b200_get_stream(const pihm_b200_ctx *ctx);
+int             pihm_b200_synchronize(pihm_b200_ctx *ctx);
+
+/* per-step host -> device pushes.
+ * forc: [PB_F_NCOL][nelem] table, reference order.  Columns BC*/
+/* are only read where the matching bc_type != 0. */
+int             pihm_b200_set_forcing(pihm_b200_ctx *ctx, const double *forc);
+/* single columns of the forcing table */
+int             pihm_b200_set_forcing_col(pihm_b200_ctx *ctx, int col,
+                                          const double *values);
+/* river bc.head|flux (river_struct.h:63-68), [nriver] */
+int             pihm_b200_set_river_bc(pihm_b200_ctx *ctx, const double *bc);
+/* the river-edge overland flows of the previous RHS call that Infil() still
+ * sees (elem.wf.ovlflow[j] for nabr[j] < 0): [3][nelem] table,
+ * only river edges are read.  Zero after create (src/initialize.c:694). */
+int             pihm_b200_set_stale_ovlflow(pihm_b200_ctx *ctx,
+                                            const double *ovl);
+
+/* ------------------------------------------------------------------------
+ * RHS.   replaces: int ODE(realtype t, N_Vector y, N_Vector ydot, void *pihm)
+ *        (src/ode.c:3-300) and everything under Hydrol() (src/hydrol.c:3-25).
+ * Block layout [SURF;UNSAT;GW;RIVSTG;RIVGW;FBRUNSAT;FBRGW] (pihm_func.h:7-15).
+ * Returns 0, or 1 when a NaN was produced (reference: CheckDy -> exit).
+ * ---------------------------------------------------------------------- */
+/* host buffers in reference order: H2D, kernels, D2H, synchronous */
+int             pihm_b200_ode_host(pihm_b200_ctx *ctx, double t,
+                                   const double *y, double *ydot);
+/* device vectors (internal order), asynchronous on the context stream */
+int             pihm_b200_ode(pihm_b200_ctx *ctx, double t,
+                              const pihm_b200_vec *y, pihm_b200_vec *ydot);
+/* NaN flag of the RHS calls since the last query (device flag, D2H) */
+int             pihm_b200_check_nan(pihm_b200_ctx *ctx);
+/* flux diagnostics of the last RHS call, reference order:
+ * elem_flux [PB_X_NCOL][nelem], rivflow [11][nriver]; either may be NULL */
+int             pihm_b200_get_fluxes(pihm_b200_ctx *ctx, double *elem_flux,
+                                     double *rivflow);
+
+/* ------------------------------------------------------------------------
+ * Device-resident N_Vector.
+ *   replaces: cvode/src/nvec_ser/nvector_serial.c:421-770 (ops) and
+ *             :76-419 (constructors), same arithmetic per component.
+ * ---------------------------------------------------------------------- */
+pihm_b200_vec  *pihm_b200_vec_new(pihm_b200_ctx *ctx);
+void            pihm_b200_vec_free(pihm_b200_vec *v);
+int64_t         pihm_b200_vec_length(const pihm_b200_vec *v);
+void           *pihm_b200_vec_devptr(pihm_b200_vec *v);
+/* host (reference order) <-> device (internal order) */
+int             pihm_b200_vec_upload(pihm_b200_vec *v, const double *host);
+int             pihm_b200_vec_download(const pihm_b200_vec *v, double *host);
+
+void            pihm_b200_nv_linearsum(double a, const pihm_b200_vec *x,
+                                       double b, const pihm_b200_vec *y,
+                                       pihm_b200_vec *z);
+void            pihm_b200_nv_const(double c, pihm_b200_vec *z);
+void            pihm_b200_nv_prod(const pihm_b200_vec *x,
+                                  const pihm_b200_vec *y, pihm_b200_vec *z);
+void            pihm_b200_nv_div(const pihm_b200_vec *x,
+                                 const pihm_b200_vec *y, pihm_b200_vec *z);
+void            pihm_b200_nv_scale(double c, const pihm_b200_vec *x,
+                                   pihm_b200_vec *z);
+void            pihm_b200_nv_abs(const pihm_b200_vec *x, pihm_b200_vec *z);
+void            pihm_b200_nv_inv(const pihm_b200_vec *x, pihm_b200_vec *z);
+void            pihm_b200_nv_addconst(const pihm_b200_vec *x, double b,
+                                      pihm_b200_vec *z);
+double          pihm_b200_nv_dotprod(const pihm_b200_vec *x,
+                                     const pihm_b200_vec *y);
+double          pihm_b200_nv_maxnorm(const pihm_b200_vec *x);
+double          pihm_b200_nv_wrmsnorm(const pihm_b200_vec *x,
+                                      const pihm_b200_vec *w);
+double          pihm_b200_nv_min(const pihm_b200_vec *x);
+
+/* ------------------------------------------------------------------------
+ * Integrator: variable-order BDF + Newton + scaled GMRES(5), all vector
+ * work on the device.
+ *   replaces: SetCVodeParam / SolveCVode / AdjCVodeMaxStep (src/ode.c:340-560)
+ *   and underneath them CVodeInit/CVode (cvode/src/cvode/cvode.c:438,1074),
+ *   CVSpgmr (cvode_spgmr.c:112), SpgmrSolve (sundials_spgmr.c:165),
+ *   CVSpilsDQJtimes (cvode_spils.c:665).
+ * ---------------------------------------------------------------------- */
+typedef struct pihm_b200_cvode pihm_b200_cvode;
+
+typedef struct pihm_b200_cvode_param {
+    double          reltol;      /* ctrl.reltol   (ode.c:388) */
+    double          abstol;      /* ctrl.abstol                */
+    double          initstep;    /* ctrl.initstep (ode.c:402)  */
+    double          maxstep;     /* ctrl.maxstep  (ode.c:414)  */
+    int64_t         mxsteps;     /* ctrl.stepsize*10 (ode.c:420) */
+    int32_t         stab_lim_det;/* TRUE (ode.c:408)           */
+    int32_t         maxl;        /* 0 -> 5 (CVSpgmr(.., PREC_NONE, 0)) */
+} pihm_b200_cvode_param;
+
+/* counters, same meaning as CVodeGetNum* / CVSpilsGetNum* */
+typedef struct pihm_b200_cvode_stats {
+    int64_t         nst, nfe, nni, ncfn, netf, nli, ncfl, nfeLS, njtimes;
+    int64_t         nor, nsetups;
+    int32_t         qlast, qcur;
+    double          hlast, hcur, tcur;
+} pihm_b200_cvode_stats;
+
+/* SetCVodeParam: CVodeCreate(CV_BDF,CV_NEWTON)+CVodeInit(t0=0, y)+tolerances+
+ * CVSpgmr.  y is copied into the integrator's history at each (re)init. */
+pihm_b200_cvode *pihm_b200_cvode_create(pihm_b200_ctx *ctx);
+void            pihm_b200_cvode_destroy(pihm_b200_cvode *cv);
+int             pihm_b200_cvode_init(pihm_b200_cvode *cv,
+                                     const pihm_b200_cvode_param *p,
+                                     double t0, const pihm_b200_vec *y0);
+/* CVodeSetMaxStep (used by AdjCVodeMaxStep, ode.c:551) */
+int             pihm_b200_cvode_set_max_step(pihm_b200_cvode *cv, double hmax);
+/* SolveCVode: CVodeSetStopTime(tout); CVode(tout, CV_NORMAL).  On return y
+ * holds y(tout), *tret = tout.  Returns 0/1 (CV_SUCCESS/CV_TSTOP_RETURN) or a
+ * negative CVODE flag value. */
+int             pihm_b200_cvode_solve(pihm_b200_cvode *cv, double tout,
+                                      pihm_b200_vec *y, double *tret);
+int             pihm_b200_cvode_get_stats(const pihm_b200_cvode *cv,
+                                          pihm_b200_cvode_stats *st);
+/* AdjCVodeMaxStep (ode.c:500-560) on the integrator's own counters */
+typedef struct pihm_b200_maxstep_ctrl {
+    double          maxstep, stepsize, stmin, nncfn, nnimax, nnimin, decr, incr;
+} pihm_b200_maxstep_ctrl;
+int             pihm_b200_adj_cvode_max_step(pihm_b200_cvode *cv,
+                                             pihm_b200_maxstep_ctrl *c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIHM_B200_H */

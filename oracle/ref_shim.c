@@ -1,0 +1,740 @@
+/*
+ * ref_shim.c -- TEST INFRASTRUCTURE ONLY (oracle/).  Not part of the product.
+ *
+ * Compiled TOGETHER WITH the unmodified MM-PIHM sources where they lie under
+ * /root/reference (see oracle/Makefile) into oracle/_ref/libpihm_ref.so
+ * (-D_PIHM_) and oracle/_ref/libpihm_fbr_ref.so (-D_PIHM_ -D_FBR_).  It plays
+ * the role of the reference's main.c (src/main.c:4-16 globals, :62-112 setup)
+ * and exposes, over a plain C ABI for ctypes:
+ *   - project loading through the reference's own ReadAlloc()/Initialize(),
+ *   - construction of a pihm_struct straight from the column tables of
+ *     include/pihm_b200.h (so a synthetic watershed needs no text files),
+ *   - the packing stub pihm_struct -> column tables (the code a maintainer
+ *     would add to the pihm driver),
+ *   - the reference ODE() (src/ode.c:3), its flux fields, and the reference
+ *     SetCVodeParam()/SolveCVode()/Summary() model-step sequence of
+ *     src/pihm.c:3-134 minus printing.
+ * Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline /
+ * --impl reference legs may load these libraries.
+ */
+#include "pihm.h"
+#include "cvode_spils.h"
+#include "pihm_b200.h"
+
+/* globals that src/main.c:4-16 defines (main.c itself is not compiled) */
+int             verbose_mode;
+int             debug_mode;
+int             append_mode;
+int             corr_mode;
+int             spinup_mode;
+int             fixed_length;
+int             tecplot;
+char            project[MAXSTRING];
+int             nelem;
+int             nriver;
+#if defined(_OPENMP)
+int             nthreads = 1;
+#endif
+
+typedef struct ref_handle
+{
+    pihm_struct     pihm;
+    N_Vector        CV_Y;
+    void           *cvode_mem;
+    int             from_files;     /* forcing tables available */
+    int             cvode_ready;
+} ref_handle;
+
+static ref_handle H;
+
+int ref_is_fbr(void)
+{
+#if defined(_FBR_)
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+int ref_set_threads(int n)
+{
+#if defined(_OPENMP)
+    if (n > 0)
+    {
+        omp_set_num_threads(n);
+    }
+    nthreads = omp_get_max_threads();
+    return nthreads;
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
+int ref_sizeof_elem(void) { return (int)sizeof(elem_struct); }
+int ref_sizeof_river(void) { return (int)sizeof(river_struct); }
+
+/*
+ * Load a project through the reference's own readers and Initialize().
+ * rundir must contain input/<project>/... and input/vegprmt.tbl
+ * (read_alloc.c:22-33 builds relative paths).
+ */
+int ref_open_project(const char *rundir, const char *proj, int verbose)
+{
+    if (chdir(rundir) != 0)
+    {
+        return -1;
+    }
+    memset(&H, 0, sizeof(H));
+    verbose_mode = verbose ? VL_NORMAL : VL_SILENT;
+    debug_mode = 0;
+    strncpy(project, proj, MAXSTRING - 1);
+#if defined(_OPENMP)
+    nthreads = omp_get_max_threads();
+#endif
+    H.pihm = (pihm_struct)calloc(1, sizeof(*H.pihm));
+    ReadAlloc(H.pihm);
+    H.CV_Y = N_VNew(NumStateVar());
+    Initialize(H.pihm, H.CV_Y, &H.cvode_mem);
+    H.from_files = 1;
+    return 0;
+}
+
+/*
+ * Build a pihm_struct directly from the column tables (no files).  Only the
+ * fields read by ODE()/Hydrol()/Summary() are filled; the rest stay zero.
+ */
+int ref_create_from_tables(const pihm_b200_mesh *m, double reltol,
+    double abstol, double initstep)
+{
+    int             i, j;
+
+#if defined(_FBR_)
+    if (!m->fbr) return -2;
+#else
+    if (m->fbr) return -2;
+#endif
+    memset(&H, 0, sizeof(H));
+    verbose_mode = VL_SILENT;
+    nelem = m->nelem;
+    nriver = m->nriver;
+#if defined(_OPENMP)
+    nthreads = omp_get_max_threads();
+#endif
+    H.pihm = (pihm_struct)calloc(1, sizeof(*H.pihm));
+    H.pihm->elem = (elem_struct *)calloc(nelem, sizeof(elem_struct));
+    H.pihm->river = (river_struct *)calloc(nriver > 0 ? nriver : 1,
+        sizeof(river_struct));
+    H.pihm->ctrl.surf_mode = m->surf_mode;
+    H.pihm->ctrl.riv_mode = m->riv_mode;
+    H.pihm->ctrl.stepsize = (int)m->stepsize;
+    H.pihm->ctrl.etstep = (int)m->stepsize;
+    H.pihm->ctrl.reltol = reltol;
+    H.pihm->ctrl.abstol = abstol;
+    H.pihm->ctrl.initstep = initstep;
+    H.pihm->ctrl.maxstep = m->stepsize;
+
+#define EF(c) (m->elem_f64[(size_t)(c) * nelem + i])
+#define EI(c) (m->elem_i32[(size_t)(c) * nelem + i])
+    for (i = 0; i < nelem; i++)
+    {
+        elem_struct    *e = &H.pihm->elem[i];
+
+        e->ind = i + 1;
+        e->topo.area = EF(PB_E_AREA);
+        e->topo.zmin = EF(PB_E_ZMIN);
+        e->topo.zmax = EF(PB_E_ZMAX);
+#if defined(_FBR_)
+        e->topo.zbed = EF(PB_E_ZBED);
+#endif
+        for (j = 0; j < NUM_EDGE; j++)
+        {
+            e->nabr[j] = EI(PB_EI_NABR0 + j);
+            e->attrib.bc_type[j] = EI(PB_EI_BC0 + j);
+#if defined(_FBR_)
+            e->attrib.fbrbc_type[j] = EI(PB_EI_FBRBC0 + j);
+#endif
+            e->topo.edge[j] = EF(PB_E_EDGE0 + j);
+            e->topo.nabrdist[j] = EF(PB_E_NABRDIST0 + j);
+            e->topo.nabr_x[j] = EF(PB_E_NABRX0 + j);
+            e->topo.nabr_y[j] = EF(PB_E_NABRY0 + j);
+        }
+        e->soil.depth = EF(PB_E_DEPTH);
+        e->soil.ksath = EF(PB_E_KSATH);
+        e->soil.ksatv = EF(PB_E_KSATV);
+        e->soil.kinfv = EF(PB_E_KINFV);
+        e->soil.dinf = EF(PB_E_DINF);
+        e->soil.alpha = EF(PB_E_ALPHA);
+        e->soil.beta = EF(PB_E_BETA);
+        e->soil.porosity = EF(PB_E_POROSITY);
+        e->soil.dmac = EF(PB_E_DMAC);
+        e->soil.kmach = EF(PB_E_KMACH);
+        e->soil.kmacv = EF(PB_E_KMACV);
+        e->soil.areafv = EF(PB_E_AREAFV);
+        e->soil.areafh = EF(PB_E_AREAFH);
+        e->lc.rough = EF(PB_E_ROUGH);
+        e->ps.rzd = EF(PB_E_RZD);
+#if defined(_FBR_)
+        e->geol.depth = EF(PB_E_GDEPTH);
+        e->geol.ksath = EF(PB_E_GKSATH);
+        e->geol.ksatv = EF(PB_E_GKSATV);
+        e->geol.alpha = EF(PB_E_GALPHA);
+        e->geol.beta = EF(PB_E_GBETA);
+        e->geol.porosity = EF(PB_E_GPOROSITY);
+#endif
+        InitWFlux(&e->wf);
+    }
+#undef EF
+#undef EI
+#define RF(c) (m->riv_f64[(size_t)(c) * nriver + i])
+#define RI(c) (m->riv_i32[(size_t)(c) * nriver + i])
+    for (i = 0; i < nriver; i++)
+    {
+        river_struct   *r = &H.pihm->river[i];
+
+        r->ind = i + 1;
+        r->leftele = RI(PB_RI_LEFTELE);
+        r->rightele = RI(PB_RI_RIGHTELE);
+        r->down = RI(PB_RI_DOWN);
+        r->attrib.riverbc_type = RI(PB_RI_BCTYPE);
+        r->shp.intrpl_ord = RI(PB_RI_INTRPL_ORD);
+        r->topo.area = RF(PB_R_AREA);
+        r->topo.zmin = RF(PB_R_ZMIN);
+        r->topo.zmax = RF(PB_R_ZMAX);
+        r->topo.zbed = RF(PB_R_ZBED);
+        r->topo.node_zmax = RF(PB_R_NODE_ZMAX);
+        r->topo.dist_left = RF(PB_R_DIST_LEFT);
+        r->topo.dist_right = RF(PB_R_DIST_RIGHT);
+        r->shp.depth = RF(PB_R_SHP_DEPTH);
+        r->shp.coeff = RF(PB_R_SHP_COEFF);
+        r->shp.length = RF(PB_R_SHP_LENGTH);
+        r->shp.width = RF(PB_R_SHP_WIDTH);
+        r->matl.rough = RF(PB_R_ROUGH);
+        r->matl.cwr = RF(PB_R_CWR);
+        r->matl.ksath = RF(PB_R_KSATH);
+        r->matl.ksatv = RF(PB_R_KSATV);
+        r->matl.bedthick = RF(PB_R_BEDTHICK);
+        r->matl.porosity = RF(PB_R_POROSITY);
+        for (j = 0; j < NUM_RIVFLX; j++)
+        {
+            r->wf.rivflow[j] = 0.0;
+        }
+    }
+#undef RF
+#undef RI
+    H.CV_Y = N_VNew(NumStateVar());
+    H.cvode_mem = CVodeCreate(CV_BDF, CV_NEWTON);
+    H.from_files = 0;
+    return 0;
+}
+
+void ref_close(void)
+{
+    if (H.CV_Y) N_VDestroy(H.CV_Y);
+    if (H.cvode_mem) CVodeFree(&H.cvode_mem);
+    if (H.pihm)
+    {
+        if (H.from_files)
+        {
+            FreeMem(H.pihm);
+        }
+        else
+        {
+            free(H.pihm->elem);
+            free(H.pihm->river);
+        }
+        free(H.pihm);
+    }
+    memset(&H, 0, sizeof(H));
+}
+
+void ref_get_dims(int *ne, int *nr, int *nsv)
+{
+    *ne = nelem;
+    *nr = nriver;
+    *nsv = NumStateVar();
+}
+
+/* ctrl: [surf_mode, riv_mode, stepsize, etstep, starttime, endtime, nstep] */
+void ref_get_ctrl(int *ictrl, double *dctrl)
+{
+    const ctrl_struct *c = &H.pihm->ctrl;
+
+    ictrl[0] = c->surf_mode;
+    ictrl[1] = c->riv_mode;
+    ictrl[2] = c->stepsize;
+    ictrl[3] = c->etstep;
+    ictrl[4] = c->starttime;
+    ictrl[5] = c->endtime;
+    ictrl[6] = c->nstep;
+    dctrl[0] = c->abstol;
+    dctrl[1] = c->reltol;
+    dctrl[2] = c->initstep;
+    dctrl[3] = c->maxstep;
+    dctrl[4] = c->stmin;
+    dctrl[5] = c->nncfn;
+    dctrl[6] = c->nnimax;
+    dctrl[7] = c->nnimin;
+    dctrl[8] = c->decr;
+    dctrl[9] = c->incr;
+}
+
+/*
+ * The packing stub: pihm->elem / pihm->river (AoS) -> column tables.
+ * This is the code INTEGRATION.md asks the pihm driver to run once after
+ * Initialize() (src/main.c:77).
+ */
+void ref_pack_tables(double *ef, int32_t *ei, double *rf, int32_t *ri)
+{
+    int             i, j;
+
+#define EF(c) (ef[(size_t)(c) * nelem + i])
+#define EI(c) (ei[(size_t)(c) * nelem + i])
+    for (i = 0; i < nelem; i++)
+    {
+        const elem_struct *e = &H.pihm->elem[i];
+
+        EF(PB_E_AREA) = e->topo.area;
+        EF(PB_E_ZMIN) = e->topo.zmin;
+        EF(PB_E_ZMAX) = e->topo.zmax;
+#if defined(_FBR_)
+        EF(PB_E_ZBED) = e->topo.zbed;
+#else
+        EF(PB_E_ZBED) = 0.0;
+#endif
+        for (j = 0; j < NUM_EDGE; j++)
+        {
+            EI(PB_EI_NABR0 + j) = e->nabr[j];
+            EI(PB_EI_BC0 + j) = e->attrib.bc_type[j];
+#if defined(_FBR_)
+            EI(PB_EI_FBRBC0 + j) = e->attrib.fbrbc_type[j];
+#else
+            EI(PB_EI_FBRBC0 + j) = 0;
+#endif
+            EF(PB_E_EDGE0 + j) = e->topo.edge[j];
+            EF(PB_E_NABRDIST0 + j) = e->topo.nabrdist[j];
+            EF(PB_E_NABRX0 + j) = e->topo.nabr_x[j];
+            EF(PB_E_NABRY0 + j) = e->topo.nabr_y[j];
+        }
+        EF(PB_E_DEPTH) = e->soil.depth;
+        EF(PB_E_KSATH) = e->soil.ksath;
+        EF(PB_E_KSATV) = e->soil.ksatv;
+        EF(PB_E_KINFV) = e->soil.kinfv;
+        EF(PB_E_DINF) = e->soil.dinf;
+        EF(PB_E_ALPHA) = e->soil.alpha;
+        EF(PB_E_BETA) = e->soil.beta;
+        EF(PB_E_POROSITY) = e->soil.porosity;
+        EF(PB_E_DMAC) = e->soil.dmac;
+        EF(PB_E_KMACH) = e->soil.kmach;
+        EF(PB_E_KMACV) = e->soil.kmacv;
+        EF(PB_E_AREAFV) = e->soil.areafv;
+        EF(PB_E_AREAFH) = e->soil.areafh;
+        EF(PB_E_ROUGH) = e->lc.rough;
+        EF(PB_E_RZD) = e->ps.rzd;
+#if defined(_FBR_)
+        EF(PB_E_GDEPTH) = e->geol.depth;
+        EF(PB_E_GKSATH) = e->geol.ksath;
+        EF(PB_E_GKSATV) = e->geol.ksatv;
+        EF(PB_E_GALPHA) = e->geol.alpha;
+        EF(PB_E_GBETA) = e->geol.beta;
+        EF(PB_E_GPOROSITY) = e->geol.porosity;
+#else
+        EF(PB_E_GDEPTH) = 0.0;
+        EF(PB_E_GKSATH) = 0.0;
+        EF(PB_E_GKSATV) = 0.0;
+        EF(PB_E_GALPHA) = 0.0;
+        EF(PB_E_GBETA) = 0.0;
+        EF(PB_E_GPOROSITY) = 0.0;
+#endif
+    }
+#undef EF
+#undef EI
+#define RF(c) (rf[(size_t)(c) * nriver + i])
+#define RI(c) (ri[(size_t)(c) * nriver + i])
+    for (i = 0; i < nriver; i++)
+    {
+        const river_struct *r = &H.pihm->river[i];
+
+        RI(PB_RI_LEFTELE) = r->leftele;
+        RI(PB_RI_RIGHTELE) = r->rightele;
+        RI(PB_RI_DOWN) = r->down;
+        RI(PB_RI_BCTYPE) = r->attrib.riverbc_type;
+        RI(PB_RI_INTRPL_ORD) = r->shp.intrpl_ord;
+        RF(PB_R_AREA) = r->topo.area;
+        RF(PB_R_ZMIN) = r->topo.zmin;
+        RF(PB_R_ZMAX) = r->topo.zmax;
+        RF(PB_R_ZBED) = r->topo.zbed;
+        RF(PB_R_NODE_ZMAX) = r->topo.node_zmax;
+        RF(PB_R_DIST_LEFT) = r->topo.dist_left;
+        RF(PB_R_DIST_RIGHT) = r->topo.dist_right;
+        RF(PB_R_SHP_DEPTH) = r->shp.depth;
+        RF(PB_R_SHP_COEFF) = r->shp.coeff;
+        RF(PB_R_SHP_LENGTH) = r->shp.length;
+        RF(PB_R_SHP_WIDTH) = r->shp.width;
+        RF(PB_R_ROUGH) = r->matl.rough;
+        RF(PB_R_CWR) = r->matl.cwr;
+        RF(PB_R_KSATH) = r->matl.ksath;
+        RF(PB_R_KSATV) = r->matl.ksatv;
+        RF(PB_R_BEDTHICK) = r->matl.bedthick;
+        RF(PB_R_POROSITY) = r->matl.porosity;
+    }
+#undef RF
+#undef RI
+}
+
+/* forcing table [PB_F_NCOL][nelem] + river bc [nriver]; get and set */
+void ref_get_forcing(double *forc, double *rivbc)
+{
+    int             i, j;
+
+    for (i = 0; i < nelem; i++)
+    {
+        const elem_struct *e = &H.pihm->elem[i];
+
+        forc[(size_t)PB_F_PCPDRP * nelem + i] = e->wf.pcpdrp;
+        forc[(size_t)PB_F_EDIR * nelem + i] = e->wf.edir;
+        forc[(size_t)PB_F_ETT * nelem + i] = e->wf.ett;
+        forc[(size_t)PB_F_WS0SURF * nelem + i] = e->ws0.surf;
+        for (j = 0; j < NUM_EDGE; j++)
+        {
+            forc[(size_t)(PB_F_BC0 + j) * nelem + i] = e->bc.head[j];
+#if defined(_FBR_)
+            forc[(size_t)(PB_F_FBRBC0 + j) * nelem + i] = e->fbr_bc.head[j];
+#else
+            forc[(size_t)(PB_F_FBRBC0 + j) * nelem + i] = 0.0;
+#endif
+        }
+    }
+    for (i = 0; i < nriver; i++)
+    {
+        rivbc[i] = H.pihm->river[i].bc.head;
+    }
+}
+
+void ref_set_forcing(const double *forc, const double *rivbc)
+{
+    int             i, j;
+
+    for (i = 0; i < nelem; i++)
+    {
+        elem_struct    *e = &H.pihm->elem[i];
+
+        e->wf.pcpdrp = forc[(size_t)PB_F_PCPDRP * nelem + i];
+        e->wf.edir = forc[(size_t)PB_F_EDIR * nelem + i];
+        e->wf.ett = forc[(size_t)PB_F_ETT * nelem + i];
+        e->ws0.surf = forc[(size_t)PB_F_WS0SURF * nelem + i];
+        for (j = 0; j < NUM_EDGE; j++)
+        {
+            e->bc.head[j] = forc[(size_t)(PB_F_BC0 + j) * nelem + i];
+#if defined(_FBR_)
+            e->fbr_bc.head[j] = forc[(size_t)(PB_F_FBRBC0 + j) * nelem + i];
+#endif
+        }
+    }
+    if (rivbc)
+    {
+        for (i = 0; i < nriver; i++)
+        {
+            H.pihm->river[i].bc.head = rivbc[i];
+        }
+    }
+}
+
+/* wf.ovlflow[3] table get/set (the H2 hidden state) */
+void ref_get_ovlflow(double *ovl)
+{
+    int             i, j;
+
+    for (i = 0; i < nelem; i++)
+        for (j = 0; j < NUM_EDGE; j++)
+            ovl[(size_t)j * nelem + i] = H.pihm->elem[i].wf.ovlflow[j];
+}
+
+void ref_set_ovlflow(const double *ovl)
+{
+    int             i, j;
+
+    for (i = 0; i < nelem; i++)
+        for (j = 0; j < NUM_EDGE; j++)
+            H.pihm->elem[i].wf.ovlflow[j] = ovl[(size_t)j * nelem + i];
+}
+
+void ref_get_y(double *y)
+{
+    memcpy(y, NV_DATA(H.CV_Y), sizeof(double) * NumStateVar());
+}
+
+void ref_set_y(const double *y)
+{
+    memcpy(NV_DATA(H.CV_Y), y, sizeof(double) * NumStateVar());
+}
+
+/* the reference RHS, src/ode.c:3 */
+int ref_ode(double t, const double *y, double *dy)
+{
+    N_Vector        vy, vdy;
+    int             flag;
+
+    vy = N_VNew(NumStateVar());
+    vdy = N_VNew(NumStateVar());
+    memcpy(NV_DATA(vy), y, sizeof(double) * NumStateVar());
+    flag = ODE((realtype)t, vy, vdy, H.pihm);
+    memcpy(dy, NV_DATA(vdy), sizeof(double) * NumStateVar());
+    N_VDestroy(vy);
+    N_VDestroy(vdy);
+    return flag;
+}
+
+/* timing helper: n back-to-back reference RHS calls, returns seconds */
+double ref_time_ode(int n)
+{
+    N_Vector        vdy = N_VNew(NumStateVar());
+    double          t0, t1;
+    int             k;
+    struct timeval  tv;
+
+    gettimeofday(&tv, NULL);
+    t0 = tv.tv_sec + 1e-6 * tv.tv_usec;
+    for (k = 0; k < n; k++)
+    {
+        ODE(0.0, H.CV_Y, vdy, H.pihm);
+    }
+    gettimeofday(&tv, NULL);
+    t1 = tv.tv_sec + 1e-6 * tv.tv_usec;
+    N_VDestroy(vdy);
+    return t1 - t0;
+}
+
+/* flux fields of the last ODE() call */
+void ref_get_fluxes(double *xf, double *rivflow)
+{
+    int             i, j;
+
+#define XF(c) (xf[(size_t)(c) * nelem + i])
+    if (xf)
+    {
+        for (i = 0; i < nelem; i++)
+        {
+            const wflux_struct *wf = &H.pihm->elem[i].wf;
+
+            for (j = 0; j < NUM_EDGE; j++)
+            {
+                XF(PB_X_OVL0 + j) = wf->ovlflow[j];
+                XF(PB_X_SUB0 + j) = wf->subsurf[j];
+#if defined(_FBR_)
+                XF(PB_X_FBRFLOW0 + j) = wf->fbrflow[j];
+#else
+                XF(PB_X_FBRFLOW0 + j) = 0.0;
+#endif
+            }
+            XF(PB_X_INFIL) = wf->infil;
+            XF(PB_X_RECHG) = wf->rechg;
+            XF(PB_X_EDIR_SURF) = wf->edir_surf;
+            XF(PB_X_EDIR_UNSAT) = wf->edir_unsat;
+            XF(PB_X_EDIR_GW) = wf->edir_gw;
+            XF(PB_X_ETT_UNSAT) = wf->ett_unsat;
+            XF(PB_X_ETT_GW) = wf->ett_gw;
+#if defined(_FBR_)
+            XF(PB_X_FBR_INFIL) = wf->fbr_infil;
+            XF(PB_X_FBR_RECHG) = wf->fbr_rechg;
+#else
+            XF(PB_X_FBR_INFIL) = 0.0;
+            XF(PB_X_FBR_RECHG) = 0.0;
+#endif
+        }
+    }
+#undef XF
+    if (rivflow)
+    {
+        for (i = 0; i < nriver; i++)
+            for (j = 0; j < NUM_RIVFLX; j++)
+                rivflow[(size_t)j * nriver + i] =
+                    H.pihm->river[i].wf.rivflow[j];
+    }
+}
+
+/*
+ * Integrator side: reference SetCVodeParam (src/ode.c:340).  SetCVodeParam
+ * keeps a static `reset` flag, so it may be called once per process for a
+ * fresh cvode_mem and afterwards re-inits (CVodeReInit) -- same as a spin-up.
+ */
+void ref_set_cvode_param(void)
+{
+    SetCVodeParam(H.pihm, H.cvode_mem, H.CV_Y);
+    H.cvode_ready = 1;
+}
+
+void ref_set_max_step(double hmax)
+{
+    H.pihm->ctrl.maxstep = hmax;
+    CVodeSetMaxStep(H.cvode_mem, (realtype)hmax);
+}
+
+/*
+ * One model step of src/pihm.c:3-134 without the print calls.
+ * from_files: ApplyBc/ApplyForc/IntcpSnowEt run as in the reference.
+ * tables: forcing was injected with ref_set_forcing().
+ * Returns the model time after the step (ctime seconds).
+ */
+int ref_model_step(int cstep, int adj_max_step)
+{
+    pihm_struct     pihm = H.pihm;
+    int             t;
+
+    if (H.from_files)
+    {
+        pihm->ctrl.cstep = cstep;
+        t = pihm->ctrl.tout[cstep];
+        ApplyBc(&pihm->forc, pihm->elem, pihm->river, t);
+        if ((t - pihm->ctrl.starttime) % pihm->ctrl.etstep == 0)
+        {
+            ApplyForc(&pihm->forc, pihm->elem, t);
+            IntcpSnowEt(t, (double)pihm->ctrl.etstep, pihm->elem, &pihm->cal);
+        }
+        SolveCVode(pihm->ctrl.starttime, &t, pihm->ctrl.tout[cstep + 1], 0.0,
+            H.cvode_mem, H.CV_Y);
+    }
+    else
+    {
+        /* starttime = 0, tout[k] = k * stepsize */
+        t = cstep * pihm->ctrl.stepsize;
+        SolveCVode(0, &t, (cstep + 1) * pihm->ctrl.stepsize, 0.0,
+            H.cvode_mem, H.CV_Y);
+    }
+    Summary(pihm->elem, pihm->river, H.CV_Y, (double)pihm->ctrl.stepsize);
+    if (adj_max_step)
+    {
+        AdjCVodeMaxStep(H.cvode_mem, &pihm->ctrl);
+    }
+    return t;
+}
+
+/* only the forcing part of a model step (files mode): lets a test pull the
+ * reference's pcpdrp/edir/ett for time tout[cstep] and push them to the GPU */
+void ref_apply_forcing(int cstep)
+{
+    pihm_struct     pihm = H.pihm;
+    int             t;
+
+    if (!H.from_files) return;
+    pihm->ctrl.cstep = cstep;
+    t = pihm->ctrl.tout[cstep];
+    ApplyBc(&pihm->forc, pihm->elem, pihm->river, t);
+    if ((t - pihm->ctrl.starttime) % pihm->ctrl.etstep == 0)
+    {
+        ApplyForc(&pihm->forc, pihm->elem, t);
+        IntcpSnowEt(t, (double)pihm->ctrl.etstep, pihm->elem, &pihm->cal);
+    }
+}
+
+/* counters: nst nfe nni ncfn netf nli ncfl nfeLS njtimes nor nsetups qlast qcur */
+void ref_get_stats(long int *s, double *d)
+{
+    int             q;
+
+    CVodeGetNumSteps(H.cvode_mem, &s[0]);
+    CVodeGetNumRhsEvals(H.cvode_mem, &s[1]);
+    CVodeGetNumNonlinSolvIters(H.cvode_mem, &s[2]);
+    CVodeGetNumNonlinSolvConvFails(H.cvode_mem, &s[3]);
+    CVodeGetNumErrTestFails(H.cvode_mem, &s[4]);
+    CVSpilsGetNumLinIters(H.cvode_mem, &s[5]);
+    CVSpilsGetNumConvFails(H.cvode_mem, &s[6]);
+    CVSpilsGetNumRhsEvals(H.cvode_mem, &s[7]);
+    CVSpilsGetNumJtimesEvals(H.cvode_mem, &s[8]);
+    CVodeGetNumStabLimOrderReds(H.cvode_mem, &s[9]);
+    CVodeGetNumLinSolvSetups(H.cvode_mem, &s[10]);
+    CVodeGetLastOrder(H.cvode_mem, &q);
+    s[11] = q;
+    CVodeGetCurrentOrder(H.cvode_mem, &q);
+    s[12] = q;
+    CVodeGetLastStep(H.cvode_mem, &d[0]);
+    CVodeGetCurrentStep(H.cvode_mem, &d[1]);
+    CVodeGetCurrentTime(H.cvode_mem, &d[2]);
+}
+
+/* element/river water states after Summary() (ws), for trajectory checks */
+void ref_get_ws(double *y)
+{
+    int             i;
+
+    for (i = 0; i < nelem; i++)
+    {
+        y[SURF(i)] = H.pihm->elem[i].ws.surf;
+        y[UNSAT(i)] = H.pihm->elem[i].ws.unsat;
+        y[GW(i)] = H.pihm->elem[i].ws.gw;
+#if defined(_FBR_)
+        y[FBRUNSAT(i)] = H.pihm->elem[i].ws.fbr_unsat;
+        y[FBRGW(i)] = H.pihm->elem[i].ws.fbr_gw;
+#endif
+    }
+    for (i = 0; i < nriver; i++)
+    {
+        y[RIVSTG(i)] = H.pihm->river[i].ws.stage;
+        y[RIVGW(i)] = H.pihm->river[i].ws.gw;
+    }
+}
+
+/* initial condition of a tables-mode handle: y -> CV_Y and ws/ws0 (InitVar,
+ * src/initialize.c:569-617) */
+void ref_init_state(const double *y)
+{
+    int             i;
+
+    ref_set_y(y);
+    for (i = 0; i < nelem; i++)
+    {
+        elem_struct    *e = &H.pihm->elem[i];
+
+        e->ws.surf = y[SURF(i)];
+        e->ws.unsat = y[UNSAT(i)];
+        e->ws.gw = y[GW(i)];
+#if defined(_FBR_)
+        e->ws.fbr_unsat = y[FBRUNSAT(i)];
+        e->ws.fbr_gw = y[FBRGW(i)];
+#endif
+        e->ws0 = e->ws;
+    }
+    for (i = 0; i < nriver; i++)
+    {
+        H.pihm->river[i].ws.stage = y[RIVSTG(i)];
+        H.pihm->river[i].ws.gw = y[RIVGW(i)];
+        H.pihm->river[i].ws0 = H.pihm->river[i].ws;
+    }
+}
+
+/*
+ * Reference N_Vector kernels for the vector-op parity tests: call the serial
+ * implementation (cvode/src/nvec_ser/nvector_serial.c) on caller buffers.
+ * op: 0 linearsum 1 const 2 prod 3 div 4 scale 5 abs 6 inv 7 addconst
+ *     8 dot 9 maxnorm 10 wrmsnorm 11 min
+ */
+double ref_nvec_op(int op, long int n, double a, const double *x, double b,
+    const double *y, double *z)
+{
+    N_Vector        vx, vy, vz;
+    double          r = 0.0;
+
+    vx = N_VMake_Serial(n, (realtype *)x);
+    vy = N_VMake_Serial(n, (realtype *)y);
+    vz = N_VMake_Serial(n, z);
+    switch (op)
+    {
+        case 0: N_VLinearSum(a, vx, b, vy, vz); break;
+        case 1: N_VConst(a, vz); break;
+        case 2: N_VProd(vx, vy, vz); break;
+        case 3: N_VDiv(vx, vy, vz); break;
+        case 4: N_VScale(a, vx, vz); break;
+        case 5: N_VAbs(vx, vz); break;
+        case 6: N_VInv(vx, vz); break;
+        case 7: N_VAddConst(vx, b, vz); break;
+        case 8: r = N_VDotProd(vx, vy); break;
+        case 9: r = N_VMaxNorm(vx); break;
+        case 10: r = N_VWrmsNorm(vx, vy); break;
+        case 11: r = N_VMin(vx); break;
+        default: r = -1.0;
+    }
+    N_VDestroy(vx);
+    N_VDestroy(vy);
+    N_VDestroy(vz);
+    return r;
+}
