@@ -134,9 +134,15 @@ int             pihm_b200_set_stream(pihm_b200_ctx *ctx, void *stream);
 void           *pihm_b200_get_stream(const pihm_b200_ctx *ctx);
 int             pihm_b200_synchronize(pihm_b200_ctx *ctx);
 
+/* kernels launched by this context so far (bench.py's gpu_launches) */
+long long       pihm_b200_launch_count(const pihm_b200_ctx *ctx);
+/* perm[internal element] = reference element (0-based), [nelem] */
+int             pihm_b200_get_permutation(const pihm_b200_ctx *ctx,
+                                          int32_t *perm);
+
 /* per-step host -> device pushes.
- * forc: [PB_F_NCOL][nelem] table, reference order.  Columns BC*/
-/* are only read where the matching bc_type != 0. */
+ * forc: [PB_F_NCOL][nelem] table, reference order.  The BC columns are only
+ * read where the matching bc_type != 0. */
 int             pihm_b200_set_forcing(pihm_b200_ctx *ctx, const double *forc);
 /* single columns of the forcing table */
 int             pihm_b200_set_forcing_col(pihm_b200_ctx *ctx, int col,
@@ -163,6 +169,9 @@ int             pihm_b200_ode(pihm_b200_ctx *ctx, double t,
                               const pihm_b200_vec *y, pihm_b200_vec *ydot);
 /* NaN flag of the RHS calls since the last query (device flag, D2H) */
 int             pihm_b200_check_nan(pihm_b200_ctx *ctx);
+/* Summary()/print need the wf.* fields of the last RHS call.
+ * Writing them costs 144 B/element per call, so it is off unless asked for. */
+int             pihm_b200_set_flux_recording(pihm_b200_ctx *ctx, int on);
 /* flux diagnostics of the last RHS call, reference order:
  * elem_flux [PB_X_NCOL][nelem], rivflow [11][nriver]; either may be NULL */
 int             pihm_b200_get_fluxes(pihm_b200_ctx *ctx, double *elem_flux,

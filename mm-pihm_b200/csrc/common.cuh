@@ -1,0 +1,127 @@
+// common.cuh -- shared declarations of libpihm_b200 (host + device).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+#include "pihm_b200.h"
+
+namespace pb {
+
+// ---- error plumbing --------------------------------------------------------
+void set_error(const std::string &msg);
+
+#define PB_CUDA(call)                                                          \
+    do {                                                                       \
+        cudaError_t e_ = (call);                                               \
+        if (e_ != cudaSuccess) {                                               \
+            pb::set_error(std::string(#call) + ": " + cudaGetErrorString(e_)); \
+            return -1;                                                         \
+        }                                                                      \
+    } while (0)
+
+#define PB_CUDA_PTR(call)                                                      \
+    do {                                                                       \
+        cudaError_t e_ = (call);                                               \
+        if (e_ != cudaSuccess) {                                               \
+            pb::set_error(std::string(#call) + ": " + cudaGetErrorString(e_)); \
+            return nullptr;                                                    \
+        }                                                                      \
+    } while (0)
+
+// ---- physical constants (src/include/pihm_const.h:7,77-82) -----------------
+#define PB_GRAV 9.80665
+#define PB_PSIMIN (-70.0)
+#define PB_DEPRSTG 1.0E-4
+#define PB_GRADMIN 5.0E-8
+#define PB_SATMIN 0.1
+#define PB_RIVGRADMIN 0.05
+#define PB_KINEMATIC 1
+#define PB_DIFF_WAVE 2
+
+// rivflow slots (pihm_const.h:130-140)
+enum { RF_UP_C2C = 0, RF_DOWN_C2C, RF_LEFT_S2C, RF_RIGHT_S2C, RF_LEFT_A2C,
+       RF_RIGHT_A2C, RF_CHANL_LKG, RF_LEFT_A2A, RF_RIGHT_A2A, RF_DOWN_A2A,
+       RF_UP_A2A };
+
+// Neighbour code of an element edge on the device:
+//   code >= 0  : neighbour element (internal index)
+//   code == -1 : domain boundary
+//   code <= -2 : river edge; c = -code-2; river = c >> 2; side = c & 3
+//                (0 = this element is the river's left bank on this edge,
+//                 1 = right bank, 2 = edge never written by RiverToElem)
+#define PB_NB_BOUNDARY (-1)
+__host__ __device__ inline int nb_river_code(int river, int side) { return -((river << 2 | side) + 2); }
+
+// Device view of one model: everything the RHS kernels read.  Passed by value.
+struct DevMesh {
+    int ne, nr;          // elements, river segments
+    int nes, nrs;        // column strides (padded)
+    int fbr, surf_mode, riv_mode;
+    int record;          // write the PB_X_* flux columns
+    double dt;
+    // offsets of the state blocks inside y / ydot (pihm_func.h:7-15)
+    long long o_unsat, o_gw, o_stg, o_rgw, o_fu, o_fg;
+    const double *ef;    // [PB_E_NCOL][nes]   static element columns
+    const int *nb;       // [3][nes]           neighbour codes
+    const int *bct;      // [3][nes]           bc_type
+    const int *fbct;     // [3][nes]           fbrbc_type
+    const double *forc;  // [PB_F_NCOL][nes]   forcing columns
+    const double *rf;    // [PB_R_NCOL][nrs]   static river columns
+    const int *ri;       // [PB_RI_NCOL][nrs]  LEFT/RIGHT = internal element idx
+    const double *rivbc; // [nrs]
+    const double *fbr_dist;  // [nrs] nabrdist(left bank) + nabrdist(right bank)
+    const int *up_ptr;   // [nr+1] CSR of upstream segments, ascending index
+    const int *up_idx;
+    double *surfh, *effkh, *sf;   // [nes] per-RHS temporaries
+    double *rivflow;     // [11][nrs]
+    double *s2c_stale;   // [2][nrs]  rivflow[LEFT/RIGHT_S2C] of the previous call
+    double *xflux;       // [PB_X_NCOL][nes] (record != 0)
+    int *nan_flag;
+};
+
+}  // namespace pb
+
+// opaque handle types of the C ABI
+struct pihm_b200_ctx {
+    pb::DevMesh dm{};
+    int device = 0;
+    int reorder = 0;
+    cudaStream_t stream = nullptr;         // owned stream
+    cudaStream_t user_stream = nullptr;    // caller's stream (pihm_b200_set_stream)
+    int use_user_stream = 0;
+    cudaStream_t s() const { return use_user_stream ? user_stream : stream; }
+    int64_t nsv = 0;
+    int rhs_launches = 0;              // kernels launched per RHS call
+    // host copies kept for permutation / validation
+    std::vector<int> perm;             // internal element -> reference element
+    std::vector<int> iperm;            // reference element -> internal element
+    std::vector<int> riv_left_edge, riv_right_edge;   // edge slot of each bank
+    // device allocations
+    double *d_ef = nullptr, *d_forc = nullptr, *d_rf = nullptr, *d_rivbc = nullptr;
+    double *d_fbr_dist = nullptr;
+    int *d_nb = nullptr, *d_bct = nullptr, *d_fbct = nullptr, *d_ri = nullptr;
+    int *d_up_ptr = nullptr, *d_up_idx = nullptr;
+    double *d_tmp = nullptr;           // surfh, effkh, sf
+    double *d_rivflow = nullptr, *d_stale = nullptr, *d_xflux = nullptr;
+    int *d_nan = nullptr;
+    int *d_perm = nullptr, *d_iperm = nullptr;   // device copies (state gather)
+    // staging for host <-> device vectors
+    double *h_pin = nullptr;           // pinned, 2 * nsv
+    double *d_stage = nullptr;         // nsv (reference order)
+    pihm_b200_vec *y_tmp = nullptr, *yd_tmp = nullptr;
+    // reduction scratch
+    double *d_red = nullptr;           // partial sums
+    double *h_red = nullptr;           // pinned scalars
+    int red_blocks = 0;
+    long long launches = 0;            // total kernel launches (for gpu_launches)
+};
+
+struct pihm_b200_vec {
+    pihm_b200_ctx *ctx = nullptr;
+    double *d = nullptr;
+    int64_t n = 0;
+    bool owns = true;
+};

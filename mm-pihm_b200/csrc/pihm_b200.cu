@@ -1,0 +1,562 @@
+// pihm_b200.cu -- context, RHS entry points and N_Vector ops of libpihm_b200.so
+// (C ABI declared in include/pihm_b200.h).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include "common.cuh"
+#include "nvec.cuh"
+#include "reorder.h"
+#include "rhs.cuh"
+
+namespace pb {
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+template <typename T>
+static int upload(T **dst, const std::vector<T> &src)
+{
+    const size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
+    PB_CUDA(cudaMalloc((void **)dst, bytes));
+    if (!src.empty()) PB_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int vec_blocks(const pihm_b200_ctx *ctx, long long n)
+{
+    long long b = (n + PB_VEC_THREADS - 1) / PB_VEC_THREADS;
+    const long long cap = (long long)ctx->red_blocks;     // SMs x 8 resident CTAs
+    return (int)std::max<long long>(1, std::min(b, cap));
+}
+template <int OP, int POST>
+static double reduce_sync(pihm_b200_ctx *ctx, long long n, const double *x, const double *y)
+{
+    const int g = vec_blocks(ctx, n);
+    unsigned int *counter = (unsigned int *)(ctx->d_nan + 2);
+    double *part = ctx->d_red + 64;
+    k_reduce<OP, POST><<<g, PB_VEC_THREADS, 0, ctx->s()>>>(n, x, y, part, counter, ctx->d_red, ctx->h_red);
+    ctx->launches++;
+    cudaStreamSynchronize(ctx->s());
+    return ctx->h_red[0];
+}
+
+}  // namespace pb
+
+using namespace pb;
+
+extern "C" {
+
+const char *pihm_b200_last_error(void) { return g_err.c_str(); }
+int pihm_b200_abi_version(void) { return PIHM_B200_ABI_VERSION; }
+
+int pihm_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+pihm_b200_ctx *pihm_b200_create(const pihm_b200_mesh *mesh, int device, int reorder)
+{
+    if (!mesh || mesh->nelem <= 0 || mesh->nriver < 0 || !mesh->elem_f64 || !mesh->elem_i32) {
+        set_error("pihm_b200_create: bad mesh descriptor");
+        return nullptr;
+    }
+    if (pihm_b200_device_count() <= device) {
+        set_error("pihm_b200_create: no CUDA device (this library has no CPU path)");
+        return nullptr;
+    }
+    const int ne = mesh->nelem, nr = mesh->nriver;
+    auto EF = [&](int c, int e) { return mesh->elem_f64[(size_t)c * ne + e]; };
+    auto EI = [&](int c, int e) { return mesh->elem_i32[(size_t)c * ne + e]; };
+    auto RF = [&](int c, int r) { return mesh->riv_f64[(size_t)c * nr + r]; };
+    auto RI = [&](int c, int r) { return mesh->riv_i32[(size_t)c * nr + r]; };
+
+    // ---- validation (what the reference would trip over at run time) -------
+    for (int r = 0; r < nr; r++) {
+        const int l = RI(PB_RI_LEFTELE, r), rt = RI(PB_RI_RIGHTELE, r), d = RI(PB_RI_DOWN, r);
+        const int ord = RI(PB_RI_INTRPL_ORD, r);
+        if (l < 1 || l > ne || rt < 1 || rt > ne) {
+            set_error("river " + std::to_string(r + 1) + ": bank element out of range");
+            return nullptr;
+        }
+        if (d == 0 || d > nr || d < -4) {   // river_flow.c:381-385 exits on unknown outlet code
+            set_error("river " + std::to_string(r + 1) + ": bad downstream code " + std::to_string(d));
+            return nullptr;
+        }
+        if (ord < 1 || ord > 4) {           // river_flow.c:539-543
+            set_error("river " + std::to_string(r + 1) + ": river order not defined");
+            return nullptr;
+        }
+    }
+    for (int e = 0; e < ne; e++)
+        for (int j = 0; j < 3; j++) {
+            const int nb = EI(PB_EI_NABR0 + j, e);
+            if (nb > ne || nb < -nr) {
+                set_error("element " + std::to_string(e + 1) + ": neighbour out of range");
+                return nullptr;
+            }
+        }
+
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce != cudaSuccess) { set_error(cudaGetErrorString(ce)); return nullptr; }
+
+    pihm_b200_ctx *ctx = new pihm_b200_ctx();
+    ctx->device = device;
+    ctx->reorder = reorder;
+    DevMesh &dm = ctx->dm;
+    dm.ne = ne; dm.nr = nr;
+    dm.nes = round_up(ne, 32); dm.nrs = round_up(std::max(nr, 1), 32);
+    dm.fbr = mesh->fbr ? 1 : 0;
+    dm.surf_mode = mesh->surf_mode; dm.riv_mode = mesh->riv_mode;
+    dm.dt = mesh->stepsize;
+    dm.o_unsat = ne; dm.o_gw = 2LL * ne; dm.o_stg = 3LL * ne; dm.o_rgw = 3LL * ne + nr;
+    dm.o_fu = 3LL * ne + 2LL * nr; dm.o_fg = 4LL * ne + 2LL * nr;
+    ctx->nsv = 3LL * ne + 2LL * nr + (dm.fbr ? 2LL * ne : 0);
+
+    // ---- internal element order -------------------------------------------
+    ctx->perm.resize(ne);
+    if (reorder) {
+        std::vector<int> nabr((size_t)3 * ne);
+        for (int j = 0; j < 3; j++)
+            for (int e = 0; e < ne; e++) nabr[(size_t)j * ne + e] = EI(PB_EI_NABR0 + j, e);
+        std::vector<int> lr((size_t)2 * nr);
+        for (int r = 0; r < nr; r++) { lr[r] = RI(PB_RI_LEFTELE, r); lr[nr + r] = RI(PB_RI_RIGHTELE, r); }
+        patch_order(ne, nr, nabr.data(), lr.data(), PB_RHS_THREADS, ctx->perm.data());
+    } else {
+        std::iota(ctx->perm.begin(), ctx->perm.end(), 0);
+    }
+    ctx->iperm.resize(ne);
+    for (int i = 0; i < ne; i++) ctx->iperm[ctx->perm[i]] = i;
+    const std::vector<int> &perm = ctx->perm, &iperm = ctx->iperm;
+
+    // ---- river bank edge slots (first match, river_flow.c:159-180) ---------
+    ctx->riv_left_edge.assign(nr, -1);
+    ctx->riv_right_edge.assign(nr, -1);
+    for (int r = 0; r < nr; r++) {
+        const int l = RI(PB_RI_LEFTELE, r) - 1, rt = RI(PB_RI_RIGHTELE, r) - 1;
+        for (int j = 0; j < 3; j++)
+            if (EI(PB_EI_NABR0 + j, l) == -(r + 1)) { ctx->riv_left_edge[r] = j; break; }
+        for (int j = 0; j < 3; j++)
+            if (EI(PB_EI_NABR0 + j, rt) == -(r + 1)) { ctx->riv_right_edge[r] = j; break; }
+    }
+
+    // ---- element columns in internal order ----------------------------------
+    const int nes = dm.nes, nrs = dm.nrs;
+    std::vector<double> ef((size_t)PB_E_NCOL * nes, 0.0);
+    for (int c = 0; c < PB_E_NCOL; c++)
+        for (int i = 0; i < ne; i++) ef[(size_t)c * nes + i] = EF(c, perm[i]);
+    std::vector<int> nb((size_t)3 * nes, PB_NB_BOUNDARY), bct((size_t)3 * nes, 0), fbct((size_t)3 * nes, 0);
+    for (int i = 0; i < ne; i++) {
+        const int e = perm[i];
+        for (int j = 0; j < 3; j++) {
+            const int n = EI(PB_EI_NABR0 + j, e);
+            int code;
+            if (n > 0) code = iperm[n - 1];
+            else if (n == 0) code = PB_NB_BOUNDARY;
+            else {
+                const int r = -n - 1;
+                int side = 2;
+                if (RI(PB_RI_LEFTELE, r) - 1 == e && ctx->riv_left_edge[r] == j) side = 0;
+                if (RI(PB_RI_RIGHTELE, r) - 1 == e && ctx->riv_right_edge[r] == j) side = 1;
+                code = nb_river_code(r, side);
+            }
+            nb[(size_t)j * nes + i] = code;
+            bct[(size_t)j * nes + i] = EI(PB_EI_BC0 + j, e);
+            fbct[(size_t)j * nes + i] = EI(PB_EI_FBRBC0 + j, e);
+        }
+    }
+    // ---- river columns --------------------------------------------------------
+    std::vector<double> rf((size_t)PB_R_NCOL * nrs, 0.0), fbr_dist(nrs, 0.0);
+    std::vector<int> ri((size_t)PB_RI_NCOL * nrs, 0);
+    std::vector<int> up_ptr(nr + 1, 0), up_idx;
+    for (int r = 0; r < nr; r++) {
+        for (int c = 0; c < PB_R_NCOL; c++) rf[(size_t)c * nrs + r] = RF(c, r);
+        for (int c = 0; c < PB_RI_NCOL; c++) ri[(size_t)c * nrs + r] = RI(c, r);
+        ri[(size_t)PB_RI_LEFTELE * nrs + r] = iperm[RI(PB_RI_LEFTELE, r) - 1];
+        ri[(size_t)PB_RI_RIGHTELE * nrs + r] = iperm[RI(PB_RI_RIGHTELE, r) - 1];
+        const int jl = ctx->riv_left_edge[r], jr = ctx->riv_right_edge[r];
+        if (jl >= 0 && jr >= 0)
+            fbr_dist[r] = EF(PB_E_NABRDIST0 + jl, RI(PB_RI_LEFTELE, r) - 1) +
+                EF(PB_E_NABRDIST0 + jr, RI(PB_RI_RIGHTELE, r) - 1);
+        else if (dm.fbr) {   // lat_flow.c:102-107 "Error finding distance between elements"
+            set_error("river " + std::to_string(r + 1) + ": bank elements do not list the river as neighbour");
+            delete ctx;
+            return nullptr;
+        }
+        const int d = RI(PB_RI_DOWN, r);
+        if (d > 0) up_ptr[d]++;          // count into slot d (= (d-1)+1)
+    }
+    for (int r = 0; r < nr; r++) up_ptr[r + 1] += up_ptr[r];
+    up_idx.resize(up_ptr[nr]);
+    {
+        std::vector<int> fill(up_ptr.begin(), up_ptr.end() - 1);
+        for (int r = 0; r < nr; r++) {   // ascending r == order of river_flow.c:94-108
+            const int d = RI(PB_RI_DOWN, r);
+            if (d > 0) up_idx[fill[d - 1]++] = r;
+        }
+    }
+
+    int rc = 0;
+    rc |= upload(&ctx->d_ef, ef);
+    rc |= upload(&ctx->d_nb, nb);
+    rc |= upload(&ctx->d_bct, bct);
+    rc |= upload(&ctx->d_fbct, fbct);
+    rc |= upload(&ctx->d_rf, rf);
+    rc |= upload(&ctx->d_ri, ri);
+    rc |= upload(&ctx->d_fbr_dist, fbr_dist);
+    rc |= upload(&ctx->d_up_ptr, up_ptr);
+    rc |= upload(&ctx->d_up_idx, up_idx);
+    rc |= upload(&ctx->d_perm, ctx->perm);
+    rc |= upload(&ctx->d_iperm, ctx->iperm);
+    auto zalloc = [&](void **p, size_t bytes) {
+        if (cudaMalloc(p, bytes) != cudaSuccess) { rc = -1; return; }
+        cudaMemset(*p, 0, bytes);
+    };
+    zalloc((void **)&ctx->d_forc, sizeof(double) * PB_F_NCOL * nes);
+    zalloc((void **)&ctx->d_rivbc, sizeof(double) * nrs);
+    zalloc((void **)&ctx->d_tmp, sizeof(double) * 3 * nes);
+    zalloc((void **)&ctx->d_rivflow, sizeof(double) * PIHM_B200_NUM_RIVFLX * nrs);
+    zalloc((void **)&ctx->d_stale, sizeof(double) * 2 * nrs);
+    zalloc((void **)&ctx->d_nan, sizeof(int) * 4);
+    zalloc((void **)&ctx->d_stage, sizeof(double) * ctx->nsv);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    ctx->red_blocks = sms * 8;
+    zalloc((void **)&ctx->d_red, sizeof(double) * (ctx->red_blocks + 64));
+    if (cudaHostAlloc((void **)&ctx->h_pin, sizeof(double) * 2 * ctx->nsv, cudaHostAllocDefault) != cudaSuccess) rc = -1;
+    if (cudaHostAlloc((void **)&ctx->h_red, sizeof(double) * 64, cudaHostAllocMapped) != cudaSuccess) rc = -1;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) rc = -1;
+    if (rc != 0) {
+        set_error(std::string("pihm_b200_create: device allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
+        pihm_b200_destroy(ctx);
+        return nullptr;
+    }
+    dm.ef = ctx->d_ef; dm.nb = ctx->d_nb; dm.bct = ctx->d_bct; dm.fbct = ctx->d_fbct;
+    dm.forc = ctx->d_forc; dm.rf = ctx->d_rf; dm.ri = ctx->d_ri; dm.rivbc = ctx->d_rivbc;
+    dm.fbr_dist = ctx->d_fbr_dist; dm.up_ptr = ctx->d_up_ptr; dm.up_idx = ctx->d_up_idx;
+    dm.surfh = ctx->d_tmp; dm.effkh = ctx->d_tmp + nes; dm.sf = ctx->d_tmp + 2 * (size_t)nes;
+    dm.rivflow = ctx->d_rivflow; dm.s2c_stale = ctx->d_stale;
+    dm.xflux = nullptr; dm.record = 0;
+    dm.nan_flag = ctx->d_nan;
+    ctx->y_tmp = pihm_b200_vec_new(ctx);
+    ctx->yd_tmp = pihm_b200_vec_new(ctx);
+    if (!ctx->y_tmp || !ctx->yd_tmp) { pihm_b200_destroy(ctx); return nullptr; }
+    return ctx;
+}
+
+void pihm_b200_destroy(pihm_b200_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    pihm_b200_vec_free(ctx->y_tmp);
+    pihm_b200_vec_free(ctx->yd_tmp);
+    void *dev[] = {ctx->d_ef, ctx->d_forc, ctx->d_rf, ctx->d_rivbc, ctx->d_fbr_dist, ctx->d_nb,
+                   ctx->d_bct, ctx->d_fbct, ctx->d_ri, ctx->d_up_ptr, ctx->d_up_idx, ctx->d_tmp,
+                   ctx->d_rivflow, ctx->d_stale, ctx->d_xflux, ctx->d_nan, ctx->d_perm,
+                   ctx->d_iperm, ctx->d_stage, ctx->d_red};
+    for (void *p : dev) if (p) cudaFree(p);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    if (ctx->h_red) cudaFreeHost(ctx->h_red);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int64_t pihm_b200_num_state_var(const pihm_b200_ctx *ctx) { return ctx ? ctx->nsv : 0; }
+
+int pihm_b200_set_stream(pihm_b200_ctx *ctx, void *stream)
+{
+    if (!ctx) return -1;
+    cudaStreamSynchronize(ctx->stream);
+    // the context keeps its own stream object alive but launches on the given one
+    ctx->user_stream = (cudaStream_t)stream;
+    ctx->use_user_stream = 1;
+    return 0;
+}
+
+void *pihm_b200_get_stream(const pihm_b200_ctx *ctx) { return ctx ? (void *)ctx->s() : nullptr; }
+
+int pihm_b200_synchronize(pihm_b200_ctx *ctx)
+{
+    PB_CUDA(cudaStreamSynchronize(ctx->s()));
+    return 0;
+}
+
+long long pihm_b200_launch_count(const pihm_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int pihm_b200_get_permutation(const pihm_b200_ctx *ctx, int32_t *perm)
+{
+    if (!ctx || !perm) return -1;
+    std::copy(ctx->perm.begin(), ctx->perm.end(), perm);
+    return 0;
+}
+
+// ---- per-step pushes ----------------------------------------------------------
+int pihm_b200_set_forcing_col(pihm_b200_ctx *ctx, int col, const double *values)
+{
+    if (!ctx || col < 0 || col >= PB_F_NCOL || !values) { set_error("set_forcing_col: bad argument"); return -1; }
+    const int ne = ctx->dm.ne;
+    double *h = ctx->h_pin;                    // nsv >= 3 ne doubles of pinned staging
+    PB_CUDA(cudaStreamSynchronize(ctx->s()));
+    for (int i = 0; i < ne; i++) h[i] = values[ctx->perm[i]];
+    PB_CUDA(cudaMemcpyAsync(ctx->d_forc + (size_t)col * ctx->dm.nes, h, sizeof(double) * ne,
+                            cudaMemcpyHostToDevice, ctx->s()));
+    PB_CUDA(cudaStreamSynchronize(ctx->s()));
+    return 0;
+}
+
+int pihm_b200_set_forcing(pihm_b200_ctx *ctx, const double *forc)
+{
+    if (!ctx || !forc) { set_error("set_forcing: bad argument"); return -1; }
+    for (int c = 0; c < PB_F_NCOL; c++) {
+        // bc columns are only read where a bc_type is set; skip the copy when unused
+        if (pihm_b200_set_forcing_col(ctx, c, forc + (size_t)c * ctx->dm.ne) != 0) return -1;
+    }
+    return 0;
+}
+
+int pihm_b200_set_river_bc(pihm_b200_ctx *ctx, const double *bc)
+{
+    if (!ctx || (!bc && ctx->dm.nr)) { set_error("set_river_bc: bad argument"); return -1; }
+    if (ctx->dm.nr == 0) return 0;
+    PB_CUDA(cudaMemcpyAsync(ctx->d_rivbc, bc, sizeof(double) * ctx->dm.nr, cudaMemcpyHostToDevice, ctx->s()));
+    PB_CUDA(cudaStreamSynchronize(ctx->s()));
+    return 0;
+}
+
+int pihm_b200_set_stale_ovlflow(pihm_b200_ctx *ctx, const double *ovl)
+{
+    if (!ctx || !ovl) { set_error("set_stale_ovlflow: bad argument"); return -1; }
+    const int ne = ctx->dm.ne, nr = ctx->dm.nr, nrs = ctx->dm.nrs;
+    if (nr == 0) return 0;
+    // elem.wf.ovlflow[j] of a bank edge is -rivflow[LEFT|RIGHT_SURF2CHANL]
+    // (river_flow.c:163,175); the next RHS call moves these rows to "stale".
+    std::vector<double> rows((size_t)2 * nrs, 0.0);
+    std::vector<int> h_ri((size_t)PB_RI_NCOL * nrs);
+    PB_CUDA(cudaMemcpy(h_ri.data(), ctx->d_ri, sizeof(int) * h_ri.size(), cudaMemcpyDeviceToHost));
+    for (int r = 0; r < nr; r++) {
+        const int l = ctx->perm[h_ri[(size_t)PB_RI_LEFTELE * nrs + r]];
+        const int rt = ctx->perm[h_ri[(size_t)PB_RI_RIGHTELE * nrs + r]];
+        if (ctx->riv_left_edge[r] >= 0) rows[r] = -ovl[(size_t)ctx->riv_left_edge[r] * ne + l];
+        if (ctx->riv_right_edge[r] >= 0) rows[nrs + r] = -ovl[(size_t)ctx->riv_right_edge[r] * ne + rt];
+    }
+    PB_CUDA(cudaStreamSynchronize(ctx->s()));
+    PB_CUDA(cudaMemcpy(ctx->d_rivflow + (size_t)RF_LEFT_S2C * nrs, rows.data(), sizeof(double) * 2 * nrs,
+                       cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int pihm_b200_set_flux_recording(pihm_b200_ctx *ctx, int on)
+{
+    if (!ctx) return -1;
+    PB_CUDA(cudaStreamSynchronize(ctx->s()));
+    if (on && !ctx->d_xflux) {
+        PB_CUDA(cudaMalloc((void **)&ctx->d_xflux, sizeof(double) * PB_X_NCOL * ctx->dm.nes));
+        PB_CUDA(cudaMemset(ctx->d_xflux, 0, sizeof(double) * PB_X_NCOL * ctx->dm.nes));
+    }
+    ctx->dm.xflux = ctx->d_xflux;
+    ctx->dm.record = on ? 1 : 0;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// RHS
+// ---------------------------------------------------------------------------
+static int launch_rhs(pihm_b200_ctx *ctx, const double *y, double *dy)
+{
+    const DevMesh &dm = ctx->dm;
+    const int eb = (dm.ne + PB_RHS_THREADS - 1) / PB_RHS_THREADS;
+    const int rb = (dm.nr + PB_RHS_THREADS - 1) / PB_RHS_THREADS;
+    k_pre<<<eb + rb, PB_RHS_THREADS, 0, ctx->s()>>>(dm, y, eb);
+    if (dm.fbr) k_main<true><<<eb + rb, PB_RHS_THREADS, 0, ctx->s()>>>(dm, y, dy, eb);
+    else k_main<false><<<eb + rb, PB_RHS_THREADS, 0, ctx->s()>>>(dm, y, dy, eb);
+    ctx->launches += 2;
+    return 0;
+}
+
+int pihm_b200_ode(pihm_b200_ctx *ctx, double t, const pihm_b200_vec *y, pihm_b200_vec *ydot)
+{
+    (void)t;    // unused by the pihm / pihm-fbr physics (ode.c:3)
+    if (!ctx || !y || !ydot || y->n != ctx->nsv || ydot->n != ctx->nsv) {
+        set_error("pihm_b200_ode: bad argument");
+        return -1;
+    }
+    launch_rhs(ctx, y->d, ydot->d);
+    return 0;
+}
+
+int pihm_b200_check_nan(pihm_b200_ctx *ctx)
+{
+    int flag = 0;
+    PB_CUDA(cudaMemcpyAsync(&flag, ctx->d_nan, sizeof(int), cudaMemcpyDeviceToHost, ctx->s()));
+    PB_CUDA(cudaStreamSynchronize(ctx->s()));
+    if (flag) PB_CUDA(cudaMemsetAsync(ctx->d_nan, 0, sizeof(int), ctx->s()));
+    return flag ? 1 : 0;
+}
+
+int pihm_b200_ode_host(pihm_b200_ctx *ctx, double t, const double *y, double *ydot)
+{
+    if (!ctx || !y || !ydot) { set_error("pihm_b200_ode_host: bad argument"); return -1; }
+    if (pihm_b200_vec_upload(ctx->y_tmp, y) != 0) return -1;
+    if (pihm_b200_ode(ctx, t, ctx->y_tmp, ctx->yd_tmp) != 0) return -1;
+    if (pihm_b200_vec_download(ctx->yd_tmp, ydot) != 0) return -1;
+    PB_CUDA(cudaGetLastError());
+    return pihm_b200_check_nan(ctx);
+}
+
+int pihm_b200_get_fluxes(pihm_b200_ctx *ctx, double *elem_flux, double *rivflow)
+{
+    if (!ctx) return -1;
+    const int ne = ctx->dm.ne, nes = ctx->dm.nes, nr = ctx->dm.nr, nrs = ctx->dm.nrs;
+    PB_CUDA(cudaStreamSynchronize(ctx->s()));
+    if (elem_flux) {
+        if (!ctx->dm.record) { set_error("get_fluxes: enable pihm_b200_set_flux_recording first"); return -1; }
+        std::vector<double> h((size_t)PB_X_NCOL * nes);
+        PB_CUDA(cudaMemcpy(h.data(), ctx->d_xflux, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+        for (int c = 0; c < PB_X_NCOL; c++)
+            for (int i = 0; i < ne; i++) elem_flux[(size_t)c * ne + ctx->perm[i]] = h[(size_t)c * nes + i];
+    }
+    if (rivflow && nr) {
+        std::vector<double> h((size_t)PIHM_B200_NUM_RIVFLX * nrs);
+        PB_CUDA(cudaMemcpy(h.data(), ctx->d_rivflow, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < PIHM_B200_NUM_RIVFLX; k++)
+            for (int r = 0; r < nr; r++) rivflow[(size_t)k * nr + r] = h[(size_t)k * nrs + r];
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// device vectors
+// ---------------------------------------------------------------------------
+pihm_b200_vec *pihm_b200_vec_new(pihm_b200_ctx *ctx)
+{
+    if (!ctx) return nullptr;
+    pihm_b200_vec *v = new pihm_b200_vec();
+    v->ctx = ctx;
+    v->n = ctx->nsv;
+    if (cudaMalloc((void **)&v->d, sizeof(double) * std::max<int64_t>(v->n, 1)) != cudaSuccess) {
+        set_error("pihm_b200_vec_new: cudaMalloc failed");
+        delete v;
+        return nullptr;
+    }
+    cudaMemsetAsync(v->d, 0, sizeof(double) * v->n, ctx->s());
+    return v;
+}
+
+void pihm_b200_vec_free(pihm_b200_vec *v)
+{
+    if (!v) return;
+    if (v->owns && v->d) { cudaStreamSynchronize(v->ctx->s()); cudaFree(v->d); }
+    delete v;
+}
+
+int64_t pihm_b200_vec_length(const pihm_b200_vec *v) { return v ? v->n : 0; }
+void *pihm_b200_vec_devptr(pihm_b200_vec *v) { return v ? v->d : nullptr; }
+
+int pihm_b200_vec_upload(pihm_b200_vec *v, const double *host)
+{
+    pihm_b200_ctx *ctx = v->ctx;
+    PB_CUDA(cudaStreamSynchronize(ctx->s()));      // staging buffer reuse
+    std::memcpy(ctx->h_pin, host, sizeof(double) * v->n);
+    if (!ctx->reorder) {
+        PB_CUDA(cudaMemcpyAsync(v->d, ctx->h_pin, sizeof(double) * v->n, cudaMemcpyHostToDevice, ctx->s()));
+    } else {
+        PB_CUDA(cudaMemcpyAsync(ctx->d_stage, ctx->h_pin, sizeof(double) * v->n, cudaMemcpyHostToDevice, ctx->s()));
+        k_permute_state<<<vec_blocks(ctx, v->n), PB_VEC_THREADS, 0, ctx->s()>>>(
+            ctx->dm.ne, ctx->dm.nr, ctx->dm.fbr, ctx->d_perm, ctx->d_stage, v->d, 1);
+        ctx->launches++;
+    }
+    return 0;
+}
+
+int pihm_b200_vec_download(const pihm_b200_vec *v, double *host)
+{
+    pihm_b200_ctx *ctx = v->ctx;
+    double *h = ctx->h_pin + ctx->nsv;
+    if (!ctx->reorder) {
+        PB_CUDA(cudaMemcpyAsync(h, v->d, sizeof(double) * v->n, cudaMemcpyDeviceToHost, ctx->s()));
+    } else {
+        k_permute_state<<<vec_blocks(ctx, v->n), PB_VEC_THREADS, 0, ctx->s()>>>(
+            ctx->dm.ne, ctx->dm.nr, ctx->dm.fbr, ctx->d_perm, v->d, ctx->d_stage, 0);
+        ctx->launches++;
+        PB_CUDA(cudaMemcpyAsync(h, ctx->d_stage, sizeof(double) * v->n, cudaMemcpyDeviceToHost, ctx->s()));
+    }
+    PB_CUDA(cudaStreamSynchronize(ctx->s()));
+    std::memcpy(host, h, sizeof(double) * v->n);
+    return 0;
+}
+
+// ---- streaming ops (nvector_serial.c:421-635) ---------------------------------
+void pihm_b200_nv_linearsum(double a, const pihm_b200_vec *x, double b, const pihm_b200_vec *y,
+                            pihm_b200_vec *z)
+{
+    pihm_b200_ctx *ctx = z->ctx;
+    const long long n = z->n;
+    const int g = vec_blocks(ctx, n);
+    // VScaleSum / VScaleDiff are the only cases that round differently from
+    // (a*x)+(b*y); they are reached only when no +-1 coefficient is involved
+    // (nvector_serial.c:435-480).
+    const bool unit = (a == 1.0 || a == -1.0 || b == 1.0 || b == -1.0);
+    const int mode = (!unit && a == b) ? LS_SCALESUM : ((!unit && a == -b) ? LS_SCALEDIFF : LS_GENERAL);
+    const bool alias = (z->d == x->d) || (z->d == y->d);
+    cudaStream_t s = ctx->s();
+    if (alias) {
+        if (mode == LS_GENERAL) k_linearsum_alias<LS_GENERAL><<<g, PB_VEC_THREADS, 0, s>>>(n, a, x->d, b, y->d, z->d);
+        else if (mode == LS_SCALESUM) k_linearsum_alias<LS_SCALESUM><<<g, PB_VEC_THREADS, 0, s>>>(n, a, x->d, b, y->d, z->d);
+        else k_linearsum_alias<LS_SCALEDIFF><<<g, PB_VEC_THREADS, 0, s>>>(n, a, x->d, b, y->d, z->d);
+    } else {
+        if (mode == LS_GENERAL) k_linearsum<LS_GENERAL><<<g, PB_VEC_THREADS, 0, s>>>(n, a, x->d, b, y->d, z->d);
+        else if (mode == LS_SCALESUM) k_linearsum<LS_SCALESUM><<<g, PB_VEC_THREADS, 0, s>>>(n, a, x->d, b, y->d, z->d);
+        else k_linearsum<LS_SCALEDIFF><<<g, PB_VEC_THREADS, 0, s>>>(n, a, x->d, b, y->d, z->d);
+    }
+    ctx->launches++;
+}
+
+#define PB_EW(OP, c, xp, yp)                                                                     \
+    do {                                                                                         \
+        pihm_b200_ctx *ctx = z->ctx;                                                             \
+        k_elementwise<OP><<<vec_blocks(ctx, z->n), PB_VEC_THREADS, 0, ctx->s()>>>(z->n, c, xp, yp, z->d); \
+        ctx->launches++;                                                                         \
+    } while (0)
+
+void pihm_b200_nv_const(double c, pihm_b200_vec *z) { PB_EW(EW_CONST, c, nullptr, nullptr); }
+void pihm_b200_nv_prod(const pihm_b200_vec *x, const pihm_b200_vec *y, pihm_b200_vec *z) { PB_EW(EW_PROD, 0.0, x->d, y->d); }
+void pihm_b200_nv_div(const pihm_b200_vec *x, const pihm_b200_vec *y, pihm_b200_vec *z) { PB_EW(EW_DIV, 0.0, x->d, y->d); }
+void pihm_b200_nv_scale(double c, const pihm_b200_vec *x, pihm_b200_vec *z)
+{
+    // c == 1 copies, c == -1 negates: both equal c * x bitwise (nvector_serial.c:558-584)
+    if (c == 1.0) {
+        if (z->d != x->d) PB_EW(EW_COPY, 0.0, x->d, nullptr);
+        return;
+    }
+    PB_EW(EW_SCALE, c, x->d, nullptr);
+}
+void pihm_b200_nv_abs(const pihm_b200_vec *x, pihm_b200_vec *z) { PB_EW(EW_ABS, 0.0, x->d, nullptr); }
+void pihm_b200_nv_inv(const pihm_b200_vec *x, pihm_b200_vec *z) { PB_EW(EW_INV, 0.0, x->d, nullptr); }
+void pihm_b200_nv_addconst(const pihm_b200_vec *x, double b, pihm_b200_vec *z) { PB_EW(EW_ADDCONST, b, x->d, nullptr); }
+
+// ---- reductions (nvector_serial.c:637-725) -------------------------------------
+double pihm_b200_nv_dotprod(const pihm_b200_vec *x, const pihm_b200_vec *y)
+{
+    return reduce_sync<RD_DOT, 0>(x->ctx, x->n, x->d, y->d);
+}
+double pihm_b200_nv_maxnorm(const pihm_b200_vec *x)
+{
+    return reduce_sync<RD_MAXABS, 0>(x->ctx, x->n, x->d, nullptr);
+}
+double pihm_b200_nv_wrmsnorm(const pihm_b200_vec *x, const pihm_b200_vec *w)
+{
+    return reduce_sync<RD_WSQ, 1>(x->ctx, x->n, x->d, w->d);
+}
+double pihm_b200_nv_min(const pihm_b200_vec *x)
+{
+    return reduce_sync<RD_MIN, 0>(x->ctx, x->n, x->d, nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,777 @@
+// rhs.cuh -- the MM-PIHM right-hand side as two sm_100a FP64 kernels.
+//
+//   k_pre  : one thread per element  -> surfh, EffKh, friction slope |grad h|
+//            one thread per river    -> all river fluxes except the upstream sums
+//   k_main : one thread per element  -> lateral + vertical fluxes, dy
+//            one thread per river    -> ordered upstream accumulation, dy
+//
+// The split is forced by the data flow of the reference: the
+// overland flux of edge (i,n) needs |grad h| of BOTH elements, and |grad h| of
+// n needs the surface heads of n's neighbours; river->element fluxes are
+// computed per river and consumed per element.
+//
+// Arithmetic follows the reference expression by expression (file:line cited
+// at each function) and this translation unit is compiled with -fmad=false, so
+// + - * / sqrt round exactly like the reference's x86-64 build; only pow/log
+// (libdevice vs glibc) can differ, by <= 2 ulp.
+#pragma once
+#include "common.cuh"
+
+namespace pb {
+
+#define EFC(c, i) (m.ef[(size_t)(c) * m.nes + (i)])
+#define RFC(c, r) (m.rf[(size_t)(c) * m.nrs + (r)])
+#define RIC(c, r) (m.ri[(size_t)(c) * m.nrs + (r)])
+#define FOC(c, i) (m.forc[(size_t)(c) * m.nes + (i)])
+#define RFLX(k, r) (m.rivflow[(size_t)(k) * m.nrs + (r)])
+#define XFC(c, i) (m.xflux[(size_t)(c) * m.nes + (i)])
+
+__device__ __forceinline__ double max0(double v) { return (v >= 0.0) ? v : 0.0; }
+
+// SurfH, src/hydrol.c:92-126
+__device__ __forceinline__ double surf_h(double surfeqv)
+{
+    if (surfeqv < 0.0) return 0.0;
+    if (surfeqv <= 0.5 * PB_DEPRSTG) return sqrt(2.0 * PB_DEPRSTG * surfeqv);
+    return PB_DEPRSTG + (surfeqv - 0.5 * PB_DEPRSTG);
+}
+
+// AvgHsurf, src/lat_flow.c:175-203
+__device__ __forceinline__ double avg_hsurf(double diff, double hsurf, double hnabr)
+{
+    if (diff > 0.0) return (hsurf > PB_DEPRSTG) ? 1.0 * (hsurf - PB_DEPRSTG) : 0.0;
+    return (hnabr > PB_DEPRSTG) ? 1.0 * (hnabr - PB_DEPRSTG) : 0.0;
+}
+
+// AvgH, src/lat_flow.c:205-225
+__device__ __forceinline__ double avg_h(double diff, double hsub, double hnabr)
+{
+    double a = 0.0;
+    if (diff > 0.0) { if (hsub > 0.0) a = hsub; }
+    else { if (hnabr > 0.0) a = hnabr; }
+    return a;
+}
+
+// DhByDl, src/lat_flow.c:227-234
+__device__ __forceinline__ double dh_by_dl(const double *l1, const double *l2, const double *h)
+{
+    return -1.0 *
+        (l1[2] * (h[1] - h[0]) + l1[1] * (h[0] - h[2]) + l1[0] * (h[2] - h[1])) /
+        (l2[2] * (l1[1] - l1[0]) + l2[1] * (l1[0] - l1[2]) + l2[0] * (l1[2] - l1[1]));
+}
+
+// EffKh, src/lat_flow.c:236-265
+__device__ __forceinline__ double eff_kh(double depth, double dmac, double kmach,
+                                         double areafv, double ksath, double gw)
+{
+    gw = (gw > 0.0) ? gw : 0.0;
+    if (gw > depth - dmac) {
+        double k1 = kmach * areafv + ksath * (1.0 - areafv);
+        double k2 = ksath;
+        double d1, d2;
+        if (gw > depth) { d1 = dmac; d2 = depth - dmac; }
+        else { d1 = gw - (depth - dmac); d2 = depth - dmac; }
+        return (k1 * d1 + k2 * d2) / (d1 + d2);
+    }
+    return ksath;
+}
+
+__device__ __forceinline__ double eff_kh_elem(const DevMesh &m, int e, double gw)
+{
+    return eff_kh(EFC(PB_E_DEPTH, e), EFC(PB_E_DMAC, e), EFC(PB_E_KMACH, e),
+                  EFC(PB_E_AREAFV, e), EFC(PB_E_KSATH, e), gw);
+}
+
+// OverLandFlow, src/lat_flow.c:267-271.  pow(0, 0.6666667) == 0 exactly, so the
+// libdevice call is skipped for dry edges (bitwise the same product).
+__device__ __forceinline__ double overland_flow(double avgh, double grad, double sf,
+                                                double crossa, double rough)
+{
+    double p = (avgh == 0.0) ? 0.0 : pow(avgh, 0.6666667);
+    return crossa * p * grad / (sqrt(sf) * rough);
+}
+
+// KrFunc, src/soil.c:3-8.  The reference spells the squared factor out twice;
+// (sqrt(s) * a) * a is the same left-to-right product.
+__device__ __forceinline__ double kr_func(double beta, double satn)
+{
+    double a = 1.0 - pow(1.0 - pow(satn, beta / (beta - 1.0)), (beta - 1.0) / beta);
+    return sqrt(satn) * a * a;
+}
+
+// KrFunc(BETA_CRACK = 2.0, s), src/vert_flow.c:258: both exponents are exact
+// (2.0 and 0.5), where a correctly rounded pow equals s*s and sqrt().
+__device__ __forceinline__ double kr_func_crack(double satn)
+{
+    double a = 1.0 - sqrt(1.0 - satn * satn);
+    return sqrt(satn) * a * a;
+}
+
+// Psi, src/vert_flow.c:272-278
+__device__ __forceinline__ double psi_func(double satn, double alpha, double beta)
+{
+    satn = (satn < PB_SATMIN) ? PB_SATMIN : satn;
+    return -pow(pow(1.0 / satn, beta / (beta - 1.0)) - 1.0, 1.0 / beta) / alpha;
+}
+
+// EffKinf, src/vert_flow.c:211-270
+__device__ __forceinline__ double eff_kinf(double kinfv, double kmacv, double areafh,
+                                           double dh_by_dz, double ksatfunc, double elemsatn,
+                                           double applrate, double surfh)
+{
+    if (areafh == 0.0) return kinfv * ksatfunc;
+    if (surfh > PB_DEPRSTG) return kinfv * (1.0 - areafh) * ksatfunc + kmacv * areafh;
+    if (applrate <= dh_by_dz * kinfv * ksatfunc) return kinfv * ksatfunc;
+    double kmax = dh_by_dz * (kmacv * areafh + kinfv * (1.0 - areafh) * ksatfunc);
+    if (applrate < kmax)
+        return kinfv * (1.0 - areafh) * ksatfunc + kmacv * areafh * kr_func_crack(elemsatn);
+    return kinfv * (1.0 - areafh) * ksatfunc + kmacv * areafh;
+}
+
+// RiverCroSectArea, src/river_flow.c:518-546
+__device__ __forceinline__ double riv_area(int order, double depth, double coeff)
+{
+    depth = (depth > 0.0) ? depth : 0.0;
+    switch (order) {
+        case 1: return depth * coeff;
+        case 2: return depth * depth / coeff;
+        case 3: return 4.0 * depth * sqrt(depth) / (3.0 * sqrt(coeff));
+        case 4: return 3.0 * pow(depth, 4.0 / 3.0) / (2.0 * pow(coeff, 1.0 / 3.0));
+    }
+    return 0.0;
+}
+
+// RiverPerim, src/river_flow.c:548-581
+__device__ __forceinline__ double riv_perim(int order, double depth, double coeff)
+{
+    depth = (depth > 0.0) ? depth : 0.0;
+    switch (order) {
+        case 1: return 2.0 * depth + coeff;
+        case 2: return 2.0 * depth * sqrt(1.0 + coeff * coeff) / coeff;
+        case 3:
+            return sqrt(depth * (1.0 + 4.0 * coeff * depth) / coeff) +
+                log(2.0 * sqrt(coeff * depth) + sqrt(1.0 + 4.0 * coeff * depth)) / (2.0 * coeff);
+        case 4:
+            return 2.0 * ((pow(depth * (1.0 + 9.0 * pow(coeff, 2.0 / 3.0) * depth), 0.5) / 3.0) +
+                (log(3.0 * pow(coeff, 1.0 / 3.0) * sqrt(depth) +
+                     pow(1.0 + 9.0 * pow(coeff, 2.0 / 3.0) * depth, 0.5)) /
+                 (9.0 * pow(coeff, 1.0 / 3.0))));
+    }
+    return 0.0;
+}
+
+// river-side view of one bank element
+struct Bank {
+    double surfh, gw, zmax, zmin, effk;
+};
+
+__device__ __forceinline__ Bank load_bank(const DevMesh &m, const double *__restrict__ y, int e)
+{
+    Bank b;
+    b.surfh = surf_h(max0(y[e]));
+    b.gw = max0(y[m.o_gw + e]);
+    b.zmax = EFC(PB_E_ZMAX, e);
+    b.zmin = EFC(PB_E_ZMIN, e);
+    b.effk = eff_kh_elem(m, e, b.gw);
+    return b;
+}
+
+// OvlFlowElemToRiver, src/river_flow.c:183-253
+__device__ __forceinline__ double ovl_elem_to_river(const Bank &b, double rzmax, double zbed,
+                                                    double stage, double cwr, double len)
+{
+    double zbank = (rzmax > b.zmax) ? rzmax : b.zmax;
+    double elem_h = b.zmax + b.surfh;
+    double rivseg_h = zbed + stage;
+    double flux;
+    if (rivseg_h > elem_h) {
+        if (elem_h > zbank)
+            flux = cwr * 2.0 * sqrt(2.0 * PB_GRAV) * len * sqrt(rivseg_h - elem_h) * (rivseg_h - zbank) / 3.0;
+        else if (zbank < rivseg_h)
+            flux = cwr * 2.0 * sqrt(2.0 * PB_GRAV) * len * sqrt(rivseg_h - zbank) * (rivseg_h - zbank) / 3.0;
+        else
+            flux = 0.0;
+    } else if (b.surfh > PB_DEPRSTG) {
+        if (rivseg_h > zbank)
+            flux = -cwr * 2.0 * sqrt(2.0 * PB_GRAV) * len * sqrt(elem_h - rivseg_h) * (elem_h - zbank) / 3.0;
+        else if (zbank < elem_h)
+            flux = -cwr * 2.0 * sqrt(2.0 * PB_GRAV) * len * sqrt(elem_h - zbank) * (elem_h - zbank) / 3.0;
+        else
+            flux = 0.0;
+    } else {
+        flux = 0.0;
+    }
+    return flux;
+}
+
+// ChanFlowElemToRiver, src/river_flow.c:427-458
+__device__ __forceinline__ double chan_elem_to_river(const Bank &b, double zbed, double stage,
+                                                     double rksath, double len, double distance)
+{
+    double diff_h = (stage + zbed) - (b.gw + b.zmin);
+    double avgh;
+    if (b.zmin > zbed) avgh = b.gw;
+    else if (b.zmin + b.gw > zbed) avgh = b.zmin + b.gw - zbed;
+    else avgh = 0.0;
+    avgh = avg_h(diff_h, stage, avgh);
+    double grad_h = diff_h / distance;
+    double avg_ksat = 0.5 * (b.effk + rksath);
+    return len * avg_ksat * grad_h * avgh;
+}
+
+// SubFlowElemToRiver, src/river_flow.c:460-496 (_ARITH_)
+__device__ __forceinline__ double sub_elem_to_river(const Bank &b, double zbed, double rzmin,
+                                                    double rgw, double effk_riv, double len,
+                                                    double distance)
+{
+    double diff_h = (rgw + rzmin) - (b.gw + b.zmin);
+    double avgh;
+    if (b.zmin > zbed) avgh = 0.0;
+    else if (b.zmin + b.gw > zbed) avgh = zbed - b.zmin;
+    else avgh = b.gw;
+    avgh = avg_h(diff_h, rgw, avgh);
+    double avg_ksat = 0.5 * (b.effk + effk_riv);
+    double grad_h = diff_h / distance;
+    return len * avg_ksat * grad_h * avgh;
+}
+
+// ---------------------------------------------------------------------------
+// river part of k_pre: RiverFlow() parallel loop, src/river_flow.c:10-86
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void river_fluxes(const DevMesh &m, const double *__restrict__ y, int r)
+{
+    const double stage = max0(y[m.o_stg + r]);
+    const double rgw = max0(y[m.o_rgw + r]);
+    const int down = RIC(PB_RI_DOWN, r);
+    const int ord = RIC(PB_RI_INTRPL_ORD, r);
+    const double zbed = RFC(PB_R_ZBED, r), rzmin = RFC(PB_R_ZMIN, r), rzmax = RFC(PB_R_ZMAX, r);
+    const double len = RFC(PB_R_SHP_LENGTH, r), coeff = RFC(PB_R_SHP_COEFF, r);
+    const double rough = RFC(PB_R_ROUGH, r);
+    const Bank L = load_bank(m, y, RIC(PB_RI_LEFTELE, r));
+    const Bank R = load_bank(m, y, RIC(PB_RI_RIGHTELE, r));
+    double rf_up = 0.0, rf_down, rf_down_a2a;
+
+    // the previous call's bank overland fluxes stay visible to Infil (H2)
+    m.s2c_stale[r] = RFLX(RF_LEFT_S2C, r);
+    m.s2c_stale[m.nrs + r] = RFLX(RF_RIGHT_S2C, r);
+
+    if (down > 0) {
+        const int d = down - 1;
+        const int bct = RIC(PB_RI_BCTYPE, r);
+        if (bct != 0) {   // BoundFluxRiver, river_flow.c:390-425
+            double flux = 0.0;
+            if (bct > 0) {
+                double total_h = stage + zbed;
+                double total_h_down = m.rivbc[r];
+                double distance = 0.5 * len;
+                double grad_h = (total_h - total_h_down) / distance;
+                double avg_perim = riv_perim(ord, stage, coeff);
+                double crossa = riv_area(ord, stage, coeff);
+                double avgh = (avg_perim == 0.0) ? 0.0 : (crossa / avg_perim);
+                flux = overland_flow(avgh, grad_h, grad_h, crossa, rough);
+            } else {
+                flux = -m.rivbc[r];
+            }
+            rf_up += flux;
+        }
+        // ChanFlowRiverToRiver, river_flow.c:255-298
+        const double stage_d = max0(y[m.o_stg + d]);
+        const double rgw_d = max0(y[m.o_rgw + d]);
+        const int ord_d = RIC(PB_RI_INTRPL_ORD, d);
+        const double len_d = RFC(PB_R_SHP_LENGTH, d), coeff_d = RFC(PB_R_SHP_COEFF, d);
+        {
+            double total_h = stage + zbed;
+            double perim = riv_perim(ord, stage, coeff);
+            double total_h_down = stage_d + RFC(PB_R_ZBED, d);
+            double perim_down = riv_perim(ord_d, stage_d, coeff_d);
+            double avg_perim = (perim + perim_down) / 2.0;
+            double avg_rough = (rough + RFC(PB_R_ROUGH, d)) / 2.0;
+            double distance = 0.5 * (len + len_d);
+            double diff_h = (m.riv_mode == PB_KINEMATIC) ? (zbed - RFC(PB_R_ZBED, d))
+                                                         : (total_h - total_h_down);
+            double grad_h = diff_h / distance;
+            double avg_sf = (grad_h > 0.0) ? grad_h : PB_RIVGRADMIN;
+            double crossa = riv_area(ord, stage, coeff);
+            double crossa_down = riv_area(ord_d, stage_d, coeff_d);
+            double avg_crossa = 0.5 * (crossa + crossa_down);
+            double avgh = (avg_perim == 0.0) ? 0.0 : (avg_crossa / avg_perim);
+            rf_down = overland_flow(avgh, grad_h, avg_sf, crossa, avg_rough);
+        }
+        // SubFlowRiverToRiver, river_flow.c:300-329 (_ARITH_)
+        {
+            const Bank DL = load_bank(m, y, RIC(PB_RI_LEFTELE, d));
+            const Bank DR = load_bank(m, y, RIC(PB_RI_RIGHTELE, d));
+            double effk = 0.5 * (L.effk + R.effk);
+            double effk_nabr = 0.5 * (DL.effk + DR.effk);
+            double total_h = rgw + rzmin;
+            double total_h_down = rgw_d + RFC(PB_R_ZMIN, d);
+            double avg_wid = (RFC(PB_R_SHP_WIDTH, r) + RFC(PB_R_SHP_WIDTH, d)) / 2.0;
+            double diff_h = total_h - total_h_down;
+            double avgh = avg_h(diff_h, rgw, rgw_d);
+            double distance = 0.5 * (len + len_d);
+            double grad_h = diff_h / distance;
+            double avg_ksat = 0.5 * (effk + effk_nabr);
+            rf_down_a2a = avg_ksat * grad_h * avgh * avg_wid;
+        }
+    } else {
+        // OutletFlux, river_flow.c:331-388
+        double discharge;
+        switch (down) {
+            case -1: {
+                double total_h = stage + zbed;
+                double total_h_down = m.rivbc[r];
+                double distance = 0.5 * len;
+                double grad_h = (total_h - total_h_down) / distance;
+                double avg_perim = riv_perim(ord, stage, coeff);
+                double crossa = riv_area(ord, stage, coeff);
+                double avgh = (avg_perim == 0.0) ? 0.0 : (crossa / avg_perim);
+                discharge = overland_flow(avgh, grad_h, grad_h, crossa, rough);
+                break;
+            }
+            case -2:
+                discharge = -m.rivbc[r];
+                break;
+            case -3: {
+                double distance = 0.5 * len;
+                double grad_h = (zbed - (RFC(PB_R_NODE_ZMAX, r) - RFC(PB_R_SHP_DEPTH, r))) / distance;
+                double avg_perim = riv_perim(ord, stage, coeff);
+                double crossa = riv_area(ord, stage, coeff);
+                discharge = sqrt(grad_h) * crossa *
+                    ((avg_perim > 0.0) ? pow(crossa / avg_perim, 2.0 / 3.0) : 0.0) / rough;
+                break;
+            }
+            case -4: {
+                double crossa = riv_area(ord, stage, coeff);
+                discharge = crossa * sqrt(PB_GRAV * stage);
+                break;
+            }
+            default:      // reference exits; rejected at pihm_b200_create
+                discharge = 0.0;
+        }
+        rf_down = discharge;
+        rf_down_a2a = 0.0;
+    }
+
+    // RiverToElem, river_flow.c:111-181
+    const double cwr = RFC(PB_R_CWR, r), rksath = RFC(PB_R_KSATH, r);
+    const double dl = RFC(PB_R_DIST_LEFT, r), dr = RFC(PB_R_DIST_RIGHT, r);
+    RFLX(RF_UP_C2C, r) = rf_up;
+    RFLX(RF_DOWN_C2C, r) = rf_down;
+    RFLX(RF_LEFT_S2C, r) = ovl_elem_to_river(L, rzmax, zbed, stage, cwr, len);
+    RFLX(RF_RIGHT_S2C, r) = ovl_elem_to_river(R, rzmax, zbed, stage, cwr, len);
+    RFLX(RF_LEFT_A2C, r) = chan_elem_to_river(L, zbed, stage, rksath, len, dl);
+    RFLX(RF_RIGHT_A2C, r) = chan_elem_to_river(R, zbed, stage, rksath, len, dr);
+    const double effk_riv = 0.5 * (L.effk + R.effk);
+    RFLX(RF_LEFT_A2A, r) = sub_elem_to_river(L, zbed, rzmin, rgw, effk_riv, len, dl);
+    RFLX(RF_RIGHT_A2A, r) = sub_elem_to_river(R, zbed, rzmin, rgw, effk_riv, len, dr);
+    RFLX(RF_DOWN_A2A, r) = rf_down_a2a;
+    RFLX(RF_UP_A2A, r) = 0.0;
+    // ChanLeak, river_flow.c:498-516
+    {
+        double diff_h;
+        if (zbed - (rgw + rzmin) > 0.0) diff_h = stage;
+        else diff_h = stage + zbed - (rgw + rzmin);
+        double grad_h = diff_h / RFC(PB_R_BEDTHICK, r);
+        RFLX(RF_CHANL_LKG, r) = RFC(PB_R_KSATV, r) * RFC(PB_R_SHP_WIDTH, r) * len * grad_h;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// element part of k_pre: SurfH (hydrol.c:10-14), EffKh of the own column, and
+// FrictSlope (lat_flow.c:118-173) reduced to |grad h| = sqrt(dhbydx^2+dhbydy^2),
+// the only form LateralFlow uses it in (lat_flow.c:33-36).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void elem_pre(const DevMesh &m, const double *__restrict__ y, int i)
+{
+    const double surfh = surf_h(max0(y[i]));
+    const double gw = max0(y[m.o_gw + i]);
+    m.surfh[i] = surfh;
+    m.effkh[i] = eff_kh_elem(m, i, gw);
+    if (m.surf_mode != PB_DIFF_WAVE) return;
+
+    const double zmax = EFC(PB_E_ZMAX, i);
+    double h[3], nx[3], ny[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const int code = m.nb[(size_t)j * m.nes + i];
+        nx[j] = EFC(PB_E_NABRX0 + j, i);
+        ny[j] = EFC(PB_E_NABRY0 + j, i);
+        if (code >= 0) {
+            h[j] = EFC(PB_E_ZMAX, code) + surf_h(max0(y[code]));
+        } else if (code == PB_NB_BOUNDARY) {
+            if (m.bct[(size_t)j * m.nes + i] == 0) h[j] = zmax + surfh;
+            else h[j] = FOC(PB_F_BC0 + j, i);
+        } else {
+            const int r = (-code - 2) >> 2;
+            const double stage = max0(y[m.o_stg + r]);
+            h[j] = (stage > RFC(PB_R_SHP_DEPTH, r)) ? RFC(PB_R_ZBED, r) + stage : RFC(PB_R_ZMAX, r);
+        }
+    }
+    const double dx = dh_by_dl(ny, nx, h);
+    const double dy = dh_by_dl(nx, ny, h);
+    m.sf[i] = sqrt(dx * dx + dy * dy);
+}
+
+// ---------------------------------------------------------------------------
+// element part of k_main
+// ---------------------------------------------------------------------------
+template <bool FBR>
+__device__ __forceinline__ void elem_main(const DevMesh &m, const double *__restrict__ y,
+                                          double *__restrict__ dy, int i)
+{
+    // ode.c:25-49
+    const double surf = max0(y[i]);
+    const double unsat = max0(y[m.o_unsat + i]);
+    const double gw = max0(y[m.o_gw + i]);
+    (void)surf;
+    const double surfh = m.surfh[i];
+    const double effkh = m.effkh[i];
+    const double area = EFC(PB_E_AREA, i);
+    const double zmin = EFC(PB_E_ZMIN, i), zmax = EFC(PB_E_ZMAX, i);
+    const double depth = EFC(PB_E_DEPTH, i), dinf = EFC(PB_E_DINF, i);
+    const double rough = EFC(PB_E_ROUGH, i);
+    const double pcpdrp = FOC(PB_F_PCPDRP, i);
+
+    // EtExtract (non-Noah), hydrol.c:51-87
+    double edir_surf = 0.0, edir_unsat = 0.0, edir_gw = 0.0, ett_unsat = 0.0, ett_gw = 0.0;
+    {
+        const double edir = FOC(PB_F_EDIR, i), ett = FOC(PB_F_ETT, i);
+        if (surfh >= PB_DEPRSTG) edir_surf = edir;
+        else if (gw > depth - dinf) edir_gw = edir;
+        else edir_unsat = edir;
+        if (gw > depth - EFC(PB_E_RZD, i)) ett_gw = ett;
+        else ett_unsat = ett;
+    }
+
+    // LateralFlow, lat_flow.c:17-51
+    double ovl[3], sub[3], ovl_infil[3];
+    const double sf_i = (m.surf_mode == PB_DIFF_WAVE) ? m.sf[i] : 0.0;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const int code = m.nb[(size_t)j * m.nes + i];
+        if (code >= 0) {
+            const int n = code;
+            const double edge = EFC(PB_E_EDGE0 + j, i), dist = EFC(PB_E_NABRDIST0 + j, i);
+            const double gw_n = max0(y[m.o_gw + n]);
+            const double zmin_n = EFC(PB_E_ZMIN, n), zmax_n = EFC(PB_E_ZMAX, n);
+            const double surfh_n = m.surfh[n];
+            // SubFlowElemToElem, lat_flow.c:273-298
+            double diff_h = (gw + zmin) - (gw_n + zmin_n);
+            double avgh = avg_h(diff_h, gw, gw_n);
+            double grad_h = diff_h / dist;
+            double avg_ksat = 0.5 * (effkh + m.effkh[n]);
+            sub[j] = avg_ksat * grad_h * avgh * edge;
+            // OvlFlowElemToElem, lat_flow.c:300-327 with avg_sf of :33-36
+            double avg_sf;
+            diff_h = (m.surf_mode == PB_KINEMATIC) ? zmax - zmax_n
+                                                   : (surfh + zmax) - (surfh_n + zmax_n);
+            avgh = avg_hsurf(diff_h, surfh, surfh_n);
+            grad_h = diff_h / dist;
+            if (m.surf_mode == PB_KINEMATIC) {
+                avg_sf = (grad_h > 0.0) ? grad_h : PB_GRADMIN;
+            } else {
+                avg_sf = 0.5 * (sf_i + m.sf[n]);
+                avg_sf = (avg_sf > PB_GRADMIN) ? avg_sf : PB_GRADMIN;
+            }
+            double avg_rough = 0.5 * (rough + EFC(PB_E_ROUGH, n));
+            double crossa = avgh * edge;
+            ovl[j] = overland_flow(avgh, grad_h, avg_sf, crossa, avg_rough);
+            ovl_infil[j] = ovl[j];
+        } else if (code == PB_NB_BOUNDARY) {
+            // BoundFluxElem, lat_flow.c:329-371
+            const int bc = m.bct[(size_t)j * m.nes + i];
+            ovl[j] = 0.0;
+            if (bc == 0) {
+                sub[j] = 0.0;
+            } else if (bc > 0) {
+                const double head = FOC(PB_F_BC0 + j, i);
+                double diff_h = gw + zmin - head;
+                double avgh = avg_h(diff_h, gw, head - zmin);
+                double grad_h = diff_h / EFC(PB_E_NABRDIST0 + j, i);
+                sub[j] = effkh * grad_h * avgh * EFC(PB_E_EDGE0 + j, i);
+            } else {
+                sub[j] = -FOC(PB_F_BC0 + j, i);
+            }
+            ovl_infil[j] = ovl[j];
+        } else {
+            // river edge: RiverToElem write-back, river_flow.c:159-180
+            const int c = -code - 2, r = c >> 2, side = c & 3;
+            if (side < 2) {
+                ovl[j] = -RFLX(RF_LEFT_S2C + side, r);
+                sub[j] = -(RFLX(RF_LEFT_A2C + side, r) + RFLX(RF_LEFT_A2A + side, r));
+                ovl_infil[j] = -m.s2c_stale[(size_t)side * m.nrs + r];
+            } else {
+                ovl[j] = sub[j] = ovl_infil[j] = 0.0;
+            }
+        }
+    }
+
+    // VerticalFlow: Infil (vert_flow.c:33-130) and Recharge (:132-170).  Both
+    // use the same satn / KrFunc / Psi in the unsaturated branch.
+    double infil, rechg;
+    {
+        const double alpha = EFC(PB_E_ALPHA, i), beta = EFC(PB_E_BETA, i);
+        const double kinfv = EFC(PB_E_KINFV, i), kmacv = EFC(PB_E_KMACV, i);
+        const double areafh = EFC(PB_E_AREAFH, i);
+        const bool sat = gw > depth - dinf;
+        double satn = 1.0, satkfunc = 1.0, psi_u = 0.0, deficit = 0.0;
+        if (!sat) {
+            deficit = depth - gw;
+            satn = unsat / deficit;
+            satn = (satn > 1.0) ? 1.0 : satn;
+            satn = (satn < PB_SATMIN) ? PB_SATMIN : satn;
+            psi_u = psi_func(satn, alpha, beta);
+            satkfunc = kr_func(beta, satn);
+        }
+        if (unsat + gw > depth) {
+            infil = 0.0;
+        } else {
+            double applrate = 0.0;
+#pragma unroll
+            for (int j = 0; j < 3; j++) applrate += -ovl_infil[j] / area;
+            applrate = (applrate > 0.0) ? applrate : 0.0;
+            applrate += pcpdrp;
+            double wetfrac = surfh / PB_DEPRSTG;
+            wetfrac = (wetfrac > 0.0) ? wetfrac : 0.0;
+            wetfrac = (wetfrac < 1.0) ? wetfrac : 1.0;
+            double dh_by_dz;
+            if (sat) {
+                // KrFunc(beta, 1.0) == 1.0 exactly (pow(1,x) = 1, pow(0,x>0) = 0)
+                dh_by_dz = (surfh + zmax - (gw + zmin)) / (0.5 * (surfh + dinf));
+                dh_by_dz = (surfh <= 0.0 && dh_by_dz > 0.0) ? 0.0 : dh_by_dz;
+                double kinf = eff_kinf(kinfv, kmacv, areafh, dh_by_dz, 1.0, 1.0, applrate, surfh);
+                infil = kinf * dh_by_dz;
+            } else {
+                double psi_c = (psi_u > PB_PSIMIN) ? psi_u : PB_PSIMIN;
+                double h_u = psi_c + zmax - 0.5 * dinf;
+                dh_by_dz = (surfh + zmax - h_u) / (0.5 * (surfh + dinf));
+                dh_by_dz = (surfh <= 0.0 && dh_by_dz > 0.0) ? 0.0 : dh_by_dz;
+                double kinf = eff_kinf(kinfv, kmacv, areafh, dh_by_dz, satkfunc, satn, applrate, surfh);
+                infil = kinf * dh_by_dz;
+                infil = (infil > 0.0) ? infil : 0.0;
+            }
+            const double ws0surf = FOC(PB_F_WS0SURF, i);
+            double infil_max = applrate + ((ws0surf > 0.0) ? ws0surf / m.dt : 0.0);
+            infil = (infil > infil_max) ? infil_max : infil;
+            infil *= wetfrac;
+        }
+        if (sat) {
+            rechg = infil;
+        } else {
+            // AvgKv (_ARITH_), vert_flow.c:172-209
+            const double ksatv = EFC(PB_E_KSATV, i), dmac = EFC(PB_E_DMAC, i);
+            double k1, k2, k3, d1, d2, d3;
+            if (deficit > dmac) {
+                k1 = satkfunc * ksatv; d1 = dmac;
+                k2 = satkfunc * ksatv; d2 = deficit - dmac;
+                k3 = ksatv; d3 = gw;
+            } else {
+                k1 = satkfunc * ksatv; d1 = deficit;
+                k2 = (areafh > 0.0) ? kmacv * areafh + ksatv * (1.0 - areafh) : ksatv;
+                d2 = dmac - deficit;
+                k3 = ksatv; d3 = gw - (dmac - deficit);
+            }
+            double kavg = (k1 * d1 + k2 * d2 + k3 * d3) / (d1 + d2 + d3);
+            double dh_by_dz = (0.5 * deficit + psi_u) / (0.5 * (deficit + gw));
+            rechg = kavg * dh_by_dz;
+            rechg = (rechg > 0.0 && unsat <= 0.0) ? 0.0 : rechg;
+            rechg = (rechg < 0.0 && gw <= 0.0) ? 0.0 : rechg;
+        }
+    }
+
+    // assemble, ode.c:108-150
+    double dsurf = 0.0, dunsat = 0.0, dgw = 0.0;
+    dsurf += pcpdrp - infil - edir_surf;
+    dunsat += infil - rechg - edir_unsat - ett_unsat;
+    dgw += rechg - edir_gw - ett_gw;
+
+    double fbr_infil = 0.0, fbr_rechg = 0.0, dfu = 0.0, dfg = 0.0, fbrflow[3] = {0.0, 0.0, 0.0};
+    if (FBR) {
+        const double fu = max0(y[m.o_fu + i]), fg = max0(y[m.o_fg + i]);
+        const double gdepth = EFC(PB_E_GDEPTH, i), gksatv = EFC(PB_E_GKSATV, i);
+        const double galpha = EFC(PB_E_GALPHA, i), gbeta = EFC(PB_E_GBETA, i);
+        const double zbed = EFC(PB_E_ZBED, i), gksath = EFC(PB_E_GKSATH, i);
+        const bool full = fg >= gdepth;
+        double deficit = 0.0, satkfunc = 1.0, psi_c = 0.0;
+        if (!full) {
+            deficit = gdepth - fg;
+            double satn = fu / deficit;
+            satn = (satn > 1.0) ? 1.0 : satn;
+            satn = (satn < PB_SATMIN) ? PB_SATMIN : satn;
+            psi_c = psi_func(satn, galpha, gbeta);
+            psi_c = (psi_c > PB_PSIMIN) ? psi_c : PB_PSIMIN;
+            satkfunc = kr_func(gbeta, satn);
+        }
+        // FbrInfil, vert_flow.c:284-330
+        if (full) {
+            fbr_infil = -EFC(PB_E_KSATV, i);
+        } else if (fu + fg > gdepth || gw <= 0.0) {
+            fbr_infil = 0.0;
+        } else {
+            double h_u = psi_c + zmin - 0.5 * deficit;
+            double dh_by_dz = (zmin + gw - h_u) / (0.5 * (gw + deficit));
+            double kavg = (gw + deficit) / (gw / EFC(PB_E_KSATV, i) + deficit / (gksatv * satkfunc));
+            fbr_infil = kavg * dh_by_dz;
+        }
+        // FbrRecharge, vert_flow.c:332-373
+        if (full) {
+            fbr_rechg = fbr_infil;
+        } else {
+            double dh_by_dz = (0.5 * deficit + psi_c) / (0.5 * (deficit + fg));
+            double kavg = (fu * gksatv * satkfunc + fg * gksatv) / (fu + fg);
+            fbr_rechg = kavg * dh_by_dz;
+            fbr_rechg = (fbr_rechg > 0.0 && fu <= 0.0) ? 0.0 : fbr_rechg;
+            fbr_rechg = (fbr_rechg < 0.0 && fg <= 0.0) ? 0.0 : fbr_rechg;
+        }
+        // lateral bedrock flow, lat_flow.c:56-115
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const int code = m.nb[(size_t)j * m.nes + i];
+            if (code == PB_NB_BOUNDARY) {
+                // FbrBoundFluxElem, lat_flow.c:392-424
+                const int bc = m.fbct[(size_t)j * m.nes + i];
+                if (bc == 0) {
+                    fbrflow[j] = 0.0;
+                } else if (bc > 0) {
+                    const double head = FOC(PB_F_FBRBC0 + j, i);
+                    double diff_h = fg + zbed - head;
+                    double avgh = avg_h(diff_h, fg, head - zbed);
+                    double grad_h = diff_h / EFC(PB_E_NABRDIST0 + j, i);
+                    fbrflow[j] = gksath * grad_h * avgh * EFC(PB_E_EDGE0 + j, i);
+                } else {
+                    fbrflow[j] = -FOC(PB_F_FBRBC0 + j, i);
+                }
+            } else {
+                int n;
+                double dist;
+                if (code >= 0) {
+                    n = code;
+                    dist = EFC(PB_E_NABRDIST0 + j, i);
+                } else {
+                    // neighbour across the river, lat_flow.c:85-100
+                    const int r = (-code - 2) >> 2;
+                    const int l = RIC(PB_RI_LEFTELE, r);
+                    n = (l == i) ? RIC(PB_RI_RIGHTELE, r) : l;
+                    dist = m.fbr_dist[r];
+                }
+                // FbrFlowElemToElem, lat_flow.c:374-390
+                const double fg_n = max0(y[m.o_fg + n]);
+                double diff_h = (fg + zbed) - (fg_n + EFC(PB_E_ZBED, n));
+                double avgh = avg_h(diff_h, fg, fg_n);
+                double grad_h = diff_h / dist;
+                double avg_ksat = 0.5 * (gksath + EFC(PB_E_GKSATH, n));
+                fbrflow[j] = avg_ksat * grad_h * avgh * EFC(PB_E_EDGE0 + j, i);
+            }
+        }
+        dgw -= fbr_infil;
+        dfu += fbr_infil - fbr_rechg;
+        dfg += fbr_rechg;
+    }
+
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        dsurf -= ovl[j] / area;
+        dgw -= sub[j] / area;
+        if (FBR) dfg -= fbrflow[j] / area;
+    }
+    const double porosity = EFC(PB_E_POROSITY, i);
+    dunsat /= porosity;
+    dgw /= porosity;
+    dy[i] = dsurf;
+    dy[m.o_unsat + i] = dunsat;
+    dy[m.o_gw + i] = dgw;
+    bool bad = isnan(dsurf) || isnan(dunsat) || isnan(dgw);
+    if (FBR) {
+        const double gporosity = EFC(PB_E_GPOROSITY, i);
+        dfu /= gporosity;
+        dfg /= gporosity;
+        dy[m.o_fu + i] = dfu;
+        dy[m.o_fg + i] = dfg;
+        bad = bad || isnan(dfu) || isnan(dfg);
+    }
+    if (bad) atomicOr(m.nan_flag, 1);   // CheckDy, ode.c:302-311
+
+    if (m.record) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            XFC(PB_X_OVL0 + j, i) = ovl[j];
+            XFC(PB_X_SUB0 + j, i) = sub[j];
+            XFC(PB_X_FBRFLOW0 + j, i) = fbrflow[j];
+        }
+        XFC(PB_X_INFIL, i) = infil;
+        XFC(PB_X_RECHG, i) = rechg;
+        XFC(PB_X_EDIR_SURF, i) = edir_surf;
+        XFC(PB_X_EDIR_UNSAT, i) = edir_unsat;
+        XFC(PB_X_EDIR_GW, i) = edir_gw;
+        XFC(PB_X_ETT_UNSAT, i) = ett_unsat;
+        XFC(PB_X_ETT_GW, i) = ett_gw;
+        XFC(PB_X_FBR_INFIL, i) = fbr_infil;
+        XFC(PB_X_FBR_RECHG, i) = fbr_rechg;
+    }
+}
+
+// river part of k_main: the serial accumulation of river_flow.c:94-108 as an
+// ordered gather over the upstream list, then ode.c:228-252
+__device__ __forceinline__ void river_main(const DevMesh &m, double *__restrict__ dy, int r)
+{
+    double up_c2c = RFLX(RF_UP_C2C, r);
+    double up_a2a = 0.0;
+    for (int k = m.up_ptr[r]; k < m.up_ptr[r + 1]; k++) {
+        const int u = m.up_idx[k];
+        up_c2c -= RFLX(RF_DOWN_C2C, u);
+        up_a2a -= RFLX(RF_DOWN_A2A, u);
+    }
+    RFLX(RF_UP_C2C, r) = up_c2c;
+    RFLX(RF_UP_A2A, r) = up_a2a;
+    const double area = RFC(PB_R_AREA, r);
+    double dstg = 0.0;
+    dstg -= up_c2c / area;
+#pragma unroll
+    for (int j = 1; j <= 6; j++) dstg -= RFLX(j, r) / area;
+    double drgw = 0.0;
+    drgw += -RFLX(RF_LEFT_A2A, r) - RFLX(RF_RIGHT_A2A, r) - RFLX(RF_DOWN_A2A, r) - up_a2a +
+        RFLX(RF_CHANL_LKG, r);
+    drgw /= RFC(PB_R_POROSITY, r) * area;
+    dy[m.o_stg + r] = dstg;
+    dy[m.o_rgw + r] = drgw;
+    if (isnan(dstg) || isnan(drgw)) atomicOr(m.nan_flag, 1);
+}
+
+// ---------------------------------------------------------------------------
+// kernels.  Grid = element blocks followed by river blocks.
+// ---------------------------------------------------------------------------
+#define PB_RHS_THREADS 128
+
+__global__ void __launch_bounds__(PB_RHS_THREADS)
+k_pre(const DevMesh m, const double *__restrict__ y, int elem_blocks)
+{
+    if ((int)blockIdx.x < elem_blocks) {
+        const int i = blockIdx.x * PB_RHS_THREADS + threadIdx.x;
+        if (i < m.ne) elem_pre(m, y, i);
+    } else {
+        const int r = (blockIdx.x - elem_blocks) * PB_RHS_THREADS + threadIdx.x;
+        if (r < m.nr) river_fluxes(m, y, r);
+    }
+}
+
+template <bool FBR>
+__global__ void __launch_bounds__(PB_RHS_THREADS)
+k_main(const DevMesh m, const double *__restrict__ y, double *__restrict__ dy, int elem_blocks)
+{
+    if ((int)blockIdx.x < elem_blocks) {
+        const int i = blockIdx.x * PB_RHS_THREADS + threadIdx.x;
+        if (i < m.ne) elem_main<FBR>(m, y, dy, i);
+    } else {
+        const int r = (blockIdx.x - elem_blocks) * PB_RHS_THREADS + threadIdx.x;
+        if (r < m.nr) river_main(m, dy, r);
+    }
+}
+
+#undef EFC
+#undef RFC
+#undef RIC
+#undef FOC
+#undef RFLX
+#undef XFC
+
+}  // namespace pb

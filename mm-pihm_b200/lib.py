@@ -1,0 +1,323 @@
+"""ctypes binding of libpihm_b200.so -- the host-side mirror of the reference
+interface for the hot path (names follow src/ode.c: ODE, SetCVodeParam,
+SolveCVode, AdjCVodeMaxStep, NumStateVar; N_V* follow nvector_serial.c).
+
+There is deliberately NO fallback: if the CUDA library is missing or no GPU
+is visible, constructing a Model raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import watershed as W
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpihm_b200.so")
+
+
+class MeshStruct(C.Structure):
+    """struct pihm_b200_mesh (include/pihm_b200.h)"""
+    _fields_ = [
+        ("nelem", C.c_int32), ("nriver", C.c_int32), ("fbr", C.c_int32),
+        ("surf_mode", C.c_int32), ("riv_mode", C.c_int32), ("reserved", C.c_int32),
+        ("stepsize", C.c_double),
+        ("elem_f64", C.c_void_p), ("elem_i32", C.c_void_p),
+        ("riv_f64", C.c_void_p), ("riv_i32", C.c_void_p),
+    ]
+
+
+class CvodeParam(C.Structure):
+    """struct pihm_b200_cvode_param"""
+    _fields_ = [("reltol", C.c_double), ("abstol", C.c_double), ("initstep", C.c_double),
+                ("maxstep", C.c_double), ("mxsteps", C.c_int64),
+                ("stab_lim_det", C.c_int32), ("maxl", C.c_int32)]
+
+
+class CvodeStats(C.Structure):
+    """struct pihm_b200_cvode_stats"""
+    _fields_ = [(k, C.c_int64) for k in ("nst", "nfe", "nni", "ncfn", "netf", "nli", "ncfl",
+                                         "nfeLS", "njtimes", "nor", "nsetups")] + \
+               [("qlast", C.c_int32), ("qcur", C.c_int32),
+                ("hlast", C.c_double), ("hcur", C.c_double), ("tcur", C.c_double)]
+
+
+class MaxStepCtrl(C.Structure):
+    """struct pihm_b200_maxstep_ctrl"""
+    _fields_ = [(k, C.c_double) for k in ("maxstep", "stepsize", "stmin", "nncfn", "nnimax",
+                                          "nnimin", "decr", "incr")]
+
+
+# every symbol include/pihm_b200.h declares (tests/test_abi.py checks the list
+# against the header and against the built library)
+_SIGS = {
+    "pihm_b200_last_error": (C.c_char_p, []),
+    "pihm_b200_abi_version": (C.c_int, []),
+    "pihm_b200_device_count": (C.c_int, []),
+    "pihm_b200_create": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int]),
+    "pihm_b200_destroy": (None, [C.c_void_p]),
+    "pihm_b200_num_state_var": (C.c_int64, [C.c_void_p]),
+    "pihm_b200_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pihm_b200_get_stream": (C.c_void_p, [C.c_void_p]),
+    "pihm_b200_synchronize": (C.c_int, [C.c_void_p]),
+    "pihm_b200_launch_count": (C.c_longlong, [C.c_void_p]),
+    "pihm_b200_get_permutation": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pihm_b200_set_forcing": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pihm_b200_set_forcing_col": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "pihm_b200_set_river_bc": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pihm_b200_set_stale_ovlflow": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pihm_b200_ode_host": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
+    "pihm_b200_ode": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
+    "pihm_b200_check_nan": (C.c_int, [C.c_void_p]),
+    "pihm_b200_set_flux_recording": (C.c_int, [C.c_void_p, C.c_int]),
+    "pihm_b200_get_fluxes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pihm_b200_vec_new": (C.c_void_p, [C.c_void_p]),
+    "pihm_b200_vec_free": (None, [C.c_void_p]),
+    "pihm_b200_vec_length": (C.c_int64, [C.c_void_p]),
+    "pihm_b200_vec_devptr": (C.c_void_p, [C.c_void_p]),
+    "pihm_b200_vec_upload": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pihm_b200_vec_download": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pihm_b200_nv_linearsum": (None, [C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
+    "pihm_b200_nv_const": (None, [C.c_double, C.c_void_p]),
+    "pihm_b200_nv_prod": (None, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pihm_b200_nv_div": (None, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pihm_b200_nv_scale": (None, [C.c_double, C.c_void_p, C.c_void_p]),
+    "pihm_b200_nv_abs": (None, [C.c_void_p, C.c_void_p]),
+    "pihm_b200_nv_inv": (None, [C.c_void_p, C.c_void_p]),
+    "pihm_b200_nv_addconst": (None, [C.c_void_p, C.c_double, C.c_void_p]),
+    "pihm_b200_nv_dotprod": (C.c_double, [C.c_void_p, C.c_void_p]),
+    "pihm_b200_nv_maxnorm": (C.c_double, [C.c_void_p]),
+    "pihm_b200_nv_wrmsnorm": (C.c_double, [C.c_void_p, C.c_void_p]),
+    "pihm_b200_nv_min": (C.c_double, [C.c_void_p]),
+    "pihm_b200_cvode_create": (C.c_void_p, [C.c_void_p]),
+    "pihm_b200_cvode_destroy": (None, [C.c_void_p]),
+    "pihm_b200_cvode_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
+    "pihm_b200_cvode_set_max_step": (C.c_int, [C.c_void_p, C.c_double]),
+    "pihm_b200_cvode_solve": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
+    "pihm_b200_cvode_get_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pihm_b200_adj_cvode_max_step": (C.c_int, [C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+def load_library():
+    """dlopen libpihm_b200.so and type every entry point.  Raises if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                "there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _check(L, rc, what):
+    if rc is None or (isinstance(rc, int) and rc < 0):
+        raise RuntimeError(f"{what}: {L.pihm_b200_last_error().decode()}")
+    return rc
+
+
+class Vec:
+    """Device-resident N_Vector (internal element order)."""
+
+    def __init__(self, model: "Model", handle=None):
+        self.model = model
+        self.L = model.L
+        self.h = handle if handle is not None else self.L.pihm_b200_vec_new(model.h)
+        if not self.h:
+            raise RuntimeError("pihm_b200_vec_new: " + self.L.pihm_b200_last_error().decode())
+        self.n = int(self.L.pihm_b200_vec_length(self.h))
+
+    def upload(self, host):
+        a = np.ascontiguousarray(host, np.float64)
+        assert a.shape == (self.n,)
+        _check(self.L, self.L.pihm_b200_vec_upload(self.h, _ptr(a)), "vec_upload")
+        return self
+
+    def download(self):
+        out = np.empty(self.n)
+        _check(self.L, self.L.pihm_b200_vec_download(self.h, _ptr(out)), "vec_download")
+        return out
+
+    def free(self):
+        if self.h:
+            self.L.pihm_b200_vec_free(self.h)
+            self.h = None
+
+
+class Model:
+    """Device mirror of pihm->elem / pihm->river: pihm_b200_create + the RHS."""
+
+    def __init__(self, tables: dict, device: int = 0, reorder: int = 0):
+        self.L = L = load_library()
+        if L.pihm_b200_device_count() <= device:
+            raise RuntimeError("no CUDA device visible: libpihm_b200 has no CPU path")
+        m = MeshStruct()
+        m.nelem, m.nriver = int(tables["nelem"]), int(tables["nriver"])
+        m.fbr = int(tables["fbr"])
+        m.surf_mode, m.riv_mode = int(tables["surf_mode"]), int(tables["riv_mode"])
+        m.stepsize = float(tables["stepsize"])
+        keep = []
+        for key, dt, ncol, n in (("elem_f64", np.float64, W.E_NCOL, m.nelem),
+                                 ("elem_i32", np.int32, W.EI_NCOL, m.nelem),
+                                 ("riv_f64", np.float64, W.R_NCOL, m.nriver),
+                                 ("riv_i32", np.int32, W.RI_NCOL, m.nriver)):
+            a = np.ascontiguousarray(tables[key], dtype=dt)
+            assert a.shape == (ncol, n), (key, a.shape)
+            keep.append(a)
+            setattr(m, key, a.ctypes.data)
+        self.h = L.pihm_b200_create(C.byref(m), device, reorder)
+        if not self.h:
+            raise RuntimeError("pihm_b200_create: " + L.pihm_b200_last_error().decode())
+        self.nelem, self.nriver, self.fbr = m.nelem, m.nriver, bool(m.fbr)
+        self.nsv = int(L.pihm_b200_num_state_var(self.h))       # NumStateVar()
+
+    # lifecycle ---------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pihm_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr: int):
+        _check(self.L, self.L.pihm_b200_set_stream(self.h, C.c_void_p(cuda_stream_ptr)), "set_stream")
+
+    def synchronize(self):
+        _check(self.L, self.L.pihm_b200_synchronize(self.h), "synchronize")
+
+    @property
+    def launches(self) -> int:
+        return int(self.L.pihm_b200_launch_count(self.h))
+
+    def permutation(self):
+        p = np.empty(self.nelem, np.int32)
+        self.L.pihm_b200_get_permutation(self.h, _ptr(p))
+        return p
+
+    # per-step pushes ---------------------------------------------------------
+    def set_forcing(self, forc, rivbc=None):
+        f = np.ascontiguousarray(forc, np.float64)
+        assert f.shape == (W.F_NCOL, self.nelem)
+        _check(self.L, self.L.pihm_b200_set_forcing(self.h, _ptr(f)), "set_forcing")
+        if rivbc is not None and self.nriver:
+            rb = np.ascontiguousarray(rivbc, np.float64)
+            _check(self.L, self.L.pihm_b200_set_river_bc(self.h, _ptr(rb)), "set_river_bc")
+
+    def set_forcing_col(self, col: int, values):
+        v = np.ascontiguousarray(values, np.float64)
+        assert v.shape == (self.nelem,)
+        _check(self.L, self.L.pihm_b200_set_forcing_col(self.h, col, _ptr(v)), "set_forcing_col")
+
+    def set_stale_ovlflow(self, ovl):
+        o = np.ascontiguousarray(ovl, np.float64)
+        assert o.shape == (3, self.nelem)
+        _check(self.L, self.L.pihm_b200_set_stale_ovlflow(self.h, _ptr(o)), "set_stale_ovlflow")
+
+    def set_flux_recording(self, on: bool):
+        _check(self.L, self.L.pihm_b200_set_flux_recording(self.h, int(on)), "set_flux_recording")
+
+    # RHS -----------------------------------------------------------------------
+    def ODE(self, t, y, ydot=None):
+        """int ODE(t, y, ydot, pihm) with host buffers (src/ode.c:3)."""
+        y = np.ascontiguousarray(y, np.float64)
+        assert y.shape == (self.nsv,)
+        if ydot is None:
+            ydot = np.empty(self.nsv)
+        rc = self.L.pihm_b200_ode_host(self.h, float(t), _ptr(y), _ptr(ydot))
+        _check(self.L, rc, "ode_host")
+        self.nan_flag = rc
+        return ydot
+
+    def ode_dev(self, t, y: Vec, ydot: Vec):
+        _check(self.L, self.L.pihm_b200_ode(self.h, float(t), y.h, ydot.h), "ode")
+
+    def check_nan(self) -> int:
+        return int(self.L.pihm_b200_check_nan(self.h))
+
+    def get_fluxes(self, elem=True):
+        xf = np.zeros((W.X_NCOL, self.nelem)) if elem else None
+        rf = np.zeros((W.NUM_RIVFLX, max(self.nriver, 1)))
+        _check(self.L, self.L.pihm_b200_get_fluxes(self.h, None if xf is None else _ptr(xf), _ptr(rf)),
+               "get_fluxes")
+        return xf, rf[:, :self.nriver]
+
+    # vectors -------------------------------------------------------------------
+    def N_VNew(self, host=None) -> Vec:
+        v = Vec(self)
+        if host is not None:
+            v.upload(host)
+        return v
+
+    def N_VLinearSum(self, a, x, b, y, z): self.L.pihm_b200_nv_linearsum(a, x.h, b, y.h, z.h)
+    def N_VConst(self, c, z): self.L.pihm_b200_nv_const(c, z.h)
+    def N_VProd(self, x, y, z): self.L.pihm_b200_nv_prod(x.h, y.h, z.h)
+    def N_VDiv(self, x, y, z): self.L.pihm_b200_nv_div(x.h, y.h, z.h)
+    def N_VScale(self, c, x, z): self.L.pihm_b200_nv_scale(c, x.h, z.h)
+    def N_VAbs(self, x, z): self.L.pihm_b200_nv_abs(x.h, z.h)
+    def N_VInv(self, x, z): self.L.pihm_b200_nv_inv(x.h, z.h)
+    def N_VAddConst(self, x, b, z): self.L.pihm_b200_nv_addconst(x.h, b, z.h)
+    def N_VDotProd(self, x, y): return float(self.L.pihm_b200_nv_dotprod(x.h, y.h))
+    def N_VMaxNorm(self, x): return float(self.L.pihm_b200_nv_maxnorm(x.h))
+    def N_VWrmsNorm(self, x, w): return float(self.L.pihm_b200_nv_wrmsnorm(x.h, w.h))
+    def N_VMin(self, x): return float(self.L.pihm_b200_nv_min(x.h))
+
+
+class Cvode:
+    """SetCVodeParam / SolveCVode / AdjCVodeMaxStep flow (src/ode.c:340-560)
+    on the device-resident BDF/Newton/SPGMR integrator."""
+
+    def __init__(self, model: Model):
+        self.model = model
+        self.L = model.L
+        self.h = self.L.pihm_b200_cvode_create(model.h)
+        if not self.h:
+            raise RuntimeError("pihm_b200_cvode_create: " + self.L.pihm_b200_last_error().decode())
+        self.ctrl = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pihm_b200_cvode_destroy(self.h)
+            self.h = None
+
+    def SetCVodeParam(self, y: Vec, reltol=1e-3, abstol=1e-4, initstep=5e-5, stepsize=60.0,
+                      stmin=1.0, nncfn=0.0, nnimax=3.0, nnimin=1.0, decr=1.2, incr=1.2, t0=0.0):
+        p = CvodeParam(reltol=reltol, abstol=abstol, initstep=initstep, maxstep=stepsize,
+                       mxsteps=int(stepsize * 10), stab_lim_det=1, maxl=0)
+        _check(self.L, self.L.pihm_b200_cvode_init(self.h, C.byref(p), float(t0), y.h), "cvode_init")
+        self.ctrl = MaxStepCtrl(maxstep=stepsize, stepsize=stepsize, stmin=stmin, nncfn=nncfn,
+                                nnimax=nnimax, nnimin=nnimin, decr=decr, incr=incr)
+
+    def SolveCVode(self, tout: float, y: Vec) -> float:
+        tret = C.c_double(0.0)
+        rc = self.L.pihm_b200_cvode_solve(self.h, float(tout), y.h, C.byref(tret))
+        if rc < 0:
+            raise RuntimeError(f"SolveCVode failed with flag {rc}: "
+                               + self.L.pihm_b200_last_error().decode())
+        return tret.value
+
+    def AdjCVodeMaxStep(self):
+        _check(self.L, self.L.pihm_b200_adj_cvode_max_step(self.h, C.byref(self.ctrl)), "adj_max_step")
+        return self.ctrl.maxstep
+
+    def stats(self) -> dict:
+        st = CvodeStats()
+        self.L.pihm_b200_cvode_get_stats(self.h, C.byref(st))
+        return {k: getattr(st, k) for k, _ in CvodeStats._fields_}

@@ -234,15 +234,14 @@ void ref_close(void)
     if (H.cvode_mem) CVodeFree(&H.cvode_mem);
     if (H.pihm)
     {
-        if (H.from_files)
-        {
-            FreeMem(H.pihm);
-        }
-        else
+        if (!H.from_files)
         {
             free(H.pihm->elem);
             free(H.pihm->river);
         }
+        /* files mode: FreeMem() (src/free_mem.c) also frees the print
+         * structures that only MapOutput() sets up; the shim never calls
+         * MapOutput, so the tables are simply left to the process exit */
         free(H.pihm);
     }
     memset(&H, 0, sizeof(H));
@@ -574,9 +573,10 @@ void ref_set_max_step(double hmax)
  * One model step of src/pihm.c:3-134 without the print calls.
  * from_files: ApplyBc/ApplyForc/IntcpSnowEt run as in the reference.
  * tables: forcing was injected with ref_set_forcing().
+ * skip_forcing: the caller already ran ref_apply_forcing(cstep).
  * Returns the model time after the step (ctime seconds).
  */
-int ref_model_step(int cstep, int adj_max_step)
+int ref_model_step(int cstep, int adj_max_step, int skip_forcing)
 {
     pihm_struct     pihm = H.pihm;
     int             t;
@@ -585,11 +585,15 @@ int ref_model_step(int cstep, int adj_max_step)
     {
         pihm->ctrl.cstep = cstep;
         t = pihm->ctrl.tout[cstep];
-        ApplyBc(&pihm->forc, pihm->elem, pihm->river, t);
-        if ((t - pihm->ctrl.starttime) % pihm->ctrl.etstep == 0)
+        if (!skip_forcing)
         {
-            ApplyForc(&pihm->forc, pihm->elem, t);
-            IntcpSnowEt(t, (double)pihm->ctrl.etstep, pihm->elem, &pihm->cal);
+            ApplyBc(&pihm->forc, pihm->elem, pihm->river, t);
+            if ((t - pihm->ctrl.starttime) % pihm->ctrl.etstep == 0)
+            {
+                ApplyForc(&pihm->forc, pihm->elem, t);
+                IntcpSnowEt(t, (double)pihm->ctrl.etstep, pihm->elem,
+                    &pihm->cal);
+            }
         }
         SolveCVode(pihm->ctrl.starttime, &t, pihm->ctrl.tout[cstep + 1], 0.0,
             H.cvode_mem, H.CV_Y);

@@ -200,8 +200,8 @@ class RefModel:
     def set_max_step(self, h):
         self.lib.ref_set_max_step(float(h))
 
-    def model_step(self, cstep: int, adj_max_step: bool = False) -> int:
-        return int(self.lib.ref_model_step(int(cstep), int(adj_max_step)))
+    def model_step(self, cstep: int, adj_max_step: bool = False, skip_forcing: bool = False) -> int:
+        return int(self.lib.ref_model_step(int(cstep), int(adj_max_step), int(skip_forcing)))
 
     def apply_forcing(self, cstep: int):
         self.lib.ref_apply_forcing(int(cstep))

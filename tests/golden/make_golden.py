@@ -1,0 +1,194 @@
+"""Generate the golden vectors in tests/golden/ FROM THE REFERENCE ITSELF.
+
+Run in the build container (needs /root/reference and `make -C oracle ref`):
+
+    python tests/golden/make_golden.py
+
+Every array written here comes out of the unmodified reference code
+(oracle/_ref/libpihm*_ref.so): the reference's ReadAlloc/Initialize on its own
+input/example project, its ODE() (src/ode.c:3) and its CVODE run
+(SetCVodeParam/SolveCVode/Summary, src/pihm.c:3-134).  The files are small and
+committed, so that the oracle port and the CUDA path stay pinned to the
+reference on machines where /root/reference does not exist (the GPU box).
+
+  example_pihm.npz / example_fbr.npz
+      tables of input/example after Initialize(); K RHS known-answer cases
+      (y, forcing, river bc, stale wf.ovlflow, dy, element fluxes, rivflow);
+      a CVODE trajectory: y after model steps 1, 5, 15, 30, 45, 60 with the
+      forcing table of each etstep and the CVODE counters.
+  synth_small_{pihm,fbr}.npz
+      same for watershed.make_named('small', dirichlet_edges=True) driven by
+      watershed.storm_forcing: RHS cases on wet/branch-rich states and a
+      2-hour trajectory through the rain pulse.
+  nvec_serial.npz
+      outputs of nvector_serial.c for the special-case table of N_VLinearSum /
+      N_VScale and the four reductions.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import reflib  # noqa: E402
+import mm_pihm_b200  # noqa: E402,F401
+from mm_pihm_b200 import watershed as W  # noqa: E402
+
+REF_ROOT = "/root/reference"
+TABLE_KEYS = ("nelem", "nriver", "fbr", "surf_mode", "riv_mode", "stepsize",
+              "elem_f64", "elem_i32", "riv_f64", "riv_i32")
+
+
+def rhs_case(m, y, forc, rivbc, stale):
+    """Run the reference ODE() on (y, forcing, hidden state) and collect outputs."""
+    m.set_forcing(forc, rivbc)
+    m.set_ovlflow(stale)
+    dy = m.ode(y)
+    xf, rf = m.get_fluxes()
+    return dict(y=y.copy(), forc=forc.copy(), rivbc=np.array(rivbc, float), stale=stale.copy(),
+                dy=dy, xflux=xf, rivflow=rf)
+
+
+def pack_cases(cases, prefix="rhs"):
+    out = {f"{prefix}_n": np.int64(len(cases))}
+    for k, c in enumerate(cases):
+        for key, v in c.items():
+            out[f"{prefix}{k}_{key}"] = v
+    return out
+
+
+def example(fbr: bool):
+    m = reflib.RefModel(fbr=fbr).open_project(REF_ROOT, "example")
+    tb = m.pack_tables()
+    ctrl = m.ctrl()
+    out = {k: tb[k] for k in TABLE_KEYS}
+    out["ctrl_reltol"], out["ctrl_abstol"], out["ctrl_initstep"] = ctrl["reltol"], ctrl["abstol"], ctrl["initstep"]
+    out["y0"] = m.get_y()
+    ne = m.nelem
+    rng = np.random.default_rng(2024)
+    cases = []
+    # trajectory with the reference's own forcing (ApplyForc + IntcpSnowEt)
+    m.set_cvode_param()
+    snaps = {1, 5, 15, 30, 45, 60}
+    traj_steps, traj_y, traj_stats, forc_steps, forc_tabs = [], [], [], [], []
+    for k in range(60):
+        m.apply_forcing(k)
+        f, rb = m.get_forcing()
+        if k % 15 == 0:
+            forc_steps.append(k)
+            forc_tabs.append(f.copy())
+        if k in (0, 7, 31, 59):
+            # RHS known-answer case on a perturbed copy of the current state;
+            # restore the hidden state afterwards so the trajectory is untouched
+            stale = m.get_ovlflow()
+            y = m.get_y()
+            yp = y * (1.0 + 0.02 * rng.standard_normal(y.shape))
+            if k == 7:      # ponded surface / wet river case
+                yp[:ne] = np.abs(yp[:ne]) + rng.uniform(0, 3e-4, ne)
+                yp[3 * ne:3 * ne + m.nriver] += rng.uniform(0, 0.3, m.nriver)
+            st = stale + (rng.standard_normal(stale.shape) * 1e-6 if k else 0.0)
+            cases.append(rhs_case(m, yp, f, rb, st))
+            m.set_forcing(f, rb)
+            m.set_ovlflow(stale)
+            # ODE() overwrote elem.ws and river fluxes; CVODE re-evaluates them
+        m.model_step(k, skip_forcing=True)
+        if k + 1 in snaps:
+            traj_steps.append(k + 1)
+            traj_y.append(m.get_y())
+            s = m.stats()
+            traj_stats.append([s[key] for key in ("nst", "nfe", "nni", "ncfn", "netf", "nli", "ncfl", "nfeLS")])
+    out.update(pack_cases(cases))
+    out["traj_steps"] = np.array(traj_steps)
+    out["traj_y"] = np.array(traj_y)
+    out["traj_stats"] = np.array(traj_stats)
+    out["forc_steps"] = np.array(forc_steps)
+    out["forc_tabs"] = np.array(forc_tabs)
+    name = "example_fbr.npz" if fbr else "example_pihm.npz"
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, "cases", len(cases), "traj", traj_steps, traj_stats[-1])
+    m.close()
+
+
+def synth(fbr: bool):
+    tb = W.make_named("small", fbr=fbr, dirichlet_edges=True)
+    m = reflib.RefModel(fbr=fbr).create_from_tables(tb)
+    ne, nr = tb["nelem"], tb["nriver"]
+    rng = np.random.default_rng(99)
+    cases = []
+    for k, (seed, t) in enumerate([(7, 3 * 3600.0), (8, 5 * 3600.0), (9, 0.0)]):
+        y = W.wet_state(tb, seed=seed, ponded_frac=0.2 + 0.3 * k)
+        forc = W.storm_forcing(tb, t, ws0_surf=np.maximum(y[:ne], 0.0) * rng.uniform(0.5, 1.5, ne))
+        rivbc = np.zeros(nr)
+        stale = np.zeros((3, ne))
+        cases.append(rhs_case(m, y, forc, rivbc, stale))
+        # second call on the same state: exercises the stale river-edge ovlflow
+        stale2 = m.get_ovlflow()
+        cases.append(rhs_case(m, y * (1 + 1e-3 * rng.standard_normal(y.shape)), forc, rivbc, stale2))
+    out = pack_cases(cases)
+    # trajectory: RelaxIc start, 2 h through the rain pulse (storm starts at 1 h)
+    m.init_state(tb["y0"])
+    m.set_ovlflow(np.zeros((3, ne)))
+    m.set_cvode_param()
+    traj_steps, traj_y, traj_stats = [], [], []
+    f = None
+    for k in range(120):
+        ws = m.get_ws()
+        if k % 15 == 0:
+            f = W.storm_forcing(tb, k * 60.0)
+        f[W.F_WS0SURF] = ws[:ne]
+        m.set_forcing(f, np.zeros(nr))
+        m.model_step(k)
+        if (k + 1) in (1, 15, 60, 90, 120):
+            traj_steps.append(k + 1)
+            traj_y.append(m.get_y())
+            s = m.stats()
+            traj_stats.append([s[key] for key in ("nst", "nfe", "nni", "ncfn", "netf", "nli", "ncfl", "nfeLS")])
+    out["traj_steps"] = np.array(traj_steps)
+    out["traj_y"] = np.array(traj_y)
+    out["traj_stats"] = np.array(traj_stats)
+    name = "synth_small_fbr.npz" if fbr else "synth_small_pihm.npz"
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, "cases", len(cases), "traj", traj_steps, traj_stats[-1])
+    m.close()
+
+
+def nvec():
+    m = reflib.RefModel(fbr=False)
+    rng = np.random.default_rng(5)
+    n = 1000
+    x = rng.standard_normal(n) * 10.0 ** rng.integers(-3, 4, n)
+    y = rng.standard_normal(n) * 10.0 ** rng.integers(-3, 4, n)
+    w = np.abs(rng.standard_normal(n)) + 0.1
+    out = dict(x=x, y=y, w=w)
+    coeffs = [(1.0, 1.0), (1.0, -1.0), (-1.0, 1.0), (1.0, 0.37), (2.5, 1.0), (-1.0, 0.41),
+              (3.3, -1.0), (0.77, 0.77), (0.77, -0.77), (1.3e-3, -4.7), (-1.0, -1.0)]
+    out["ls_coeffs"] = np.array(coeffs)
+    out["ls_z"] = np.array([m.nvec_op(0, a=a, x=x, b=b, y=y)[1] for a, b in coeffs])
+    scales = [1.0, -1.0, 0.3, -2.5e-4]
+    out["sc_c"] = np.array(scales)
+    out["sc_z"] = np.array([m.nvec_op(4, a=c, x=x, y=y)[1] for c in scales])
+    out["prod"] = m.nvec_op(2, x=x, y=y)[1]
+    out["div"] = m.nvec_op(3, x=x, y=w)[1]
+    out["abs"] = m.nvec_op(5, x=x, y=y)[1]
+    out["inv"] = m.nvec_op(6, x=w, y=y)[1]
+    out["addconst"] = m.nvec_op(7, x=x, b=0.125, y=y)[1]
+    out["dot"] = m.nvec_op(8, x=x, y=y)[0]
+    out["maxnorm"] = m.nvec_op(9, x=x, y=y)[0]
+    out["wrms"] = m.nvec_op(10, x=x, y=w)[0]
+    out["min"] = m.nvec_op(11, x=x, y=y)[0]
+    np.savez_compressed(os.path.join(HERE, "nvec_serial.npz"), **out)
+    print("nvec_serial.npz", out["dot"], out["wrms"])
+
+
+if __name__ == "__main__":
+    example(False)
+    example(True)
+    synth(False)
+    synth(True)
+    nvec()

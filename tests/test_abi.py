@@ -1,0 +1,79 @@
+"""CPU-side checks of the drop-in boundary: the C ABI library loads, exports
+every symbol include/pihm_b200.h declares, the Python mirror types every one
+of them, the column enums agree, and without a GPU the product refuses to run
+(no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import mm_pihm_b200  # noqa: F401
+from mm_pihm_b200 import lib, watershed as W
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "pihm_b200.h")
+
+
+def header_text():
+    with open(HEADER) as f:
+        txt = f.read()
+    return re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+
+
+def declared_symbols():
+    return sorted(set(re.findall(r"\b(pihm_b200_[a-z0-9_]+)\s*\(", header_text())))
+
+
+def test_library_exports_every_declared_symbol():
+    L = lib.load_library()
+    syms = declared_symbols()
+    assert len(syms) >= 40
+    for s in syms:
+        assert hasattr(L, s), f"libpihm_b200.so does not export {s}"
+    assert sorted(lib._SIGS) == syms, "lib.py mirror and header disagree"
+    assert L.pihm_b200_abi_version() == 1
+
+
+def test_enums_match_python_mirror():
+    txt = header_text()
+    for enum, prefix, pyprefix in (("pihm_b200_elem_col", "PB_E_", "E_"),
+                                   ("pihm_b200_elem_icol", "PB_EI_", "EI_"),
+                                   ("pihm_b200_elem_forc_col", "PB_F_", "F_"),
+                                   ("pihm_b200_riv_col", "PB_R_", "R_"),
+                                   ("pihm_b200_riv_icol", "PB_RI_", "RI_"),
+                                   ("pihm_b200_elem_flux_col", "PB_X_", "X_")):
+        body = re.search(r"enum\s+%s\s*\{(.*?)\}" % enum, txt, flags=re.S).group(1)
+        names = [n.strip().split("=")[0].strip() for n in body.split(",") if n.strip()]
+        for idx, name in enumerate(names):
+            assert getattr(W, pyprefix + name[len(prefix):]) == idx, name
+
+
+def test_struct_layouts():
+    assert ctypes.sizeof(lib.MeshStruct) == 64
+    assert ctypes.sizeof(lib.CvodeParam) == 48
+    assert ctypes.sizeof(lib.MaxStepCtrl) == 64
+    assert ctypes.sizeof(lib.CvodeStats) == 11 * 8 + 2 * 4 + 3 * 8
+
+
+def test_no_cpu_fallback():
+    L = lib.load_library()
+    if L.pihm_b200_device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        lib.Model(W.make_named("tiny"))
+    # the raw C entry point refuses too
+    m = lib.MeshStruct()
+    assert not L.pihm_b200_create(ctypes.byref(m), 0, 0)
+    assert L.pihm_b200_last_error()
+
+
+def test_product_never_imports_oracle():
+    """the product package must not reference oracle/ anywhere"""
+    pkg = os.path.join(ROOT, "mm-pihm_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                with open(os.path.join(dirpath, f)) as fh:
+                    src = fh.read()
+                assert "oraclelib" not in src and "reflib" not in src and "pihm_oracle" not in src, f
