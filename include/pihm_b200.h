@@ -169,6 +169,10 @@ int             pihm_b200_ode(pihm_b200_ctx *ctx, double t,
                               const pihm_b200_vec *y, pihm_b200_vec *ydot);
 /* NaN flag of the RHS calls since the last query (device flag, D2H) */
 int             pihm_b200_check_nan(pihm_b200_ctx *ctx);
+/* The part of Summary() (src/update.c:19-47) that feeds back into the RHS:
+ * ws0.surf = y[SURF] for the next model step's Infil() (vert_flow.c:122).
+ * Runs on the device (no y round trip); call after every SolveCVode. */
+int             pihm_b200_summary(pihm_b200_ctx *ctx, const pihm_b200_vec *y);
 /* Summary()/print need the wf.* fields of the last RHS call.
  * Writing them costs 144 B/element per call, so it is off unless asked for. */
 int             pihm_b200_set_flux_recording(pihm_b200_ctx *ctx, int on);

@@ -1,0 +1,376 @@
+// cvode_kernels.cuh -- fused vector kernels of the device-resident BDF/Newton/
+// SPGMR integrator.
+//
+// Each kernel replaces a run of N_V* calls of CVODE 2.9.0 / SPGMR and performs,
+// per component, exactly the floating-point operations of that run in the same
+// order (the special-case forms of N_VLinearSum_Serial included; file:line
+// cited per kernel).  Scalars produced by one kernel and consumed by the next
+// (WRMS norms, Gram-Schmidt coefficients) stay in device memory (`sc[]`) so the
+// host is not in the loop; the host reads them from a mapped pinned mirror only
+// where CVODE's control flow branches on them.
+//
+// Reductions: per-thread grid-stride partials -> warp shuffles -> block partials
+// in `part`; the last block to finish sums the partials in index order and
+// stores the RAW sum (or min) to sc[slot] and its host mirror.  Consumers apply
+// sqrt( /N) themselves, so a multi-GPU build can all-reduce the raw value in
+// between.  Compiled with -fmad=false.
+#pragma once
+#include "common.cuh"
+#include "nvec.cuh"
+
+namespace pb {
+
+// device / host scalar slots
+enum {
+    SC_EWT_MIN = 0,   // min(reltol*|y|+abstol)
+    SC_EWT_NRM,       // sum (zn0*ewt)^2
+    SC_BSUM,          // sum (b*ewt)^2
+    SC_VNRM,          // sum (vtemp*ewt)^2  (DQ increment)
+    SC_VK2,           // dot(V[k],V[k]) before Gram-Schmidt
+    SC_H0,            // SC_H0+i = dot(V[i],V[k]), i = 0..5
+    SC_NEW2 = SC_H0 + 6,   // dot(V[k],V[k]) after Gram-Schmidt
+    SC_DEL,           // sum (b*ewt)^2 of the Newton correction
+    SC_ACNRM,         // sum (acor*ewt)^2
+    SC_ETA_M1,        // sum (zn[q]*ewt)^2
+    SC_ETA_P1,        // sum ((acor - cquot zn[qmax])*ewt)^2
+    SC_STAB1,         // sum (zn[q]*ewt)^2
+    SC_STAB2,         // sum (zn[q-1]*ewt)^2
+    SC_TMP,
+    SC_COUNT = 32
+};
+
+struct RedBuf {
+    double *part;            // [SC_COUNT][max_blocks]
+    unsigned int *counter;
+    double *sc;              // device scalars
+    volatile double *hsc;    // mapped host mirror
+    int max_blocks;
+};
+
+template <bool IS_MIN>
+__device__ __forceinline__ double red_block(double v)
+{
+    __shared__ double sh[PB_VEC_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double w = __shfl_down_sync(0xffffffffu, v, o);
+        v = IS_MIN ? ((w < v) ? w : v) : v + w;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();             // protect sh[] across successive calls
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        v = (lane < PB_VEC_THREADS / 32) ? sh[lane] : (IS_MIN ? __longlong_as_double(0x7ff0000000000000LL) : 0.0);
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            const double w = __shfl_down_sync(0xffffffffu, v, o);
+            v = IS_MIN ? ((w < v) ? w : v) : v + w;
+        }
+    }
+    return v;
+}
+
+// finish up to 2 reductions of one kernel.  slotA: sum (or min if MIN_A); slotB: sum, -1 = none
+template <bool MIN_A>
+__device__ __forceinline__ void red_finish(const RedBuf &rb, double a, int slotA, double b, int slotB)
+{
+    a = red_block<MIN_A>(a);
+    if (slotB >= 0) b = red_block<false>(b);
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+        rb.part[(size_t)slotA * rb.max_blocks + blockIdx.x] = a;
+        if (slotB >= 0) rb.part[(size_t)slotB * rb.max_blocks + blockIdx.x] = b;
+        __threadfence();
+        last = (atomicAdd(rb.counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    double sa = MIN_A ? __longlong_as_double(0x7ff0000000000000LL) : 0.0, sb = 0.0;
+    const volatile double *pa = rb.part + (size_t)slotA * rb.max_blocks;
+    const volatile double *pb_ = rb.part + (size_t)(slotB >= 0 ? slotB : slotA) * rb.max_blocks;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += PB_VEC_THREADS) {
+        const double va = pa[k];
+        sa = MIN_A ? ((va < sa) ? va : sa) : sa + va;
+        if (slotB >= 0) sb += pb_[k];
+    }
+    sa = red_block<MIN_A>(sa);
+    if (slotB >= 0) sb = red_block<false>(sb);
+    if (threadIdx.x == 0) {
+        rb.sc[slotA] = sa;
+        rb.hsc[slotA] = sa;
+        if (slotB >= 0) { rb.sc[slotB] = sb; rb.hsc[slotB] = sb; }
+        *rb.counter = 0u;
+    }
+}
+
+#define PB_GRID_STRIDE(i, n)                                                  \
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x,      \
+                   stride_ = (long long)gridDim.x * blockDim.x;               \
+         i < (n); i += stride_)
+
+// cvEwtSetSS (cvode.c:4081-4090: Abs, Scale, AddConst, Min, Inv) fused with the
+// "too much accuracy" norm N_VWrmsNorm(zn[0], ewt) (cvode.c:1376)
+static __global__ void __launch_bounds__(PB_VEC_THREADS)
+k_ewt(long long n, double reltol, double abstol, const double *__restrict__ y,
+      double *__restrict__ ewt, RedBuf rb)
+{
+    double mn = __longlong_as_double(0x7ff0000000000000LL), s = 0.0;
+    PB_GRID_STRIDE(i, n) {
+        const double yi = y[i];
+        double t = fabs(yi);
+        t = reltol * t;
+        t = t + abstol;
+        mn = (t < mn) ? t : mn;
+        const double w = 1.0 / t;
+        ewt[i] = w;
+        const double p = yi * w;
+        s += p * p;
+    }
+    red_finish<true>(rb, mn, SC_EWT_MIN, s, SC_EWT_NRM);
+}
+
+struct ZnPtrs { double *z[6]; };
+
+// cvPredict (cvode.c:2285-2287) / cvRestore (:2887-2889): the q(q+1)/2 in-place
+// N_VLinearSum(1, zn[j-1], +-1, zn[j], zn[j-1]) per component, in registers
+template <int SIGN>
+__global__ void __launch_bounds__(PB_VEC_THREADS)
+k_predict(long long n, int q, ZnPtrs zn)
+{
+    PB_GRID_STRIDE(i, n) {
+        double z[6];
+#pragma unroll
+        for (int j = 0; j < 6; j++) if (j <= q) z[j] = zn.z[j][i];
+        for (int k = 1; k <= q; k++)
+#pragma unroll
+            for (int j = 5; j >= 1; j--)
+                if (j <= q && j >= k) z[j - 1] = (SIGN > 0) ? z[j - 1] + z[j] : z[j - 1] - z[j];
+#pragma unroll
+        for (int j = 0; j < 5; j++) if (j < q) zn.z[j][i] = z[j];
+    }
+}
+
+struct Coef6 { double c[6]; };
+
+// cvRescale (cvode.c:2257-2260): zn[j] *= eta^j, j = 1..q (factors from the host)
+static __global__ void __launch_bounds__(PB_VEC_THREADS)
+k_rescale(long long n, int q, ZnPtrs zn, Coef6 f)
+{
+    PB_GRID_STRIDE(i, n) {
+#pragma unroll
+        for (int j = 1; j < 6; j++) if (j <= q) zn.z[j][i] = f.c[j] * zn.z[j][i];
+    }
+}
+
+// cvNlsNewton/cvNewtonIteration residual (cvode.c:2700-2701, 2744-2745) fused
+// with CVSpgmrSolve's norm test (cvode_spgmr.c:370) and SpgmrSolve's initial
+// residual scaling (sundials_spgmr.c:209-233):
+//   first : acor = 0 ; y = zn0
+//   tempv = rl1*zn1 + acor ; b = gamma*ftemp - tempv
+//   V0 = ewt * b ;  S = sum (b*ewt)^2   [bnorm = sqrt(S/N), beta = sqrt(S)]
+template <bool FIRST>
+__global__ void __launch_bounds__(PB_VEC_THREADS)
+k_newton_res(long long n, double rl1, double gamma, const double *__restrict__ zn0,
+             const double *__restrict__ zn1, const double *__restrict__ ftemp,
+             const double *__restrict__ ewt, double *__restrict__ acor, double *__restrict__ y,
+             double *__restrict__ b, double *__restrict__ V0, RedBuf rb)
+{
+    double s = 0.0;
+    PB_GRID_STRIDE(i, n) {
+        double ac;
+        if (FIRST) { ac = 0.0; acor[i] = 0.0; y[i] = zn0[i]; }
+        else ac = acor[i];
+        double t = rl1 * zn1[i] + ac;
+        t = gamma * ftemp[i] - t;
+        b[i] = t;
+        const double p = ewt[i] * t;
+        V0[i] = p;
+        s += p * p;
+    }
+    red_finish<false>(rb, s, SC_BSUM, 0.0, -1);
+}
+
+// Krylov step, part a (sundials_spgmr.c:264 or :341, then :278):
+//   V[l] = c * V[l]   (normalisation, c = 1/r_norm or 1/Hes[l][l-1])
+//   vtemp = V[l] / ewt ;  SC_VNRM = sum (vtemp*ewt)^2   (cvode_spils.c:679)
+static __global__ void __launch_bounds__(PB_VEC_THREADS)
+k_krylov_a(long long n, double c, double *__restrict__ Vl, const double *__restrict__ ewt,
+           double *__restrict__ vtemp, RedBuf rb)
+{
+    double s = 0.0;
+    PB_GRID_STRIDE(i, n) {
+        const double v = c * Vl[i];
+        Vl[i] = v;
+        const double w = ewt[i];
+        const double t = v / w;
+        vtemp[i] = t;
+        const double p = t * w;
+        s += p * p;
+    }
+    red_finish<false>(rb, s, SC_VNRM, 0.0, -1);
+}
+
+// part b (cvode_spils.c:679-684): sig = 1/||vtemp||_wrms ; work = sig*vtemp + y
+static __global__ void __launch_bounds__(PB_VEC_THREADS)
+k_krylov_b(long long n, double n_global, const double *__restrict__ sc,
+           const double *__restrict__ vtemp, const double *__restrict__ y,
+           double *__restrict__ work)
+{
+    const double sig = 1.0 / sqrt(sc[SC_VNRM] / n_global);
+    PB_GRID_STRIDE(i, n) work[i] = sig * vtemp[i] + y[i];
+}
+
+// part c (cvode_spils.c:697-699 VScaleDiff, :619 VLin1, sundials_spgmr.c:305-311)
+//   Jv = siginv*(Jv - fy) ; z = (-gamma)*Jv + vtemp ; V[l+1] = ewt * z
+//   SC_VK2 = dot(V[l+1],V[l+1]) ; SC_H0 = dot(V[0],V[l+1])   (ModifiedGS :50,:57)
+static __global__ void __launch_bounds__(PB_VEC_THREADS)
+k_krylov_c(long long n, double n_global, double gamma, const double *__restrict__ sc,
+           const double *__restrict__ vtemp, const double *__restrict__ fy,
+           const double *__restrict__ ewt, const double *__restrict__ V0,
+           double *__restrict__ Vk, RedBuf rb)
+{
+    const double sig = 1.0 / sqrt(sc[SC_VNRM] / n_global);
+    const double siginv = 1.0 / sig;
+    const double mg = -gamma;
+    double s = 0.0, h = 0.0;
+    PB_GRID_STRIDE(i, n) {
+        double jv = siginv * (Vk[i] - fy[i]);
+        double z = mg * jv + vtemp[i];
+        z = ewt[i] * z;
+        Vk[i] = z;
+        s += z * z;
+        h += V0[i] * z;
+    }
+    red_finish<false>(rb, s, SC_VK2, h, SC_H0);
+}
+
+// Modified Gram-Schmidt step (sundials_iterative.c:56-63), chained on device:
+//   V[k] += (-h_prev) * V[prev]          (Vaxpy form of N_VLinearSum)
+//   next dot: SC_H0+inext = dot(V[inext], V[k])   or, when Vnext == V[k] itself,
+//   SC_NEW2 = dot(V[k], V[k])
+static __global__ void __launch_bounds__(PB_VEC_THREADS)
+k_mgs_step(long long n, const double *__restrict__ sc, int slot_prev,
+           const double *__restrict__ Vprev, const double *Vnext, double *Vk,
+           int slot_next, RedBuf rb)
+{
+    const double mh = -sc[slot_prev];
+    const bool self = (Vnext == Vk);
+    double s = 0.0;
+    PB_GRID_STRIDE(i, n) {
+        const double v = Vk[i] + mh * Vprev[i];
+        Vk[i] = v;
+        s += (self ? v : Vnext[i]) * v;
+    }
+    red_finish<false>(rb, s, slot_next, 0.0, -1);
+}
+
+struct KryPtrs { const double *v[5]; };
+
+// End of SpgmrSolve + CVSpgmrSolve + Newton update, fused:
+//   xcor = sum_k yg[k]*V[k]  (Vaxpy chain from 0, sundials_spgmr.c:348-357)
+//   xcor = xcor / ewt ; x = 0 + xcor ; b = x         (:366-378, cvode_spgmr.c:389)
+//   del^2 sum = sum (b*ewt)^2 ; acor += b ; y = zn0 + acor   (cvode.c:2762-2764)
+static __global__ void __launch_bounds__(PB_VEC_THREADS)
+k_spgmr_final(long long n, int krydim, KryPtrs V, Coef6 yg, const double *__restrict__ ewt,
+              const double *__restrict__ zn0, double *__restrict__ acor, double *__restrict__ y,
+              RedBuf rb)
+{
+    double s = 0.0;
+    PB_GRID_STRIDE(i, n) {
+        double xc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 5; k++) if (k < krydim) xc = xc + yg.c[k] * V.v[k][i];
+        const double w = ewt[i];
+        xc = xc / w;
+        const double b = 0.0 + xc;
+        const double p = b * w;
+        s += p * p;
+        const double ac = acor[i] + b;
+        acor[i] = ac;
+        y[i] = zn0[i] + ac;
+    }
+    red_finish<false>(rb, s, SC_DEL, 0.0, -1);
+}
+
+// Newton update when the linear solve returned b itself (early outs of
+// CVSpgmrSolve, cvode_spgmr.c:371-374 and sundials_spgmr.c:238-239):
+//   ZERO_B: b = 0 first.   del^2 = sum (b*ewt)^2 ; acor += b ; y = zn0 + acor
+template <bool ZERO_B>
+__global__ void __launch_bounds__(PB_VEC_THREADS)
+k_newton_update(long long n, const double *__restrict__ bvec, const double *__restrict__ ewt,
+                const double *__restrict__ zn0, double *__restrict__ acor, double *__restrict__ y,
+                RedBuf rb)
+{
+    double s = 0.0;
+    PB_GRID_STRIDE(i, n) {
+        const double b = ZERO_B ? 0.0 : bvec[i];
+        const double p = b * ewt[i];
+        s += p * p;
+        const double ac = acor[i] + b;
+        acor[i] = ac;
+        y[i] = zn0[i] + ac;
+    }
+    red_finish<false>(rb, s, SC_DEL, 0.0, -1);
+}
+
+// sum (x*w)^2 into one slot; optionally a second vector into a second slot
+// (N_VWrmsNorm, nvector_serial.c:669-686; pairs: cvBDFStab cvode.c:3267-3268)
+static __global__ void __launch_bounds__(PB_VEC_THREADS)
+k_wsq(long long n, const double *__restrict__ x1, const double *x2, const double *__restrict__ w,
+      int slot1, int slot2, RedBuf rb)
+{
+    double s1 = 0.0, s2 = 0.0;
+    PB_GRID_STRIDE(i, n) {
+        const double wi = w[i];
+        const double p = x1[i] * wi;
+        s1 += p * p;
+        if (slot2 >= 0) { const double r = x2[i] * wi; s2 += r * r; }
+    }
+    red_finish<false>(rb, s1, slot1, s2, slot2);
+}
+
+// cvCompleteStep (cvode.c:3010-3016): zn[j] += l[j]*acor (Vaxpy), j = 0..q,
+// and the optional save zn[qmax] = acor
+static __global__ void __launch_bounds__(PB_VEC_THREADS)
+k_complete(long long n, int q, ZnPtrs zn, Coef6 l, const double *__restrict__ acor, double *save)
+{
+    PB_GRID_STRIDE(i, n) {
+        const double a = acor[i];
+#pragma unroll
+        for (int j = 0; j < 6; j++) if (j <= q) zn.z[j][i] = zn.z[j][i] + l.c[j] * a;
+        if (save) save[i] = a;
+    }
+}
+
+// cvComputeEtaqm1 / cvComputeEtaqp1 norms (cvode.c:3097, :3118-3119):
+//   SC_ETA_M1 = sum (znq*ewt)^2 ; tempv = (-cquot)*znmax + acor ; SC_ETA_P1 = sum (tempv*ewt)^2
+static __global__ void __launch_bounds__(PB_VEC_THREADS)
+k_eta(long long n, int do_m1, int do_p1, double cquot, const double *znq, const double *znmax,
+      const double *__restrict__ acor, const double *__restrict__ ewt, RedBuf rb)
+{
+    double s1 = 0.0, s2 = 0.0;
+    const double mc = -cquot;
+    PB_GRID_STRIDE(i, n) {
+        const double w = ewt[i];
+        if (do_m1) { const double p = znq[i] * w; s1 += p * p; }
+        if (do_p1) { const double t = mc * znmax[i] + acor[i]; const double p = t * w; s2 += p * p; }
+    }
+    red_finish<false>(rb, s1, SC_ETA_M1, s2, SC_ETA_P1);
+}
+
+// CVodeGetDky with k = 0 (cvode.c:1545-1556): Horner form, VLin1 per term
+static __global__ void __launch_bounds__(PB_VEC_THREADS)
+k_dky(long long n, int q, double s, ZnPtrs zn, double *__restrict__ dky)
+{
+    PB_GRID_STRIDE(i, n) {
+        double d = 0.0;
+#pragma unroll
+        for (int j = 5; j >= 0; j--)
+            if (j <= q) d = (j == q) ? zn.z[j][i] : s * d + zn.z[j][i];
+        dky[i] = d;
+    }
+}
+
+}  // namespace pb

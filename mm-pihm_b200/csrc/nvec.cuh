@@ -145,7 +145,7 @@ k_reduce(long long n, const double *__restrict__ x, const double *__restrict__ y
 }
 
 // reference order <-> internal order of the state blocks
-__global__ void __launch_bounds__(PB_VEC_THREADS)
+static __global__ void __launch_bounds__(PB_VEC_THREADS)
 k_permute_state(int ne, int nr, int fbr, const int *__restrict__ perm,
                 const double *__restrict__ src, double *__restrict__ dst, int to_internal)
 {

@@ -352,6 +352,17 @@ int pihm_b200_set_stale_ovlflow(pihm_b200_ctx *ctx, const double *ovl)
     return 0;
 }
 
+// Summary()'s effect on the hot path (src/update.c:19-47): ws0.surf = y[SURF],
+// which Infil() reads during the next model step (vert_flow.c:122).  Done on
+// the device: one D2D copy of the SURF block into the forcing table.
+int pihm_b200_summary(pihm_b200_ctx *ctx, const pihm_b200_vec *y)
+{
+    if (!ctx || !y || y->n != ctx->nsv) { set_error("pihm_b200_summary: bad argument"); return -1; }
+    PB_CUDA(cudaMemcpyAsync(ctx->d_forc + (size_t)PB_F_WS0SURF * ctx->dm.nes, y->d,
+                            sizeof(double) * ctx->dm.ne, cudaMemcpyDeviceToDevice, ctx->s()));
+    return 0;
+}
+
 int pihm_b200_set_flux_recording(pihm_b200_ctx *ctx, int on)
 {
     if (!ctx) return -1;

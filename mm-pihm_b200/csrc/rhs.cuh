@@ -742,7 +742,7 @@ __device__ __forceinline__ void river_main(const DevMesh &m, double *__restrict_
 // ---------------------------------------------------------------------------
 #define PB_RHS_THREADS 128
 
-__global__ void __launch_bounds__(PB_RHS_THREADS)
+static __global__ void __launch_bounds__(PB_RHS_THREADS)
 k_pre(const DevMesh m, const double *__restrict__ y, int elem_blocks)
 {
     if ((int)blockIdx.x < elem_blocks) {

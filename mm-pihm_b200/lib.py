@@ -71,6 +71,7 @@ _SIGS = {
     "pihm_b200_ode_host": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "pihm_b200_ode": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "pihm_b200_check_nan": (C.c_int, [C.c_void_p]),
+    "pihm_b200_summary": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pihm_b200_set_flux_recording": (C.c_int, [C.c_void_p, C.c_int]),
     "pihm_b200_get_fluxes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pihm_b200_vec_new": (C.c_void_p, [C.c_void_p]),
@@ -230,6 +231,10 @@ class Model:
         o = np.ascontiguousarray(ovl, np.float64)
         assert o.shape == (3, self.nelem)
         _check(self.L, self.L.pihm_b200_set_stale_ovlflow(self.h, _ptr(o)), "set_stale_ovlflow")
+
+    def Summary(self, y: "Vec"):
+        """ws0.surf <- y[SURF] on the device (the RHS-relevant part of Summary, src/update.c:47)"""
+        _check(self.L, self.L.pihm_b200_summary(self.h, y.h), "summary")
 
     def set_flux_recording(self, on: bool):
         _check(self.L, self.L.pihm_b200_set_flux_recording(self.h, int(on)), "set_flux_recording")

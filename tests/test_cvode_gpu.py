@@ -1,0 +1,115 @@
+"""Integrated-state parity: the device BDF/Newton/SPGMR integrator driven
+through SetCVodeParam / SolveCVode / Summary against trajectories produced by
+the reference's own CVODE run (tests/golden/*.npz, made by make_golden.py).
+
+Acceptance: |y_gpu - y_ref| <= 10 * (reltol*|y_ref| + abstol)
+for every component after the simulated period; CVODE counters are reported
+and must stay within 15 % (step sequences are not bit-reproducible: libdevice
+pow differs from glibc in the last ulp and reductions are tree sums)."""
+import numpy as np
+import pytest
+
+from helpers import golden_tables, load_golden
+import mm_pihm_b200  # noqa: F401
+from mm_pihm_b200 import lib, watershed as W
+
+pytestmark = pytest.mark.gpu
+RELTOL, ABSTOL, MULT = 1e-3, 1e-4, 10.0
+STAT_KEYS = ("nst", "nfe", "nni", "ncfn", "netf", "nli", "ncfl", "nfeLS")
+
+
+def check_state(y, yref, tag):
+    bound = MULT * (RELTOL * np.abs(yref) + ABSTOL)
+    err = np.abs(y - yref)
+    worst = (err / bound).max()
+    assert worst <= 1.0, f"{tag}: state error {worst:.3f} x bound at {np.argmax(err / bound)}"
+    return worst
+
+
+def check_stats(st, ref_row, tag, tol=0.15):
+    for k, r in zip(STAT_KEYS, ref_row):
+        v = st[k]
+        if r >= 50:
+            assert abs(v - r) <= tol * r, f"{tag}: counter {k} = {v}, reference {r}"
+
+
+@pytest.mark.parametrize("name", ["example_pihm.npz", "example_fbr.npz"])
+@pytest.mark.parametrize("reorder", [0, 1])
+def test_example_trajectory(name, reorder):
+    """BASELINE config[0]: the bundled input/example project, first simulated hour,
+    forcing tables taken from the reference's ApplyForc/IntcpSnowEt."""
+    g = load_golden(name)
+    tb = golden_tables(g)
+    model = lib.Model(tb, reorder=reorder)
+    cv = lib.Cvode(model)
+    y = model.N_VNew(g["y0"])
+    forc = {int(k): f for k, f in zip(g["forc_steps"], g["forc_tabs"])}
+    cv.SetCVodeParam(y, reltol=float(g["ctrl_reltol"]), abstol=float(g["ctrl_abstol"]),
+                     initstep=float(g["ctrl_initstep"]), stepsize=tb["stepsize"])
+    snaps = {int(s): (yy, st) for s, yy, st in zip(g["traj_steps"], g["traj_y"], g["traj_stats"])}
+    for k in range(60):
+        if k in forc:
+            f = forc[k].copy()
+            model.set_forcing(f, np.zeros(tb["nriver"]))
+        model.Summary(y)                              # ws0.surf of this step = y_surf now
+        t = cv.SolveCVode((k + 1) * 60.0, y)
+        assert t == (k + 1) * 60.0
+        if k + 1 in snaps:
+            yref, sref = snaps[k + 1]
+            w = check_state(y.download(), yref, f"{name} step {k + 1}")
+            st = cv.stats()
+            print(f"{name} reorder={reorder} step {k + 1}: err {w:.3f} x bound; "
+                  f"nst {st['nst']} (ref {sref[0]}), nfe+nfeLS {st['nfe'] + st['nfeLS']} (ref {sref[1] + sref[7]})")
+            if k + 1 == 60:
+                check_stats(st, sref, name)
+    cv.close(); model.close()
+
+
+@pytest.mark.parametrize("fbr", [False, True])
+def test_synthetic_trajectory(fbr):
+    """2400-triangle synthetic watershed, 2 simulated hours through the rain pulse."""
+    g = load_golden("synth_small_fbr.npz" if fbr else "synth_small_pihm.npz")
+    tb = W.make_named("small", fbr=fbr, dirichlet_edges=True)
+    model = lib.Model(tb, reorder=1)
+    cv = lib.Cvode(model)
+    y = model.N_VNew(tb["y0"])
+    cv.SetCVodeParam(y)
+    snaps = {int(s): (yy, st) for s, yy, st in zip(g["traj_steps"], g["traj_y"], g["traj_stats"])}
+    for k in range(120):
+        if k % 15 == 0:
+            model.set_forcing(W.storm_forcing(tb, k * 60.0), np.zeros(tb["nriver"]))
+        model.Summary(y)
+        cv.SolveCVode((k + 1) * 60.0, y)
+        if k + 1 in snaps:
+            yref, sref = snaps[k + 1]
+            w = check_state(y.download(), yref, f"synth fbr={fbr} step {k + 1}")
+            st = cv.stats()
+            print(f"synth fbr={fbr} step {k + 1}: err {w:.3f} x bound; nst {st['nst']} (ref {sref[0]}), "
+                  f"rhs {st['nfe'] + st['nfeLS']} (ref {sref[1] + sref[7]})")
+            if k + 1 == 120:
+                check_stats(st, sref, "synth")
+    cv.close(); model.close()
+
+
+def test_reinit_and_max_step_controller():
+    """SetCVodeParam twice (spin-up re-init, ode.c:351-360) and AdjCVodeMaxStep (ode.c:500-560)"""
+    tb = W.make_named("tiny")
+    model = lib.Model(tb)
+    cv = lib.Cvode(model)
+    y = model.N_VNew(tb["y0"])
+    model.set_forcing(W.storm_forcing(tb, 3 * 3600.0), np.zeros(tb["nriver"]))
+    outs = []
+    for rep in range(2):
+        y.upload(tb["y0"])
+        model.set_stale_ovlflow(np.zeros((3, tb["nelem"])))
+        model.set_forcing_col(W.F_WS0SURF, np.zeros(tb["nelem"]))
+        cv.SetCVodeParam(y)
+        for k in range(5):
+            model.Summary(y)
+            cv.SolveCVode((k + 1) * 60.0, y)
+            hmax = cv.AdjCVodeMaxStep()
+            assert 1.0 <= hmax <= 60.0
+        outs.append((y.download(), cv.stats()))
+    assert np.array_equal(outs[0][0], outs[1][0])          # deterministic restart
+    assert outs[0][1]["nst"] == outs[1][1]["nst"] > 0
+    cv.close(); model.close()

@@ -117,15 +117,19 @@ def test_rhs_no_river_and_ragged_sizes():
 
 
 def test_rhs_nan_flag():
-    """CheckDy: a NaN in y must raise the device flag (reference exits, ode.c:305-310)"""
+    """CheckDy: a NaN in dy must raise the device flag (the reference exits,
+    ode.c:305-310).  A NaN *state* is clamped to 0 by `y >= 0 ? y : 0` in both
+    codes (ode.c:31), so the NaN is injected through the forcing."""
     tb = W.make_named("tiny")
     model = lib.Model(tb)
     y = tb["y0"].copy()
-    y[5] = np.nan
+    f = W.storm_forcing(tb, 0.0)
+    f[W.F_PCPDRP, 5] = np.nan
+    model.set_forcing(f)
+    dy = model.ODE(0.0, y)
+    assert model.nan_flag == 1 and np.isnan(dy[5])
     model.set_forcing(W.storm_forcing(tb, 0.0))
     model.ODE(0.0, y)
-    assert model.nan_flag == 1
-    model.ODE(0.0, tb["y0"])
     assert model.nan_flag == 0
     model.close()
 
