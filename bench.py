@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the MM-PIHM hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--size 1M|100k|...] [--fbr]
+
+A "step" is one 60 s model step of the synthetic watershed (SolveCVode +
+Summary, src/pihm.c:53-57) during the rain pulse of the synthetic storm.
+Metric (BASELINE.json): simulated days per wall-second at 1M triangles, with
+RHS evals/s and the achieved HBM GB/s of the RHS kernels beside it.
+
+Prints ONE JSON line (rank 0).  --impl reference times the reference's own CPU
+implementation (oracle/_ref, OpenMP on all host cores) on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import mm_pihm_b200  # noqa: E402,F401
+from mm_pihm_b200 import watershed as W  # noqa: E402
+
+T0 = 2 * 3600.0          # model time of step 0: one hour into the 6 h rain pulse
+STEP = 60.0
+B_RHS = {False: 376.0, True: 476.0}     # algorithmic bytes / element / RHS
+
+
+def forcing_at(tb, k):
+    return W.storm_forcing(tb, T0 + k * STEP)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, device=0):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); smax.append(float(p[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------- ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mm_pihm_b200 import lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world > 1:
+        raise SystemExit("multi-GPU mesh partitioning is not built yet (see DESIGN.md, row e)")
+
+    fbr = bool(args.fbr)
+    tb = W.make_named(args.size, fbr=fbr)
+    ne, nr = tb["nelem"], tb["nriver"]
+    model = lib.Model(tb, device=local, reorder=args.reorder)
+    stream = torch.cuda.current_stream()
+    model.set_stream(stream.cuda_stream)
+    cv = lib.Cvode(model)
+    y = model.N_VNew(tb["y0"])
+    K, Wu = args.steps, args.warmup
+
+    def reset():
+        y.upload(tb["y0"])
+        model.set_stale_ovlflow(np.zeros((3, ne)))
+        model.set_forcing(forcing_at(tb, 0), np.zeros(nr))
+        cv.SetCVodeParam(y)
+
+    def step(k, e2e=False, host_forc=None, host_y=None):
+        if e2e:
+            # the drop-in driver's per-step traffic: forcing columns in, state out
+            for c in (W.F_PCPDRP, W.F_EDIR, W.F_ETT):
+                model.set_forcing_col(c, host_forc[c])
+        elif k % 15 == 0:
+            model.set_forcing(forcing_at(tb, k), np.zeros(nr))
+        model.Summary(y)
+        cv.SolveCVode((k + 1) * STEP, y)
+        if e2e:
+            model.L.pihm_b200_vec_download(y.h, host_y.ctypes.data)
+
+    # ---- device-resident timing ------------------------------------------------
+    reset()
+    for k in range(Wu):
+        step(k)
+    st0 = cv.stats(); l0 = model.launches
+    clocks = ClockSampler(local); clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for k in range(Wu, Wu + K):
+        step(k)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop()
+    st1 = cv.stats(); l1 = model.launches
+    rhs_evals = (st1["nfe"] + st1["nfeLS"]) - (st0["nfe"] + st0["nfeLS"])
+    nst = st1["nst"] - st0["nst"]
+    value = (K * STEP / 86400.0) / (ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers --------------------------
+    reset()
+    host_y = np.empty(model.nsv)
+    forc_tabs = {k: forcing_at(tb, k) for k in range(0, Wu + K + 15, 15)}
+    for k in range(Wu):
+        step(k, e2e=True, host_forc=forc_tabs[(k // 15) * 15], host_y=host_y)
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for k in range(Wu, Wu + K):
+        step(k, e2e=True, host_forc=forc_tabs[(k // 15) * 15], host_y=host_y)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms_e2e = ev0.elapsed_time(ev1)
+    e2e_value = (K * STEP / 86400.0) / (ms_e2e * 1e-3)
+
+    # ---- RHS kernels: live CUDA-event duration over back-to-back launches ----------
+    yv = y
+    yd = model.N_VNew()
+    nrep = 30
+    for _ in range(3):
+        model.ode_dev(0.0, yv, yd)
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for _ in range(nrep):
+        model.ode_dev(0.0, yv, yd)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    rhs_ms = ev0.elapsed_time(ev1) / nrep
+    peak, peak_src = measured_peak()
+    achieved = B_RHS[fbr] * ne / (rhs_ms * 1e-3) / 1e9
+
+    out = {
+        "metric": "simulated days/wall-sec at 1M triangles; RHS evals/s and achieved HBM GB/s",
+        "value": value, "unit": "sim-days/s", "n_gpus": world, "steps": K, "warmup": Wu,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"pihm{'-fbr' if fbr else ''} synthetic {args.size}-triangle watershed "
+                               f"({ne} elements, {nr} river segments), 60 s model steps in the rain pulse "
+                               f"(t0 = 2 h), reltol 1e-3 abstol 1e-4",
+                   "nelem": ne, "nriver": nr, "nsv": model.nsv, "reorder": args.reorder,
+                   "l2": "RHS working set 376 B x nelem and 21 state-sized vectors exceed the 126 MB L2"},
+        "rhs_evals_per_s": rhs_evals / (ms * 1e-3), "rhs_evals": rhs_evals, "cvode_steps": nst,
+        "rhs_ms": rhs_ms,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "kernel": "k_pre + k_main (one RHS)",
+                     "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": B_RHS[fbr] * ne},
+        "e2e": {"value": e2e_value, "unit": "sim-days/s", "ms_per_step": ms_e2e / K,
+                "h2d_bytes_per_step": 3 * 8 * ne, "d2h_bytes_per_step": 8 * model.nsv},
+        "gpu_launches": int(l1 - l0),
+        "clocks": clk,
+    }
+    if not args.no_cpu:
+        out["cpu_baseline"] = cpu_reference(tb, fbr, steps=args.cpu_steps, warmup=Wu)
+    print(json.dumps(out))
+
+
+# --------------------------------------------------------------------------- reference / CPU baseline
+def cpu_reference(tb, fbr, steps, warmup):
+    """The reference's own CPU implementation (oracle/_ref: unmodified MM-PIHM +
+    CVODE compiled from /root/reference) on the same workload, all host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import reflib
+    ne, nr = tb["nelem"], tb["nriver"]
+    cores = os.cpu_count() or 1
+    cvomp = (not fbr) and ne >= 30000            # README.md:65-67: OpenMP N_Vector above ~30k elements
+    ref = reflib.RefModel(fbr=fbr, cvode_omp=cvomp, threads=cores).create_from_tables(tb)
+    ref.init_state(tb["y0"])
+    ref.set_ovlflow(np.zeros((3, ne)))
+    ref.set_cvode_param()
+    f = None
+    t_start = None
+    for k in range(warmup + steps):
+        if k == warmup:
+            s0 = ref.stats()
+            t_start = time.perf_counter()
+        if k % 15 == 0 or f is None:
+            f = forcing_at(tb, k)
+        f[W.F_WS0SURF] = ref.get_ws()[:ne]
+        ref.set_forcing(f, np.zeros(nr))
+        ref.model_step(k)
+    dt = time.perf_counter() - t_start
+    s1 = ref.stats()
+    rhs = (s1["nfe"] + s1["nfeLS"]) - (s0["nfe"] + s0["nfeLS"])
+    return {"value": (steps * STEP / 86400.0) / dt, "unit": "sim-days/s", "cores": ref.threads,
+            "kind": "reference",
+            "sample": f"{steps} model steps (after {warmup} warm-up) of the same watershed and forcing; "
+                      f"reference ODE() with OpenMP, {'OpenMP' if cvomp else 'serial'} N_Vector",
+            "seconds": dt, "rhs_evals_per_s": rhs / dt, "ms_per_step": 1e3 * dt / steps}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    fbr = bool(args.fbr)
+    tb = W.make_named(args.size, fbr=fbr)
+    steps = min(args.steps, args.ref_max_steps)
+    cb = cpu_reference(tb, fbr, steps=steps, warmup=args.warmup)
+    out = {
+        "impl": "reference",
+        "metric": "simulated days/wall-sec at 1M triangles; RHS evals/s and achieved HBM GB/s",
+        "value": cb["value"], "unit": "sim-days/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"pihm{'-fbr' if fbr else ''} synthetic {args.size}-triangle watershed "
+                               f"({tb['nelem']} elements, {tb['nriver']} river segments), 60 s model steps in "
+                               f"the rain pulse (t0 = 2 h), reltol 1e-3 abstol 1e-4"},
+        "rhs_evals_per_s": cb["rhs_evals_per_s"],
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "sim-days/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", default="1M", choices=sorted(W.SIZES))
+    ap.add_argument("--fbr", action="store_true")
+    ap.add_argument("--reorder", type=int, default=1)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--ref-max-steps", type=int, default=30)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
