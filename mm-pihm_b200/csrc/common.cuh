@@ -64,18 +64,20 @@ struct DevMesh {
     double dt;
     // offsets of the state blocks inside y / ydot (pihm_func.h:7-15)
     long long o_unsat, o_gw, o_stg, o_rgw, o_fu, o_fg;
-    const double *ef;    // [PB_E_NCOL][nes]   static element columns
+    const double *es;    // [ntile][PB_E_NCOL][32] static element columns, warp-tiled
+    const double *ft;    // [ntile][4][32]     hot forcing columns (pcpdrp, edir, ett, ws0.surf), warp-tiled
+    const double4 *snb;  // [nes] static neighbour record  {zmin, zmax, rough, zbed}
+    double4 *dnb;        // [nes] dynamic neighbour record {surfh, EffKh, |grad h|, gw}, written by k_pre
     const int *nb;       // [3][nes]           neighbour codes
     const int *bct;      // [3][nes]           bc_type
     const int *fbct;     // [3][nes]           fbrbc_type
-    const double *forc;  // [PB_F_NCOL][nes]   forcing columns
+    const double *forc;  // [PB_F_NCOL][nes]   flat forcing table; the kernels read only its bc columns
     const double *rf;    // [PB_R_NCOL][nrs]   static river columns
     const int *ri;       // [PB_RI_NCOL][nrs]  LEFT/RIGHT = internal element idx
     const double *rivbc; // [nrs]
     const double *fbr_dist;  // [nrs] nabrdist(left bank) + nabrdist(right bank)
     const int *up_ptr;   // [nr+1] CSR of upstream segments, ascending index
     const int *up_idx;
-    double *surfh, *effkh, *sf;   // [nes] per-RHS temporaries
     double *rivflow;     // [11][nrs]
     double *s2c_stale;   // [2][nrs]  rivflow[LEFT/RIGHT_S2C] of the previous call
     double *xflux;       // [PB_X_NCOL][nes] (record != 0)
@@ -100,11 +102,11 @@ struct pihm_b200_ctx {
     std::vector<int> iperm;            // reference element -> internal element
     std::vector<int> riv_left_edge, riv_right_edge;   // edge slot of each bank
     // device allocations
-    double *d_ef = nullptr, *d_forc = nullptr, *d_rf = nullptr, *d_rivbc = nullptr;
+    double *d_es = nullptr, *d_ft = nullptr, *d_forc = nullptr, *d_rf = nullptr, *d_rivbc = nullptr;
+    double4 *d_snb = nullptr, *d_dnb = nullptr;
     double *d_fbr_dist = nullptr;
     int *d_nb = nullptr, *d_bct = nullptr, *d_fbct = nullptr, *d_ri = nullptr;
     int *d_up_ptr = nullptr, *d_up_idx = nullptr;
-    double *d_tmp = nullptr;           // surfh, effkh, sf
     double *d_rivflow = nullptr, *d_stale = nullptr, *d_xflux = nullptr;
     int *d_nan = nullptr;
     int *d_perm = nullptr, *d_iperm = nullptr;   // device copies (state gather)

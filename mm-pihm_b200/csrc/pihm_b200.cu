@@ -148,9 +148,16 @@ pihm_b200_ctx *pihm_b200_create(const pihm_b200_mesh *mesh, int device, int reor
 
     // ---- element columns in internal order ----------------------------------
     const int nes = dm.nes, nrs = dm.nrs;
-    std::vector<double> ef((size_t)PB_E_NCOL * nes, 0.0);
-    for (int c = 0; c < PB_E_NCOL; c++)
-        for (int i = 0; i < ne; i++) ef[(size_t)c * nes + i] = EF(c, perm[i]);
+    // warp-tiled static table [ntile][PB_E_NCOL][32] (padding lanes repeat a benign 1.0)
+    const int ntile = nes / 32;
+    std::vector<double> es((size_t)ntile * TS_NCOL * 32, 1.0);
+    for (int i = 0; i < ne; i++)
+        for (int c = 0; c < PB_E_NCOL; c++)
+            es[((size_t)(i >> 5) * TS_NCOL + tile_slot_of(c)) * 32 + (i & 31)] = EF(c, perm[i]);
+    std::vector<double4> snb(nes, make_double4(0.0, 0.0, 1.0, 0.0));
+    for (int i = 0; i < ne; i++)
+        snb[i] = make_double4(EF(PB_E_ZMIN, perm[i]), EF(PB_E_ZMAX, perm[i]), EF(PB_E_ROUGH, perm[i]),
+                              EF(PB_E_ZBED, perm[i]));
     std::vector<int> nb((size_t)3 * nes, PB_NB_BOUNDARY), bct((size_t)3 * nes, 0), fbct((size_t)3 * nes, 0);
     for (int i = 0; i < ne; i++) {
         const int e = perm[i];
@@ -203,7 +210,8 @@ pihm_b200_ctx *pihm_b200_create(const pihm_b200_mesh *mesh, int device, int reor
     }
 
     int rc = 0;
-    rc |= upload(&ctx->d_ef, ef);
+    rc |= upload(&ctx->d_es, es);
+    rc |= upload(&ctx->d_snb, snb);
     rc |= upload(&ctx->d_nb, nb);
     rc |= upload(&ctx->d_bct, bct);
     rc |= upload(&ctx->d_fbct, fbct);
@@ -220,7 +228,8 @@ pihm_b200_ctx *pihm_b200_create(const pihm_b200_mesh *mesh, int device, int reor
     };
     zalloc((void **)&ctx->d_forc, sizeof(double) * PB_F_NCOL * nes);
     zalloc((void **)&ctx->d_rivbc, sizeof(double) * nrs);
-    zalloc((void **)&ctx->d_tmp, sizeof(double) * 3 * nes);
+    zalloc((void **)&ctx->d_ft, sizeof(double) * 4 * nes);
+    zalloc((void **)&ctx->d_dnb, sizeof(double4) * nes);
     zalloc((void **)&ctx->d_rivflow, sizeof(double) * PIHM_B200_NUM_RIVFLX * nrs);
     zalloc((void **)&ctx->d_stale, sizeof(double) * 2 * nrs);
     zalloc((void **)&ctx->d_nan, sizeof(int) * 4);
@@ -237,10 +246,9 @@ pihm_b200_ctx *pihm_b200_create(const pihm_b200_mesh *mesh, int device, int reor
         pihm_b200_destroy(ctx);
         return nullptr;
     }
-    dm.ef = ctx->d_ef; dm.nb = ctx->d_nb; dm.bct = ctx->d_bct; dm.fbct = ctx->d_fbct;
+    dm.es = ctx->d_es; dm.ft = ctx->d_ft; dm.snb = ctx->d_snb; dm.dnb = ctx->d_dnb; dm.nb = ctx->d_nb; dm.bct = ctx->d_bct; dm.fbct = ctx->d_fbct;
     dm.forc = ctx->d_forc; dm.rf = ctx->d_rf; dm.ri = ctx->d_ri; dm.rivbc = ctx->d_rivbc;
     dm.fbr_dist = ctx->d_fbr_dist; dm.up_ptr = ctx->d_up_ptr; dm.up_idx = ctx->d_up_idx;
-    dm.surfh = ctx->d_tmp; dm.effkh = ctx->d_tmp + nes; dm.sf = ctx->d_tmp + 2 * (size_t)nes;
     dm.rivflow = ctx->d_rivflow; dm.s2c_stale = ctx->d_stale;
     dm.xflux = nullptr; dm.record = 0;
     dm.nan_flag = ctx->d_nan;
@@ -257,8 +265,8 @@ void pihm_b200_destroy(pihm_b200_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     pihm_b200_vec_free(ctx->y_tmp);
     pihm_b200_vec_free(ctx->yd_tmp);
-    void *dev[] = {ctx->d_ef, ctx->d_forc, ctx->d_rf, ctx->d_rivbc, ctx->d_fbr_dist, ctx->d_nb,
-                   ctx->d_bct, ctx->d_fbct, ctx->d_ri, ctx->d_up_ptr, ctx->d_up_idx, ctx->d_tmp,
+    void *dev[] = {ctx->d_es, ctx->d_ft, ctx->d_snb, ctx->d_dnb, ctx->d_forc, ctx->d_rf, ctx->d_rivbc, ctx->d_fbr_dist, ctx->d_nb,
+                   ctx->d_bct, ctx->d_fbct, ctx->d_ri, ctx->d_up_ptr, ctx->d_up_idx,
                    ctx->d_rivflow, ctx->d_stale, ctx->d_xflux, ctx->d_nan, ctx->d_perm,
                    ctx->d_iperm, ctx->d_stage, ctx->d_red};
     for (void *p : dev) if (p) cudaFree(p);
@@ -305,8 +313,20 @@ int pihm_b200_set_forcing_col(pihm_b200_ctx *ctx, int col, const double *values)
     double *h = ctx->h_pin;                    // nsv >= 3 ne doubles of pinned staging
     PB_CUDA(cudaStreamSynchronize(ctx->s()));
     for (int i = 0; i < ne; i++) h[i] = values[ctx->perm[i]];
-    PB_CUDA(cudaMemcpyAsync(ctx->d_forc + (size_t)col * ctx->dm.nes, h, sizeof(double) * ne,
-                            cudaMemcpyHostToDevice, ctx->s()));
+    if (col <= PB_F_WS0SURF) {
+        // hot column -> warp-tiled table: 256 B rows, destination pitch 4 x 256 B
+        const int full = ne / 32, rem = ne % 32;
+        double *dst = ctx->d_ft + (size_t)col * 32;
+        if (full)
+            PB_CUDA(cudaMemcpy2DAsync(dst, 4 * 32 * sizeof(double), h, 32 * sizeof(double), 32 * sizeof(double),
+                                      full, cudaMemcpyHostToDevice, ctx->s()));
+        if (rem)
+            PB_CUDA(cudaMemcpyAsync(dst + (size_t)full * 4 * 32, h + (size_t)full * 32, rem * sizeof(double),
+                                    cudaMemcpyHostToDevice, ctx->s()));
+    } else {
+        PB_CUDA(cudaMemcpyAsync(ctx->d_forc + (size_t)col * ctx->dm.nes, h, sizeof(double) * ne,
+                                cudaMemcpyHostToDevice, ctx->s()));
+    }
     PB_CUDA(cudaStreamSynchronize(ctx->s()));
     return 0;
 }
@@ -358,8 +378,14 @@ int pihm_b200_set_stale_ovlflow(pihm_b200_ctx *ctx, const double *ovl)
 int pihm_b200_summary(pihm_b200_ctx *ctx, const pihm_b200_vec *y)
 {
     if (!ctx || !y || y->n != ctx->nsv) { set_error("pihm_b200_summary: bad argument"); return -1; }
-    PB_CUDA(cudaMemcpyAsync(ctx->d_forc + (size_t)PB_F_WS0SURF * ctx->dm.nes, y->d,
-                            sizeof(double) * ctx->dm.ne, cudaMemcpyDeviceToDevice, ctx->s()));
+    const int ne = ctx->dm.ne, full = ne / 32, rem = ne % 32;
+    double *dst = ctx->d_ft + (size_t)PB_F_WS0SURF * 32;
+    if (full)
+        PB_CUDA(cudaMemcpy2DAsync(dst, 4 * 32 * sizeof(double), y->d, 32 * sizeof(double), 32 * sizeof(double),
+                                  full, cudaMemcpyDeviceToDevice, ctx->s()));
+    if (rem)
+        PB_CUDA(cudaMemcpyAsync(dst + (size_t)full * 4 * 32, y->d + (size_t)full * 32, rem * sizeof(double),
+                                cudaMemcpyDeviceToDevice, ctx->s()));
     return 0;
 }
 

@@ -19,14 +19,108 @@
 
 namespace pb {
 
-#define EFC(c, i) (m.ef[(size_t)(c) * m.nes + (i)])
+// Static element columns are stored warp-tiled ("AoSoA-32"): tile t = i >> 5
+// holds all columns of its 32 elements contiguously, 256 B per column, in the
+// slot order below.  Each warp owns one tile: lane 0 issues ONE bulk async copy
+// (cp.async.bulk, the TMA engine; SASS UBLKCP) of the contiguous slot range its
+// kernel needs into shared memory and the warp waits on an mbarrier while its
+// neighbour gathers are in flight -- the whole 5-7 KB of per-warp inputs is one
+// memory transaction instead of ~25 dependent LDG waves.
+#define PB_TILE 32
+enum {   // k_pre reads [TS_PRE0, TS_PRE1), k_main [TS_MAIN0, TS_MAIN1 / TS_FBR1)
+    TS_NABRX0 = 0, TS_NABRX1, TS_NABRX2, TS_NABRY0, TS_NABRY1, TS_NABRY2, TS_KMACH, TS_AREAFV, TS_KSATH,
+    TS_ZMAX, TS_DEPTH, TS_DMAC,
+    TS_AREA, TS_ZMIN, TS_EDGE0, TS_EDGE1, TS_EDGE2, TS_NABRDIST0, TS_NABRDIST1, TS_NABRDIST2,
+    TS_DINF, TS_ALPHA, TS_BETA, TS_KINFV, TS_KMACV, TS_AREAFH, TS_KSATV, TS_POROSITY, TS_ROUGH, TS_RZD,
+    TS_ZBED, TS_GDEPTH, TS_GKSATH, TS_GKSATV, TS_GALPHA, TS_GBETA, TS_GPOROSITY,
+    TS_NCOL,
+    TS_PRE0 = TS_NABRX0, TS_PRE1 = TS_AREA, TS_MAIN0 = TS_ZMAX, TS_MAIN1 = TS_ZBED, TS_FBR1 = TS_NCOL
+};
+// ABI column (include/pihm_b200.h) -> tile slot; used by the host packer
+__host__ __device__ inline int tile_slot_of(int abi_col)
+{
+    switch (abi_col) {
+        case PB_E_AREA: return TS_AREA;  case PB_E_ZMIN: return TS_ZMIN;  case PB_E_ZMAX: return TS_ZMAX;
+        case PB_E_ZBED: return TS_ZBED;
+        case PB_E_EDGE0: return TS_EDGE0; case PB_E_EDGE1: return TS_EDGE1; case PB_E_EDGE2: return TS_EDGE2;
+        case PB_E_NABRDIST0: return TS_NABRDIST0; case PB_E_NABRDIST1: return TS_NABRDIST1;
+        case PB_E_NABRDIST2: return TS_NABRDIST2;
+        case PB_E_NABRX0: return TS_NABRX0; case PB_E_NABRX1: return TS_NABRX1; case PB_E_NABRX2: return TS_NABRX2;
+        case PB_E_NABRY0: return TS_NABRY0; case PB_E_NABRY1: return TS_NABRY1; case PB_E_NABRY2: return TS_NABRY2;
+        case PB_E_DEPTH: return TS_DEPTH; case PB_E_KSATH: return TS_KSATH; case PB_E_KSATV: return TS_KSATV;
+        case PB_E_KINFV: return TS_KINFV; case PB_E_DINF: return TS_DINF; case PB_E_ALPHA: return TS_ALPHA;
+        case PB_E_BETA: return TS_BETA; case PB_E_POROSITY: return TS_POROSITY; case PB_E_DMAC: return TS_DMAC;
+        case PB_E_KMACH: return TS_KMACH; case PB_E_KMACV: return TS_KMACV; case PB_E_AREAFV: return TS_AREAFV;
+        case PB_E_AREAFH: return TS_AREAFH; case PB_E_ROUGH: return TS_ROUGH; case PB_E_RZD: return TS_RZD;
+        case PB_E_GDEPTH: return TS_GDEPTH; case PB_E_GKSATH: return TS_GKSATH; case PB_E_GKSATV: return TS_GKSATV;
+        case PB_E_GALPHA: return TS_GALPHA; case PB_E_GBETA: return TS_GBETA; case PB_E_GPOROSITY: return TS_GPOROSITY;
+    }
+    return -1;
+}
+// global-memory access to a tile slot of an arbitrary element (river kernels, fbr gathers)
+#define TSC(slot, i) (m.es[((size_t)((i) >> 5) * TS_NCOL + (slot)) * PB_TILE + ((i) & 31)])
+#define FTC(c, i) (m.ft[((size_t)((i) >> 5) * 4 + (c)) * PB_TILE + ((i) & 31)])
+
+// ---- TMA bulk copy + mbarrier (PTX; no CUTLASS dependency) ---------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned phase)
+{
+    asm volatile("{\n .reg .pred P1;\n LAB_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                 " @P1 bra DONE;\n bra LAB_WAIT;\n DONE:\n }" ::"r"(bar), "r"(phase) : "memory");
+}
+
 #define RFC(c, r) (m.rf[(size_t)(c) * m.nrs + (r)])
 #define RIC(c, r) (m.ri[(size_t)(c) * m.nrs + (r)])
-#define FOC(c, i) (m.forc[(size_t)(c) * m.nes + (i)])
+#define FOC(c, i) (m.forc[(size_t)(c) * m.nes + (i)])   /* bc columns only (rare path) */
 #define RFLX(k, r) (m.rivflow[(size_t)(k) * m.nrs + (r)])
 #define XFC(c, i) (m.xflux[(size_t)(c) * m.nes + (i)])
 
 __device__ __forceinline__ double max0(double v) { return (v >= 0.0) ? v : 0.0; }
+
+// a / b for a finite b > 0.  IEEE gives 0/b = 0 with the sign of a, i.e. a
+// itself; taking that shortcut in a branch keeps zero numerators (dry edges,
+// dry surface) out of the FP64 division's denormal/zero slow path, which a
+// whole warp otherwise pays for (ncu: 21 % of k_main's instructions).
+// a, or 1.0 where a == 0.  Written as opaque PTX: in C++ the optimiser sees
+// that the quotient of the substituted lanes is discarded and divides the raw
+// zero again (checked in the SASS).
+__device__ __forceinline__ double nonzero_or_one(double a)
+{
+    double r;
+    asm("{ .reg .pred p; setp.neu.f64 p, %1, 0d0000000000000000; selp.f64 %0, %1, 0d3FF0000000000000, p; }"
+        : "=d"(r) : "d"(a));
+    return r;
+}
+__device__ __forceinline__ double div_pos(double a, double b)
+{
+    // branch-free on purpose: the compiler if-converts a guard anyway, and then
+    // the zero lanes would still send the warp into __cuda_sm20_div_rn_f64_full.
+    // Zero lanes divide 1.0 instead (fast path) and the result is discarded.
+    const bool nz = (a != 0.0);
+    const double q = nonzero_or_one(a) / b;
+    return nz ? q : a;
+}
+// general divisor (either sign, finite, non-zero): 0/b = a*b in sign and value
+__device__ __forceinline__ double div_any(double a, double b)
+{
+    const bool plain = (a != 0.0) || !(fabs(b) > 0.0) || isinf(b);
+    const double q = (plain ? a : nonzero_or_one(a)) / b;
+    return plain ? q : a * b;
+}
 
 // SurfH, src/hydrol.c:92-126
 __device__ __forceinline__ double surf_h(double surfeqv)
@@ -55,9 +149,9 @@ __device__ __forceinline__ double avg_h(double diff, double hsub, double hnabr)
 // DhByDl, src/lat_flow.c:227-234
 __device__ __forceinline__ double dh_by_dl(const double *l1, const double *l2, const double *h)
 {
-    return -1.0 *
-        (l1[2] * (h[1] - h[0]) + l1[1] * (h[0] - h[2]) + l1[0] * (h[2] - h[1])) /
-        (l2[2] * (l1[1] - l1[0]) + l2[1] * (l1[0] - l1[2]) + l2[0] * (l1[2] - l1[1]));
+    return div_any(-1.0 *
+        (l1[2] * (h[1] - h[0]) + l1[1] * (h[0] - h[2]) + l1[0] * (h[2] - h[1])),
+        (l2[2] * (l1[1] - l1[0]) + l2[1] * (l1[0] - l1[2]) + l2[0] * (l1[2] - l1[1])));
 }
 
 // EffKh, src/lat_flow.c:236-265
@@ -78,8 +172,8 @@ __device__ __forceinline__ double eff_kh(double depth, double dmac, double kmach
 
 __device__ __forceinline__ double eff_kh_elem(const DevMesh &m, int e, double gw)
 {
-    return eff_kh(EFC(PB_E_DEPTH, e), EFC(PB_E_DMAC, e), EFC(PB_E_KMACH, e),
-                  EFC(PB_E_AREAFV, e), EFC(PB_E_KSATH, e), gw);
+    return eff_kh(TSC(TS_DEPTH, e), TSC(TS_DMAC, e), TSC(TS_KMACH, e),
+                  TSC(TS_AREAFV, e), TSC(TS_KSATH, e), gw);
 }
 
 // OverLandFlow, src/lat_flow.c:267-271.  pow(0, 0.6666667) == 0 exactly, so the
@@ -88,7 +182,7 @@ __device__ __forceinline__ double overland_flow(double avgh, double grad, double
                                                 double crossa, double rough)
 {
     double p = (avgh == 0.0) ? 0.0 : pow(avgh, 0.6666667);
-    return crossa * p * grad / (sqrt(sf) * rough);
+    return div_pos(crossa * p * grad, sqrt(sf) * rough);
 }
 
 // KrFunc, src/soil.c:3-8.  The reference spells the squared factor out twice;
@@ -170,8 +264,8 @@ __device__ __forceinline__ Bank load_bank(const DevMesh &m, const double *__rest
     Bank b;
     b.surfh = surf_h(max0(y[e]));
     b.gw = max0(y[m.o_gw + e]);
-    b.zmax = EFC(PB_E_ZMAX, e);
-    b.zmin = EFC(PB_E_ZMIN, e);
+    b.zmax = TSC(TS_ZMAX, e);
+    b.zmin = TSC(TS_ZMIN, e);
     b.effk = eff_kh_elem(m, e, b.gw);
     return b;
 }
@@ -214,7 +308,7 @@ __device__ __forceinline__ double chan_elem_to_river(const Bank &b, double zbed,
     else if (b.zmin + b.gw > zbed) avgh = b.zmin + b.gw - zbed;
     else avgh = 0.0;
     avgh = avg_h(diff_h, stage, avgh);
-    double grad_h = diff_h / distance;
+    double grad_h = div_pos(diff_h, distance);
     double avg_ksat = 0.5 * (b.effk + rksath);
     return len * avg_ksat * grad_h * avgh;
 }
@@ -231,7 +325,7 @@ __device__ __forceinline__ double sub_elem_to_river(const Bank &b, double zbed, 
     else avgh = b.gw;
     avgh = avg_h(diff_h, rgw, avgh);
     double avg_ksat = 0.5 * (b.effk + effk_riv);
-    double grad_h = diff_h / distance;
+    double grad_h = div_pos(diff_h, distance);
     return len * avg_ksat * grad_h * avgh;
 }
 
@@ -289,7 +383,7 @@ __device__ __forceinline__ void river_fluxes(const DevMesh &m, const double *__r
             double distance = 0.5 * (len + len_d);
             double diff_h = (m.riv_mode == PB_KINEMATIC) ? (zbed - RFC(PB_R_ZBED, d))
                                                          : (total_h - total_h_down);
-            double grad_h = diff_h / distance;
+            double grad_h = div_pos(diff_h, distance);
             double avg_sf = (grad_h > 0.0) ? grad_h : PB_RIVGRADMIN;
             double crossa = riv_area(ord, stage, coeff);
             double crossa_down = riv_area(ord_d, stage_d, coeff_d);
@@ -309,7 +403,7 @@ __device__ __forceinline__ void river_fluxes(const DevMesh &m, const double *__r
             double diff_h = total_h - total_h_down;
             double avgh = avg_h(diff_h, rgw, rgw_d);
             double distance = 0.5 * (len + len_d);
-            double grad_h = diff_h / distance;
+            double grad_h = div_pos(diff_h, distance);
             double avg_ksat = 0.5 * (effk + effk_nabr);
             rf_down_a2a = avg_ksat * grad_h * avgh * avg_wid;
         }
@@ -371,7 +465,7 @@ __device__ __forceinline__ void river_fluxes(const DevMesh &m, const double *__r
         double diff_h;
         if (zbed - (rgw + rzmin) > 0.0) diff_h = stage;
         else diff_h = stage + zbed - (rgw + rzmin);
-        double grad_h = diff_h / RFC(PB_R_BEDTHICK, r);
+        double grad_h = div_pos(diff_h, RFC(PB_R_BEDTHICK, r));
         RFLX(RF_CHANL_LKG, r) = RFC(PB_R_KSATV, r) * RFC(PB_R_SHP_WIDTH, r) * len * grad_h;
     }
 }
@@ -379,37 +473,59 @@ __device__ __forceinline__ void river_fluxes(const DevMesh &m, const double *__r
 // ---------------------------------------------------------------------------
 // element part of k_pre: SurfH (hydrol.c:10-14), EffKh of the own column, and
 // FrictSlope (lat_flow.c:118-173) reduced to |grad h| = sqrt(dhbydx^2+dhbydy^2),
-// the only form LateralFlow uses it in (lat_flow.c:33-36).
+// the only form LateralFlow uses it in (lat_flow.c:33-36).  The results go into
+// the 32-byte "dynamic neighbour record" {surfh, effkh, |grad h|, gw} that
+// k_main gathers with one sector per neighbour.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void elem_pre(const DevMesh &m, const double *__restrict__ y, int i)
+__device__ __forceinline__ void elem_pre(const DevMesh &m, const double *__restrict__ y, int i,
+                                         const double *st, unsigned bar)
 {
-    const double surfh = surf_h(max0(y[i]));
-    const double gw = max0(y[m.o_gw + i]);
-    m.surfh[i] = surfh;
-    m.effkh[i] = eff_kh_elem(m, i, gw);
-    if (m.surf_mode != PB_DIFF_WAVE) return;
-
-    const double zmax = EFC(PB_E_ZMAX, i);
-    double h[3], nx[3], ny[3];
+    // st: this lane's column 0 of the warp's shared-memory tile slab (slots TS_PRE0..TS_PRE1)
+#define EC(c) st[((c) - TS_PRE0) * PB_TILE]
+    // neighbour codes first, then every gather unconditionally (non-element
+    // edges gather the element itself) so the loads are in flight together
+    int code[3], nn[3];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-        const int code = m.nb[(size_t)j * m.nes + i];
-        nx[j] = EFC(PB_E_NABRX0 + j, i);
-        ny[j] = EFC(PB_E_NABRY0 + j, i);
-        if (code >= 0) {
-            h[j] = EFC(PB_E_ZMAX, code) + surf_h(max0(y[code]));
-        } else if (code == PB_NB_BOUNDARY) {
-            if (m.bct[(size_t)j * m.nes + i] == 0) h[j] = zmax + surfh;
-            else h[j] = FOC(PB_F_BC0 + j, i);
-        } else {
-            const int r = (-code - 2) >> 2;
-            const double stage = max0(y[m.o_stg + r]);
-            h[j] = (stage > RFC(PB_R_SHP_DEPTH, r)) ? RFC(PB_R_ZBED, r) + stage : RFC(PB_R_ZMAX, r);
-        }
+        code[j] = m.nb[(size_t)j * m.nes + i];
+        nn[j] = (code[j] >= 0) ? code[j] : i;
     }
-    const double dx = dh_by_dl(ny, nx, h);
-    const double dy = dh_by_dl(nx, ny, h);
-    m.sf[i] = sqrt(dx * dx + dy * dy);
+    double ysn[3], zmaxn[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        ysn[j] = y[nn[j]];
+        zmaxn[j] = m.snb[nn[j]].y;
+    }
+    const double surfh = surf_h(max0(y[i]));
+    const double gw = max0(y[m.o_gw + i]);
+    mbar_wait(bar, 0);          // the tile slab has landed
+    const double effkh = eff_kh(EC(TS_DEPTH), EC(TS_DMAC), EC(TS_KMACH), EC(TS_AREAFV),
+                                EC(TS_KSATH), gw);
+    double sf = 0.0;
+    if (m.surf_mode == PB_DIFF_WAVE) {
+        const double zmax = EC(TS_ZMAX);
+        double h[3], nx[3], ny[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            nx[j] = EC(TS_NABRX0 + j);
+            ny[j] = EC(TS_NABRY0 + j);
+            if (code[j] >= 0) {
+                h[j] = zmaxn[j] + surf_h(max0(ysn[j]));
+            } else if (code[j] == PB_NB_BOUNDARY) {
+                if (m.bct[(size_t)j * m.nes + i] == 0) h[j] = zmax + surfh;
+                else h[j] = FOC(PB_F_BC0 + j, i);
+            } else {
+                const int r = (-code[j] - 2) >> 2;
+                const double stage = max0(y[m.o_stg + r]);
+                h[j] = (stage > RFC(PB_R_SHP_DEPTH, r)) ? RFC(PB_R_ZBED, r) + stage : RFC(PB_R_ZMAX, r);
+            }
+        }
+        const double dx = dh_by_dl(ny, nx, h);
+        const double dy = dh_by_dl(nx, ny, h);
+        sf = sqrt(dx * dx + dy * dy);
+    }
+    m.dnb[i] = make_double4(surfh, effkh, sf, gw);
+#undef EC
 }
 
 // ---------------------------------------------------------------------------
@@ -417,67 +533,81 @@ __device__ __forceinline__ void elem_pre(const DevMesh &m, const double *__restr
 // ---------------------------------------------------------------------------
 template <bool FBR>
 __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__restrict__ y,
-                                          double *__restrict__ dy, int i)
+                                          double *__restrict__ dy, int i, const double *st,
+                                          const double *f, unsigned bar)
 {
+    // st / f: this lane's column 0 of the warp's shared-memory slabs (static slots
+    // TS_MAIN0.., hot forcing columns), filled by the bulk copies issued in k_main
+#define EC(c) st[((c) - TS_MAIN0) * PB_TILE]
+    // ---- loads: neighbour codes, then all gathers (unconditional) ---------------
+    int code[3], nn[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        code[j] = m.nb[(size_t)j * m.nes + i];
+        nn[j] = (code[j] >= 0) ? code[j] : i;
+    }
+    double4 dn[3], sn[3];     // {surfh, effkh, sf, gw} and {zmin, zmax, rough, zbed} of the neighbours
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        dn[j] = m.dnb[nn[j]];
+        sn[j] = m.snb[nn[j]];
+    }
+    const double4 own = m.dnb[i];
     // ode.c:25-49
-    const double surf = max0(y[i]);
     const double unsat = max0(y[m.o_unsat + i]);
-    const double gw = max0(y[m.o_gw + i]);
-    (void)surf;
-    const double surfh = m.surfh[i];
-    const double effkh = m.effkh[i];
-    const double area = EFC(PB_E_AREA, i);
-    const double zmin = EFC(PB_E_ZMIN, i), zmax = EFC(PB_E_ZMAX, i);
-    const double depth = EFC(PB_E_DEPTH, i), dinf = EFC(PB_E_DINF, i);
-    const double rough = EFC(PB_E_ROUGH, i);
-    const double pcpdrp = FOC(PB_F_PCPDRP, i);
+    mbar_wait(bar, 0);          // static + forcing slabs have landed
+    const double gw = own.w;
+    const double surfh = own.x;
+    const double effkh = own.y;
+    const double area = EC(TS_AREA);
+    const double zmin = EC(TS_ZMIN), zmax = EC(TS_ZMAX);
+    const double depth = EC(TS_DEPTH), dinf = EC(TS_DINF);
+    const double rough = EC(TS_ROUGH);
+    const double pcpdrp = f[0 * PB_TILE];
 
     // EtExtract (non-Noah), hydrol.c:51-87
     double edir_surf = 0.0, edir_unsat = 0.0, edir_gw = 0.0, ett_unsat = 0.0, ett_gw = 0.0;
     {
-        const double edir = FOC(PB_F_EDIR, i), ett = FOC(PB_F_ETT, i);
+        const double edir = f[1 * PB_TILE], ett = f[2 * PB_TILE];
         if (surfh >= PB_DEPRSTG) edir_surf = edir;
         else if (gw > depth - dinf) edir_gw = edir;
         else edir_unsat = edir;
-        if (gw > depth - EFC(PB_E_RZD, i)) ett_gw = ett;
+        if (gw > depth - EC(TS_RZD)) ett_gw = ett;
         else ett_unsat = ett;
     }
 
     // LateralFlow, lat_flow.c:17-51
     double ovl[3], sub[3], ovl_infil[3];
-    const double sf_i = (m.surf_mode == PB_DIFF_WAVE) ? m.sf[i] : 0.0;
+    const double sf_i = own.z;
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-        const int code = m.nb[(size_t)j * m.nes + i];
-        if (code >= 0) {
-            const int n = code;
-            const double edge = EFC(PB_E_EDGE0 + j, i), dist = EFC(PB_E_NABRDIST0 + j, i);
-            const double gw_n = max0(y[m.o_gw + n]);
-            const double zmin_n = EFC(PB_E_ZMIN, n), zmax_n = EFC(PB_E_ZMAX, n);
-            const double surfh_n = m.surfh[n];
+        if (code[j] >= 0) {
+            const double edge = EC(TS_EDGE0 + j), dist = EC(TS_NABRDIST0 + j);
+            const double gw_n = dn[j].w, surfh_n = dn[j].x;
+            const double zmin_n = sn[j].x, zmax_n = sn[j].y;
             // SubFlowElemToElem, lat_flow.c:273-298
             double diff_h = (gw + zmin) - (gw_n + zmin_n);
             double avgh = avg_h(diff_h, gw, gw_n);
-            double grad_h = diff_h / dist;
-            double avg_ksat = 0.5 * (effkh + m.effkh[n]);
+            double grad_h = div_pos(diff_h, dist);
+            double avg_ksat = 0.5 * (effkh + dn[j].y);
             sub[j] = avg_ksat * grad_h * avgh * edge;
             // OvlFlowElemToElem, lat_flow.c:300-327 with avg_sf of :33-36
             double avg_sf;
             diff_h = (m.surf_mode == PB_KINEMATIC) ? zmax - zmax_n
                                                    : (surfh + zmax) - (surfh_n + zmax_n);
             avgh = avg_hsurf(diff_h, surfh, surfh_n);
-            grad_h = diff_h / dist;
+            grad_h = div_pos(diff_h, dist);
             if (m.surf_mode == PB_KINEMATIC) {
                 avg_sf = (grad_h > 0.0) ? grad_h : PB_GRADMIN;
             } else {
-                avg_sf = 0.5 * (sf_i + m.sf[n]);
+                avg_sf = 0.5 * (sf_i + dn[j].z);
                 avg_sf = (avg_sf > PB_GRADMIN) ? avg_sf : PB_GRADMIN;
             }
-            double avg_rough = 0.5 * (rough + EFC(PB_E_ROUGH, n));
+            double avg_rough = 0.5 * (rough + sn[j].z);
             double crossa = avgh * edge;
             ovl[j] = overland_flow(avgh, grad_h, avg_sf, crossa, avg_rough);
             ovl_infil[j] = ovl[j];
-        } else if (code == PB_NB_BOUNDARY) {
+        } else if (code[j] == PB_NB_BOUNDARY) {
             // BoundFluxElem, lat_flow.c:329-371
             const int bc = m.bct[(size_t)j * m.nes + i];
             ovl[j] = 0.0;
@@ -487,15 +617,15 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
                 const double head = FOC(PB_F_BC0 + j, i);
                 double diff_h = gw + zmin - head;
                 double avgh = avg_h(diff_h, gw, head - zmin);
-                double grad_h = diff_h / EFC(PB_E_NABRDIST0 + j, i);
-                sub[j] = effkh * grad_h * avgh * EFC(PB_E_EDGE0 + j, i);
+                double grad_h = div_pos(diff_h, EC(TS_NABRDIST0 + j));
+                sub[j] = effkh * grad_h * avgh * EC(TS_EDGE0 + j);
             } else {
                 sub[j] = -FOC(PB_F_BC0 + j, i);
             }
             ovl_infil[j] = ovl[j];
         } else {
             // river edge: RiverToElem write-back, river_flow.c:159-180
-            const int c = -code - 2, r = c >> 2, side = c & 3;
+            const int c = -code[j] - 2, r = c >> 2, side = c & 3;
             if (side < 2) {
                 ovl[j] = -RFLX(RF_LEFT_S2C + side, r);
                 sub[j] = -(RFLX(RF_LEFT_A2C + side, r) + RFLX(RF_LEFT_A2A + side, r));
@@ -510,14 +640,14 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
     // use the same satn / KrFunc / Psi in the unsaturated branch.
     double infil, rechg;
     {
-        const double alpha = EFC(PB_E_ALPHA, i), beta = EFC(PB_E_BETA, i);
-        const double kinfv = EFC(PB_E_KINFV, i), kmacv = EFC(PB_E_KMACV, i);
-        const double areafh = EFC(PB_E_AREAFH, i);
+        const double alpha = EC(TS_ALPHA), beta = EC(TS_BETA);
+        const double kinfv = EC(TS_KINFV), kmacv = EC(TS_KMACV);
+        const double areafh = EC(TS_AREAFH);
         const bool sat = gw > depth - dinf;
         double satn = 1.0, satkfunc = 1.0, psi_u = 0.0, deficit = 0.0;
         if (!sat) {
             deficit = depth - gw;
-            satn = unsat / deficit;
+            satn = div_pos(unsat, deficit);
             satn = (satn > 1.0) ? 1.0 : satn;
             satn = (satn < PB_SATMIN) ? PB_SATMIN : satn;
             psi_u = psi_func(satn, alpha, beta);
@@ -528,10 +658,10 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
         } else {
             double applrate = 0.0;
 #pragma unroll
-            for (int j = 0; j < 3; j++) applrate += -ovl_infil[j] / area;
+            for (int j = 0; j < 3; j++) applrate += div_pos(-ovl_infil[j], area);
             applrate = (applrate > 0.0) ? applrate : 0.0;
             applrate += pcpdrp;
-            double wetfrac = surfh / PB_DEPRSTG;
+            double wetfrac = div_pos(surfh, PB_DEPRSTG);
             wetfrac = (wetfrac > 0.0) ? wetfrac : 0.0;
             wetfrac = (wetfrac < 1.0) ? wetfrac : 1.0;
             double dh_by_dz;
@@ -550,7 +680,7 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
                 infil = kinf * dh_by_dz;
                 infil = (infil > 0.0) ? infil : 0.0;
             }
-            const double ws0surf = FOC(PB_F_WS0SURF, i);
+            const double ws0surf = f[3 * PB_TILE];
             double infil_max = applrate + ((ws0surf > 0.0) ? ws0surf / m.dt : 0.0);
             infil = (infil > infil_max) ? infil_max : infil;
             infil *= wetfrac;
@@ -559,7 +689,7 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
             rechg = infil;
         } else {
             // AvgKv (_ARITH_), vert_flow.c:172-209
-            const double ksatv = EFC(PB_E_KSATV, i), dmac = EFC(PB_E_DMAC, i);
+            const double ksatv = EC(TS_KSATV), dmac = EC(TS_DMAC);
             double k1, k2, k3, d1, d2, d3;
             if (deficit > dmac) {
                 k1 = satkfunc * ksatv; d1 = dmac;
@@ -588,14 +718,14 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
     double fbr_infil = 0.0, fbr_rechg = 0.0, dfu = 0.0, dfg = 0.0, fbrflow[3] = {0.0, 0.0, 0.0};
     if (FBR) {
         const double fu = max0(y[m.o_fu + i]), fg = max0(y[m.o_fg + i]);
-        const double gdepth = EFC(PB_E_GDEPTH, i), gksatv = EFC(PB_E_GKSATV, i);
-        const double galpha = EFC(PB_E_GALPHA, i), gbeta = EFC(PB_E_GBETA, i);
-        const double zbed = EFC(PB_E_ZBED, i), gksath = EFC(PB_E_GKSATH, i);
+        const double gdepth = EC(TS_GDEPTH), gksatv = EC(TS_GKSATV);
+        const double galpha = EC(TS_GALPHA), gbeta = EC(TS_GBETA);
+        const double zbed = EC(TS_ZBED), gksath = EC(TS_GKSATH);
         const bool full = fg >= gdepth;
         double deficit = 0.0, satkfunc = 1.0, psi_c = 0.0;
         if (!full) {
             deficit = gdepth - fg;
-            double satn = fu / deficit;
+            double satn = div_pos(fu, deficit);
             satn = (satn > 1.0) ? 1.0 : satn;
             satn = (satn < PB_SATMIN) ? PB_SATMIN : satn;
             psi_c = psi_func(satn, galpha, gbeta);
@@ -604,13 +734,13 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
         }
         // FbrInfil, vert_flow.c:284-330
         if (full) {
-            fbr_infil = -EFC(PB_E_KSATV, i);
+            fbr_infil = -EC(TS_KSATV);
         } else if (fu + fg > gdepth || gw <= 0.0) {
             fbr_infil = 0.0;
         } else {
             double h_u = psi_c + zmin - 0.5 * deficit;
             double dh_by_dz = (zmin + gw - h_u) / (0.5 * (gw + deficit));
-            double kavg = (gw + deficit) / (gw / EFC(PB_E_KSATV, i) + deficit / (gksatv * satkfunc));
+            double kavg = (gw + deficit) / (gw / EC(TS_KSATV) + deficit / (gksatv * satkfunc));
             fbr_infil = kavg * dh_by_dz;
         }
         // FbrRecharge, vert_flow.c:332-373
@@ -636,8 +766,8 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
                     const double head = FOC(PB_F_FBRBC0 + j, i);
                     double diff_h = fg + zbed - head;
                     double avgh = avg_h(diff_h, fg, head - zbed);
-                    double grad_h = diff_h / EFC(PB_E_NABRDIST0 + j, i);
-                    fbrflow[j] = gksath * grad_h * avgh * EFC(PB_E_EDGE0 + j, i);
+                    double grad_h = div_pos(diff_h, EC(TS_NABRDIST0 + j));
+                    fbrflow[j] = gksath * grad_h * avgh * EC(TS_EDGE0 + j);
                 } else {
                     fbrflow[j] = -FOC(PB_F_FBRBC0 + j, i);
                 }
@@ -646,7 +776,7 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
                 double dist;
                 if (code >= 0) {
                     n = code;
-                    dist = EFC(PB_E_NABRDIST0 + j, i);
+                    dist = EC(TS_NABRDIST0 + j);
                 } else {
                     // neighbour across the river, lat_flow.c:85-100
                     const int r = (-code - 2) >> 2;
@@ -656,11 +786,11 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
                 }
                 // FbrFlowElemToElem, lat_flow.c:374-390
                 const double fg_n = max0(y[m.o_fg + n]);
-                double diff_h = (fg + zbed) - (fg_n + EFC(PB_E_ZBED, n));
+                double diff_h = (fg + zbed) - (fg_n + m.snb[n].w);
                 double avgh = avg_h(diff_h, fg, fg_n);
-                double grad_h = diff_h / dist;
-                double avg_ksat = 0.5 * (gksath + EFC(PB_E_GKSATH, n));
-                fbrflow[j] = avg_ksat * grad_h * avgh * EFC(PB_E_EDGE0 + j, i);
+                double grad_h = div_pos(diff_h, dist);
+                double avg_ksat = 0.5 * (gksath + TSC(TS_GKSATH, n));
+                fbrflow[j] = avg_ksat * grad_h * avgh * EC(TS_EDGE0 + j);
             }
         }
         dgw -= fbr_infil;
@@ -670,21 +800,21 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
 
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-        dsurf -= ovl[j] / area;
-        dgw -= sub[j] / area;
-        if (FBR) dfg -= fbrflow[j] / area;
+        dsurf -= div_pos(ovl[j], area);
+        dgw -= div_pos(sub[j], area);
+        if (FBR) dfg -= div_pos(fbrflow[j], area);
     }
-    const double porosity = EFC(PB_E_POROSITY, i);
-    dunsat /= porosity;
-    dgw /= porosity;
+    const double porosity = EC(TS_POROSITY);
+    dunsat = div_pos(dunsat, porosity);
+    dgw = div_pos(dgw, porosity);
     dy[i] = dsurf;
     dy[m.o_unsat + i] = dunsat;
     dy[m.o_gw + i] = dgw;
     bool bad = isnan(dsurf) || isnan(dunsat) || isnan(dgw);
     if (FBR) {
-        const double gporosity = EFC(PB_E_GPOROSITY, i);
-        dfu /= gporosity;
-        dfg /= gporosity;
+        const double gporosity = EC(TS_GPOROSITY);
+        dfu = div_pos(dfu, gporosity);
+        dfg = div_pos(dfg, gporosity);
         dy[m.o_fu + i] = dfu;
         dy[m.o_fg + i] = dfg;
         bad = bad || isnan(dfu) || isnan(dfg);
@@ -708,6 +838,7 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
         XFC(PB_X_FBR_INFIL, i) = fbr_infil;
         XFC(PB_X_FBR_RECHG, i) = fbr_rechg;
     }
+#undef EC
 }
 
 // river part of k_main: the serial accumulation of river_flow.c:94-108 as an
@@ -725,9 +856,9 @@ __device__ __forceinline__ void river_main(const DevMesh &m, double *__restrict_
     RFLX(RF_UP_A2A, r) = up_a2a;
     const double area = RFC(PB_R_AREA, r);
     double dstg = 0.0;
-    dstg -= up_c2c / area;
+    dstg -= div_pos(up_c2c, area);
 #pragma unroll
-    for (int j = 1; j <= 6; j++) dstg -= RFLX(j, r) / area;
+    for (int j = 1; j <= 6; j++) dstg -= div_pos(RFLX(j, r), area);
     double drgw = 0.0;
     drgw += -RFLX(RF_LEFT_A2A, r) - RFLX(RF_RIGHT_A2A, r) - RFLX(RF_DOWN_A2A, r) - up_a2a +
         RFLX(RF_CHANL_LKG, r);
@@ -741,13 +872,35 @@ __device__ __forceinline__ void river_main(const DevMesh &m, double *__restrict_
 // kernels.  Grid = element blocks followed by river blocks.
 // ---------------------------------------------------------------------------
 #define PB_RHS_THREADS 128
+#define PB_RHS_WARPS (PB_RHS_THREADS / 32)
+#ifndef PB_PRE_MINB
+#define PB_PRE_MINB 8      // <= 64 registers: the element part fits, the (tiny) river part may spill
+#endif
+#ifndef PB_MAIN_MINB
+#define PB_MAIN_MINB 5
+#endif
 
-static __global__ void __launch_bounds__(PB_RHS_THREADS)
+// Grid = element blocks (one warp per 32-element tile) followed by river blocks.
+static __global__ void __launch_bounds__(PB_RHS_THREADS, PB_PRE_MINB)
 k_pre(const DevMesh m, const double *__restrict__ y, int elem_blocks)
 {
+    constexpr int NC = TS_PRE1 - TS_PRE0;
+    __shared__ __align__(128) double s_tile[PB_RHS_WARPS][NC * PB_TILE];
+    __shared__ __align__(8) unsigned long long s_bar[PB_RHS_WARPS];
     if ((int)blockIdx.x < elem_blocks) {
-        const int i = blockIdx.x * PB_RHS_THREADS + threadIdx.x;
-        if (i < m.ne) elem_pre(m, y, i);
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int tile = blockIdx.x * PB_RHS_WARPS + warp;
+        if (tile * PB_TILE >= m.ne) return;
+        const unsigned bar = smem_u32(&s_bar[warp]);
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            mbar_expect_tx(bar, NC * PB_TILE * 8);
+            tma_bulk_g2s(smem_u32(&s_tile[warp][0]), m.es + ((size_t)tile * TS_NCOL + TS_PRE0) * PB_TILE,
+                         NC * PB_TILE * 8, bar);
+        }
+        __syncwarp();
+        const int i = tile * PB_TILE + lane;
+        if (i < m.ne) elem_pre(m, y, i, &s_tile[warp][lane], bar);
     } else {
         const int r = (blockIdx.x - elem_blocks) * PB_RHS_THREADS + threadIdx.x;
         if (r < m.nr) river_fluxes(m, y, r);
@@ -755,19 +908,35 @@ k_pre(const DevMesh m, const double *__restrict__ y, int elem_blocks)
 }
 
 template <bool FBR>
-__global__ void __launch_bounds__(PB_RHS_THREADS)
+__global__ void __launch_bounds__(PB_RHS_THREADS, PB_MAIN_MINB)
 k_main(const DevMesh m, const double *__restrict__ y, double *__restrict__ dy, int elem_blocks)
 {
+    constexpr int NC = (FBR ? TS_FBR1 : TS_MAIN1) - TS_MAIN0;
+    __shared__ __align__(128) double s_tile[PB_RHS_WARPS][NC * PB_TILE];
+    __shared__ __align__(128) double s_forc[PB_RHS_WARPS][4 * PB_TILE];
+    __shared__ __align__(8) unsigned long long s_bar[PB_RHS_WARPS];
     if ((int)blockIdx.x < elem_blocks) {
-        const int i = blockIdx.x * PB_RHS_THREADS + threadIdx.x;
-        if (i < m.ne) elem_main<FBR>(m, y, dy, i);
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int tile = blockIdx.x * PB_RHS_WARPS + warp;
+        if (tile * PB_TILE >= m.ne) return;
+        const unsigned bar = smem_u32(&s_bar[warp]);
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            mbar_expect_tx(bar, (NC + 4) * PB_TILE * 8);
+            tma_bulk_g2s(smem_u32(&s_tile[warp][0]), m.es + ((size_t)tile * TS_NCOL + TS_MAIN0) * PB_TILE,
+                         NC * PB_TILE * 8, bar);
+            tma_bulk_g2s(smem_u32(&s_forc[warp][0]), m.ft + (size_t)tile * 4 * PB_TILE, 4 * PB_TILE * 8, bar);
+        }
+        __syncwarp();
+        const int i = tile * PB_TILE + lane;
+        if (i < m.ne) elem_main<FBR>(m, y, dy, i, &s_tile[warp][lane], &s_forc[warp][lane], bar);
     } else {
         const int r = (blockIdx.x - elem_blocks) * PB_RHS_THREADS + threadIdx.x;
         if (r < m.nr) river_main(m, dy, r);
     }
 }
 
-#undef EFC
+#undef TSC
 #undef RFC
 #undef RIC
 #undef FOC

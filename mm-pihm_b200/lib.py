@@ -15,7 +15,7 @@ import numpy as np
 from . import watershed as W
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpihm_b200.so")
+LIB_PATH = os.environ.get("PIHM_B200_LIB", os.path.join(HERE, "libpihm_b200.so"))
 
 
 class MeshStruct(C.Structure):
