@@ -100,6 +100,15 @@ _SIGS = {
     "pihm_b200_cvode_get_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pihm_b200_adj_cvode_max_step": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
+# include/pihm_b200_sundials.h
+_SUNDIALS_SIGS = {
+    "N_VNew_PihmB200": (C.c_void_p, [C.c_void_p]),
+    "N_VDestroy_PihmB200": (None, [C.c_void_p]),
+    "N_VPihmB200_Push": (C.c_int, [C.c_void_p]),
+    "N_VPihmB200_Pull": (C.c_int, [C.c_void_p]),
+    "N_VPihmB200_Device": (C.c_void_p, [C.c_void_p]),
+    "PihmB200_ODE": (C.c_int, [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
 
 _lib = None
 
@@ -113,7 +122,7 @@ def load_library():
                 f"{LIB_PATH} not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
                 "there is no CPU fallback")
         L = C.CDLL(LIB_PATH)
-        for name, (res, args) in _SIGS.items():
+        for name, (res, args) in list(_SIGS.items()) + list(_SUNDIALS_SIGS.items()):
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args

@@ -742,3 +742,62 @@ double ref_nvec_op(int op, long int n, double a, const double *x, double b,
     N_VDestroy(vz);
     return r;
 }
+
+/*
+ * The reference CVODE (this library) driven with an EXTERNAL N_Vector and RHS
+ * callback -- the drop-in of INTEGRATION.md: same call sequence as
+ * SetCVodeParam()/SolveCVode() (src/ode.c:340-498), with N_VNew_PihmB200's
+ * vector and PihmB200_ODE in place of N_VNew_Serial / ODE.
+ */
+static void    *X_mem;
+static N_Vector X_y;
+
+int ref_ext_cvode_init(void *nv_y, void *rhs_fn, void *user_data, double reltol,
+    double abstol, double initstep, double maxstep, long int mxsteps)
+{
+    int             flag;
+
+    X_y = (N_Vector)nv_y;
+    X_mem = CVodeCreate(CV_BDF, CV_NEWTON);
+    if (X_mem == NULL) return -1;
+    flag = CVodeInit(X_mem, (CVRhsFn)rhs_fn, 0.0, X_y);
+    if (flag < 0) return flag;
+    flag = CVodeSStolerances(X_mem, (realtype)reltol, (realtype)abstol);
+    if (flag < 0) return flag;
+    CVodeSetUserData(X_mem, user_data);
+    CVodeSetInitStep(X_mem, (realtype)initstep);
+    CVodeSetStabLimDet(X_mem, TRUE);
+    CVodeSetMaxStep(X_mem, (realtype)maxstep);
+    CVodeSetMaxNumSteps(X_mem, mxsteps);
+    return CVSpgmr(X_mem, PREC_NONE, 0);
+}
+
+int ref_ext_cvode_solve(double tout, double *tret)
+{
+    realtype        solvert;
+    int             flag;
+
+    flag = CVodeSetStopTime(X_mem, (realtype)tout);
+    if (flag < 0) return flag;
+    flag = CVode(X_mem, (realtype)tout, X_y, &solvert, CV_NORMAL);
+    *tret = solvert;
+    return flag;
+}
+
+void ref_ext_cvode_stats(long int *s)
+{
+    CVodeGetNumSteps(X_mem, &s[0]);
+    CVodeGetNumRhsEvals(X_mem, &s[1]);
+    CVodeGetNumNonlinSolvIters(X_mem, &s[2]);
+    CVodeGetNumNonlinSolvConvFails(X_mem, &s[3]);
+    CVodeGetNumErrTestFails(X_mem, &s[4]);
+    CVSpilsGetNumLinIters(X_mem, &s[5]);
+    CVSpilsGetNumConvFails(X_mem, &s[6]);
+    CVSpilsGetNumRhsEvals(X_mem, &s[7]);
+}
+
+void ref_ext_cvode_free(void)
+{
+    if (X_mem) CVodeFree(&X_mem);
+    X_mem = NULL;
+}

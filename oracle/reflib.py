@@ -224,3 +224,36 @@ class RefModel:
         r = self.lib.ref_nvec_op(op, n, float(a), None if xx is None else _ptr(xx),
                                  float(b), None if yy is None else _ptr(yy), _ptr(z))
         return r, z
+
+
+class RefCvodeExternal:
+    """The reference CVODE (private copy of libpihm_ref.so) running on an external
+    N_Vector / RHS callback: N_VNew_PihmB200 + PihmB200_ODE."""
+
+    def __init__(self, nv_y_ptr: int, rhs_fn_ptr: int, user_data_ptr: int, reltol=1e-3,
+                 abstol=1e-4, initstep=5e-5, maxstep=60.0, mxsteps=600):
+        self.model = RefModel(fbr=False)
+        L = self.model.lib
+        L.ref_ext_cvode_init.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                         C.c_double, C.c_double, C.c_long]
+        L.ref_ext_cvode_solve.argtypes = [C.c_double, C.POINTER(C.c_double)]
+        rc = L.ref_ext_cvode_init(nv_y_ptr, rhs_fn_ptr, user_data_ptr, reltol, abstol, initstep,
+                                  maxstep, mxsteps)
+        if rc != 0:
+            raise RuntimeError(f"ref_ext_cvode_init failed ({rc})")
+
+    def solve(self, tout: float) -> float:
+        t = C.c_double()
+        rc = self.model.lib.ref_ext_cvode_solve(float(tout), C.byref(t))
+        if rc < 0:
+            raise RuntimeError(f"reference CVode failed ({rc})")
+        return t.value
+
+    def stats(self):
+        s = (C.c_long * 8)()
+        self.model.lib.ref_ext_cvode_stats(s)
+        keys = ["nst", "nfe", "nni", "ncfn", "netf", "nli", "ncfl", "nfeLS"]
+        return {k: int(s[i]) for i, k in enumerate(keys)}
+
+    def free(self):
+        self.model.lib.ref_ext_cvode_free()

@@ -25,6 +25,16 @@ def declared_symbols():
     return sorted(set(re.findall(r"\b(pihm_b200_[a-z0-9_]+)\s*\(", header_text())))
 
 
+def test_sundials_header_symbols_exported():
+    with open(os.path.join(ROOT, "include", "pihm_b200_sundials.h")) as f:
+        txt = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    syms = sorted(set(re.findall(r"\b(N_V[A-Za-z0-9_]*PihmB200[A-Za-z0-9_]*|PihmB200_ODE)\s*\(", txt)))
+    assert syms == sorted(lib._SUNDIALS_SIGS), syms
+    L = lib.load_library()
+    for s in syms:
+        assert hasattr(L, s)
+
+
 def test_library_exports_every_declared_symbol():
     L = lib.load_library()
     syms = declared_symbols()
