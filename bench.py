@@ -33,6 +33,9 @@ from mm_pihm_b200 import watershed as W  # noqa: E402
 T0 = 2 * 3600.0          # model time of step 0: one hour into the 6 h rain pulse
 STEP = 60.0
 B_RHS = {False: 376.0, True: 476.0}     # algorithmic bytes / element / RHS
+# dram__bytes_read.sum + dram__bytes_write.sum of one RHS (k_pre + k_main) from the committed
+# ncu --set full capture (profiles/); None where no capture exists
+RHS_TRAFFIC_BYTES = {("1M", False): 504.0e6}
 
 
 def forcing_at(tb, k):
@@ -107,20 +110,47 @@ def run_ours(args):
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    if world > 1:
-        raise SystemExit("multi-GPU mesh partitioning is not built yet (see DESIGN.md, row e)")
-
     fbr = bool(args.fbr)
-    tb = W.make_named(args.size, fbr=fbr)
+    size = args.size
+    if world > 1:
+        # weak scaling: 1M triangles per GPU (BASELINE config[4]: 8M triangles on 8 GPUs)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        size = {2: "2M", 4: "4M", 8: "8M"}.get(world)
+        if size is None:
+            raise SystemExit("--gpus must be 1, 2, 4 or 8")
+    tb = W.make_named(size, fbr=fbr)
+    ne_glob, nr_glob = tb["nelem"], tb["nriver"]
+    if world > 1:
+        from mm_pihm_b200 import partition as PT
+        part = PT.partition(tb, world, parts=[rank])[0]
+        y0 = tb["y0"][part["state_idx"]]
+        tb = part                                    # local tables (owned + ghosts) from here on
+        model = lib.Model(tb, device=local)
+        uid = [lib.Model.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        model.comm_init(rank, world, uid[0])
+    else:
+        y0 = tb["y0"]
+        model = lib.Model(tb, device=local, reorder=args.reorder)
     ne, nr = tb["nelem"], tb["nriver"]
-    model = lib.Model(tb, device=local, reorder=args.reorder)
     stream = torch.cuda.current_stream()
     model.set_stream(stream.cuda_stream)
     cv = lib.Cvode(model)
-    y = model.N_VNew(tb["y0"])
+    y = model.N_VNew(y0)
+    tb["y0"] = y0
     K, Wu = args.steps, args.warmup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     def reset():
         y.upload(tb["y0"])
@@ -147,18 +177,21 @@ def run_ours(args):
     st0 = cv.stats(); l0 = model.launches
     clocks = ClockSampler(local); clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
+    barrier()
     ev0.record(stream)
     for k in range(Wu, Wu + K):
         step(k)
     ev1.record(stream)
-    torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1)
+    barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
     clk = clocks.stop()
     st1 = cv.stats(); l1 = model.launches
     rhs_evals = (st1["nfe"] + st1["nfeLS"]) - (st0["nfe"] + st0["nfeLS"])
     nst = st1["nst"] - st0["nst"]
-    value = (K * STEP / 86400.0) / (ms * 1e-3)
+    # whole-job throughput: simulated days per second, scaled by the mesh size in units of
+    # 1M triangles (== sim-days/s at 1M triangles for N = 1; N GPUs carry N x 1M triangles)
+    mtri = ne_glob / 1.0e6 if world > 1 else 1.0
+    value = (K * STEP / 86400.0) / (ms * 1e-3) * mtri
 
     # ---- end to end through the C ABI with host buffers --------------------------
     reset()
@@ -166,14 +199,14 @@ def run_ours(args):
     forc_tabs = {k: forcing_at(tb, k) for k in range(0, Wu + K + 15, 15)}
     for k in range(Wu):
         step(k, e2e=True, host_forc=forc_tabs[(k // 15) * 15], host_y=host_y)
-    torch.cuda.synchronize()
+    barrier()
     ev0.record(stream)
     for k in range(Wu, Wu + K):
         step(k, e2e=True, host_forc=forc_tabs[(k // 15) * 15], host_y=host_y)
     ev1.record(stream)
-    torch.cuda.synchronize()
-    ms_e2e = ev0.elapsed_time(ev1)
-    e2e_value = (K * STEP / 86400.0) / (ms_e2e * 1e-3)
+    barrier()
+    ms_e2e = max_over_ranks(ev0.elapsed_time(ev1))
+    e2e_value = (K * STEP / 86400.0) / (ms_e2e * 1e-3) * mtri
 
     # ---- RHS kernels: live CUDA-event duration over back-to-back launches ----------
     yv = y
@@ -181,40 +214,57 @@ def run_ours(args):
     nrep = 30
     for _ in range(3):
         model.ode_dev(0.0, yv, yd)
-    torch.cuda.synchronize()
+    barrier()
     ev0.record(stream)
     for _ in range(nrep):
         model.ode_dev(0.0, yv, yd)
     ev1.record(stream)
-    torch.cuda.synchronize()
-    rhs_ms = ev0.elapsed_time(ev1) / nrep
+    barrier()
+    rhs_ms = max_over_ranks(ev0.elapsed_time(ev1)) / nrep
     peak, peak_src = measured_peak()
-    achieved = B_RHS[fbr] * ne / (rhs_ms * 1e-3) / 1e9
+    achieved = B_RHS[fbr] * model.nown_elem / (rhs_ms * 1e-3) / 1e9      # per GPU
+    if world > 1:
+        tot = torch.tensor([float(rhs_evals), float(l1 - l0)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        rhs_evals = int(tot[0].item())
+    if rank != 0:
+        cv.close(); model.close()
+        dist.destroy_process_group()
+        return
 
     out = {
         "metric": "simulated days/wall-sec at 1M triangles; RHS evals/s and achieved HBM GB/s",
         "value": value, "unit": "sim-days/s", "n_gpus": world, "steps": K, "warmup": Wu,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"pihm{'-fbr' if fbr else ''} synthetic {args.size}-triangle watershed "
-                               f"({ne} elements, {nr} river segments), 60 s model steps in the rain pulse "
-                               f"(t0 = 2 h), reltol 1e-3 abstol 1e-4",
-                   "nelem": ne, "nriver": nr, "nsv": model.nsv, "reorder": args.reorder,
+        "config": {"workload": f"pihm{'-fbr' if fbr else ''} synthetic {size}-triangle watershed "
+                               f"({ne_glob} elements, {nr_glob} river segments), 60 s model steps in the rain pulse "
+                               f"(t0 = 2 h), reltol 1e-3 abstol 1e-4"
+                               + (f"; mesh partitioned over {world} GPUs (1M triangles each), NCCL halo exchange "
+                                  f"per RHS + scalar all-reduce per norm; value = sim-days/s x (triangles / 1M)"
+                                  if world > 1 else ""),
+                   "nelem": ne_glob, "nriver": nr_glob, "nsv": model.nsv_global if world > 1 else model.nsv,
+                   "reorder": args.reorder, "parallelism": f"mesh-partition x{world}",
                    "l2": "RHS working set 376 B x nelem and 21 state-sized vectors exceed the 126 MB L2"},
         "rhs_evals_per_s": rhs_evals / (ms * 1e-3), "rhs_evals": rhs_evals, "cvode_steps": nst,
         "rhs_ms": rhs_ms,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "kernel": "k_pre + k_main (one RHS)",
+                     "frac": achieved / peak, "traffic": RHS_TRAFFIC_BYTES.get((size, fbr)),
+                     "kernel": "k_pre + k_main (one RHS evaluation, per GPU)",
                      "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": B_RHS[fbr] * ne},
+                     "algorithmic_bytes_per_launch": B_RHS[fbr] * model.nown_elem,
+                     "traffic_source": "profiles/r01_rhs_1M_ncu_summary.md (ncu --set full, dram read+write)"},
         "e2e": {"value": e2e_value, "unit": "sim-days/s", "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": 3 * 8 * ne, "d2h_bytes_per_step": 8 * model.nsv},
         "gpu_launches": int(l1 - l0),
         "clocks": clk,
     }
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         out["cpu_baseline"] = cpu_reference(tb, fbr, steps=args.cpu_steps, warmup=Wu)
     print(json.dumps(out))
+    cv.close(); model.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # --------------------------------------------------------------------------- reference / CPU baseline
@@ -256,13 +306,16 @@ def run_reference(args):
     if rank != 0:
         return
     fbr = bool(args.fbr)
-    tb = W.make_named(args.size, fbr=fbr)
+    size = {1: args.size, 2: "2M", 4: "4M", 8: "8M"}.get(args.gpus, args.size)
+    args.size = size
+    tb = W.make_named(size, fbr=fbr)
     steps = min(args.steps, args.ref_max_steps)
     cb = cpu_reference(tb, fbr, steps=steps, warmup=args.warmup)
     out = {
         "impl": "reference",
         "metric": "simulated days/wall-sec at 1M triangles; RHS evals/s and achieved HBM GB/s",
-        "value": cb["value"], "unit": "sim-days/s", "n_gpus": args.gpus, "steps": steps,
+        "value": cb["value"] * (tb["nelem"] / 1.0e6 if args.gpus > 1 else 1.0), "unit": "sim-days/s",
+        "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"pihm{'-fbr' if fbr else ''} synthetic {args.size}-triangle watershed "

@@ -127,6 +127,52 @@ int             pihm_b200_device_count(void);
 pihm_b200_ctx  *pihm_b200_create(const pihm_b200_mesh *mesh, int device,
                                  int reorder);
 void            pihm_b200_destroy(pihm_b200_ctx *ctx);
+
+/* ------------------------------------------------------------------------
+ * Multi-GPU: the mesh is partitioned, one process (rank) per GPU (SURVEY 8(e);
+ * the reference itself is shared-memory only).  A partition's local
+ * mesh is an ordinary pihm_b200_mesh whose first nown_elem elements and
+ * nown_riv rivers are owned and whose remaining entities are ghosts, grouped
+ * by owner rank.  y / ydot of such a context hold the owned unknowns only.
+ * ---------------------------------------------------------------------- */
+typedef struct pihm_b200_partition pihm_b200_partition;
+/* host-only: split `global` into nparts (the tables must stay alive) */
+pihm_b200_partition *pihm_b200_partition_create(const pihm_b200_mesh *global,
+                                                int nparts);
+void            pihm_b200_partition_destroy(pihm_b200_partition *p);
+/* sizes[8] = {ne_local, nr_local, ne_owned, nr_owned, n_neighbours,
+ *             n_send_elem, n_send_riv, 0} */
+int             pihm_b200_partition_sizes(const pihm_b200_partition *p, int part,
+                                          int32_t *sizes);
+/* local column tables, global ids of the local entities, exchange maps */
+int             pihm_b200_partition_fill(const pihm_b200_partition *p, int part,
+                    double *elem_f64, int32_t *elem_i32, double *riv_f64,
+                    int32_t *riv_i32, int32_t *elem_gid, int32_t *riv_gid,
+                    int32_t *nbr_rank, int32_t *send_e_ptr, int32_t *send_e_idx,
+                    int32_t *recv_e_cnt, int32_t *send_r_ptr,
+                    int32_t *send_r_idx, int32_t *recv_r_cnt);
+pihm_b200_ctx  *pihm_b200_create_part(const pihm_b200_mesh *local, int device,
+                                      int reorder, int nown_elem, int nown_riv);
+int             pihm_b200_set_halo(pihm_b200_ctx *ctx, int n_neighbours,
+                    const int32_t *nbr_rank, const int32_t *send_e_ptr,
+                    const int32_t *send_e_idx, const int32_t *recv_e_cnt,
+                    const int32_t *send_r_ptr, const int32_t *send_r_idx,
+                    const int32_t *recv_r_cnt);
+/* NCCL communicator: rank 0 makes the 128-byte id, the launcher broadcasts it.
+ * After comm_init every RHS call starts with the halo exchange (grouped
+ * ncclSend/ncclRecv of {surf, gw[, fbr_gw]} / {stage, gw} records) and every
+ * reduction of the integrator is followed by a scalar ncclAllReduce. */
+int             pihm_b200_comm_unique_id(void *out128);
+int             pihm_b200_comm_init(pihm_b200_ctx *ctx, int rank, int nranks,
+                                    const void *id128);
+int64_t         pihm_b200_num_state_var_global(const pihm_b200_ctx *ctx);
+/* transport-free access to the exchange (single-process emulation of several
+ * ranks on one GPU, used by the tests): packed send records of y, and the
+ * ghost records of this context */
+int             pihm_b200_halo_pack_host(pihm_b200_ctx *ctx,
+                    const pihm_b200_vec *y, double *elem_rec, double *riv_rec);
+int             pihm_b200_set_ghosts(pihm_b200_ctx *ctx, const double *elem_rec,
+                                     const double *riv_rec);
 /* number of ODE unknowns, NumStateVar() (src/ode.c:313-339) */
 int64_t         pihm_b200_num_state_var(const pihm_b200_ctx *ctx);
 /* run all work of this context on `stream` (a cudaStream_t); NULL = default */

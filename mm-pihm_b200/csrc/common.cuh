@@ -57,7 +57,11 @@ __host__ __device__ inline int nb_river_code(int river, int side) { return -((ri
 
 // Device view of one model: everything the RHS kernels read.  Passed by value.
 struct DevMesh {
-    int ne, nr;          // elements, river segments
+    int ne, nr;          // local elements / river segments (owned + ghosts)
+    int nown, rown;      // owned ones come first; single GPU: nown == ne, rown == nr
+    int gs;              // doubles per ghost element record (2, or 3 with fbr)
+    const double *gel;   // [ne - nown][gs] ghost element records {surf, gw[, fbr_gw]}
+    const double *gri;   // [nr - rown][2]  ghost river records {stage, gw}
     int nes, nrs;        // column strides (padded)
     int fbr, surf_mode, riv_mode;
     int record;          // write the PB_X_* flux columns
@@ -86,6 +90,14 @@ struct DevMesh {
 
 }  // namespace pb
 
+struct pihm_b200_ctx;
+namespace pb {
+// comm.cu: NCCL (dlopen'ed) halo exchange and scalar all-reduce
+int comm_halo_exchange(pihm_b200_ctx *ctx);
+int comm_allreduce(pihm_b200_ctx *ctx, double *dev_ptr, int count, int op /*0 sum, 1 min, 2 max*/);
+void comm_destroy(pihm_b200_ctx *ctx);
+}  // namespace pb
+
 // opaque handle types of the C ABI
 struct pihm_b200_ctx {
     pb::DevMesh dm{};
@@ -110,6 +122,14 @@ struct pihm_b200_ctx {
     double *d_rivflow = nullptr, *d_stale = nullptr, *d_xflux = nullptr;
     int *d_nan = nullptr;
     int *d_perm = nullptr, *d_iperm = nullptr;   // device copies (state gather)
+    // multi-GPU: ghost buffers, send lists, communicator (comm.cu)
+    double *d_gel = nullptr, *d_gri = nullptr, *d_send_e = nullptr, *d_send_r = nullptr;
+    int *d_send_e_idx = nullptr, *d_send_r_idx = nullptr;
+    std::vector<int> nbr_rank, send_e_ptr, recv_e_cnt, send_r_ptr, recv_r_cnt;
+    int nse = 0, nsr = 0;
+    void *comm = nullptr;              // ncclComm_t
+    int rank = 0, nranks = 1;
+    long long nsv_global = 0;
     // staging for host <-> device vectors
     double *h_pin = nullptr;           // pinned, 2 * nsv
     double *d_stage = nullptr;         // nsv (reference order)

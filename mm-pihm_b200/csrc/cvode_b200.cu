@@ -91,7 +91,16 @@ struct pihm_b200_cvode {
 
     cudaStream_t s() const { return ctx->s(); }
     void count(int k = 1) { ctx->launches += k; }
-    void sync() { cudaStreamSynchronize(ctx->s()); }
+    // Multi-GPU: kernels leave rank-local partial sums in d_sc; red() all-reduces
+    // the slots in stream order and sync() then fetches the global values.
+    double *h_sc_map = nullptr;          // mapped mirror the kernels write (single GPU: == h_sc)
+    void sync()
+    {
+        if (ctx->nranks > 1)
+            cudaMemcpyAsync(h_sc, d_sc, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, ctx->s());
+        cudaStreamSynchronize(ctx->s());
+    }
+    void red(int slot, int n = 1, int op = 0) { if (ctx->nranks > 1) comm_allreduce(ctx, d_sc + slot, n, op); }
     // N_VWrmsNorm = SUNRsqrt(sum / N)  (nvector_serial.c:685)
     double wrms(int slot) const { const double v = h_sc[slot] / n_global; return (v <= 0.0) ? 0.0 : std::sqrt(v); }
 
@@ -122,6 +131,8 @@ struct pihm_b200_cvode {
     {
         k_ewt<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, reltol, abstol, zn[0], ewt, rb);
         count();
+        red(SC_EWT_MIN, 1, 1);
+        red(SC_EWT_NRM);
         ewt_pending = true;
     }
 
@@ -321,6 +332,7 @@ int pihm_b200_cvode::spgmrSolve(bool *b_is_zero)
             krydim = l_plus_1;
             // A-tilde V[l]: right scaling, DQ J*v, I - gamma J, left scaling, first MGS dot
             k_krylov_a<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, cnorm, V[lk], ewt, vtemp, rb);
+            red(SC_VNRM);
             k_krylov_b<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, n_global, d_sc, vtemp, y, ytemp);
             count(2);
             rhs(ytemp, V[l_plus_1]);     // Jv = f(tn, y + sig*v)   (cvode_spils.c:687)
@@ -329,6 +341,8 @@ int pihm_b200_cvode::spgmrSolve(bool *b_is_zero)
             k_krylov_c<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, n_global, gamma, d_sc, vtemp, ftemp, ewt,
                                                             V[0], V[l_plus_1], rb);
             count();
+            red(SC_VK2);
+            red(SC_H0);
             // ModifiedGS (sundials_iterative.c:44-92), i0 = 0 since k <= p
             for (int i = 0; i < l_plus_1; i++) {
                 const double *vnext = (i + 1 < l_plus_1) ? V[i + 1] : V[l_plus_1];
@@ -336,6 +350,7 @@ int pihm_b200_cvode::spgmrSolve(bool *b_is_zero)
                 k_mgs_step<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, d_sc, SC_H0 + i, V[i], vnext,
                                                                 V[l_plus_1], slot_next, rb);
                 count();
+                red(slot_next);
             }
             sync();
             const double vk_norm = rsqrt_s(h_sc[SC_VK2]);
@@ -347,8 +362,9 @@ int pihm_b200_cvode::spgmrSolve(bool *b_is_zero)
                 double new_norm_2 = 0.0;
                 for (int i = 0; i < l_plus_1; i++) {
                     k_reduce<RD_DOT, 0><<<blocks, PB_VEC_THREADS, 0, s()>>>(
-                        N, V[i], V[l_plus_1], d_part, d_counter, d_sc + SC_TMP, h_sc + SC_TMP);
+                        N, V[i], V[l_plus_1], d_part, d_counter, d_sc + SC_TMP, h_sc_map + SC_TMP);
                     count();
+                    red(SC_TMP);
                     sync();
                     const double new_product = h_sc[SC_TMP];
                     temp = 1000.0 * Hes[i][lk];
@@ -465,6 +481,7 @@ int pihm_b200_cvode::cvNewtonIteration()
             k_newton_res<false><<<blocks, PB_VEC_THREADS, 0, s()>>>(N, rl1, gamma, zn[0], zn[1], ftemp, ewt,
                                                                     acor, y, tempv, V[0], rb);
         count();
+        red(SC_BSUM);
         sync();
         if (ewt_pending) {               // deferred checks of cvode.c:1349-1388
             ewt_pending = false;
@@ -503,6 +520,7 @@ int pihm_b200_cvode::cvNewtonIteration()
         if (retval < 0) return CV_LSOLVE_FAIL;
         if (retval > 0) return CONV_FAIL;      // setupNonNull == FALSE (cvode_spgmr.c:262)
 
+        red(SC_DEL);
         sync();
         del = wrms(SC_DEL);
         if (m > 0) crate = std::max(CRDOWN * crate, del / delp);
@@ -513,6 +531,7 @@ int pihm_b200_cvode::cvNewtonIteration()
             } else {
                 k_wsq<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, acor, nullptr, ewt, SC_ACNRM, -1, rb);
                 count();
+                red(SC_ACNRM);
                 sync();
                 acnrm = wrms(SC_ACNRM);
             }
@@ -684,6 +703,7 @@ void pihm_b200_cvode::cvPrepareNextStep(double dsm)
     if (do_m1 || do_p1) {
         k_eta<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, do_m1, do_p1, cquot, zn[q], zn[qmax], acor, ewt, rb);
         count();
+        red(SC_ETA_M1, 2);
         sync();
         if (do_m1) {
             const double ddn = wrms(SC_ETA_M1) * tq[1];
@@ -708,6 +728,7 @@ void pihm_b200_cvode::cvBDFStab()
         for (int i = 1; i <= q - 1; i++) factorial *= i;
         k_wsq<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, zn[q], zn[q - 1], ewt, SC_STAB1, SC_STAB2, rb);
         count();
+        red(SC_STAB1, 2);
         sync();
         const double sq = factorial * q * (q + 1) * acnrm / std::max(tq[5], TINY);
         const double sqm1 = factorial * q * wrms(SC_STAB1);
@@ -1045,7 +1066,7 @@ pihm_b200_cvode *pihm_b200_cvode_create(pihm_b200_ctx *ctx)
     pihm_b200_cvode *cv = new pihm_b200_cvode();
     cv->ctx = ctx;
     cv->N = ctx->nsv;
-    cv->n_global = (double)ctx->nsv;
+    cv->n_global = (double)ctx->nsv_global;      // N of the WRMS norms: all ranks' unknowns
     cv->blocks = (int)std::max<long long>(1, std::min<long long>((cv->N + PB_VEC_THREADS - 1) / PB_VEC_THREADS,
                                                                   ctx->red_blocks));
     const size_t bytes = sizeof(double) * (size_t)std::max<long long>(cv->N, 1);
@@ -1072,7 +1093,20 @@ pihm_b200_cvode *pihm_b200_cvode_create(pihm_b200_ctx *ctx)
     cv->rb.part = cv->d_part;
     cv->rb.counter = cv->d_counter;
     cv->rb.sc = cv->d_sc;
-    cv->rb.hsc = cv->h_sc;
+    cv->h_sc_map = cv->h_sc;
+    cv->rb.hsc = cv->h_sc_map;
+    if (ctx->nranks > 1) {
+        // kernels keep writing their (rank-local) values to the mapped mirror; the host
+        // reads a separate pinned copy that sync() fills after the all-reduces
+        double *pinned = nullptr;
+        if (cudaHostAlloc((void **)&pinned, sizeof(double) * SC_COUNT, cudaHostAllocDefault) != cudaSuccess) {
+            set_error("cvode_create: pinned scalar buffer");
+            pihm_b200_cvode_destroy(cv);
+            return nullptr;
+        }
+        std::memset(pinned, 0, sizeof(double) * SC_COUNT);
+        cv->h_sc = pinned;
+    }
     cv->rb.max_blocks = ctx->red_blocks;
     cv->wrap_a.ctx = cv->wrap_b.ctx = ctx;
     cv->wrap_a.n = cv->wrap_b.n = cv->N;
@@ -1089,6 +1123,7 @@ void pihm_b200_cvode_destroy(pihm_b200_cvode *cv)
                      cv->vtemp, cv->ytemp, cv->d_part, cv->d_sc};
     for (double *p : all) if (p) cudaFree(p);
     if (cv->d_counter) cudaFree(cv->d_counter);
+    if (cv->h_sc_map && cv->h_sc_map != cv->h_sc) cudaFreeHost(cv->h_sc_map);
     if (cv->h_sc) cudaFreeHost(cv->h_sc);
     delete cv;
 }
@@ -1139,7 +1174,16 @@ int pihm_b200_cvode_solve(pihm_b200_cvode *cv, double tout, pihm_b200_vec *y, do
 {
     if (!cv || !cv->initialised || !y || y->n != cv->N || !tret) { set_error("cvode_solve: bad argument"); return CV_ILL_INPUT; }
     const int flag = cv->solve(tout, y->d, tret);
-    if (flag >= 0 && pihm_b200_check_nan(cv->ctx)) {
+    int nan_any = (flag >= 0) ? pihm_b200_check_nan(cv->ctx) : 0;
+    if (cv->ctx->nranks > 1) {      // every rank must take the same exit
+        double v = (double)nan_any;
+        cudaMemcpyAsync(cv->d_sc + SC_TMP, &v, sizeof(double), cudaMemcpyHostToDevice, cv->ctx->s());
+        comm_allreduce(cv->ctx, cv->d_sc + SC_TMP, 1, 2);
+        cudaMemcpyAsync(&v, cv->d_sc + SC_TMP, sizeof(double), cudaMemcpyDeviceToHost, cv->ctx->s());
+        cudaStreamSynchronize(cv->ctx->s());
+        nan_any = v > 0.0;
+    }
+    if (flag >= 0 && nan_any) {
         set_error("NAN error in dy (CheckDy, src/ode.c:302-311)");
         return CV_RHSFUNC_FAIL;
     }

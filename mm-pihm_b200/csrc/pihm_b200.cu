@@ -63,6 +63,16 @@ int pihm_b200_device_count(void)
 // ---------------------------------------------------------------------------
 pihm_b200_ctx *pihm_b200_create(const pihm_b200_mesh *mesh, int device, int reorder)
 {
+    if (!mesh) { set_error("pihm_b200_create: bad mesh descriptor"); return nullptr; }
+    return pihm_b200_create_part(mesh, device, reorder, mesh->nelem, mesh->nriver);
+}
+
+// One partition of a larger mesh (mm-pihm_b200/csrc/partition.cpp): the first
+// nown_elem elements / nown_riv rivers of the local tables are owned, the rest
+// are ghosts that receive their state through the halo exchange.
+pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int reorder, int nown_elem,
+                                     int nown_riv)
+{
     if (!mesh || mesh->nelem <= 0 || mesh->nriver < 0 || !mesh->elem_f64 || !mesh->elem_i32) {
         set_error("pihm_b200_create: bad mesh descriptor");
         return nullptr;
@@ -72,6 +82,15 @@ pihm_b200_ctx *pihm_b200_create(const pihm_b200_mesh *mesh, int device, int reor
         return nullptr;
     }
     const int ne = mesh->nelem, nr = mesh->nriver;
+    if (nown_elem < 1 || nown_elem > ne || nown_riv < 0 || nown_riv > nr) {
+        set_error("pihm_b200_create_part: owned counts out of range");
+        return nullptr;
+    }
+    const bool partitioned = (nown_elem != ne) || (nown_riv != nr);
+    if (partitioned && reorder) {
+        set_error("pihm_b200_create_part: a partition is already in locality order (reorder must be 0)");
+        return nullptr;
+    }
     auto EF = [&](int c, int e) { return mesh->elem_f64[(size_t)c * ne + e]; };
     auto EI = [&](int c, int e) { return mesh->elem_i32[(size_t)c * ne + e]; };
     auto RF = [&](int c, int r) { return mesh->riv_f64[(size_t)c * nr + r]; };
@@ -111,13 +130,20 @@ pihm_b200_ctx *pihm_b200_create(const pihm_b200_mesh *mesh, int device, int reor
     ctx->reorder = reorder;
     DevMesh &dm = ctx->dm;
     dm.ne = ne; dm.nr = nr;
+    dm.nown = nown_elem; dm.rown = nown_riv;
+    dm.gs = mesh->fbr ? 3 : 2;
     dm.nes = round_up(ne, 32); dm.nrs = round_up(std::max(nr, 1), 32);
     dm.fbr = mesh->fbr ? 1 : 0;
     dm.surf_mode = mesh->surf_mode; dm.riv_mode = mesh->riv_mode;
     dm.dt = mesh->stepsize;
-    dm.o_unsat = ne; dm.o_gw = 2LL * ne; dm.o_stg = 3LL * ne; dm.o_rgw = 3LL * ne + nr;
-    dm.o_fu = 3LL * ne + 2LL * nr; dm.o_fg = 4LL * ne + 2LL * nr;
-    ctx->nsv = 3LL * ne + 2LL * nr + (dm.fbr ? 2LL * ne : 0);
+    // y / ydot hold the OWNED unknowns only, in the block layout of pihm_func.h:7-15
+    {
+        const long long no = nown_elem, ro = nown_riv;
+        dm.o_unsat = no; dm.o_gw = 2 * no; dm.o_stg = 3 * no; dm.o_rgw = 3 * no + ro;
+        dm.o_fu = 3 * no + 2 * ro; dm.o_fg = 4 * no + 2 * ro;
+        ctx->nsv = 3 * no + 2 * ro + (dm.fbr ? 2 * no : 0);
+        ctx->nsv_global = ctx->nsv;
+    }
 
     // ---- internal element order -------------------------------------------
     ctx->perm.resize(ne);
@@ -191,7 +217,7 @@ pihm_b200_ctx *pihm_b200_create(const pihm_b200_mesh *mesh, int device, int reor
         if (jl >= 0 && jr >= 0)
             fbr_dist[r] = EF(PB_E_NABRDIST0 + jl, RI(PB_RI_LEFTELE, r) - 1) +
                 EF(PB_E_NABRDIST0 + jr, RI(PB_RI_RIGHTELE, r) - 1);
-        else if (dm.fbr) {   // lat_flow.c:102-107 "Error finding distance between elements"
+        else if (dm.fbr && r < nown_riv) {   // lat_flow.c:102-107 "Error finding distance between elements"
             set_error("river " + std::to_string(r + 1) + ": bank elements do not list the river as neighbour");
             delete ctx;
             return nullptr;
@@ -234,6 +260,8 @@ pihm_b200_ctx *pihm_b200_create(const pihm_b200_mesh *mesh, int device, int reor
     zalloc((void **)&ctx->d_stale, sizeof(double) * 2 * nrs);
     zalloc((void **)&ctx->d_nan, sizeof(int) * 4);
     zalloc((void **)&ctx->d_stage, sizeof(double) * ctx->nsv);
+    zalloc((void **)&ctx->d_gel, sizeof(double) * dm.gs * (size_t)std::max(ne - nown_elem, 1));
+    zalloc((void **)&ctx->d_gri, sizeof(double) * 2 * (size_t)std::max(nr - nown_riv, 1));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     ctx->red_blocks = sms * 8;
@@ -250,6 +278,7 @@ pihm_b200_ctx *pihm_b200_create(const pihm_b200_mesh *mesh, int device, int reor
     dm.forc = ctx->d_forc; dm.rf = ctx->d_rf; dm.ri = ctx->d_ri; dm.rivbc = ctx->d_rivbc;
     dm.fbr_dist = ctx->d_fbr_dist; dm.up_ptr = ctx->d_up_ptr; dm.up_idx = ctx->d_up_idx;
     dm.rivflow = ctx->d_rivflow; dm.s2c_stale = ctx->d_stale;
+    dm.gel = ctx->d_gel; dm.gri = ctx->d_gri;
     dm.xflux = nullptr; dm.record = 0;
     dm.nan_flag = ctx->d_nan;
     ctx->y_tmp = pihm_b200_vec_new(ctx);
@@ -268,7 +297,9 @@ void pihm_b200_destroy(pihm_b200_ctx *ctx)
     void *dev[] = {ctx->d_es, ctx->d_ft, ctx->d_snb, ctx->d_dnb, ctx->d_forc, ctx->d_rf, ctx->d_rivbc, ctx->d_fbr_dist, ctx->d_nb,
                    ctx->d_bct, ctx->d_fbct, ctx->d_ri, ctx->d_up_ptr, ctx->d_up_idx,
                    ctx->d_rivflow, ctx->d_stale, ctx->d_xflux, ctx->d_nan, ctx->d_perm,
-                   ctx->d_iperm, ctx->d_stage, ctx->d_red};
+                   ctx->d_iperm, ctx->d_stage, ctx->d_red, ctx->d_gel, ctx->d_gri, ctx->d_send_e, ctx->d_send_r,
+                   ctx->d_send_e_idx, ctx->d_send_r_idx};
+    pb::comm_destroy(ctx);
     for (void *p : dev) if (p) cudaFree(p);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->h_red) cudaFreeHost(ctx->h_red);
@@ -378,7 +409,7 @@ int pihm_b200_set_stale_ovlflow(pihm_b200_ctx *ctx, const double *ovl)
 int pihm_b200_summary(pihm_b200_ctx *ctx, const pihm_b200_vec *y)
 {
     if (!ctx || !y || y->n != ctx->nsv) { set_error("pihm_b200_summary: bad argument"); return -1; }
-    const int ne = ctx->dm.ne, full = ne / 32, rem = ne % 32;
+    const int ne = ctx->dm.nown, full = ne / 32, rem = ne % 32;
     double *dst = ctx->d_ft + (size_t)PB_F_WS0SURF * 32;
     if (full)
         PB_CUDA(cudaMemcpy2DAsync(dst, 4 * 32 * sizeof(double), y->d, 32 * sizeof(double), 32 * sizeof(double),
@@ -386,6 +417,73 @@ int pihm_b200_summary(pihm_b200_ctx *ctx, const pihm_b200_vec *y)
     if (rem)
         PB_CUDA(cudaMemcpyAsync(dst + (size_t)full * 4 * 32, y->d + (size_t)full * 32, rem * sizeof(double),
                                 cudaMemcpyDeviceToDevice, ctx->s()));
+    return 0;
+}
+
+// Ghost records written from the host: lets ONE process emulate all ranks of a
+// partitioned run on one GPU (tests), and is what a non-NCCL transport would call.
+int pihm_b200_set_ghosts(pihm_b200_ctx *ctx, const double *elem_rec, const double *riv_rec)
+{
+    if (!ctx) return -1;
+    const int ng = ctx->dm.ne - ctx->dm.nown, nrg = ctx->dm.nr - ctx->dm.rown;
+    PB_CUDA(cudaStreamSynchronize(ctx->s()));
+    if (ng > 0 && elem_rec)
+        PB_CUDA(cudaMemcpy(ctx->d_gel, elem_rec, sizeof(double) * ctx->dm.gs * ng, cudaMemcpyHostToDevice));
+    if (nrg > 0 && riv_rec)
+        PB_CUDA(cudaMemcpy(ctx->d_gri, riv_rec, sizeof(double) * 2 * nrg, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// Exchange maps of the halo exchange (from pihm_b200_partition_fill)
+int pihm_b200_set_halo(pihm_b200_ctx *ctx, int nn, const int32_t *nbr_rank, const int32_t *send_e_ptr,
+                       const int32_t *send_e_idx, const int32_t *recv_e_cnt, const int32_t *send_r_ptr,
+                       const int32_t *send_r_idx, const int32_t *recv_r_cnt)
+{
+    if (!ctx || nn < 0) { set_error("set_halo: bad argument"); return -1; }
+    ctx->nbr_rank.assign(nbr_rank, nbr_rank + nn);
+    ctx->send_e_ptr.assign(send_e_ptr, send_e_ptr + nn + 1);
+    ctx->send_r_ptr.assign(send_r_ptr, send_r_ptr + nn + 1);
+    ctx->recv_e_cnt.assign(recv_e_cnt, recv_e_cnt + nn);
+    ctx->recv_r_cnt.assign(recv_r_cnt, recv_r_cnt + nn);
+    ctx->nse = nn ? send_e_ptr[nn] : 0;
+    ctx->nsr = nn ? send_r_ptr[nn] : 0;
+    long long re = 0, rr = 0;
+    for (int k = 0; k < nn; k++) { re += recv_e_cnt[k]; rr += recv_r_cnt[k]; }
+    if (re != ctx->dm.ne - ctx->dm.nown || rr != ctx->dm.nr - ctx->dm.rown) {
+        set_error("set_halo: receive counts do not match the ghost counts of the local mesh");
+        return -1;
+    }
+    for (int k = 0; k < ctx->nse; k++)
+        if (send_e_idx[k] < 0 || send_e_idx[k] >= ctx->dm.nown) { set_error("set_halo: send index not owned"); return -1; }
+    for (int k = 0; k < ctx->nsr; k++)
+        if (send_r_idx[k] < 0 || send_r_idx[k] >= ctx->dm.rown) { set_error("set_halo: river send index not owned"); return -1; }
+    PB_CUDA(cudaStreamSynchronize(ctx->s()));
+    for (void *p : {(void *)ctx->d_send_e, (void *)ctx->d_send_r, (void *)ctx->d_send_e_idx, (void *)ctx->d_send_r_idx})
+        if (p) cudaFree(p);
+    PB_CUDA(cudaMalloc((void **)&ctx->d_send_e, sizeof(double) * ctx->dm.gs * (size_t)std::max(ctx->nse, 1)));
+    PB_CUDA(cudaMalloc((void **)&ctx->d_send_r, sizeof(double) * 2 * (size_t)std::max(ctx->nsr, 1)));
+    PB_CUDA(cudaMalloc((void **)&ctx->d_send_e_idx, sizeof(int) * (size_t)std::max(ctx->nse, 1)));
+    PB_CUDA(cudaMalloc((void **)&ctx->d_send_r_idx, sizeof(int) * (size_t)std::max(ctx->nsr, 1)));
+    if (ctx->nse) PB_CUDA(cudaMemcpy(ctx->d_send_e_idx, send_e_idx, sizeof(int) * ctx->nse, cudaMemcpyHostToDevice));
+    if (ctx->nsr) PB_CUDA(cudaMemcpy(ctx->d_send_r_idx, send_r_idx, sizeof(int) * ctx->nsr, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// the packed send records of a state vector, on the host (single-process emulation / tests)
+int pihm_b200_halo_pack_host(pihm_b200_ctx *ctx, const pihm_b200_vec *y, double *elem_rec, double *riv_rec)
+{
+    if (!ctx || !y) return -1;
+    const int n = ctx->nse + ctx->nsr;
+    if (n > 0) {
+        k_halo_pack<<<(n + 255) / 256, 256, 0, ctx->s()>>>(ctx->dm, y->d, ctx->nse, ctx->d_send_e_idx, ctx->d_send_e,
+                                                           ctx->nsr, ctx->d_send_r_idx, ctx->d_send_r);
+        ctx->launches++;
+    }
+    PB_CUDA(cudaStreamSynchronize(ctx->s()));
+    if (ctx->nse && elem_rec)
+        PB_CUDA(cudaMemcpy(elem_rec, ctx->d_send_e, sizeof(double) * ctx->dm.gs * ctx->nse, cudaMemcpyDeviceToHost));
+    if (ctx->nsr && riv_rec)
+        PB_CUDA(cudaMemcpy(riv_rec, ctx->d_send_r, sizeof(double) * 2 * ctx->nsr, cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -408,11 +506,23 @@ int pihm_b200_set_flux_recording(pihm_b200_ctx *ctx, int on)
 static int launch_rhs(pihm_b200_ctx *ctx, const double *y, double *dy)
 {
     const DevMesh &dm = ctx->dm;
-    const int eb = (dm.ne + PB_RHS_THREADS - 1) / PB_RHS_THREADS;
+    if (ctx->nranks > 1) {
+        // one-ring(+) halo exchange of neighbour and river states before the RHS
+        const int n = ctx->nse + ctx->nsr;
+        if (n > 0) {
+            k_halo_pack<<<(n + 255) / 256, 256, 0, ctx->s()>>>(dm, y, ctx->nse, ctx->d_send_e_idx, ctx->d_send_e,
+                                                               ctx->nsr, ctx->d_send_r_idx, ctx->d_send_r);
+            ctx->launches++;
+        }
+        if (pb::comm_halo_exchange(ctx) != 0) return -1;
+    }
+    const int eb = (dm.ne + PB_RHS_THREADS - 1) / PB_RHS_THREADS;      // k_pre: owned + ghost elements
     const int rb = (dm.nr + PB_RHS_THREADS - 1) / PB_RHS_THREADS;
+    const int eb_own = (dm.nown + PB_RHS_THREADS - 1) / PB_RHS_THREADS; // k_main: owned only
+    const int rb_own = (dm.rown + PB_RHS_THREADS - 1) / PB_RHS_THREADS;
     k_pre<<<eb + rb, PB_RHS_THREADS, 0, ctx->s()>>>(dm, y, eb);
-    if (dm.fbr) k_main<true><<<eb + rb, PB_RHS_THREADS, 0, ctx->s()>>>(dm, y, dy, eb);
-    else k_main<false><<<eb + rb, PB_RHS_THREADS, 0, ctx->s()>>>(dm, y, dy, eb);
+    if (dm.fbr) k_main<true><<<eb_own + rb_own, PB_RHS_THREADS, 0, ctx->s()>>>(dm, y, dy, eb_own);
+    else k_main<false><<<eb_own + rb_own, PB_RHS_THREADS, 0, ctx->s()>>>(dm, y, dy, eb_own);
     ctx->launches += 2;
     return 0;
 }
@@ -424,8 +534,7 @@ int pihm_b200_ode(pihm_b200_ctx *ctx, double t, const pihm_b200_vec *y, pihm_b20
         set_error("pihm_b200_ode: bad argument");
         return -1;
     }
-    launch_rhs(ctx, y->d, ydot->d);
-    return 0;
+    return launch_rhs(ctx, y->d, ydot->d);
 }
 
 int pihm_b200_check_nan(pihm_b200_ctx *ctx)

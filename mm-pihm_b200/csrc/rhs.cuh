@@ -91,6 +91,31 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned phase)
 
 __device__ __forceinline__ double max0(double v) { return (v >= 0.0) ? v : 0.0; }
 
+// State access in a partitioned run: local entities [0, nown) / [0, rown) are
+// the rank's own unknowns inside y; the rest are ghosts whose values arrived
+// with the halo exchange as records {surf, gw[, fbr_gw]} / {stage, gw}.
+// Single-GPU: nown == ne, rown == nr, the ghost branch is never taken.
+__device__ __forceinline__ double y_surf(const DevMesh &m, const double *__restrict__ y, int i)
+{
+    return (i < m.nown) ? y[i] : m.gel[(size_t)(i - m.nown) * m.gs];
+}
+__device__ __forceinline__ double y_gw(const DevMesh &m, const double *__restrict__ y, int i)
+{
+    return (i < m.nown) ? y[m.o_gw + i] : m.gel[(size_t)(i - m.nown) * m.gs + 1];
+}
+__device__ __forceinline__ double y_fg(const DevMesh &m, const double *__restrict__ y, int i)
+{
+    return (i < m.nown) ? y[m.o_fg + i] : m.gel[(size_t)(i - m.nown) * m.gs + 2];
+}
+__device__ __forceinline__ double y_stage(const DevMesh &m, const double *__restrict__ y, int r)
+{
+    return (r < m.rown) ? y[m.o_stg + r] : m.gri[(size_t)(r - m.rown) * 2];
+}
+__device__ __forceinline__ double y_rgw(const DevMesh &m, const double *__restrict__ y, int r)
+{
+    return (r < m.rown) ? y[m.o_rgw + r] : m.gri[(size_t)(r - m.rown) * 2 + 1];
+}
+
 // a / b for a finite b > 0.  IEEE gives 0/b = 0 with the sign of a, i.e. a
 // itself; taking that shortcut in a branch keeps zero numerators (dry edges,
 // dry surface) out of the FP64 division's denormal/zero slow path, which a
@@ -262,8 +287,8 @@ struct Bank {
 __device__ __forceinline__ Bank load_bank(const DevMesh &m, const double *__restrict__ y, int e)
 {
     Bank b;
-    b.surfh = surf_h(max0(y[e]));
-    b.gw = max0(y[m.o_gw + e]);
+    b.surfh = surf_h(max0(y_surf(m, y, e)));
+    b.gw = max0(y_gw(m, y, e));
     b.zmax = TSC(TS_ZMAX, e);
     b.zmin = TSC(TS_ZMIN, e);
     b.effk = eff_kh_elem(m, e, b.gw);
@@ -334,8 +359,8 @@ __device__ __forceinline__ double sub_elem_to_river(const Bank &b, double zbed, 
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void river_fluxes(const DevMesh &m, const double *__restrict__ y, int r)
 {
-    const double stage = max0(y[m.o_stg + r]);
-    const double rgw = max0(y[m.o_rgw + r]);
+    const double stage = max0(y_stage(m, y, r));
+    const double rgw = max0(y_rgw(m, y, r));
     const int down = RIC(PB_RI_DOWN, r);
     const int ord = RIC(PB_RI_INTRPL_ORD, r);
     const double zbed = RFC(PB_R_ZBED, r), rzmin = RFC(PB_R_ZMIN, r), rzmax = RFC(PB_R_ZMAX, r);
@@ -369,8 +394,8 @@ __device__ __forceinline__ void river_fluxes(const DevMesh &m, const double *__r
             rf_up += flux;
         }
         // ChanFlowRiverToRiver, river_flow.c:255-298
-        const double stage_d = max0(y[m.o_stg + d]);
-        const double rgw_d = max0(y[m.o_rgw + d]);
+        const double stage_d = max0(y_stage(m, y, d));
+        const double rgw_d = max0(y_rgw(m, y, d));
         const int ord_d = RIC(PB_RI_INTRPL_ORD, d);
         const double len_d = RFC(PB_R_SHP_LENGTH, d), coeff_d = RFC(PB_R_SHP_COEFF, d);
         {
@@ -493,11 +518,11 @@ __device__ __forceinline__ void elem_pre(const DevMesh &m, const double *__restr
     double ysn[3], zmaxn[3];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-        ysn[j] = y[nn[j]];
+        ysn[j] = y_surf(m, y, nn[j]);
         zmaxn[j] = m.snb[nn[j]].y;
     }
-    const double surfh = surf_h(max0(y[i]));
-    const double gw = max0(y[m.o_gw + i]);
+    const double surfh = surf_h(max0(y_surf(m, y, i)));
+    const double gw = max0(y_gw(m, y, i));
     mbar_wait(bar, 0);          // the tile slab has landed
     const double effkh = eff_kh(EC(TS_DEPTH), EC(TS_DMAC), EC(TS_KMACH), EC(TS_AREAFV),
                                 EC(TS_KSATH), gw);
@@ -516,7 +541,7 @@ __device__ __forceinline__ void elem_pre(const DevMesh &m, const double *__restr
                 else h[j] = FOC(PB_F_BC0 + j, i);
             } else {
                 const int r = (-code[j] - 2) >> 2;
-                const double stage = max0(y[m.o_stg + r]);
+                const double stage = max0(y_stage(m, y, r));
                 h[j] = (stage > RFC(PB_R_SHP_DEPTH, r)) ? RFC(PB_R_ZBED, r) + stage : RFC(PB_R_ZMAX, r);
             }
         }
@@ -785,7 +810,7 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
                     dist = m.fbr_dist[r];
                 }
                 // FbrFlowElemToElem, lat_flow.c:374-390
-                const double fg_n = max0(y[m.o_fg + n]);
+                const double fg_n = max0(y_fg(m, y, n));
                 double diff_h = (fg + zbed) - (fg_n + m.snb[n].w);
                 double avgh = avg_h(diff_h, fg, fg_n);
                 double grad_h = div_pos(diff_h, dist);
@@ -918,7 +943,7 @@ k_main(const DevMesh m, const double *__restrict__ y, double *__restrict__ dy, i
     if ((int)blockIdx.x < elem_blocks) {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         const int tile = blockIdx.x * PB_RHS_WARPS + warp;
-        if (tile * PB_TILE >= m.ne) return;
+        if (tile * PB_TILE >= m.nown) return;
         const unsigned bar = smem_u32(&s_bar[warp]);
         if (lane == 0) {
             mbar_init(bar, 1);
@@ -929,10 +954,29 @@ k_main(const DevMesh m, const double *__restrict__ y, double *__restrict__ dy, i
         }
         __syncwarp();
         const int i = tile * PB_TILE + lane;
-        if (i < m.ne) elem_main<FBR>(m, y, dy, i, &s_tile[warp][lane], &s_forc[warp][lane], bar);
+        if (i < m.nown) elem_main<FBR>(m, y, dy, i, &s_tile[warp][lane], &s_forc[warp][lane], bar);
     } else {
         const int r = (blockIdx.x - elem_blocks) * PB_RHS_THREADS + threadIdx.x;
-        if (r < m.nr) river_main(m, dy, r);
+        if (r < m.rown) river_main(m, dy, r);
+    }
+}
+
+// Halo pack: the owned values other ranks need, as records in their ghost order
+//   elements {surf, gw[, fbr_gw]} (gs doubles), rivers {stage, gw}
+static __global__ void __launch_bounds__(256)
+k_halo_pack(const DevMesh m, const double *__restrict__ y, int nse, const int *__restrict__ send_e,
+            double *__restrict__ buf_e, int nsr, const int *__restrict__ send_r, double *__restrict__ buf_r)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nse) {
+        const int i = send_e[k];
+        buf_e[(size_t)k * m.gs] = y[i];
+        buf_e[(size_t)k * m.gs + 1] = y[m.o_gw + i];
+        if (m.gs == 3) buf_e[(size_t)k * m.gs + 2] = y[m.o_fg + i];
+    } else if (k < nse + nsr) {
+        const int r = send_r[k - nse];
+        buf_r[(size_t)(k - nse) * 2] = y[m.o_stg + r];
+        buf_r[(size_t)(k - nse) * 2 + 1] = y[m.o_rgw + r];
     }
 }
 

@@ -58,6 +58,17 @@ _SIGS = {
     "pihm_b200_device_count": (C.c_int, []),
     "pihm_b200_create": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int]),
     "pihm_b200_destroy": (None, [C.c_void_p]),
+    "pihm_b200_partition_create": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "pihm_b200_partition_destroy": (None, [C.c_void_p]),
+    "pihm_b200_partition_sizes": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "pihm_b200_partition_fill": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 13),
+    "pihm_b200_create_part": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "pihm_b200_set_halo": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 7),
+    "pihm_b200_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "pihm_b200_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "pihm_b200_num_state_var_global": (C.c_int64, [C.c_void_p]),
+    "pihm_b200_halo_pack_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pihm_b200_set_ghosts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pihm_b200_num_state_var": (C.c_int64, [C.c_void_p]),
     "pihm_b200_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pihm_b200_get_stream": (C.c_void_p, [C.c_void_p]),
@@ -172,6 +183,8 @@ class Model:
     """Device mirror of pihm->elem / pihm->river: pihm_b200_create + the RHS."""
 
     def __init__(self, tables: dict, device: int = 0, reorder: int = 0):
+        """tables: a whole watershed, or one part from partition.partition() (it then carries
+        nown_elem / nown_riv and the exchange maps; y vectors hold the owned unknowns only)"""
         self.L = L = load_library()
         if L.pihm_b200_device_count() <= device:
             raise RuntimeError("no CUDA device visible: libpihm_b200 has no CPU path")
@@ -189,10 +202,22 @@ class Model:
             assert a.shape == (ncol, n), (key, a.shape)
             keep.append(a)
             setattr(m, key, a.ctypes.data)
-        self.h = L.pihm_b200_create(C.byref(m), device, reorder)
+        self.part = tables if "nown_elem" in tables else None
+        if self.part is None:
+            self.h = L.pihm_b200_create(C.byref(m), device, reorder)
+        else:
+            self.h = L.pihm_b200_create_part(C.byref(m), device, 0, int(tables["nown_elem"]),
+                                             int(tables["nown_riv"]))
         if not self.h:
             raise RuntimeError("pihm_b200_create: " + L.pihm_b200_last_error().decode())
         self.nelem, self.nriver, self.fbr = m.nelem, m.nriver, bool(m.fbr)
+        self.nown_elem = int(tables.get("nown_elem", m.nelem))
+        self.nown_riv = int(tables.get("nown_riv", m.nriver))
+        if self.part is not None:
+            t = tables
+            arrs = [np.ascontiguousarray(t[k], np.int32) for k in
+                    ("nbr_rank", "send_e_ptr", "send_e_idx", "recv_e_cnt", "send_r_ptr", "send_r_idx", "recv_r_cnt")]
+            _check(L, L.pihm_b200_set_halo(self.h, len(t["nbr_rank"]), *[_ptr(a) for a in arrs]), "set_halo")
         self.nsv = int(L.pihm_b200_num_state_var(self.h))       # NumStateVar()
 
     # lifecycle ---------------------------------------------------------------
@@ -206,6 +231,34 @@ class Model:
             self.close()
         except Exception:
             pass
+
+    # multi-GPU ---------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        L = load_library()
+        buf = C.create_string_buffer(128)
+        _check(L, L.pihm_b200_comm_unique_id(buf), "comm_unique_id")
+        return buf.raw
+
+    def comm_init(self, rank: int, nranks: int, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        _check(self.L, self.L.pihm_b200_comm_init(self.h, rank, nranks, buf), "comm_init")
+
+    @property
+    def nsv_global(self) -> int:
+        return int(self.L.pihm_b200_num_state_var_global(self.h))
+
+    def halo_pack_host(self, y: "Vec"):
+        nse, nsr = len(self.part["send_e_idx"]), len(self.part["send_r_idx"])
+        gs = 3 if self.fbr else 2
+        e = np.zeros(max(nse, 1) * gs); r = np.zeros(max(nsr, 1) * 2)
+        _check(self.L, self.L.pihm_b200_halo_pack_host(self.h, y.h, _ptr(e), _ptr(r)), "halo_pack_host")
+        return e[:nse * gs], r[:nsr * 2]
+
+    def set_ghosts(self, elem_rec, riv_rec):
+        e = np.ascontiguousarray(elem_rec, np.float64); r = np.ascontiguousarray(riv_rec, np.float64)
+        _check(self.L, self.L.pihm_b200_set_ghosts(self.h, _ptr(e) if e.size else None,
+                                                   _ptr(r) if r.size else None), "set_ghosts")
 
     def set_stream(self, cuda_stream_ptr: int):
         _check(self.L, self.L.pihm_b200_set_stream(self.h, C.c_void_p(cuda_stream_ptr)), "set_stream")

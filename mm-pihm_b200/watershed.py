@@ -58,7 +58,7 @@ DX = 20.0
 
 SIZES = {            # name -> (nx, ny); triangles = 2 nx ny   
     "tiny": (8, 6), "small": (40, 30), "10k": (100, 50), "100k": (250, 200),
-    "1M": (1000, 500), "8M": (2000, 2000),
+    "1M": (1000, 500), "2M": (1000, 1000), "4M": (2000, 1000), "8M": (2000, 2000),
 }
 
 
