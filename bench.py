@@ -195,8 +195,13 @@ def run_ours(args):
 
     # ---- end to end through the C ABI with host buffers --------------------------
     reset()
-    host_y = np.empty(model.nsv)
-    forc_tabs = {k: forcing_at(tb, k) for k in range(0, Wu + K + 15, 15)}
+    # pinned host buffers, as the contract asks: the C ABI copies straight from / into them
+    host_y = torch.empty(model.nsv, dtype=torch.float64).pin_memory().numpy()
+    forc_tabs = {}
+    for k in range(0, Wu + K + 15, 15):
+        t = torch.from_numpy(forcing_at(tb, k)).pin_memory()
+        forc_tabs[k] = t.numpy()
+        forc_tabs[("keep", k)] = t
     for k in range(Wu):
         step(k, e2e=True, host_forc=forc_tabs[(k // 15) * 15], host_y=host_y)
     barrier()

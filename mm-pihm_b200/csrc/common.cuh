@@ -131,7 +131,6 @@ struct pihm_b200_ctx {
     int rank = 0, nranks = 1;
     long long nsv_global = 0;
     // staging for host <-> device vectors
-    double *h_pin = nullptr;           // pinned, 2 * nsv
     double *d_stage = nullptr;         // nsv (reference order)
     pihm_b200_vec *y_tmp = nullptr, *yd_tmp = nullptr;
     // reduction scratch

@@ -164,4 +164,17 @@ k_permute_state(int ne, int nr, int fbr, const int *__restrict__ perm,
     }
 }
 
+// one forcing column, reference order -> internal order; hot columns (pcpdrp, edir, ett,
+// ws0.surf) go to the warp-tiled table [tile][4][32], bc columns to the flat table
+static __global__ void __launch_bounds__(256)
+k_scatter_forcing(int ne, int nes, int col, const int *__restrict__ perm, const double *__restrict__ src,
+                  double *__restrict__ ft, double *__restrict__ forc)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ne) return;
+    const double v = src[perm[i]];
+    if (col <= PB_F_WS0SURF) ft[((size_t)(i >> 5) * 4 + col) * 32 + (i & 31)] = v;
+    else forc[(size_t)col * nes + i] = v;
+}
+
 }  // namespace pb

@@ -259,14 +259,13 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
     zalloc((void **)&ctx->d_rivflow, sizeof(double) * PIHM_B200_NUM_RIVFLX * nrs);
     zalloc((void **)&ctx->d_stale, sizeof(double) * 2 * nrs);
     zalloc((void **)&ctx->d_nan, sizeof(int) * 4);
-    zalloc((void **)&ctx->d_stage, sizeof(double) * ctx->nsv);
+    zalloc((void **)&ctx->d_stage, sizeof(double) * std::max<long long>(ctx->nsv, ne));
     zalloc((void **)&ctx->d_gel, sizeof(double) * dm.gs * (size_t)std::max(ne - nown_elem, 1));
     zalloc((void **)&ctx->d_gri, sizeof(double) * 2 * (size_t)std::max(nr - nown_riv, 1));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     ctx->red_blocks = sms * 8;
     zalloc((void **)&ctx->d_red, sizeof(double) * (ctx->red_blocks + 64));
-    if (cudaHostAlloc((void **)&ctx->h_pin, sizeof(double) * 2 * ctx->nsv, cudaHostAllocDefault) != cudaSuccess) rc = -1;
     if (cudaHostAlloc((void **)&ctx->h_red, sizeof(double) * 64, cudaHostAllocMapped) != cudaSuccess) rc = -1;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) rc = -1;
     if (rc != 0) {
@@ -281,6 +280,11 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
     dm.gel = ctx->d_gel; dm.gri = ctx->d_gri;
     dm.xflux = nullptr; dm.record = 0;
     dm.nan_flag = ctx->d_nan;
+    if (const char *cv = std::getenv("PIHM_B200_CARVEOUT")) {     // tuning knob (percent of L1 given to smem)
+        const int pct = std::atoi(cv);
+        cudaFuncSetAttribute(k_main<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(k_main<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
     ctx->y_tmp = pihm_b200_vec_new(ctx);
     ctx->yd_tmp = pihm_b200_vec_new(ctx);
     if (!ctx->y_tmp || !ctx->yd_tmp) { pihm_b200_destroy(ctx); return nullptr; }
@@ -301,7 +305,6 @@ void pihm_b200_destroy(pihm_b200_ctx *ctx)
                    ctx->d_send_e_idx, ctx->d_send_r_idx};
     pb::comm_destroy(ctx);
     for (void *p : dev) if (p) cudaFree(p);
-    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->h_red) cudaFreeHost(ctx->h_red);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -341,24 +344,13 @@ int pihm_b200_set_forcing_col(pihm_b200_ctx *ctx, int col, const double *values)
 {
     if (!ctx || col < 0 || col >= PB_F_NCOL || !values) { set_error("set_forcing_col: bad argument"); return -1; }
     const int ne = ctx->dm.ne;
-    double *h = ctx->h_pin;                    // nsv >= 3 ne doubles of pinned staging
-    PB_CUDA(cudaStreamSynchronize(ctx->s()));
-    for (int i = 0; i < ne; i++) h[i] = values[ctx->perm[i]];
-    if (col <= PB_F_WS0SURF) {
-        // hot column -> warp-tiled table: 256 B rows, destination pitch 4 x 256 B
-        const int full = ne / 32, rem = ne % 32;
-        double *dst = ctx->d_ft + (size_t)col * 32;
-        if (full)
-            PB_CUDA(cudaMemcpy2DAsync(dst, 4 * 32 * sizeof(double), h, 32 * sizeof(double), 32 * sizeof(double),
-                                      full, cudaMemcpyHostToDevice, ctx->s()));
-        if (rem)
-            PB_CUDA(cudaMemcpyAsync(dst + (size_t)full * 4 * 32, h + (size_t)full * 32, rem * sizeof(double),
-                                    cudaMemcpyHostToDevice, ctx->s()));
-    } else {
-        PB_CUDA(cudaMemcpyAsync(ctx->d_forc + (size_t)col * ctx->dm.nes, h, sizeof(double) * ne,
-                                cudaMemcpyHostToDevice, ctx->s()));
-    }
-    PB_CUDA(cudaStreamSynchronize(ctx->s()));
+    // straight from the caller's buffer (fast when it is pinned) into device staging, then one
+    // kernel applies the internal element order and the tile layout
+    PB_CUDA(cudaMemcpyAsync(ctx->d_stage, values, sizeof(double) * ne, cudaMemcpyHostToDevice, ctx->s()));
+    k_scatter_forcing<<<(ne + 255) / 256, 256, 0, ctx->s()>>>(ne, ctx->dm.nes, col, ctx->d_perm, ctx->d_stage,
+                                                              ctx->d_ft, ctx->d_forc);
+    ctx->launches++;
+    PB_CUDA(cudaStreamSynchronize(ctx->s()));      // the caller may reuse `values`
     return 0;
 }
 
@@ -608,33 +600,30 @@ void *pihm_b200_vec_devptr(pihm_b200_vec *v) { return v ? v->d : nullptr; }
 int pihm_b200_vec_upload(pihm_b200_vec *v, const double *host)
 {
     pihm_b200_ctx *ctx = v->ctx;
-    PB_CUDA(cudaStreamSynchronize(ctx->s()));      // staging buffer reuse
-    std::memcpy(ctx->h_pin, host, sizeof(double) * v->n);
     if (!ctx->reorder) {
-        PB_CUDA(cudaMemcpyAsync(v->d, ctx->h_pin, sizeof(double) * v->n, cudaMemcpyHostToDevice, ctx->s()));
+        PB_CUDA(cudaMemcpyAsync(v->d, host, sizeof(double) * v->n, cudaMemcpyHostToDevice, ctx->s()));
     } else {
-        PB_CUDA(cudaMemcpyAsync(ctx->d_stage, ctx->h_pin, sizeof(double) * v->n, cudaMemcpyHostToDevice, ctx->s()));
+        PB_CUDA(cudaMemcpyAsync(ctx->d_stage, host, sizeof(double) * v->n, cudaMemcpyHostToDevice, ctx->s()));
         k_permute_state<<<vec_blocks(ctx, v->n), PB_VEC_THREADS, 0, ctx->s()>>>(
             ctx->dm.ne, ctx->dm.nr, ctx->dm.fbr, ctx->d_perm, ctx->d_stage, v->d, 1);
         ctx->launches++;
     }
+    PB_CUDA(cudaStreamSynchronize(ctx->s()));      // the caller may reuse `host`
     return 0;
 }
 
 int pihm_b200_vec_download(const pihm_b200_vec *v, double *host)
 {
     pihm_b200_ctx *ctx = v->ctx;
-    double *h = ctx->h_pin + ctx->nsv;
     if (!ctx->reorder) {
-        PB_CUDA(cudaMemcpyAsync(h, v->d, sizeof(double) * v->n, cudaMemcpyDeviceToHost, ctx->s()));
+        PB_CUDA(cudaMemcpyAsync(host, v->d, sizeof(double) * v->n, cudaMemcpyDeviceToHost, ctx->s()));
     } else {
         k_permute_state<<<vec_blocks(ctx, v->n), PB_VEC_THREADS, 0, ctx->s()>>>(
             ctx->dm.ne, ctx->dm.nr, ctx->dm.fbr, ctx->d_perm, v->d, ctx->d_stage, 0);
         ctx->launches++;
-        PB_CUDA(cudaMemcpyAsync(h, ctx->d_stage, sizeof(double) * v->n, cudaMemcpyDeviceToHost, ctx->s()));
+        PB_CUDA(cudaMemcpyAsync(host, ctx->d_stage, sizeof(double) * v->n, cudaMemcpyDeviceToHost, ctx->s()));
     }
     PB_CUDA(cudaStreamSynchronize(ctx->s()));
-    std::memcpy(host, h, sizeof(double) * v->n);
     return 0;
 }
 
