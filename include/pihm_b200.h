@@ -215,6 +215,9 @@ int             pihm_b200_ode(pihm_b200_ctx *ctx, double t,
                               const pihm_b200_vec *y, pihm_b200_vec *ydot);
 /* NaN flag of the RHS calls since the last query (device flag, D2H) */
 int             pihm_b200_check_nan(pihm_b200_ctx *ctx);
+/* test hook: the inlined pow of the RHS kernels against libdevice pow() */
+int             pihm_b200_test_pow(int n, const double *x, const double *y,
+                                   double *fast, double *ref);
 /* The part of Summary() (src/update.c:19-47) that feeds back into the RHS:
  * ws0.surf = y[SURF] for the next model step's Infil() (vert_flow.c:122).
  * Runs on the device (no y round trip); call after every SolveCVode. */

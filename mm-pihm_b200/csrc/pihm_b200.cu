@@ -479,6 +479,20 @@ int pihm_b200_halo_pack_host(pihm_b200_ctx *ctx, const pihm_b200_vec *y, double 
     return 0;
 }
 
+// test hook (not part of the reference interface): pow_pos vs libdevice pow on n pairs
+int pihm_b200_test_pow(int n, const double *x, const double *y, double *fast, double *ref)
+{
+    double *d = nullptr;
+    PB_CUDA(cudaMalloc((void **)&d, sizeof(double) * 4 * (size_t)n));
+    PB_CUDA(cudaMemcpy(d, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+    PB_CUDA(cudaMemcpy(d + n, y, sizeof(double) * n, cudaMemcpyHostToDevice));
+    k_test_pow<<<(n + 255) / 256, 256>>>(n, d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n);
+    PB_CUDA(cudaMemcpy(fast, d + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    PB_CUDA(cudaMemcpy(ref, d + 3 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return 0;
+}
+
 int pihm_b200_set_flux_recording(pihm_b200_ctx *ctx, int on)
 {
     if (!ctx) return -1;

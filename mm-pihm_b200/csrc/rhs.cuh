@@ -16,6 +16,7 @@
 // (libdevice vs glibc) can differ, by <= 2 ulp.
 #pragma once
 #include "common.cuh"
+#include "fastpow.cuh"
 
 namespace pb {
 
@@ -206,7 +207,7 @@ __device__ __forceinline__ double eff_kh_elem(const DevMesh &m, int e, double gw
 __device__ __forceinline__ double overland_flow(double avgh, double grad, double sf,
                                                 double crossa, double rough)
 {
-    double p = (avgh == 0.0) ? 0.0 : pow(avgh, 0.6666667);
+    double p = (avgh == 0.0) ? 0.0 : pow_pos(avgh, 0.6666667);
     return div_pos(crossa * p * grad, sqrt(sf) * rough);
 }
 
@@ -214,8 +215,24 @@ __device__ __forceinline__ double overland_flow(double avgh, double grad, double
 // (sqrt(s) * a) * a is the same left-to-right product.
 __device__ __forceinline__ double kr_func(double beta, double satn)
 {
-    double a = 1.0 - pow(1.0 - pow(satn, beta / (beta - 1.0)), (beta - 1.0) / beta);
+    double a = 1.0 - pow_pos(1.0 - pow_pos(satn, beta / (beta - 1.0)), (beta - 1.0) / beta);
     return sqrt(satn) * a * a;
+}
+
+// KrFunc(beta, satn) and Psi(satn, alpha, beta) (vert_flow.c:272-278) of the same
+// element: the four pow() form two independent pairs, pow(s, m) / pow(1/s, m) and
+// pow(1 - A, (b-1)/b) / pow(C - 1, 1/b), each evaluated as one interleaved
+// straight-line block (pow_pos2).  Values are those of kr_func() / psi_func().
+__device__ __forceinline__ void vg_kr_psi(double satn, double alpha, double beta, double &kr, double &psi)
+{
+    const double m1 = beta / (beta - 1.0);
+    const double sp = (satn < PB_SATMIN) ? PB_SATMIN : satn;
+    double A, C, B, D;
+    pow_pos2(satn, m1, 1.0 / sp, m1, A, C);
+    pow_pos2(1.0 - A, (beta - 1.0) / beta, C - 1.0, 1.0 / beta, B, D);
+    const double a = 1.0 - B;
+    kr = sqrt(satn) * a * a;
+    psi = -D / alpha;
 }
 
 // KrFunc(BETA_CRACK = 2.0, s), src/vert_flow.c:258: both exponents are exact
@@ -230,7 +247,7 @@ __device__ __forceinline__ double kr_func_crack(double satn)
 __device__ __forceinline__ double psi_func(double satn, double alpha, double beta)
 {
     satn = (satn < PB_SATMIN) ? PB_SATMIN : satn;
-    return -pow(pow(1.0 / satn, beta / (beta - 1.0)) - 1.0, 1.0 / beta) / alpha;
+    return -pow_pos(pow_pos(1.0 / satn, beta / (beta - 1.0)) - 1.0, 1.0 / beta) / alpha;
 }
 
 // EffKinf, src/vert_flow.c:211-270
@@ -675,8 +692,7 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
             satn = div_pos(unsat, deficit);
             satn = (satn > 1.0) ? 1.0 : satn;
             satn = (satn < PB_SATMIN) ? PB_SATMIN : satn;
-            psi_u = psi_func(satn, alpha, beta);
-            satkfunc = kr_func(beta, satn);
+            vg_kr_psi(satn, alpha, beta, satkfunc, psi_u);
         }
         if (unsat + gw > depth) {
             infil = 0.0;
@@ -753,9 +769,8 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
             double satn = div_pos(fu, deficit);
             satn = (satn > 1.0) ? 1.0 : satn;
             satn = (satn < PB_SATMIN) ? PB_SATMIN : satn;
-            psi_c = psi_func(satn, galpha, gbeta);
+            vg_kr_psi(satn, galpha, gbeta, satkfunc, psi_c);
             psi_c = (psi_c > PB_PSIMIN) ? psi_c : PB_PSIMIN;
-            satkfunc = kr_func(gbeta, satn);
         }
         // FbrInfil, vert_flow.c:284-330
         if (full) {
@@ -978,6 +993,19 @@ k_halo_pack(const DevMesh m, const double *__restrict__ y, int nse, const int *_
         buf_r[(size_t)(k - nse) * 2] = y[m.o_stg + r];
         buf_r[(size_t)(k - nse) * 2 + 1] = y[m.o_rgw + r];
     }
+}
+
+// test hook: pow_pos() against libdevice pow() (tests/test_fastpow_gpu.py)
+static __global__ void k_test_pow(int n, const double *__restrict__ x, const double *__restrict__ y,
+                                  double *__restrict__ fast, double *__restrict__ ref)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double a, b;
+    pow_pos2(x[i], y[i], x[n - 1 - i], y[n - 1 - i], a, b);
+    fast[i] = a;
+    if (b != pow_pos(x[n - 1 - i], y[n - 1 - i]) && !(b != b)) fast[i] = -1.0;   // pair form == single form
+    ref[i] = pow(x[i], y[i]);
 }
 
 #undef TSC

@@ -83,6 +83,7 @@ _SIGS = {
     "pihm_b200_ode": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "pihm_b200_check_nan": (C.c_int, [C.c_void_p]),
     "pihm_b200_summary": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pihm_b200_test_pow": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pihm_b200_set_flux_recording": (C.c_int, [C.c_void_p, C.c_int]),
     "pihm_b200_get_fluxes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pihm_b200_vec_new": (C.c_void_p, [C.c_void_p]),
