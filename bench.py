@@ -72,6 +72,16 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         time.sleep(0.25)
         self.proc.terminate()
+        if not self.rows:       # timed region shorter than the sampling period: one direct query
+            try:
+                q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                     "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                     "clocks_event_reasons.sw_power_cap")
+                out = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20)
+                self.rows = [l.strip() for l in out.stdout.splitlines() if l.strip()]
+            except Exception:
+                pass
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:

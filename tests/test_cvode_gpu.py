@@ -126,3 +126,38 @@ def test_reinit_and_max_step_controller():
     assert np.array_equal(outs[0][0], outs[1][0])          # deterministic restart
     assert outs[0][1]["nst"] == outs[1][1]["nst"] > 0
     cv.close(); model.close()
+
+
+def test_100k_lockstep_with_live_reference():
+    """BASELINE config[1]: synthetic 100k-triangle watershed with river network on 1 B200,
+    RHS + CVODE correctness against the reference run on the same box (oracle/_ref)."""
+    import reflib
+    if not reflib.available(False):
+        pytest.skip("oracle/_ref not present")
+    tb = W.make_named("100k")
+    ne, nr = tb["nelem"], tb["nriver"]
+    ref = reflib.RefModel(fbr=False, cvode_omp=False).create_from_tables(tb)
+    ref.init_state(tb["y0"]); ref.set_ovlflow(np.zeros((3, ne))); ref.set_cvode_param()
+    model = lib.Model(tb, reorder=1)
+    cv = lib.Cvode(model)
+    y = model.N_VNew(tb["y0"])
+    cv.SetCVodeParam(y)
+    nsteps = 12
+    for k in range(nsteps):
+        if k % 15 == 0:
+            f = W.storm_forcing(tb, 2 * 3600.0 + k * 60.0)
+            model.set_forcing(f, np.zeros(nr))
+        fr = f.copy(); fr[W.F_WS0SURF] = ref.get_ws()[:ne]
+        ref.set_forcing(fr, np.zeros(nr))
+        ref.model_step(k)
+        model.Summary(y)
+        cv.SolveCVode((k + 1) * 60.0, y)
+    yr, yg = ref.get_y(), y.download()
+    sr, sg = ref.stats(), cv.stats()
+    unit = RELTOL * np.abs(yr) + ABSTOL
+    err = (np.abs(yg - yr) / unit).max()
+    print(f"100k: {nsteps} model steps, err {err:.3e} x (reltol|y|+abstol); nst {sg['nst']}/{sr['nst']} "
+          f"nfe {sg['nfe']}/{sr['nfe']} nli {sg['nli']}/{sr['nli']}")
+    assert err <= MULT
+    assert abs(sg["nst"] - sr["nst"]) <= 0.25 * sr["nst"]
+    ref.close(); cv.close(); model.close()
