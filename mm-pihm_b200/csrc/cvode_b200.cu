@@ -13,6 +13,7 @@
 // N_V* calls are replaced by the fused kernels of cvode_kernels.cuh and the
 // host only synchronises where CVODE branches on a norm.
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -101,6 +102,25 @@ struct pihm_b200_cvode {
         cudaStreamSynchronize(ctx->s());
     }
     void red(int slot, int n = 1, int op = 0) { if (ctx->nranks > 1) comm_allreduce(ctx, d_sc + slot, n, op); }
+    // Every reduction kernel gets a ticket; the kernel's finishing thread stores it to the
+    // mapped host mirror after its results.  sync_spin() waits for the newest ticket by polling
+    // that word (~2 us) instead of cudaStreamSynchronize (~15 us); use it only when the last
+    // kernel launched was a reduction kernel.
+    long long seq_ctr = 0;
+    RedBuf &R() { rb.seq = (double)(++seq_ctr); return rb; }
+    void sync_spin()
+    {
+        if (ctx->nranks > 1) { sync(); return; }
+        volatile double *tk = h_sc_map + SC_SEQ;
+        const double want = (double)seq_ctr;
+        for (long long it = 0; *tk != want; it++) {
+            if ((it & 0xfff) == 0xfff && cudaStreamQuery(ctx->s()) != cudaErrorNotReady) {
+                cudaStreamSynchronize(ctx->s());      // finished (or failed) without the ticket: stop spinning
+                break;
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+    }
     // N_VWrmsNorm = SUNRsqrt(sum / N)  (nvector_serial.c:685)
     double wrms(int slot) const { const double v = h_sc[slot] / n_global; return (v <= 0.0) ? 0.0 : std::sqrt(v); }
 
@@ -129,7 +149,7 @@ struct pihm_b200_cvode {
     }
     void launch_ewt()                                    // efun + tolsf norm (cvode.c:1349,1376)
     {
-        k_ewt<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, reltol, abstol, zn[0], ewt, rb);
+        k_ewt<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, reltol, abstol, zn[0], ewt, R());
         count();
         red(SC_EWT_MIN, 1, 1);
         red(SC_EWT_NRM);
@@ -331,7 +351,7 @@ int pihm_b200_cvode::spgmrSolve(bool *b_is_zero)
             const int l_plus_1 = lk + 1;
             krydim = l_plus_1;
             // A-tilde V[l]: right scaling, DQ J*v, I - gamma J, left scaling, first MGS dot
-            k_krylov_a<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, cnorm, V[lk], ewt, vtemp, rb);
+            k_krylov_a<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, cnorm, V[lk], ewt, vtemp, R());
             red(SC_VNRM);
             k_krylov_b<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, n_global, d_sc, vtemp, y, ytemp);
             count(2);
@@ -339,7 +359,7 @@ int pihm_b200_cvode::spgmrSolve(bool *b_is_zero)
             nfes++;
             njtimes++;
             k_krylov_c<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, n_global, gamma, d_sc, vtemp, ftemp, ewt,
-                                                            V[0], V[l_plus_1], rb);
+                                                            V[0], V[l_plus_1], R());
             count();
             red(SC_VK2);
             red(SC_H0);
@@ -348,11 +368,11 @@ int pihm_b200_cvode::spgmrSolve(bool *b_is_zero)
                 const double *vnext = (i + 1 < l_plus_1) ? V[i + 1] : V[l_plus_1];
                 const int slot_next = (i + 1 < l_plus_1) ? SC_H0 + i + 1 : SC_NEW2;
                 k_mgs_step<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, d_sc, SC_H0 + i, V[i], vnext,
-                                                                V[l_plus_1], slot_next, rb);
+                                                                V[l_plus_1], slot_next, R());
                 count();
                 red(slot_next);
             }
-            sync();
+            sync_spin();
             const double vk_norm = rsqrt_s(h_sc[SC_VK2]);
             for (int i = 0; i < l_plus_1; i++) Hes[i][lk] = h_sc[SC_H0 + i];
             double new_vk_norm = rsqrt_s(h_sc[SC_NEW2]);
@@ -476,13 +496,13 @@ int pihm_b200_cvode::cvNewtonIteration()
     for (;;) {
         if (m == 0)
             k_newton_res<true><<<blocks, PB_VEC_THREADS, 0, s()>>>(N, rl1, gamma, zn[0], zn[1], ftemp, ewt,
-                                                                   acor, y, tempv, V[0], rb);
+                                                                   acor, y, tempv, V[0], R());
         else
             k_newton_res<false><<<blocks, PB_VEC_THREADS, 0, s()>>>(N, rl1, gamma, zn[0], zn[1], ftemp, ewt,
-                                                                    acor, y, tempv, V[0], rb);
+                                                                    acor, y, tempv, V[0], R());
         count();
         red(SC_BSUM);
-        sync();
+        sync_spin();
         if (ewt_pending) {               // deferred checks of cvode.c:1349-1388
             ewt_pending = false;
             if (h_sc[SC_EWT_MIN] <= 0.0) return CV_ILL_INPUT;
@@ -495,9 +515,9 @@ int pihm_b200_cvode::cvNewtonIteration()
         if (bnorm <= deltar) {
             // x = b (first iteration) or x = 0
             if (mnewt > 0)
-                k_newton_update<true><<<blocks, PB_VEC_THREADS, 0, s()>>>(N, tempv, ewt, zn[0], acor, y, rb);
+                k_newton_update<true><<<blocks, PB_VEC_THREADS, 0, s()>>>(N, tempv, ewt, zn[0], acor, y, R());
             else
-                k_newton_update<false><<<blocks, PB_VEC_THREADS, 0, s()>>>(N, tempv, ewt, zn[0], acor, y, rb);
+                k_newton_update<false><<<blocks, PB_VEC_THREADS, 0, s()>>>(N, tempv, ewt, zn[0], acor, y, R());
             count();
             retval = 0;
         } else {
@@ -506,12 +526,12 @@ int pihm_b200_cvode::cvNewtonIteration()
             retval = spgmrSolve(&zero);
             if (retval == 0) {
                 if (zero || krydim_last == 0) {
-                    k_newton_update<true><<<blocks, PB_VEC_THREADS, 0, s()>>>(N, tempv, ewt, zn[0], acor, y, rb);
+                    k_newton_update<true><<<blocks, PB_VEC_THREADS, 0, s()>>>(N, tempv, ewt, zn[0], acor, y, R());
                 } else {
                     KryPtrs kp{};
                     Coef6 c{};
                     for (int k = 0; k < krydim_last; k++) { kp.v[k] = V[k]; c.c[k] = yg[k]; }
-                    k_spgmr_final<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, krydim_last, kp, c, ewt, zn[0], acor, y, rb);
+                    k_spgmr_final<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, krydim_last, kp, c, ewt, zn[0], acor, y, R());
                 }
                 count();
             }
@@ -521,7 +541,7 @@ int pihm_b200_cvode::cvNewtonIteration()
         if (retval > 0) return CONV_FAIL;      // setupNonNull == FALSE (cvode_spgmr.c:262)
 
         red(SC_DEL);
-        sync();
+        sync_spin();
         del = wrms(SC_DEL);
         if (m > 0) crate = std::max(CRDOWN * crate, del / delp);
         dcon = del * std::min(1.0, crate) / tq[4];
@@ -529,10 +549,10 @@ int pihm_b200_cvode::cvNewtonIteration()
             if (m == 0) {
                 acnrm = del;
             } else {
-                k_wsq<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, acor, nullptr, ewt, SC_ACNRM, -1, rb);
+                k_wsq<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, acor, nullptr, ewt, SC_ACNRM, -1, R());
                 count();
                 red(SC_ACNRM);
-                sync();
+                sync_spin();
                 acnrm = wrms(SC_ACNRM);
             }
             return CV_SUCCESS;
@@ -701,10 +721,10 @@ void pihm_b200_cvode::cvPrepareNextStep(double dsm)
     etaqm1 = 0.0;
     etaqp1 = 0.0;
     if (do_m1 || do_p1) {
-        k_eta<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, do_m1, do_p1, cquot, zn[q], zn[qmax], acor, ewt, rb);
+        k_eta<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, do_m1, do_p1, cquot, zn[q], zn[qmax], acor, ewt, R());
         count();
         red(SC_ETA_M1, 2);
-        sync();
+        sync_spin();
         if (do_m1) {
             const double ddn = wrms(SC_ETA_M1) * tq[1];
             etaqm1 = 1.0 / (rpowerR(BIAS1 * ddn, 1.0 / q) + ADDON);
@@ -726,10 +746,10 @@ void pihm_b200_cvode::cvBDFStab()
             for (int i = 5; i >= 2; i--) ssdat[i][k] = ssdat[i - 1][k];
         int factorial = 1;
         for (int i = 1; i <= q - 1; i++) factorial *= i;
-        k_wsq<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, zn[q], zn[q - 1], ewt, SC_STAB1, SC_STAB2, rb);
+        k_wsq<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, zn[q], zn[q - 1], ewt, SC_STAB1, SC_STAB2, R());
         count();
         red(SC_STAB1, 2);
-        sync();
+        sync_spin();
         const double sq = factorial * q * (q + 1) * acnrm / std::max(tq[5], TINY);
         const double sqm1 = factorial * q * wrms(SC_STAB1);
         const double sqm2 = factorial * wrms(SC_STAB2);

@@ -36,6 +36,7 @@ enum {
     SC_STAB1,         // sum (zn[q]*ewt)^2
     SC_STAB2,         // sum (zn[q-1]*ewt)^2
     SC_TMP,
+    SC_SEQ,           // ticket of the last finished reduction kernel (host spin-wait)
     SC_COUNT = 32
 };
 
@@ -45,6 +46,7 @@ struct RedBuf {
     double *sc;              // device scalars
     volatile double *hsc;    // mapped host mirror
     int max_blocks;
+    double seq;              // ticket written to hsc[SC_SEQ] after the results
 };
 
 template <bool IS_MIN>
@@ -102,6 +104,8 @@ __device__ __forceinline__ void red_finish(const RedBuf &rb, double a, int slotA
         rb.hsc[slotA] = sa;
         if (slotB >= 0) { rb.sc[slotB] = sb; rb.hsc[slotB] = sb; }
         *rb.counter = 0u;
+        __threadfence_system();          // results visible to the host before the ticket
+        rb.hsc[SC_SEQ] = rb.seq;
     }
 }
 
