@@ -218,6 +218,14 @@ int             pihm_b200_check_nan(pihm_b200_ctx *ctx);
 /* test hook: the inlined pow of the RHS kernels against libdevice pow() */
 int             pihm_b200_test_pow(int n, const double *x, const double *y,
                                    double *fast, double *ref);
+/* test hook: the branch-free division of the RHS kernels against `/`;
+ * ok[i] = 0 where the operands are outside its domain (kernels recompute
+ * such elements with the hardware division), -1 on an internal mismatch */
+int             pihm_b200_test_div(int n, const double *a, const double *b,
+                                   double *fast, double *ok, double *ref);
+/* diagnostic: elements recomputed on the exact (hardware `/`, pow()) path
+ * since the context was created */
+long long       pihm_b200_slow_path_count(pihm_b200_ctx *ctx);
 /* The part of Summary() (src/update.c:19-47) that feeds back into the RHS:
  * ws0.surf = y[SURF] for the next model step's Infil() (vert_flow.c:122).
  * Runs on the device (no y round trip); call after every SolveCVode. */

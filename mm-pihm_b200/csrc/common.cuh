@@ -86,6 +86,8 @@ struct DevMesh {
     double *s2c_stale;   // [2][nrs]  rivflow[LEFT/RIGHT_S2C] of the previous call
     double *xflux;       // [PB_X_NCOL][nes] (record != 0)
     int *nan_flag;
+    unsigned long long *slow_count;   // elements recomputed by elem_main_exact (diagnostic)
+    const DevMesh *self;              // device copy of this struct (for non-inlined rare paths)
 };
 
 }  // namespace pb
@@ -121,6 +123,8 @@ struct pihm_b200_ctx {
     int *d_up_ptr = nullptr, *d_up_idx = nullptr;
     double *d_rivflow = nullptr, *d_stale = nullptr, *d_xflux = nullptr;
     int *d_nan = nullptr;
+    unsigned long long *d_slow = nullptr;
+    pb::DevMesh *d_dm = nullptr;
     int *d_perm = nullptr, *d_iperm = nullptr;   // device copies (state gather)
     // multi-GPU: ghost buffers, send lists, communicator (comm.cu)
     double *d_gel = nullptr, *d_gri = nullptr, *d_send_e = nullptr, *d_send_r = nullptr;

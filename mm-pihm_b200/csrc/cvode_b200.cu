@@ -16,7 +16,11 @@
 #include <atomic>
 #include <cfloat>
 #include <cmath>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 #include "common.cuh"
 #include "cvode_kernels.cuh"
 
@@ -108,7 +112,27 @@ struct pihm_b200_cvode {
     // kernel launched was a reduction kernel.
     long long seq_ctr = 0;
     RedBuf &R() { rb.seq = (double)(++seq_ctr); return rb; }
+    // PIHM_B200_PROFILE=1: host wait time per sync and in-situ RHS event times, printed at destroy
+    bool prof = false;
+    long long prof_nsync = 0, prof_wait_ns = 0, prof_solve_ns = 0;
+    std::vector<cudaEvent_t> prof_ev;
+    size_t prof_used = 0;
+    static long long now_ns()
+    {
+        return std::chrono::duration_cast<std::chrono::nanoseconds>(
+                   std::chrono::steady_clock::now().time_since_epoch()).count();
+    }
     void sync_spin()
+    {
+        if (prof) {
+            const long long t0 = now_ns();
+            sync_spin_();
+            prof_wait_ns += now_ns() - t0;
+            prof_nsync++;
+        } else
+            sync_spin_();
+    }
+    void sync_spin_()
     {
         if (ctx->nranks > 1) { sync(); return; }
         volatile double *tk = h_sc_map + SC_SEQ;
@@ -129,6 +153,13 @@ struct pihm_b200_cvode {
     {
         wrap_a.d = const_cast<double *>(yin);
         wrap_b.d = ydot;
+        if (prof && prof_used + 2 <= prof_ev.size()) {
+            cudaEventRecord(prof_ev[prof_used], s());
+            pihm_b200_ode(ctx, tn, &wrap_a, &wrap_b);
+            cudaEventRecord(prof_ev[prof_used + 1], s());
+            prof_used += 2;
+            return;
+        }
         pihm_b200_ode(ctx, tn, &wrap_a, &wrap_b);
     }
     ZnPtrs znp() const { ZnPtrs p; for (int j = 0; j < 6; j++) p.z[j] = zn[j]; return p; }
@@ -1115,6 +1146,13 @@ pihm_b200_cvode *pihm_b200_cvode_create(pihm_b200_ctx *ctx)
     cv->rb.sc = cv->d_sc;
     cv->h_sc_map = cv->h_sc;
     cv->rb.hsc = cv->h_sc_map;
+    if (const char *e = getenv("PIHM_B200_PROFILE")) {
+        cv->prof = atoi(e) != 0;
+        if (cv->prof) {
+            cv->prof_ev.resize(16384);
+            for (cudaEvent_t &ev : cv->prof_ev) cudaEventCreate(&ev);
+        }
+    }
     if (ctx->nranks > 1) {
         // kernels keep writing their (rank-local) values to the mapped mirror; the host
         // reads a separate pinned copy that sync() fills after the all-reduces
@@ -1138,6 +1176,19 @@ void pihm_b200_cvode_destroy(pihm_b200_cvode *cv)
 {
     if (!cv) return;
     cudaStreamSynchronize(cv->ctx->s());
+    if (cv->prof) {
+        double rhs_ms = 0.0;
+        for (size_t i = 0; i + 1 < cv->prof_used; i += 2) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, cv->prof_ev[i], cv->prof_ev[i + 1]);
+            rhs_ms += ms;
+        }
+        fprintf(stderr, "[pihm_b200 profile] solve %.3f ms  host-wait %.3f ms in %lld syncs  "
+                        "rhs(in situ) %.3f ms over %zu evals (%.1f us each)  launches %lld\n",
+                cv->prof_solve_ns * 1e-6, cv->prof_wait_ns * 1e-6, cv->prof_nsync, rhs_ms, cv->prof_used / 2,
+                cv->prof_used ? rhs_ms * 2e3 / cv->prof_used : 0.0, (long long)cv->ctx->launches);
+        for (cudaEvent_t e : cv->prof_ev) cudaEventDestroy(e);
+    }
     double *all[] = {cv->zn[0], cv->zn[1], cv->zn[2], cv->zn[3], cv->zn[4], cv->zn[5], cv->ewt, cv->acor,
                      cv->tempv, cv->ftemp, cv->V[0], cv->V[1], cv->V[2], cv->V[3], cv->V[4], cv->V[5],
                      cv->vtemp, cv->ytemp, cv->d_part, cv->d_sc};
@@ -1193,7 +1244,9 @@ int pihm_b200_cvode_set_max_step(pihm_b200_cvode *cv, double hmax)
 int pihm_b200_cvode_solve(pihm_b200_cvode *cv, double tout, pihm_b200_vec *y, double *tret)
 {
     if (!cv || !cv->initialised || !y || y->n != cv->N || !tret) { set_error("cvode_solve: bad argument"); return CV_ILL_INPUT; }
+    const long long t_solve0 = cv->prof ? pihm_b200_cvode::now_ns() : 0;
     const int flag = cv->solve(tout, y->d, tret);
+    if (cv->prof) { cudaStreamSynchronize(cv->ctx->s()); cv->prof_solve_ns += pihm_b200_cvode::now_ns() - t_solve0; }
     int nan_any = (flag >= 0) ? pihm_b200_check_nan(cv->ctx) : 0;
     if (cv->ctx->nranks > 1) {      // every rank must take the same exit
         double v = (double)nan_any;

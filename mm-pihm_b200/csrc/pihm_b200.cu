@@ -259,6 +259,8 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
     zalloc((void **)&ctx->d_rivflow, sizeof(double) * PIHM_B200_NUM_RIVFLX * nrs);
     zalloc((void **)&ctx->d_stale, sizeof(double) * 2 * nrs);
     zalloc((void **)&ctx->d_nan, sizeof(int) * 4);
+    zalloc((void **)&ctx->d_slow, sizeof(unsigned long long));
+    zalloc((void **)&ctx->d_dm, sizeof(DevMesh));
     zalloc((void **)&ctx->d_stage, sizeof(double) * std::max<long long>(ctx->nsv, ne));
     zalloc((void **)&ctx->d_gel, sizeof(double) * dm.gs * (size_t)std::max(ne - nown_elem, 1));
     zalloc((void **)&ctx->d_gri, sizeof(double) * 2 * (size_t)std::max(nr - nown_riv, 1));
@@ -280,6 +282,13 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
     dm.gel = ctx->d_gel; dm.gri = ctx->d_gri;
     dm.xflux = nullptr; dm.record = 0;
     dm.nan_flag = ctx->d_nan;
+    dm.slow_count = ctx->d_slow;
+    dm.self = ctx->d_dm;
+    if (cudaMemcpy(ctx->d_dm, &dm, sizeof(DevMesh), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("pihm_b200_create: DevMesh upload failed");
+        pihm_b200_destroy(ctx);
+        return nullptr;
+    }
     if (const char *cv = std::getenv("PIHM_B200_CARVEOUT")) {     // tuning knob (percent of L1 given to smem)
         const int pct = std::atoi(cv);
         cudaFuncSetAttribute(k_main<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
@@ -302,7 +311,7 @@ void pihm_b200_destroy(pihm_b200_ctx *ctx)
                    ctx->d_bct, ctx->d_fbct, ctx->d_ri, ctx->d_up_ptr, ctx->d_up_idx,
                    ctx->d_rivflow, ctx->d_stale, ctx->d_xflux, ctx->d_nan, ctx->d_perm,
                    ctx->d_iperm, ctx->d_stage, ctx->d_red, ctx->d_gel, ctx->d_gri, ctx->d_send_e, ctx->d_send_r,
-                   ctx->d_send_e_idx, ctx->d_send_r_idx};
+                   ctx->d_send_e_idx, ctx->d_send_r_idx, ctx->d_slow, ctx->d_dm};
     pb::comm_destroy(ctx);
     for (void *p : dev) if (p) cudaFree(p);
     if (ctx->h_red) cudaFreeHost(ctx->h_red);
@@ -331,6 +340,15 @@ int pihm_b200_synchronize(pihm_b200_ctx *ctx)
 }
 
 long long pihm_b200_launch_count(const pihm_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+long long pihm_b200_slow_path_count(pihm_b200_ctx *ctx)
+{
+    if (!ctx) return -1;
+    unsigned long long v = 0;
+    if (cudaMemcpyAsync(&v, ctx->d_slow, sizeof(v), cudaMemcpyDeviceToHost, ctx->s()) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->s()) != cudaSuccess) { set_error("slow_path_count: copy failed"); return -1; }
+    return (long long)v;
+}
 
 int pihm_b200_get_permutation(const pihm_b200_ctx *ctx, int32_t *perm)
 {
@@ -493,6 +511,21 @@ int pihm_b200_test_pow(int n, const double *x, const double *y, double *fast, do
     return 0;
 }
 
+// test hook: the branch-free division of the RHS kernels vs the hardware division
+int pihm_b200_test_div(int n, const double *a, const double *b, double *fast, double *ok, double *ref)
+{
+    double *d = nullptr;
+    PB_CUDA(cudaMalloc((void **)&d, sizeof(double) * 5 * (size_t)n));
+    PB_CUDA(cudaMemcpy(d, a, sizeof(double) * n, cudaMemcpyHostToDevice));
+    PB_CUDA(cudaMemcpy(d + n, b, sizeof(double) * n, cudaMemcpyHostToDevice));
+    k_test_div<<<(n + 255) / 256, 256>>>(n, d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n, d + 4 * (size_t)n);
+    PB_CUDA(cudaMemcpy(fast, d + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    PB_CUDA(cudaMemcpy(ok, d + 3 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    PB_CUDA(cudaMemcpy(ref, d + 4 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return 0;
+}
+
 int pihm_b200_set_flux_recording(pihm_b200_ctx *ctx, int on)
 {
     if (!ctx) return -1;
@@ -503,6 +536,7 @@ int pihm_b200_set_flux_recording(pihm_b200_ctx *ctx, int on)
     }
     ctx->dm.xflux = ctx->d_xflux;
     ctx->dm.record = on ? 1 : 0;
+    PB_CUDA(cudaMemcpy(ctx->d_dm, &ctx->dm, sizeof(DevMesh), cudaMemcpyHostToDevice));
     return 0;
 }
 

@@ -17,6 +17,7 @@
 #pragma once
 #include "common.cuh"
 #include "fastpow.cuh"
+#include "fdiv.cuh"
 
 namespace pb {
 
@@ -573,14 +574,42 @@ __device__ __forceinline__ void elem_pre(const DevMesh &m, const double *__restr
 // ---------------------------------------------------------------------------
 // element part of k_main
 // ---------------------------------------------------------------------------
-template <bool FBR>
-__device__ __forceinline__ void elem_main(const DevMesh &m, const double *__restrict__ y,
+// KrFunc(beta, satn) and Psi(satn, alpha, beta) (vert_flow.c:272-278) of the same
+// element.  The four pow() form two independent pairs, pow(s, m) / pow(1/s, m) and
+// pow(1 - A, (b-1)/b) / pow(C - 1, 1/b); with Arith<true> all of it is one
+// straight-line block and the pairs interleave.  Values are those of kr_func() /
+// psi_func().
+template <bool FAST>
+__device__ __forceinline__ void vg_kr_psi_a(Arith<FAST> &A, double satn, double alpha, double beta,
+                                            double &kr, double &psi)
+{
+    if (!FAST) { vg_kr_psi(satn, alpha, beta, kr, psi); return; }
+    const double rb = A.rcp(beta);
+    const double m1 = A.quo(beta, beta - 1.0);
+    const double m2 = A.div(beta - 1.0, beta, rb);
+    const double m3 = A.div(1.0, beta, rb);
+    const double sp = (satn < PB_SATMIN) ? PB_SATMIN : satn;
+    const double Av = A.powp(satn, m1);
+    const double Cv = A.powp(A.div(1.0, sp), m1);
+    const double Bv = A.powp(1.0 - Av, m2);
+    const double Dv = A.powp(Cv - 1.0, m3);
+    const double a = 1.0 - Bv;
+    kr = sqrt(satn) * a * a;
+    psi = A.div(-Dv, alpha);
+}
+
+// FAST: every division / pow goes through Arith<true> (fdiv.cuh) and the
+// function returns false, without having written anything, when one of them
+// left the fast-path domain; the caller then runs the FAST = false version.
+template <bool FBR, bool FAST>
+__device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__restrict__ y,
                                           double *__restrict__ dy, int i, const double *st,
                                           const double *f, unsigned bar)
 {
     // st / f: this lane's column 0 of the warp's shared-memory slabs (static slots
     // TS_MAIN0.., hot forcing columns), filled by the bulk copies issued in k_main
 #define EC(c) st[((c) - TS_MAIN0) * PB_TILE]
+    Arith<FAST> A;
     // ---- loads: neighbour codes, then all gathers (unconditional) ---------------
     int code[3], nn[3];
 #pragma unroll
@@ -606,6 +635,7 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
     const double depth = EC(TS_DEPTH), dinf = EC(TS_DINF);
     const double rough = EC(TS_ROUGH);
     const double pcpdrp = f[0 * PB_TILE];
+    const double r_area = A.rcp(area);
 
     // EtExtract (non-Noah), hydrol.c:51-87
     double edir_surf = 0.0, edir_unsat = 0.0, edir_gw = 0.0, ett_unsat = 0.0, ett_gw = 0.0;
@@ -618,19 +648,25 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
         else ett_unsat = ett;
     }
 
-    // LateralFlow, lat_flow.c:17-51
+    // LateralFlow, lat_flow.c:17-51.  The element-to-element formulas run for all
+    // three edges as one straight-line block (an edge without an element behind it
+    // sees the element itself: every difference is zero); boundary and river edges
+    // are patched afterwards.
     double ovl[3], sub[3], ovl_infil[3];
     const double sf_i = own.z;
+    {
+        double num[3], den[3], avgh_s[3];
 #pragma unroll
-    for (int j = 0; j < 3; j++) {
-        if (code[j] >= 0) {
-            const double edge = EC(TS_EDGE0 + j), dist = EC(TS_NABRDIST0 + j);
+        for (int j = 0; j < 3; j++) {
+            const double edge = EC(TS_EDGE0 + j);
+            const double dist = (code[j] >= 0) ? EC(TS_NABRDIST0 + j) : 1.0;
+            const double r_dist = A.rcp(dist);
             const double gw_n = dn[j].w, surfh_n = dn[j].x;
             const double zmin_n = sn[j].x, zmax_n = sn[j].y;
             // SubFlowElemToElem, lat_flow.c:273-298
             double diff_h = (gw + zmin) - (gw_n + zmin_n);
             double avgh = avg_h(diff_h, gw, gw_n);
-            double grad_h = div_pos(diff_h, dist);
+            double grad_h = A.div(diff_h, dist, r_dist);
             double avg_ksat = 0.5 * (effkh + dn[j].y);
             sub[j] = avg_ksat * grad_h * avgh * edge;
             // OvlFlowElemToElem, lat_flow.c:300-327 with avg_sf of :33-36
@@ -638,42 +674,61 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
             diff_h = (m.surf_mode == PB_KINEMATIC) ? zmax - zmax_n
                                                    : (surfh + zmax) - (surfh_n + zmax_n);
             avgh = avg_hsurf(diff_h, surfh, surfh_n);
-            grad_h = div_pos(diff_h, dist);
+            grad_h = A.div(diff_h, dist, r_dist);
             if (m.surf_mode == PB_KINEMATIC) {
                 avg_sf = (grad_h > 0.0) ? grad_h : PB_GRADMIN;
             } else {
                 avg_sf = 0.5 * (sf_i + dn[j].z);
                 avg_sf = (avg_sf > PB_GRADMIN) ? avg_sf : PB_GRADMIN;
             }
-            double avg_rough = 0.5 * (rough + sn[j].z);
-            double crossa = avgh * edge;
-            ovl[j] = overland_flow(avgh, grad_h, avg_sf, crossa, avg_rough);
+            const double avg_rough = 0.5 * (rough + sn[j].z);
+            avgh_s[j] = avgh;
+            den[j] = sqrt(avg_sf) * avg_rough;
+            num[j] = avgh * edge;                     // crossa; crossa * p * grad left to right (lat_flow.c:270)
+            ovl_infil[j] = grad_h;                    // parked: grad_h of the overland flux
+        }
+        // OverLandFlow, lat_flow.c:267-271: pow(0, 0.6666667) == 0 exactly, so a warp whose
+        // edges are all dry skips the three pows (bitwise the same products)
+        double p[3] = {0.0, 0.0, 0.0};
+        if (__any_sync(__activemask(), (avgh_s[0] != 0.0) | (avgh_s[1] != 0.0) | (avgh_s[2] != 0.0))) {
+#pragma unroll
+            for (int j = 0; j < 3; j++) p[j] = A.powp(avgh_s[j], 0.6666667);
+        }
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            ovl[j] = A.div(num[j] * p[j] * ovl_infil[j], den[j]);
             ovl_infil[j] = ovl[j];
-        } else if (code[j] == PB_NB_BOUNDARY) {
-            // BoundFluxElem, lat_flow.c:329-371
-            const int bc = m.bct[(size_t)j * m.nes + i];
-            ovl[j] = 0.0;
-            if (bc == 0) {
-                sub[j] = 0.0;
-            } else if (bc > 0) {
-                const double head = FOC(PB_F_BC0 + j, i);
-                double diff_h = gw + zmin - head;
-                double avgh = avg_h(diff_h, gw, head - zmin);
-                double grad_h = div_pos(diff_h, EC(TS_NABRDIST0 + j));
-                sub[j] = effkh * grad_h * avgh * EC(TS_EDGE0 + j);
-            } else {
-                sub[j] = -FOC(PB_F_BC0 + j, i);
-            }
-            ovl_infil[j] = ovl[j];
-        } else {
-            // river edge: RiverToElem write-back, river_flow.c:159-180
-            const int c = -code[j] - 2, r = c >> 2, side = c & 3;
-            if (side < 2) {
-                ovl[j] = -RFLX(RF_LEFT_S2C + side, r);
-                sub[j] = -(RFLX(RF_LEFT_A2C + side, r) + RFLX(RF_LEFT_A2A + side, r));
-                ovl_infil[j] = -m.s2c_stale[(size_t)side * m.nrs + r];
-            } else {
-                ovl[j] = sub[j] = ovl_infil[j] = 0.0;
+        }
+    }
+    if ((code[0] | code[1] | code[2]) < 0) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            if (code[j] == PB_NB_BOUNDARY) {
+                // BoundFluxElem, lat_flow.c:329-371
+                const int bc = m.bct[(size_t)j * m.nes + i];
+                ovl[j] = 0.0;
+                if (bc == 0) {
+                    sub[j] = 0.0;
+                } else if (bc > 0) {
+                    const double head = FOC(PB_F_BC0 + j, i);
+                    double diff_h = gw + zmin - head;
+                    double avgh = avg_h(diff_h, gw, head - zmin);
+                    double grad_h = div_pos(diff_h, EC(TS_NABRDIST0 + j));
+                    sub[j] = effkh * grad_h * avgh * EC(TS_EDGE0 + j);
+                } else {
+                    sub[j] = -FOC(PB_F_BC0 + j, i);
+                }
+                ovl_infil[j] = ovl[j];
+            } else if (code[j] < 0) {
+                // river edge: RiverToElem write-back, river_flow.c:159-180
+                const int c = -code[j] - 2, r = c >> 2, side = c & 3;
+                if (side < 2) {
+                    ovl[j] = -RFLX(RF_LEFT_S2C + side, r);
+                    sub[j] = -(RFLX(RF_LEFT_A2C + side, r) + RFLX(RF_LEFT_A2A + side, r));
+                    ovl_infil[j] = -m.s2c_stale[(size_t)side * m.nrs + r];
+                } else {
+                    ovl[j] = sub[j] = ovl_infil[j] = 0.0;
+                }
             }
         }
     }
@@ -689,40 +744,40 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
         double satn = 1.0, satkfunc = 1.0, psi_u = 0.0, deficit = 0.0;
         if (!sat) {
             deficit = depth - gw;
-            satn = div_pos(unsat, deficit);
+            satn = A.div(unsat, deficit);
             satn = (satn > 1.0) ? 1.0 : satn;
             satn = (satn < PB_SATMIN) ? PB_SATMIN : satn;
-            vg_kr_psi(satn, alpha, beta, satkfunc, psi_u);
+            vg_kr_psi_a<FAST>(A, satn, alpha, beta, satkfunc, psi_u);
         }
         if (unsat + gw > depth) {
             infil = 0.0;
         } else {
             double applrate = 0.0;
 #pragma unroll
-            for (int j = 0; j < 3; j++) applrate += div_pos(-ovl_infil[j], area);
+            for (int j = 0; j < 3; j++) applrate += A.div(-ovl_infil[j], area, r_area);
             applrate = (applrate > 0.0) ? applrate : 0.0;
             applrate += pcpdrp;
-            double wetfrac = div_pos(surfh, PB_DEPRSTG);
+            double wetfrac = A.div(surfh, PB_DEPRSTG);
             wetfrac = (wetfrac > 0.0) ? wetfrac : 0.0;
             wetfrac = (wetfrac < 1.0) ? wetfrac : 1.0;
             double dh_by_dz;
             if (sat) {
                 // KrFunc(beta, 1.0) == 1.0 exactly (pow(1,x) = 1, pow(0,x>0) = 0)
-                dh_by_dz = (surfh + zmax - (gw + zmin)) / (0.5 * (surfh + dinf));
+                dh_by_dz = A.quo(surfh + zmax - (gw + zmin), 0.5 * (surfh + dinf));
                 dh_by_dz = (surfh <= 0.0 && dh_by_dz > 0.0) ? 0.0 : dh_by_dz;
                 double kinf = eff_kinf(kinfv, kmacv, areafh, dh_by_dz, 1.0, 1.0, applrate, surfh);
                 infil = kinf * dh_by_dz;
             } else {
                 double psi_c = (psi_u > PB_PSIMIN) ? psi_u : PB_PSIMIN;
                 double h_u = psi_c + zmax - 0.5 * dinf;
-                dh_by_dz = (surfh + zmax - h_u) / (0.5 * (surfh + dinf));
+                dh_by_dz = A.quo(surfh + zmax - h_u, 0.5 * (surfh + dinf));
                 dh_by_dz = (surfh <= 0.0 && dh_by_dz > 0.0) ? 0.0 : dh_by_dz;
                 double kinf = eff_kinf(kinfv, kmacv, areafh, dh_by_dz, satkfunc, satn, applrate, surfh);
                 infil = kinf * dh_by_dz;
                 infil = (infil > 0.0) ? infil : 0.0;
             }
             const double ws0surf = f[3 * PB_TILE];
-            double infil_max = applrate + ((ws0surf > 0.0) ? ws0surf / m.dt : 0.0);
+            double infil_max = applrate + ((ws0surf > 0.0) ? A.quo(ws0surf, m.dt) : 0.0);
             infil = (infil > infil_max) ? infil_max : infil;
             infil *= wetfrac;
         }
@@ -742,8 +797,8 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
                 d2 = dmac - deficit;
                 k3 = ksatv; d3 = gw - (dmac - deficit);
             }
-            double kavg = (k1 * d1 + k2 * d2 + k3 * d3) / (d1 + d2 + d3);
-            double dh_by_dz = (0.5 * deficit + psi_u) / (0.5 * (deficit + gw));
+            double kavg = A.quo(k1 * d1 + k2 * d2 + k3 * d3, d1 + d2 + d3);
+            double dh_by_dz = A.quo(0.5 * deficit + psi_u, 0.5 * (deficit + gw));
             rechg = kavg * dh_by_dz;
             rechg = (rechg > 0.0 && unsat <= 0.0) ? 0.0 : rechg;
             rechg = (rechg < 0.0 && gw <= 0.0) ? 0.0 : rechg;
@@ -766,10 +821,10 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
         double deficit = 0.0, satkfunc = 1.0, psi_c = 0.0;
         if (!full) {
             deficit = gdepth - fg;
-            double satn = div_pos(fu, deficit);
+            double satn = A.div(fu, deficit);
             satn = (satn > 1.0) ? 1.0 : satn;
             satn = (satn < PB_SATMIN) ? PB_SATMIN : satn;
-            vg_kr_psi(satn, galpha, gbeta, satkfunc, psi_c);
+            vg_kr_psi_a<FAST>(A, satn, galpha, gbeta, satkfunc, psi_c);
             psi_c = (psi_c > PB_PSIMIN) ? psi_c : PB_PSIMIN;
         }
         // FbrInfil, vert_flow.c:284-330
@@ -779,16 +834,16 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
             fbr_infil = 0.0;
         } else {
             double h_u = psi_c + zmin - 0.5 * deficit;
-            double dh_by_dz = (zmin + gw - h_u) / (0.5 * (gw + deficit));
-            double kavg = (gw + deficit) / (gw / EC(TS_KSATV) + deficit / (gksatv * satkfunc));
+            double dh_by_dz = A.quo(zmin + gw - h_u, 0.5 * (gw + deficit));
+            double kavg = A.quo(gw + deficit, A.quo(gw, EC(TS_KSATV)) + A.quo(deficit, gksatv * satkfunc));
             fbr_infil = kavg * dh_by_dz;
         }
         // FbrRecharge, vert_flow.c:332-373
         if (full) {
             fbr_rechg = fbr_infil;
         } else {
-            double dh_by_dz = (0.5 * deficit + psi_c) / (0.5 * (deficit + fg));
-            double kavg = (fu * gksatv * satkfunc + fg * gksatv) / (fu + fg);
+            double dh_by_dz = A.quo(0.5 * deficit + psi_c, 0.5 * (deficit + fg));
+            double kavg = A.quo(fu * gksatv * satkfunc + fg * gksatv, fu + fg);
             fbr_rechg = kavg * dh_by_dz;
             fbr_rechg = (fbr_rechg > 0.0 && fu <= 0.0) ? 0.0 : fbr_rechg;
             fbr_rechg = (fbr_rechg < 0.0 && fg <= 0.0) ? 0.0 : fbr_rechg;
@@ -796,8 +851,7 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
         // lateral bedrock flow, lat_flow.c:56-115
 #pragma unroll
         for (int j = 0; j < 3; j++) {
-            const int code = m.nb[(size_t)j * m.nes + i];
-            if (code == PB_NB_BOUNDARY) {
+            if (code[j] == PB_NB_BOUNDARY) {
                 // FbrBoundFluxElem, lat_flow.c:392-424
                 const int bc = m.fbct[(size_t)j * m.nes + i];
                 if (bc == 0) {
@@ -814,12 +868,12 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
             } else {
                 int n;
                 double dist;
-                if (code >= 0) {
-                    n = code;
+                if (code[j] >= 0) {
+                    n = code[j];
                     dist = EC(TS_NABRDIST0 + j);
                 } else {
                     // neighbour across the river, lat_flow.c:85-100
-                    const int r = (-code - 2) >> 2;
+                    const int r = (-code[j] - 2) >> 2;
                     const int l = RIC(PB_RI_LEFTELE, r);
                     n = (l == i) ? RIC(PB_RI_RIGHTELE, r) : l;
                     dist = m.fbr_dist[r];
@@ -828,7 +882,7 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
                 const double fg_n = max0(y_fg(m, y, n));
                 double diff_h = (fg + zbed) - (fg_n + m.snb[n].w);
                 double avgh = avg_h(diff_h, fg, fg_n);
-                double grad_h = div_pos(diff_h, dist);
+                double grad_h = A.div(diff_h, dist);
                 double avg_ksat = 0.5 * (gksath + TSC(TS_GKSATH, n));
                 fbrflow[j] = avg_ksat * grad_h * avgh * EC(TS_EDGE0 + j);
             }
@@ -840,21 +894,27 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
 
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-        dsurf -= div_pos(ovl[j], area);
-        dgw -= div_pos(sub[j], area);
-        if (FBR) dfg -= div_pos(fbrflow[j], area);
+        dsurf -= A.div(ovl[j], area, r_area);
+        dgw -= A.div(sub[j], area, r_area);
+        if (FBR) dfg -= A.div(fbrflow[j], area, r_area);
     }
     const double porosity = EC(TS_POROSITY);
-    dunsat = div_pos(dunsat, porosity);
-    dgw = div_pos(dgw, porosity);
+    const double r_por = A.rcp(porosity);
+    dunsat = A.div(dunsat, porosity, r_por);
+    dgw = A.div(dgw, porosity, r_por);
+    if (FBR) {
+        const double gporosity = EC(TS_GPOROSITY);
+        const double r_gpor = A.rcp(gporosity);
+        dfu = A.div(dfu, gporosity, r_gpor);
+        dfg = A.div(dfg, gporosity, r_gpor);
+    }
+    if (FAST && !A.ok) return false;        // nothing written yet: the caller recomputes this element
+
     dy[i] = dsurf;
     dy[m.o_unsat + i] = dunsat;
     dy[m.o_gw + i] = dgw;
     bool bad = isnan(dsurf) || isnan(dunsat) || isnan(dgw);
     if (FBR) {
-        const double gporosity = EC(TS_GPOROSITY);
-        dfu = div_pos(dfu, gporosity);
-        dfg = div_pos(dfg, gporosity);
         dy[m.o_fu + i] = dfu;
         dy[m.o_fg + i] = dfg;
         bad = bad || isnan(dfu) || isnan(dfg);
@@ -878,9 +938,22 @@ __device__ __forceinline__ void elem_main(const DevMesh &m, const double *__rest
         XFC(PB_X_FBR_INFIL, i) = fbr_infil;
         XFC(PB_X_FBR_RECHG, i) = fbr_rechg;
     }
+    return true;
 #undef EC
 }
 
+// the rare elements whose arithmetic left the fast-path domain: plain `/` and pow()
+template <bool FBR>
+__device__ __noinline__ void elem_main_exact(const DevMesh *gm, const double *__restrict__ y,
+                                             double *__restrict__ dy, int i, const double *st,
+                                             const double *f, unsigned bar)
+{
+    const DevMesh &m = *gm;
+    elem_main<FBR, false>(m, y, dy, i, st, f, bar);
+    if (m.slow_count) atomicAdd(m.slow_count, 1ULL);
+}
+
+// ---------------------------------------------------------------------------
 // river part of k_main: the serial accumulation of river_flow.c:94-108 as an
 // ordered gather over the upstream list, then ode.c:228-252
 __device__ __forceinline__ void river_main(const DevMesh &m, double *__restrict__ dy, int r)
@@ -969,7 +1042,10 @@ k_main(const DevMesh m, const double *__restrict__ y, double *__restrict__ dy, i
         }
         __syncwarp();
         const int i = tile * PB_TILE + lane;
-        if (i < m.nown) elem_main<FBR>(m, y, dy, i, &s_tile[warp][lane], &s_forc[warp][lane], bar);
+        if (i < m.nown) {
+            if (!elem_main<FBR, true>(m, y, dy, i, &s_tile[warp][lane], &s_forc[warp][lane], bar))
+                elem_main_exact<FBR>(m.self, y, dy, i, &s_tile[warp][lane], &s_forc[warp][lane], bar);
+        }
     } else {
         const int r = (blockIdx.x - elem_blocks) * PB_RHS_THREADS + threadIdx.x;
         if (r < m.rown) river_main(m, dy, r);
@@ -1006,6 +1082,26 @@ static __global__ void k_test_pow(int n, const double *__restrict__ x, const dou
     fast[i] = a;
     if (b != pow_pos(x[n - 1 - i], y[n - 1 - i]) && !(b != b)) fast[i] = -1.0;   // pair form == single form
     ref[i] = pow(x[i], y[i]);
+}
+
+// test hook: Arith<true> division against the hardware `/` (tests/test_fastpow_gpu.py);
+// ok[i] = 0 where the operands left the branch-free domain (the kernels then recompute)
+static __global__ void k_test_div(int n, const double *__restrict__ a, const double *__restrict__ b,
+                                  double *__restrict__ fast, double *__restrict__ ok, double *__restrict__ ref)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Arith<true> A;
+    const double q = A.quo(a[i], b[i]);
+    const bool ok1 = A.ok;
+    // shared-reciprocal form for positive divisors must agree with the single form
+    const double bp = fabs(b[i]);
+    const double r = A.rcp(bp);
+    const double q2 = A.div(a[i], bp, r), q3 = A.div(a[n - 1 - i], bp, r);
+    fast[i] = q;
+    ok[i] = ok1 ? 1.0 : 0.0;
+    ref[i] = a[i] / b[i];
+    if (A.ok && bp > 0.0 && (q2 != a[i] / bp || q3 != a[n - 1 - i] / bp) && q2 == q2 && q3 == q3) ok[i] = -1.0;
 }
 
 #undef TSC

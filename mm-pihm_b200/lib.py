@@ -74,6 +74,7 @@ _SIGS = {
     "pihm_b200_get_stream": (C.c_void_p, [C.c_void_p]),
     "pihm_b200_synchronize": (C.c_int, [C.c_void_p]),
     "pihm_b200_launch_count": (C.c_longlong, [C.c_void_p]),
+    "pihm_b200_slow_path_count": (C.c_longlong, [C.c_void_p]),
     "pihm_b200_get_permutation": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pihm_b200_set_forcing": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pihm_b200_set_forcing_col": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
@@ -84,6 +85,7 @@ _SIGS = {
     "pihm_b200_check_nan": (C.c_int, [C.c_void_p]),
     "pihm_b200_summary": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pihm_b200_test_pow": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pihm_b200_test_div": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pihm_b200_set_flux_recording": (C.c_int, [C.c_void_p, C.c_int]),
     "pihm_b200_get_fluxes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pihm_b200_vec_new": (C.c_void_p, [C.c_void_p]),
@@ -266,6 +268,9 @@ class Model:
 
     def synchronize(self):
         _check(self.L, self.L.pihm_b200_synchronize(self.h), "synchronize")
+
+    def slow_path_count(self) -> int:
+        return int(self.L.pihm_b200_slow_path_count(self.h))
 
     @property
     def launches(self) -> int:

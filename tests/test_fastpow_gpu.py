@@ -35,3 +35,46 @@ def test_edge_cases_take_the_fallback():
     fast, ref = run(x, y)
     assert np.array_equal(fast, ref, equal_nan=True), (fast, ref)
     assert fast[0] == 0.0 and fast[1] == 1.0 and fast[2] == 1.0
+
+
+# ---- Arith<true> division (csrc/fdiv.cuh) against the hardware `/` ------------------------
+
+def run_div(a, b):
+    L = lib.load_library()
+    a = np.ascontiguousarray(a, np.float64); b = np.ascontiguousarray(b, np.float64)
+    fast = np.empty_like(a); ok = np.empty_like(a); ref = np.empty_like(a)
+    assert L.pihm_b200_test_div(len(a), a.ctypes.data, b.ctypes.data, fast.ctypes.data,
+                                ok.ctypes.data, ref.ctypes.data) == 0
+    return fast, ok, ref
+
+
+def test_division_bitwise_on_the_rhs_domain():
+    rng = np.random.default_rng(1)
+    n = 1 << 21
+    sgn = rng.choice([-1.0, 1.0], n)
+    # fluxes / head differences over areas, distances, porosities, conductivities ...
+    a = sgn * 10.0 ** rng.uniform(-30, 12, n)
+    a[rng.random(n) < 0.1] = 0.0
+    a[rng.random(n) < 0.02] = -0.0
+    b = 10.0 ** rng.uniform(-12, 8, n)
+    b[: n // 8] = rng.uniform(0.5, 2.0, n // 8)               # mantissa sweep near 1
+    b[n // 8: n // 4] *= -1.0                                 # quo() takes either sign
+    fast, ok, ref = run_div(a, b)
+    assert (ok >= 0).all(), "shared-reciprocal form disagrees with `/`"
+    assert (ok == 1).all(), f"{(ok != 1).sum()} operand pairs left the branch-free domain"
+    same = (fast == ref) & (np.signbit(fast) == np.signbit(ref))
+    assert same.all(), f"{(~same).sum()} of {n} quotients differ from the hardware division"
+    # and the hardware division is IEEE: identical to the host's
+    with np.errstate(all="ignore"):
+        assert np.array_equal(ref, a / b)
+
+
+def test_division_flags_everything_outside_its_domain():
+    a = np.array([1e-300, 5e-324, 1.0, 1e300, 1e-200, np.inf, np.nan, 1.0, 1.0, 0.0, 0.0, 0.0, 3.0, 1e308])
+    b = np.array([3.0, 3.0, 1e308, 1e-300, 1e200, 2.0, 2.0, 0.0, np.inf, 0.0, np.inf, np.nan, np.nan, 1e-10])
+    fast, ok, ref = run_div(a, b)
+    assert (ok >= 0).all()
+    good = ok == 1
+    # wherever the flag stays up the quotient is the hardware one; everything else is recomputed
+    assert np.array_equal(fast[good], ref[good])
+    assert not good[[0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13]].any(), ok
