@@ -520,11 +520,46 @@ __device__ __forceinline__ void river_fluxes(const DevMesh &m, const double *__r
 // the 32-byte "dynamic neighbour record" {surfh, effkh, |grad h|, gw} that
 // k_main gathers with one sector per neighbour.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void elem_pre(const DevMesh &m, const double *__restrict__ y, int i,
+// SurfH / EffKh / DhByDl through Arith<FAST>: with FAST the whole of elem_pre is one
+// straight-line block (selects instead of branches around sqrt and `/`)
+template <bool FAST>
+__device__ __forceinline__ double surf_h_a(Arith<FAST> &A, double surfeqv)
+{
+    if (!FAST) return surf_h(surfeqv);
+    const double lo = A.sqrtp(2.0 * PB_DEPRSTG * ((surfeqv > 0.0) ? surfeqv : 0.0));
+    const double hi = PB_DEPRSTG + (surfeqv - 0.5 * PB_DEPRSTG);
+    return (surfeqv < 0.0) ? 0.0 : ((surfeqv <= 0.5 * PB_DEPRSTG) ? lo : hi);
+}
+template <bool FAST>
+__device__ __forceinline__ double eff_kh_a(Arith<FAST> &A, double depth, double dmac, double kmach,
+                                           double areafv, double ksath, double gw)
+{
+    if (!FAST) return eff_kh(depth, dmac, kmach, areafv, ksath, gw);
+    gw = (gw > 0.0) ? gw : 0.0;
+    const bool mac = gw > depth - dmac;
+    const double k1 = kmach * areafv + ksath * (1.0 - areafv);
+    const double d2 = depth - dmac;
+    const double d1 = (gw > depth) ? dmac : gw - (depth - dmac);
+    const double q = A.quo(mac ? k1 * d1 + ksath * d2 : 1.0, mac ? d1 + d2 : 1.0);
+    return mac ? q : ksath;
+}
+template <bool FAST>
+__device__ __forceinline__ double dh_by_dl_a(Arith<FAST> &A, const double *l1, const double *l2, const double *h)
+{
+    if (!FAST) return dh_by_dl(l1, l2, h);
+    return A.quo(-1.0 *
+        (l1[2] * (h[1] - h[0]) + l1[1] * (h[0] - h[2]) + l1[0] * (h[2] - h[1])),
+        (l2[2] * (l1[1] - l1[0]) + l2[1] * (l1[0] - l1[2]) + l2[0] * (l1[2] - l1[1])));
+}
+
+// returns false (nothing written) when FAST arithmetic left its domain
+template <bool FAST>
+__device__ __forceinline__ bool elem_pre(const DevMesh &m, const double *__restrict__ y, int i,
                                          const double *st, unsigned bar)
 {
     // st: this lane's column 0 of the warp's shared-memory tile slab (slots TS_PRE0..TS_PRE1)
 #define EC(c) st[((c) - TS_PRE0) * PB_TILE]
+    Arith<FAST> A;
     // neighbour codes first, then every gather unconditionally (non-element
     // edges gather the element itself) so the loads are in flight together
     int code[3], nn[3];
@@ -539,11 +574,11 @@ __device__ __forceinline__ void elem_pre(const DevMesh &m, const double *__restr
         ysn[j] = y_surf(m, y, nn[j]);
         zmaxn[j] = m.snb[nn[j]].y;
     }
-    const double surfh = surf_h(max0(y_surf(m, y, i)));
+    const double surfh = surf_h_a<FAST>(A, max0(y_surf(m, y, i)));
     const double gw = max0(y_gw(m, y, i));
     mbar_wait(bar, 0);          // the tile slab has landed
-    const double effkh = eff_kh(EC(TS_DEPTH), EC(TS_DMAC), EC(TS_KMACH), EC(TS_AREAFV),
-                                EC(TS_KSATH), gw);
+    const double effkh = eff_kh_a<FAST>(A, EC(TS_DEPTH), EC(TS_DMAC), EC(TS_KMACH), EC(TS_AREAFV),
+                                        EC(TS_KSATH), gw);
     double sf = 0.0;
     if (m.surf_mode == PB_DIFF_WAVE) {
         const double zmax = EC(TS_ZMAX);
@@ -552,23 +587,38 @@ __device__ __forceinline__ void elem_pre(const DevMesh &m, const double *__restr
         for (int j = 0; j < 3; j++) {
             nx[j] = EC(TS_NABRX0 + j);
             ny[j] = EC(TS_NABRY0 + j);
-            if (code[j] >= 0) {
-                h[j] = zmaxn[j] + surf_h(max0(ysn[j]));
-            } else if (code[j] == PB_NB_BOUNDARY) {
-                if (m.bct[(size_t)j * m.nes + i] == 0) h[j] = zmax + surfh;
-                else h[j] = FOC(PB_F_BC0 + j, i);
-            } else {
-                const int r = (-code[j] - 2) >> 2;
-                const double stage = max0(y_stage(m, y, r));
-                h[j] = (stage > RFC(PB_R_SHP_DEPTH, r)) ? RFC(PB_R_ZBED, r) + stage : RFC(PB_R_ZMAX, r);
+            h[j] = zmaxn[j] + surf_h_a<FAST>(A, max0(ysn[j]));
+        }
+        if ((code[0] | code[1] | code[2]) < 0) {
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                if (code[j] == PB_NB_BOUNDARY) {
+                    if (m.bct[(size_t)j * m.nes + i] == 0) h[j] = zmax + surfh;
+                    else h[j] = FOC(PB_F_BC0 + j, i);
+                } else if (code[j] < 0) {
+                    const int r = (-code[j] - 2) >> 2;
+                    const double stage = max0(y_stage(m, y, r));
+                    h[j] = (stage > RFC(PB_R_SHP_DEPTH, r)) ? RFC(PB_R_ZBED, r) + stage : RFC(PB_R_ZMAX, r);
+                }
             }
         }
-        const double dx = dh_by_dl(ny, nx, h);
-        const double dy = dh_by_dl(nx, ny, h);
-        sf = sqrt(dx * dx + dy * dy);
+        const double dx = dh_by_dl_a<FAST>(A, ny, nx, h);
+        const double dy = dh_by_dl_a<FAST>(A, nx, ny, h);
+        sf = A.sqrtp(dx * dx + dy * dy);
     }
+    if (FAST && !A.ok) return false;
     m.dnb[i] = make_double4(surfh, effkh, sf, gw);
+    return true;
 #undef EC
+}
+
+template <int DUMMY>
+__device__ __noinline__ void elem_pre_exact(const DevMesh *gm, const double *__restrict__ y, int i,
+                                            const double *st, unsigned bar)
+{
+    const DevMesh &m = *gm;
+    elem_pre<false>(m, y, i, st, bar);
+    if (m.slow_count) atomicAdd(m.slow_count, 1ULL);
 }
 
 // ---------------------------------------------------------------------------
@@ -594,7 +644,7 @@ __device__ __forceinline__ void vg_kr_psi_a(Arith<FAST> &A, double satn, double 
     const double Bv = A.powp(1.0 - Av, m2);
     const double Dv = A.powp(Cv - 1.0, m3);
     const double a = 1.0 - Bv;
-    kr = sqrt(satn) * a * a;
+    kr = A.sqrtp(satn) * a * a;
     psi = A.div(-Dv, alpha);
 }
 
@@ -683,7 +733,7 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
             }
             const double avg_rough = 0.5 * (rough + sn[j].z);
             avgh_s[j] = avgh;
-            den[j] = sqrt(avg_sf) * avg_rough;
+            den[j] = A.sqrtp(avg_sf) * avg_rough;
             num[j] = avgh * edge;                     // crossa; crossa * p * grad left to right (lat_flow.c:270)
             ovl_infil[j] = grad_h;                    // parked: grad_h of the overland flux
         }
@@ -1013,7 +1063,10 @@ k_pre(const DevMesh m, const double *__restrict__ y, int elem_blocks)
         }
         __syncwarp();
         const int i = tile * PB_TILE + lane;
-        if (i < m.ne) elem_pre(m, y, i, &s_tile[warp][lane], bar);
+        if (i < m.ne) {
+            if (!elem_pre<true>(m, y, i, &s_tile[warp][lane], bar))
+                elem_pre_exact<0>(m.self, y, i, &s_tile[warp][lane], bar);
+        }
     } else {
         const int r = (blockIdx.x - elem_blocks) * PB_RHS_THREADS + threadIdx.x;
         if (r < m.nr) river_fluxes(m, y, r);
@@ -1102,6 +1155,10 @@ static __global__ void k_test_div(int n, const double *__restrict__ a, const dou
     ok[i] = ok1 ? 1.0 : 0.0;
     ref[i] = a[i] / b[i];
     if (A.ok && bp > 0.0 && (q2 != a[i] / bp || q3 != a[n - 1 - i] / bp) && q2 == q2 && q3 == q3) ok[i] = -1.0;
+    Arith<true> S;
+    const double sq = S.sqrtp(bp);
+    if (S.ok && sq != sqrt(bp)) ok[i] = -2.0;
+    if (!S.ok && bp >= 1e-290 && bp < 1e300) ok[i] = -3.0;
 }
 
 #undef TSC

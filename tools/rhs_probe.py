@@ -23,4 +23,4 @@ for _ in range(n):
     m.ode_dev(0.0, yv, yd)
 m.synchronize()
 print("rhs us/eval %.1f" % ((time.perf_counter() - t0) / n * 1e6), os.environ.get("PIHM_B200_LIB", "default"))
-print("rhs_probe ok", size, fbr, np.isfinite(yd.download()).all())
+print("rhs_probe ok", size, fbr, np.isfinite(yd.download()).all(), "exact-path elements:", m.slow_path_count(), "of", (n + 3) * tb["nelem"] * 2)
