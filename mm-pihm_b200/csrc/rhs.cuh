@@ -517,7 +517,7 @@ __device__ __forceinline__ void river_fluxes(const DevMesh &m, const double *__r
 // element part of k_pre: SurfH (hydrol.c:10-14), EffKh of the own column, and
 // FrictSlope (lat_flow.c:118-173) reduced to |grad h| = sqrt(dhbydx^2+dhbydy^2),
 // the only form LateralFlow uses it in (lat_flow.c:33-36).  The results go into
-// the 32-byte "dynamic neighbour record" {surfh, effkh, |grad h|, gw} that
+// the 32-byte "dynamic neighbour record" {surfh, effkh, |grad h|, (surfh-D)^(2/3)} that
 // k_main gathers with one sector per neighbour.
 // ---------------------------------------------------------------------------
 // SurfH / EffKh / DhByDl through Arith<FAST>: with FAST the whole of elem_pre is one
@@ -606,8 +606,13 @@ __device__ __forceinline__ bool elem_pre(const DevMesh &m, const double *__restr
         const double dy = dh_by_dl_a<FAST>(A, nx, ny, h);
         sf = A.sqrtp(dx * dx + dy * dy);
     }
+    // pow(avg_h, 0.6666667) of OverLandFlow (lat_flow.c:270): AvgHsurf (lat_flow.c:175-203)
+    // returns the depth above DEPRSTG of the UPWIND element, so the power is a
+    // per-element quantity -- evaluated once here instead of once per edge side
+    const double hd = (surfh > PB_DEPRSTG) ? 1.0 * (surfh - PB_DEPRSTG) : 0.0;
+    const double p23 = A.powp(hd, 0.6666667);
     if (FAST && !A.ok) return false;
-    m.dnb[i] = make_double4(surfh, effkh, sf, gw);
+    m.dnb[i] = make_double4(surfh, effkh, sf, p23);
     return true;
 #undef EC
 }
@@ -667,17 +672,19 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
         code[j] = m.nb[(size_t)j * m.nes + i];
         nn[j] = (code[j] >= 0) ? code[j] : i;
     }
-    double4 dn[3], sn[3];     // {surfh, effkh, sf, gw} and {zmin, zmax, rough, zbed} of the neighbours
+    double4 dn[3], sn[3];     // {surfh, effkh, sf, p23} and {zmin, zmax, rough, zbed} of the neighbours
+    double gwn[3];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
         dn[j] = m.dnb[nn[j]];
         sn[j] = m.snb[nn[j]];
+        gwn[j] = max0(y_gw(m, y, nn[j]));
     }
     const double4 own = m.dnb[i];
     // ode.c:25-49
     const double unsat = max0(y[m.o_unsat + i]);
+    const double gw = max0(y[m.o_gw + i]);
     mbar_wait(bar, 0);          // static + forcing slabs have landed
-    const double gw = own.w;
     const double surfh = own.x;
     const double effkh = own.y;
     const double area = EC(TS_AREA);
@@ -705,13 +712,13 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
     double ovl[3], sub[3], ovl_infil[3];
     const double sf_i = own.z;
     {
-        double num[3], den[3], avgh_s[3];
+        double num[3], den[3], p[3];
 #pragma unroll
         for (int j = 0; j < 3; j++) {
             const double edge = EC(TS_EDGE0 + j);
             const double dist = (code[j] >= 0) ? EC(TS_NABRDIST0 + j) : 1.0;
             const double r_dist = A.rcp(dist);
-            const double gw_n = dn[j].w, surfh_n = dn[j].x;
+            const double gw_n = gwn[j], surfh_n = dn[j].x;
             const double zmin_n = sn[j].x, zmax_n = sn[j].y;
             // SubFlowElemToElem, lat_flow.c:273-298
             double diff_h = (gw + zmin) - (gw_n + zmin_n);
@@ -732,18 +739,12 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
                 avg_sf = (avg_sf > PB_GRADMIN) ? avg_sf : PB_GRADMIN;
             }
             const double avg_rough = 0.5 * (rough + sn[j].z);
-            avgh_s[j] = avgh;
+            p[j] = (diff_h > 0.0) ? own.w : dn[j].w;   // pow(avgh, 0.6666667) of the upwind element (k_pre)
             den[j] = A.sqrtp(avg_sf) * avg_rough;
             num[j] = avgh * edge;                     // crossa; crossa * p * grad left to right (lat_flow.c:270)
             ovl_infil[j] = grad_h;                    // parked: grad_h of the overland flux
         }
-        // OverLandFlow, lat_flow.c:267-271: pow(0, 0.6666667) == 0 exactly, so a warp whose
-        // edges are all dry skips the three pows (bitwise the same products)
-        double p[3] = {0.0, 0.0, 0.0};
-        if (__any_sync(__activemask(), (avgh_s[0] != 0.0) | (avgh_s[1] != 0.0) | (avgh_s[2] != 0.0))) {
-#pragma unroll
-            for (int j = 0; j < 3; j++) p[j] = A.powp(avgh_s[j], 0.6666667);
-        }
+        // OverLandFlow, lat_flow.c:267-271
 #pragma unroll
         for (int j = 0; j < 3; j++) {
             ovl[j] = A.div(num[j] * p[j] * ovl_infil[j], den[j]);
@@ -1040,7 +1041,7 @@ __device__ __forceinline__ void river_main(const DevMesh &m, double *__restrict_
 #define PB_PRE_MINB 8      // <= 64 registers: the element part fits, the (tiny) river part may spill
 #endif
 #ifndef PB_MAIN_MINB
-#define PB_MAIN_MINB 5
+#define PB_MAIN_MINB 6
 #endif
 
 // Grid = element blocks (one warp per 32-element tile) followed by river blocks.
@@ -1083,7 +1084,13 @@ k_main(const DevMesh m, const double *__restrict__ y, double *__restrict__ dy, i
     __shared__ __align__(8) unsigned long long s_bar[PB_RHS_WARPS];
     if ((int)blockIdx.x < elem_blocks) {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        // last tiles first: k_pre ran in ascending order, so its most recent tiles (static
+        // columns shared by both kernels, neighbour records, y) are still in the L2
+#ifndef PB_MAIN_FORWARD
+        const int tile = (elem_blocks - 1 - (int)blockIdx.x) * PB_RHS_WARPS + warp;
+#else
         const int tile = blockIdx.x * PB_RHS_WARPS + warp;
+#endif
         if (tile * PB_TILE >= m.nown) return;
         const unsigned bar = smem_u32(&s_bar[warp]);
         if (lane == 0) {
