@@ -71,7 +71,8 @@ struct DevMesh {
     const double *es;    // [ntile][PB_E_NCOL][32] static element columns, warp-tiled
     const double *ft;    // [ntile][4][32]     hot forcing columns (pcpdrp, edir, ett, ws0.surf), warp-tiled
     const double4 *snb;  // [nes] static neighbour record  {zmin, zmax, rough, zbed}
-    double4 *dnb;        // [nes] dynamic neighbour record {surfh, EffKh, |grad h|, gw}, written by k_pre
+    double4 *dnb;        // [nes] dynamic neighbour record {surfh, EffKh, |grad h|, (surfh-D)^(2/3)}, written by k_pre
+    double2 *vg;         // [nes] {KrFunc(beta, satn), Psi(satn)} of the unsaturated zone, written by k_pre
     const int *nb;       // [3][nes]           neighbour codes
     const int *bct;      // [3][nes]           bc_type
     const int *fbct;     // [3][nes]           fbrbc_type
@@ -111,6 +112,10 @@ struct pihm_b200_ctx {
     cudaStream_t s() const { return use_user_stream ? user_stream : stream; }
     int64_t nsv = 0;
     int rhs_launches = 0;              // kernels launched per RHS call
+    int pre_grid = 0, main_grid = 0;   // persistent RHS grids (SMs x resident CTAs)
+    int pre_smem = 0, main_smem = 0;   // dynamic shared memory of the stage rings
+    cudaAccessPolicyWindow l2_window{}; // persisting-L2 window over the neighbour records
+    int l2_on = 0;
     // host copies kept for permutation / validation
     std::vector<int> perm;             // internal element -> reference element
     std::vector<int> iperm;            // reference element -> internal element
@@ -118,6 +123,7 @@ struct pihm_b200_ctx {
     // device allocations
     double *d_es = nullptr, *d_ft = nullptr, *d_forc = nullptr, *d_rf = nullptr, *d_rivbc = nullptr;
     double4 *d_snb = nullptr, *d_dnb = nullptr;
+    double2 *d_vg = nullptr;
     double *d_fbr_dist = nullptr;
     int *d_nb = nullptr, *d_bct = nullptr, *d_fbct = nullptr, *d_ri = nullptr;
     int *d_up_ptr = nullptr, *d_up_idx = nullptr;

@@ -153,7 +153,7 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
             for (int e = 0; e < ne; e++) nabr[(size_t)j * ne + e] = EI(PB_EI_NABR0 + j, e);
         std::vector<int> lr((size_t)2 * nr);
         for (int r = 0; r < nr; r++) { lr[r] = RI(PB_RI_LEFTELE, r); lr[nr + r] = RI(PB_RI_RIGHTELE, r); }
-        patch_order(ne, nr, nabr.data(), lr.data(), PB_RHS_THREADS, ctx->perm.data());
+        patch_order(ne, nr, nabr.data(), lr.data(), PB_PATCH, ctx->perm.data());
     } else {
         std::iota(ctx->perm.begin(), ctx->perm.end(), 0);
     }
@@ -204,6 +204,13 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
             fbct[(size_t)j * nes + i] = EI(PB_EI_FBRBC0 + j, e);
         }
     }
+    // the neighbour codes ride in the tile slab as int32 [3][32] (pseudo-columns TS_NB0/1)
+    for (int t = 0; t < ntile; t++) {
+        int *dst = reinterpret_cast<int *>(&es[((size_t)t * TS_NCOL + TS_NB0) * 32]);
+        for (int j = 0; j < 3; j++)
+            for (int l = 0; l < 32; l++) dst[j * 32 + l] = nb[(size_t)j * nes + (size_t)t * 32 + l];
+        for (int l = 96; l < 128; l++) dst[l] = 0;
+    }
     // ---- river columns --------------------------------------------------------
     std::vector<double> rf((size_t)PB_R_NCOL * nrs, 0.0), fbr_dist(nrs, 0.0);
     std::vector<int> ri((size_t)PB_RI_NCOL * nrs, 0);
@@ -237,7 +244,6 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
 
     int rc = 0;
     rc |= upload(&ctx->d_es, es);
-    rc |= upload(&ctx->d_snb, snb);
     rc |= upload(&ctx->d_nb, nb);
     rc |= upload(&ctx->d_bct, bct);
     rc |= upload(&ctx->d_fbct, fbct);
@@ -255,7 +261,13 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
     zalloc((void **)&ctx->d_forc, sizeof(double) * PB_F_NCOL * nes);
     zalloc((void **)&ctx->d_rivbc, sizeof(double) * nrs);
     zalloc((void **)&ctx->d_ft, sizeof(double) * 4 * nes);
-    zalloc((void **)&ctx->d_dnb, sizeof(double4) * nes);
+    // neighbour records [dnb | snb] in ONE allocation: the L2 access-policy window below covers both
+    zalloc((void **)&ctx->d_dnb, sizeof(double4) * nes * 2);
+    if (rc == 0) {
+        ctx->d_snb = ctx->d_dnb + nes;
+        if (cudaMemcpy(ctx->d_snb, snb.data(), sizeof(double4) * nes, cudaMemcpyHostToDevice) != cudaSuccess) rc = -1;
+    }
+    zalloc((void **)&ctx->d_vg, sizeof(double2) * nes);
     zalloc((void **)&ctx->d_rivflow, sizeof(double) * PIHM_B200_NUM_RIVFLX * nrs);
     zalloc((void **)&ctx->d_stale, sizeof(double) * 2 * nrs);
     zalloc((void **)&ctx->d_nan, sizeof(int) * 4);
@@ -275,7 +287,7 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
         pihm_b200_destroy(ctx);
         return nullptr;
     }
-    dm.es = ctx->d_es; dm.ft = ctx->d_ft; dm.snb = ctx->d_snb; dm.dnb = ctx->d_dnb; dm.nb = ctx->d_nb; dm.bct = ctx->d_bct; dm.fbct = ctx->d_fbct;
+    dm.es = ctx->d_es; dm.ft = ctx->d_ft; dm.snb = ctx->d_snb; dm.dnb = ctx->d_dnb; dm.vg = ctx->d_vg; dm.nb = ctx->d_nb; dm.bct = ctx->d_bct; dm.fbct = ctx->d_fbct;
     dm.forc = ctx->d_forc; dm.rf = ctx->d_rf; dm.ri = ctx->d_ri; dm.rivbc = ctx->d_rivbc;
     dm.fbr_dist = ctx->d_fbr_dist; dm.up_ptr = ctx->d_up_ptr; dm.up_idx = ctx->d_up_idx;
     dm.rivflow = ctx->d_rivflow; dm.s2c_stale = ctx->d_stale;
@@ -289,10 +301,62 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
         pihm_b200_destroy(ctx);
         return nullptr;
     }
-    if (const char *cv = std::getenv("PIHM_B200_CARVEOUT")) {     // tuning knob (percent of L1 given to smem)
-        const int pct = std::atoi(cv);
-        cudaFuncSetAttribute(k_main<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        cudaFuncSetAttribute(k_main<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    // persistent RHS kernels: opt in to the ring's dynamic shared memory, size the grids to
+    // what is resident at once (SMs x CTAs per SM)
+    {
+        cudaDeviceProp prop;
+        cudaGetDeviceProperties(&prop, ctx->device);
+        const int pre_smem = PreCfg::ring_t::smem_bytes();
+        const int main_smem = dm.fbr ? MainCfg<true>::ring_t::smem_bytes() : MainCfg<false>::ring_t::smem_bytes();
+        int bpre = 0, bmain = 0;
+        cudaError_t e = cudaFuncSetAttribute(k_pre, cudaFuncAttributeMaxDynamicSharedMemorySize, pre_smem);
+        if (e == cudaSuccess)
+            e = dm.fbr ? cudaFuncSetAttribute(k_main<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, main_smem)
+                       : cudaFuncSetAttribute(k_main<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, main_smem);
+        if (e == cudaSuccess)
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpre, k_pre, PB_RHS_THREADS, pre_smem);
+        if (e == cudaSuccess)
+            e = dm.fbr ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bmain, k_main<true>, PB_RHS_THREADS, main_smem)
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bmain, k_main<false>, PB_RHS_THREADS, main_smem);
+        if (e != cudaSuccess || bpre < 1 || bmain < 1) {
+            set_error(std::string("pihm_b200_create: RHS kernel configuration failed: ") + cudaGetErrorString(e));
+            pihm_b200_destroy(ctx);
+            return nullptr;
+        }
+        if (const char *ov = std::getenv("PIHM_B200_PRE_CTAS")) bpre = std::max(1, std::min(bpre, std::atoi(ov)));
+        if (const char *ov = std::getenv("PIHM_B200_MAIN_CTAS")) bmain = std::max(1, std::min(bmain, std::atoi(ov)));
+        ctx->pre_grid = prop.multiProcessorCount * bpre;
+        ctx->main_grid = prop.multiProcessorCount * bmain;
+        ctx->pre_smem = pre_smem;
+        ctx->main_smem = main_smem;
+        // B200's 126 MB L2 as a scratchpad: the 64 B / element of neighbour records (written by
+        // k_pre, gathered three times per element by k_main, 64 MB at 1M triangles) are marked
+        // persisting, everything else that passes through the RHS stream keeps normal priority --
+        // the gathers then hit L2 instead of HBM and the records never travel to DRAM and back.
+        const char *pe = std::getenv("PIHM_B200_L2_PERSIST");
+        // Measured (r01, 1M triangles): RHS 127.6 -> 125.2 us, but the integrator's vector kernels lose
+        // the 61 MB set aside (model step 6.98 -> 7.34 ms), so it is opt-in: PIHM_B200_L2_PERSIST=1.
+        if (pe && std::atoi(pe) != 0 && prop.persistingL2CacheMaxSize > 0) {
+            const size_t rec = sizeof(double4) * (size_t)nes * 2;
+            const size_t win = std::min(rec, (size_t)prop.accessPolicyMaxWindowSize);
+            const size_t keep = std::min(win, (size_t)prop.persistingL2CacheMaxSize);
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, keep) == cudaSuccess) {
+                ctx->l2_window.base_ptr = ctx->d_dnb;
+                ctx->l2_window.num_bytes = win;
+                ctx->l2_window.hitRatio = (float)std::min(1.0, (double)keep / (double)win);
+                ctx->l2_window.hitProp = cudaAccessPropertyPersisting;
+                ctx->l2_window.missProp = cudaAccessPropertyStreaming;
+                ctx->l2_on = 1;
+                cudaStreamAttrValue av;
+                av.accessPolicyWindow = ctx->l2_window;
+                cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+            }
+            if (std::getenv("PIHM_B200_VERBOSE"))
+                fprintf(stderr, "pihm_b200: L2 %d MB, persisting max %d MB, window max %d MB -> records %zu MB, keep %zu MB\n",
+                        prop.l2CacheSize >> 20, prop.persistingL2CacheMaxSize >> 20, prop.accessPolicyMaxWindowSize >> 20,
+                        rec >> 20, keep >> 20);
+            cudaGetLastError();
+        }
     }
     ctx->y_tmp = pihm_b200_vec_new(ctx);
     ctx->yd_tmp = pihm_b200_vec_new(ctx);
@@ -305,9 +369,10 @@ void pihm_b200_destroy(pihm_b200_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->l2_on) cudaCtxResetPersistingL2Cache();   // hand the set-aside lines back
     pihm_b200_vec_free(ctx->y_tmp);
     pihm_b200_vec_free(ctx->yd_tmp);
-    void *dev[] = {ctx->d_es, ctx->d_ft, ctx->d_snb, ctx->d_dnb, ctx->d_forc, ctx->d_rf, ctx->d_rivbc, ctx->d_fbr_dist, ctx->d_nb,
+    void *dev[] = {ctx->d_es, ctx->d_ft, ctx->d_dnb, ctx->d_vg, ctx->d_forc, ctx->d_rf, ctx->d_rivbc, ctx->d_fbr_dist, ctx->d_nb,
                    ctx->d_bct, ctx->d_fbct, ctx->d_ri, ctx->d_up_ptr, ctx->d_up_idx,
                    ctx->d_rivflow, ctx->d_stale, ctx->d_xflux, ctx->d_nan, ctx->d_perm,
                    ctx->d_iperm, ctx->d_stage, ctx->d_red, ctx->d_gel, ctx->d_gri, ctx->d_send_e, ctx->d_send_r,
@@ -328,6 +393,12 @@ int pihm_b200_set_stream(pihm_b200_ctx *ctx, void *stream)
     // the context keeps its own stream object alive but launches on the given one
     ctx->user_stream = (cudaStream_t)stream;
     ctx->use_user_stream = 1;
+    if (ctx->l2_on) {
+        cudaStreamAttrValue av;
+        av.accessPolicyWindow = ctx->l2_window;
+        cudaStreamSetAttribute(ctx->user_stream, cudaStreamAttributeAccessPolicyWindow, &av);
+        cudaGetLastError();
+    }
     return 0;
 }
 
@@ -556,13 +627,15 @@ static int launch_rhs(pihm_b200_ctx *ctx, const double *y, double *dy)
         }
         if (pb::comm_halo_exchange(ctx) != 0) return -1;
     }
-    const int eb = (dm.ne + PB_RHS_THREADS - 1) / PB_RHS_THREADS;      // k_pre: owned + ghost elements
-    const int rb = (dm.nr + PB_RHS_THREADS - 1) / PB_RHS_THREADS;
-    const int eb_own = (dm.nown + PB_RHS_THREADS - 1) / PB_RHS_THREADS; // k_main: owned only
-    const int rb_own = (dm.rown + PB_RHS_THREADS - 1) / PB_RHS_THREADS;
-    k_pre<<<eb + rb, PB_RHS_THREADS, 0, ctx->s()>>>(dm, y, eb);
-    if (dm.fbr) k_main<true><<<eb_own + rb_own, PB_RHS_THREADS, 0, ctx->s()>>>(dm, y, dy, eb_own);
-    else k_main<false><<<eb_own + rb_own, PB_RHS_THREADS, 0, ctx->s()>>>(dm, y, dy, eb_own);
+    // work items = 32-entity tiles; k_pre: owned + ghost, k_main: owned only
+    const int te = (dm.ne + PB_TILE - 1) / PB_TILE, tr = (dm.nr + PB_TILE - 1) / PB_TILE;
+    const int te_own = (dm.nown + PB_TILE - 1) / PB_TILE, tr_own = (dm.rown + PB_TILE - 1) / PB_TILE;
+    const auto groups = [](int t) { return (t + PB_RING_GROUP - 1) / PB_RING_GROUP; };
+    const int gpre = std::max(1, std::min(ctx->pre_grid, groups(te) + groups(tr)));
+    const int gmain = std::max(1, std::min(ctx->main_grid, groups(te_own) + groups(tr_own)));
+    k_pre<<<gpre, PB_RHS_THREADS, ctx->pre_smem, ctx->s()>>>(dm, y, te, tr);
+    if (dm.fbr) k_main<true><<<gmain, PB_RHS_THREADS, ctx->main_smem, ctx->s()>>>(dm, y, dy, te_own, tr_own);
+    else k_main<false><<<gmain, PB_RHS_THREADS, ctx->main_smem, ctx->s()>>>(dm, y, dy, te_own, tr_own);
     ctx->launches += 2;
     return 0;
 }

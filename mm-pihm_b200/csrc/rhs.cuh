@@ -23,17 +23,31 @@ namespace pb {
 
 // Static element columns are stored warp-tiled ("AoSoA-32"): tile t = i >> 5
 // holds all columns of its 32 elements contiguously, 256 B per column, in the
-// slot order below.  Each warp owns one tile: lane 0 issues ONE bulk async copy
-// (cp.async.bulk, the TMA engine; SASS UBLKCP) of the contiguous slot range its
-// kernel needs into shared memory and the warp waits on an mbarrier while its
-// neighbour gathers are in flight -- the whole 5-7 KB of per-warp inputs is one
-// memory transaction instead of ~25 dependent LDG waves.
+// slot order below; the three neighbour codes of the tile (int32 [3][32]) ride
+// along as two pseudo-columns.  One warp works on one tile at a time.  Both RHS
+// kernels are persistent: a CTA owns a ring of PB_*_STAGES shared-memory stages,
+// each filled by ONE bulk async copy (cp.async.bulk, the TMA engine; SASS UBLKCP)
+// of the contiguous slot range the kernel needs (+ one for the forcing columns),
+// completion signalled on the stage's mbarrier.  Warps take tiles by ticket; the
+// warp that finishes a tile re-arms its stage with the tile PB_*_STAGES tickets
+// ahead, so (STAGES - WARPS) tile loads per CTA are always in flight while the
+// warps compute -- the loads no longer sit at the head of every warp's
+// dependency chain (ncu r01: both kernels were latency-, not bandwidth-bound).
 #define PB_TILE 32
+// PB_VG_IN_PRE: KrFunc/Psi of the unsaturated zone are evaluated by k_pre (which has
+// issue slots to spare) and handed to k_main through m.vg; otherwise k_main does it.
 enum {   // k_pre reads [TS_PRE0, TS_PRE1), k_main [TS_MAIN0, TS_MAIN1 / TS_FBR1)
     TS_NABRX0 = 0, TS_NABRX1, TS_NABRX2, TS_NABRY0, TS_NABRY1, TS_NABRY2, TS_KMACH, TS_AREAFV, TS_KSATH,
-    TS_ZMAX, TS_DEPTH, TS_DMAC,
-    TS_AREA, TS_ZMIN, TS_EDGE0, TS_EDGE1, TS_EDGE2, TS_NABRDIST0, TS_NABRDIST1, TS_NABRDIST2,
-    TS_DINF, TS_ALPHA, TS_BETA, TS_KINFV, TS_KMACV, TS_AREAFH, TS_KSATV, TS_POROSITY, TS_ROUGH, TS_RZD,
+#ifdef PB_VG_IN_PRE
+    TS_ALPHA, TS_BETA,
+    TS_ZMAX, TS_DEPTH, TS_DMAC, TS_DINF, TS_NB0, TS_NB1,
+    TS_AREA,
+#else
+    TS_ZMAX, TS_DEPTH, TS_DMAC, TS_NB0, TS_NB1,
+    TS_AREA, TS_DINF, TS_ALPHA, TS_BETA,
+#endif
+    TS_ZMIN, TS_EDGE0, TS_EDGE1, TS_EDGE2, TS_NABRDIST0, TS_NABRDIST1, TS_NABRDIST2,
+    TS_KINFV, TS_KMACV, TS_AREAFH, TS_KSATV, TS_POROSITY, TS_ROUGH, TS_RZD,
     TS_ZBED, TS_GDEPTH, TS_GKSATH, TS_GKSATV, TS_GALPHA, TS_GBETA, TS_GPOROSITY,
     TS_NCOL,
     TS_PRE0 = TS_NABRX0, TS_PRE1 = TS_AREA, TS_MAIN0 = TS_ZMAX, TS_MAIN1 = TS_ZBED, TS_FBR1 = TS_NCOL
@@ -552,21 +566,49 @@ __device__ __forceinline__ double dh_by_dl_a(Arith<FAST> &A, const double *l1, c
         (l2[2] * (l1[1] - l1[0]) + l2[1] * (l1[0] - l1[2]) + l2[0] * (l1[2] - l1[1])));
 }
 
+// KrFunc(beta, satn) and Psi(satn, alpha, beta) (vert_flow.c:272-278) of the same
+// element.  The four pow() form two independent pairs, pow(s, m) / pow(1/s, m) and
+// pow(1 - A, (b-1)/b) / pow(C - 1, 1/b); with Arith<true> all of it is one
+// straight-line block and the pairs interleave.  Values are those of kr_func() /
+// psi_func().
+template <bool FAST>
+__device__ __forceinline__ void vg_kr_psi_a(Arith<FAST> &A, double satn, double alpha, double beta,
+                                            double &kr, double &psi)
+{
+    if (!FAST) { vg_kr_psi(satn, alpha, beta, kr, psi); return; }
+    const double rb = A.rcp(beta);
+    const double m1 = A.quo(beta, beta - 1.0);
+    const double m2 = A.div(beta - 1.0, beta, rb);
+    const double m3 = A.div(1.0, beta, rb);
+    const double sp = (satn < PB_SATMIN) ? PB_SATMIN : satn;
+    const double Av = A.powp(satn, m1);
+    const double Cv = A.powp(A.div(1.0, sp), m1);
+    const double Bv = A.powp(1.0 - Av, m2);
+    const double Dv = A.powp(Cv - 1.0, m3);
+    const double a = 1.0 - Bv;
+    kr = A.sqrtp(satn) * a * a;
+    psi = A.div(-Dv, alpha);
+}
+
 // returns false (nothing written) when FAST arithmetic left its domain
 template <bool FAST>
 __device__ __forceinline__ bool elem_pre(const DevMesh &m, const double *__restrict__ y, int i,
-                                         const double *st, unsigned bar)
+                                         const double *st, unsigned bar, unsigned phase)
 {
-    // st: this lane's column 0 of the warp's shared-memory tile slab (slots TS_PRE0..TS_PRE1)
+    // st: this lane's column 0 of the stage's tile slab (slots TS_PRE0..TS_PRE1)
 #define EC(c) st[((c) - TS_PRE0) * PB_TILE]
     Arith<FAST> A;
+    mbar_wait(bar, phase);      // the tile slab has landed (it was requested STAGES tiles ago)
     // neighbour codes first, then every gather unconditionally (non-element
     // edges gather the element itself) so the loads are in flight together
     int code[3], nn[3];
+    {
+        const int *nbs = reinterpret_cast<const int *>(st - (i & 31) + (TS_NB0 - TS_PRE0) * PB_TILE);
 #pragma unroll
-    for (int j = 0; j < 3; j++) {
-        code[j] = m.nb[(size_t)j * m.nes + i];
-        nn[j] = (code[j] >= 0) ? code[j] : i;
+        for (int j = 0; j < 3; j++) {
+            code[j] = nbs[j * PB_TILE + (i & 31)];
+            nn[j] = (code[j] >= 0) ? code[j] : i;
+        }
     }
     double ysn[3], zmaxn[3];
 #pragma unroll
@@ -576,7 +618,6 @@ __device__ __forceinline__ bool elem_pre(const DevMesh &m, const double *__restr
     }
     const double surfh = surf_h_a<FAST>(A, max0(y_surf(m, y, i)));
     const double gw = max0(y_gw(m, y, i));
-    mbar_wait(bar, 0);          // the tile slab has landed
     const double effkh = eff_kh_a<FAST>(A, EC(TS_DEPTH), EC(TS_DMAC), EC(TS_KMACH), EC(TS_AREAFV),
                                         EC(TS_KSATH), gw);
     double sf = 0.0;
@@ -611,66 +652,63 @@ __device__ __forceinline__ bool elem_pre(const DevMesh &m, const double *__restr
     // per-element quantity -- evaluated once here instead of once per edge side
     const double hd = (surfh > PB_DEPRSTG) ? 1.0 * (surfh - PB_DEPRSTG) : 0.0;
     const double p23 = A.powp(hd, 0.6666667);
+    // KrFunc / Psi of the unsaturated zone (Infil vert_flow.c:84-91, Recharge :157-160): they
+    // depend on the element's own state only, and this kernel has FP64 issue slots to spare
+    // while its gathers are in flight.  Ghost elements need none (k_main runs on owned ones).
+#ifdef PB_VG_IN_PRE
+    double kr = 1.0, psi = 0.0;
+    const bool vg_on = (i < m.nown) && !(gw > EC(TS_DEPTH) - EC(TS_DINF));
+    if (__any_sync(__activemask(), vg_on)) {
+        const double unsat = max0(y[m.o_unsat + ((i < m.nown) ? i : 0)]);
+        double satn = A.div(unsat, vg_on ? EC(TS_DEPTH) - gw : 1.0);
+        satn = (satn > 1.0) ? 1.0 : satn;
+        satn = (satn < PB_SATMIN) ? PB_SATMIN : satn;
+        vg_kr_psi_a<FAST>(A, vg_on ? satn : 1.0, EC(TS_ALPHA), EC(TS_BETA), kr, psi);
+    }
+#endif
     if (FAST && !A.ok) return false;
     m.dnb[i] = make_double4(surfh, effkh, sf, p23);
+#ifdef PB_VG_IN_PRE
+    if (i < m.nown) m.vg[i] = make_double2(kr, psi);
+#endif
     return true;
 #undef EC
 }
 
 template <int DUMMY>
 __device__ __noinline__ void elem_pre_exact(const DevMesh *gm, const double *__restrict__ y, int i,
-                                            const double *st, unsigned bar)
+                                            const double *st, unsigned bar, unsigned phase)
 {
     const DevMesh &m = *gm;
-    elem_pre<false>(m, y, i, st, bar);
+    elem_pre<false>(m, y, i, st, bar, phase);
     if (m.slow_count) atomicAdd(m.slow_count, 1ULL);
 }
 
 // ---------------------------------------------------------------------------
 // element part of k_main
 // ---------------------------------------------------------------------------
-// KrFunc(beta, satn) and Psi(satn, alpha, beta) (vert_flow.c:272-278) of the same
-// element.  The four pow() form two independent pairs, pow(s, m) / pow(1/s, m) and
-// pow(1 - A, (b-1)/b) / pow(C - 1, 1/b); with Arith<true> all of it is one
-// straight-line block and the pairs interleave.  Values are those of kr_func() /
-// psi_func().
-template <bool FAST>
-__device__ __forceinline__ void vg_kr_psi_a(Arith<FAST> &A, double satn, double alpha, double beta,
-                                            double &kr, double &psi)
-{
-    if (!FAST) { vg_kr_psi(satn, alpha, beta, kr, psi); return; }
-    const double rb = A.rcp(beta);
-    const double m1 = A.quo(beta, beta - 1.0);
-    const double m2 = A.div(beta - 1.0, beta, rb);
-    const double m3 = A.div(1.0, beta, rb);
-    const double sp = (satn < PB_SATMIN) ? PB_SATMIN : satn;
-    const double Av = A.powp(satn, m1);
-    const double Cv = A.powp(A.div(1.0, sp), m1);
-    const double Bv = A.powp(1.0 - Av, m2);
-    const double Dv = A.powp(Cv - 1.0, m3);
-    const double a = 1.0 - Bv;
-    kr = A.sqrtp(satn) * a * a;
-    psi = A.div(-Dv, alpha);
-}
-
 // FAST: every division / pow goes through Arith<true> (fdiv.cuh) and the
 // function returns false, without having written anything, when one of them
 // left the fast-path domain; the caller then runs the FAST = false version.
 template <bool FBR, bool FAST>
 __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__restrict__ y,
                                           double *__restrict__ dy, int i, const double *st,
-                                          const double *f, unsigned bar)
+                                          const double *f, unsigned bar, unsigned phase)
 {
-    // st / f: this lane's column 0 of the warp's shared-memory slabs (static slots
-    // TS_MAIN0.., hot forcing columns), filled by the bulk copies issued in k_main
+    // st / f: this lane's column 0 of the stage's slabs (static slots TS_MAIN0.., hot
+    // forcing columns), filled by the bulk copies issued STAGES tiles ago in k_main
 #define EC(c) st[((c) - TS_MAIN0) * PB_TILE]
     Arith<FAST> A;
+    mbar_wait(bar, phase);      // static + forcing slabs have landed
     // ---- loads: neighbour codes, then all gathers (unconditional) ---------------
     int code[3], nn[3];
+    {
+        const int *nbs = reinterpret_cast<const int *>(st - (i & 31) + (TS_NB0 - TS_MAIN0) * PB_TILE);
 #pragma unroll
-    for (int j = 0; j < 3; j++) {
-        code[j] = m.nb[(size_t)j * m.nes + i];
-        nn[j] = (code[j] >= 0) ? code[j] : i;
+        for (int j = 0; j < 3; j++) {
+            code[j] = nbs[j * PB_TILE + (i & 31)];
+            nn[j] = (code[j] >= 0) ? code[j] : i;
+        }
     }
     double4 dn[3], sn[3];     // {surfh, effkh, sf, p23} and {zmin, zmax, rough, zbed} of the neighbours
     double gwn[3];
@@ -681,10 +719,12 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
         gwn[j] = max0(y_gw(m, y, nn[j]));
     }
     const double4 own = m.dnb[i];
+#ifdef PB_VG_IN_PRE
+    const double2 vg = m.vg[i];         // {KrFunc, Psi} of the unsaturated zone (k_pre)
+#endif
     // ode.c:25-49
     const double unsat = max0(y[m.o_unsat + i]);
     const double gw = max0(y[m.o_gw + i]);
-    mbar_wait(bar, 0);          // static + forcing slabs have landed
     const double surfh = own.x;
     const double effkh = own.y;
     const double area = EC(TS_AREA);
@@ -788,7 +828,6 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
     // use the same satn / KrFunc / Psi in the unsaturated branch.
     double infil, rechg;
     {
-        const double alpha = EC(TS_ALPHA), beta = EC(TS_BETA);
         const double kinfv = EC(TS_KINFV), kmacv = EC(TS_KMACV);
         const double areafh = EC(TS_AREAFH);
         const bool sat = gw > depth - dinf;
@@ -798,7 +837,12 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
             satn = A.div(unsat, deficit);
             satn = (satn > 1.0) ? 1.0 : satn;
             satn = (satn < PB_SATMIN) ? PB_SATMIN : satn;
-            vg_kr_psi_a<FAST>(A, satn, alpha, beta, satkfunc, psi_u);
+#ifdef PB_VG_IN_PRE
+            satkfunc = vg.x;
+            psi_u = vg.y;
+#else
+            vg_kr_psi_a<FAST>(A, satn, EC(TS_ALPHA), EC(TS_BETA), satkfunc, psi_u);
+#endif
         }
         if (unsat + gw > depth) {
             infil = 0.0;
@@ -997,10 +1041,10 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
 template <bool FBR>
 __device__ __noinline__ void elem_main_exact(const DevMesh *gm, const double *__restrict__ y,
                                              double *__restrict__ dy, int i, const double *st,
-                                             const double *f, unsigned bar)
+                                             const double *f, unsigned bar, unsigned phase)
 {
     const DevMesh &m = *gm;
-    elem_main<FBR, false>(m, y, dy, i, st, f, bar);
+    elem_main<FBR, false>(m, y, dy, i, st, f, bar, phase);
     if (m.slow_count) atomicAdd(m.slow_count, 1ULL);
 }
 
@@ -1033,82 +1077,194 @@ __device__ __forceinline__ void river_main(const DevMesh &m, double *__restrict_
 }
 
 // ---------------------------------------------------------------------------
-// kernels.  Grid = element blocks followed by river blocks.
+// kernels: persistent CTAs, one ring of TMA-filled stages per CTA (see the top of
+// this file).  Tickets q = 0, 1, .. of CTA b map to tile (q / 8 * gridDim.x + b) * 8 + q % 8,
+// i.e. the 8 warps of a CTA work on 8 consecutive tiles (two locality patches) at a time, so
+// most neighbour gathers hit lines another lane of the same CTA has brought into L1.  The
+// river tiles (32 segments per warp; few, slow) come first, padded to a whole group, then
+// the element tiles.
 // ---------------------------------------------------------------------------
-#define PB_RHS_THREADS 128
-#define PB_RHS_WARPS (PB_RHS_THREADS / 32)
+#ifndef PB_RHS_WARPS
+#define PB_RHS_WARPS 10
+#endif
+#define PB_RHS_THREADS (PB_RHS_WARPS * 32)
+#ifndef PB_PRE_STAGES
+#define PB_PRE_STAGES 13
+#endif
+#ifndef PB_MAIN_STAGES
+#define PB_MAIN_STAGES 13
+#endif
+#ifndef PB_MAIN_STAGES_FBR
+#define PB_MAIN_STAGES_FBR 12
+#endif
 #ifndef PB_PRE_MINB
-#define PB_PRE_MINB 8      // <= 64 registers: the element part fits, the (tiny) river part may spill
+#define PB_PRE_MINB 3      // CTAs of 10 warps per SM: 3 -> 64 registers
 #endif
 #ifndef PB_MAIN_MINB
-#define PB_MAIN_MINB 6
+#define PB_MAIN_MINB 2      // 2 CTAs of 10 warps -> 96 registers, no spills
 #endif
+#ifndef PB_MAIN_MINB_FBR
+#define PB_MAIN_MINB_FBR 2
+#endif
+#define PB_PATCH 128       // elements per locality patch of the internal ordering (reorder.h)
 
-// Grid = element blocks (one warp per 32-element tile) followed by river blocks.
+#ifndef PB_RING_GROUP
+#define PB_RING_GROUP 1     // consecutive tiles a CTA takes at a time (1: tile t goes to CTA t mod grid)
+#endif
+template <int STAGES, int STAGE_BYTES> struct Ring {
+    unsigned char *base;
+    unsigned bar0;           // shared-space address of the first mbarrier
+    volatile int *seq;       // per stage: tiles finished on it (= index of the phase it is in)
+    int *ticket;
+    __device__ __forceinline__ Ring(unsigned char *smem)
+        : base(smem), bar0(smem_u32(smem + (size_t)STAGES * STAGE_BYTES)),
+          seq(reinterpret_cast<volatile int *>(smem + (size_t)STAGES * STAGE_BYTES + 8 * STAGES)),
+          ticket(reinterpret_cast<int *>(smem + (size_t)STAGES * STAGE_BYTES + 12 * STAGES)) {}
+    __device__ __forceinline__ void init()
+    {
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < STAGES; s++) { mbar_init(bar0 + 8 * s, 1); seq[s] = 0; }
+            *ticket = 0;
+        }
+        __syncthreads();
+    }
+    // A parity wait cannot tell phase n+1 from phase n-1, so before waiting for the copy of
+    // its tile (phase n of the stage) a warp makes sure the stage has left phase n-1, i.e.
+    // the previous tile on it is finished and the stage has been re-armed or is about to be.
+    __device__ __forceinline__ void acquire(int s, int n) const
+    {
+        while (seq[s] != n) { }
+    }
+    __device__ __forceinline__ void release(int s, int n) { seq[s] = n + 1; }
+    __device__ __forceinline__ int take(int lane)
+    {
+        int q = 0;
+        if (lane == 0) q = atomicAdd(ticket, 1);
+        return __shfl_sync(0xffffffffu, q, 0);
+    }
+    __device__ __forceinline__ unsigned bar(int s) const { return bar0 + 8 * s; }
+    __device__ __forceinline__ unsigned char *stage(int s) const { return base + (size_t)s * STAGE_BYTES; }
+    static constexpr int smem_bytes() { return STAGES * STAGE_BYTES + 12 * STAGES + 16; }
+};
+
+template <bool FBR> struct MainCfg {
+    static constexpr int NC = (FBR ? TS_FBR1 : TS_MAIN1) - TS_MAIN0;
+    static constexpr int SBS = NC * PB_TILE * 8, SBF = 4 * PB_TILE * 8, SB = SBS + SBF;
+    static constexpr int STAGES = FBR ? PB_MAIN_STAGES_FBR : PB_MAIN_STAGES;
+    static constexpr int MINB = FBR ? PB_MAIN_MINB_FBR : PB_MAIN_MINB;
+    typedef Ring<STAGES, SB> ring_t;
+};
+struct PreCfg {
+    static constexpr int NC = TS_PRE1 - TS_PRE0;
+    static constexpr int SB = NC * PB_TILE * 8;
+    typedef Ring<PB_PRE_STAGES, SB> ring_t;
+};
+
 static __global__ void __launch_bounds__(PB_RHS_THREADS, PB_PRE_MINB)
-k_pre(const DevMesh m, const double *__restrict__ y, int elem_blocks)
+k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r)
 {
-    constexpr int NC = TS_PRE1 - TS_PRE0;
-    __shared__ __align__(128) double s_tile[PB_RHS_WARPS][NC * PB_TILE];
-    __shared__ __align__(8) unsigned long long s_bar[PB_RHS_WARPS];
-    if ((int)blockIdx.x < elem_blocks) {
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        const int tile = blockIdx.x * PB_RHS_WARPS + warp;
-        if (tile * PB_TILE >= m.ne) return;
-        const unsigned bar = smem_u32(&s_bar[warp]);
-        if (lane == 0) {
-            mbar_init(bar, 1);
-            mbar_expect_tx(bar, NC * PB_TILE * 8);
-            tma_bulk_g2s(smem_u32(&s_tile[warp][0]), m.es + ((size_t)tile * TS_NCOL + TS_PRE0) * PB_TILE,
-                         NC * PB_TILE * 8, bar);
+    constexpr int SB = PreCfg::SB;
+    extern __shared__ __align__(128) unsigned char smem[];
+    PreCfg::ring_t ring(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = gridDim.x, b = blockIdx.x;
+    const int gr = (ntile_r + PB_RING_GROUP - 1) / PB_RING_GROUP;         // river groups
+    const int qe0 = (gr > b) ? (gr - b + G - 1) / G * PB_RING_GROUP : 0; // first element ticket of this CTA
+    ring.init();
+    auto item = [&](int q) {    // tile index in [river groups | element tiles]
+        return ((long long)(q / PB_RING_GROUP) * G + b) * PB_RING_GROUP + q % PB_RING_GROUP;
+    };
+    // request the tile of element ticket q (no-op past the end)
+    auto request = [&](int q) {
+        const long long tile = item(q) - (long long)gr * PB_RING_GROUP;
+        if (tile < ntile_e) {
+            const int s = (q - qe0) % PB_PRE_STAGES;
+            mbar_expect_tx(ring.bar(s), SB);
+            tma_bulk_g2s(smem_u32(ring.stage(s)), m.es + ((size_t)tile * TS_NCOL + TS_PRE0) * PB_TILE, SB, ring.bar(s));
         }
-        __syncwarp();
-        const int i = tile * PB_TILE + lane;
+    };
+    if (lane == 0)
+        for (int k = warp; k < PB_PRE_STAGES; k += PB_RHS_WARPS) request(qe0 + k);
+    const long long r_end = (long long)gr * PB_RING_GROUP, e_end = r_end + ntile_e;
+    for (;;) {
+        const int q = ring.take(lane);
+        const long long g = item(q);
+        if (g >= e_end) break;
+        if (g < r_end) {
+            const int r = (int)g * PB_TILE + lane;
+            if (r < m.nr) river_fluxes(m, y, r);
+            continue;
+        }
+        const int k = q - qe0, s = k % PB_PRE_STAGES, n = k / PB_PRE_STAGES;
+        const unsigned phase = (unsigned)n & 1u;
+        ring.acquire(s, n);
+        const int i = (int)(g - r_end) * PB_TILE + lane;
+        const double *st = reinterpret_cast<const double *>(ring.stage(s)) + lane;
         if (i < m.ne) {
-            if (!elem_pre<true>(m, y, i, &s_tile[warp][lane], bar))
-                elem_pre_exact<0>(m.self, y, i, &s_tile[warp][lane], bar);
+            if (!elem_pre<true>(m, y, i, st, ring.bar(s), phase))
+                elem_pre_exact<0>(m.self, y, i, st, ring.bar(s), phase);
+        } else {
+            mbar_wait(ring.bar(s), phase);
         }
-    } else {
-        const int r = (blockIdx.x - elem_blocks) * PB_RHS_THREADS + threadIdx.x;
-        if (r < m.nr) river_fluxes(m, y, r);
+        __syncwarp();           // every lane is done with the stage: hand it to the tile STAGES tickets ahead
+        if (lane == 0) { ring.release(s, n); request(q + PB_PRE_STAGES); }
     }
 }
 
 template <bool FBR>
-__global__ void __launch_bounds__(PB_RHS_THREADS, PB_MAIN_MINB)
-k_main(const DevMesh m, const double *__restrict__ y, double *__restrict__ dy, int elem_blocks)
+__global__ void __launch_bounds__(PB_RHS_THREADS, MainCfg<FBR>::MINB)
+k_main(const DevMesh m, const double *__restrict__ y, double *__restrict__ dy, int ntile_e, int ntile_r)
 {
-    constexpr int NC = (FBR ? TS_FBR1 : TS_MAIN1) - TS_MAIN0;
-    __shared__ __align__(128) double s_tile[PB_RHS_WARPS][NC * PB_TILE];
-    __shared__ __align__(128) double s_forc[PB_RHS_WARPS][4 * PB_TILE];
-    __shared__ __align__(8) unsigned long long s_bar[PB_RHS_WARPS];
-    if ((int)blockIdx.x < elem_blocks) {
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        // last tiles first: k_pre ran in ascending order, so its most recent tiles (static
-        // columns shared by both kernels, neighbour records, y) are still in the L2
-#ifndef PB_MAIN_FORWARD
-        const int tile = (elem_blocks - 1 - (int)blockIdx.x) * PB_RHS_WARPS + warp;
-#else
-        const int tile = blockIdx.x * PB_RHS_WARPS + warp;
-#endif
-        if (tile * PB_TILE >= m.nown) return;
-        const unsigned bar = smem_u32(&s_bar[warp]);
-        if (lane == 0) {
-            mbar_init(bar, 1);
-            mbar_expect_tx(bar, (NC + 4) * PB_TILE * 8);
-            tma_bulk_g2s(smem_u32(&s_tile[warp][0]), m.es + ((size_t)tile * TS_NCOL + TS_MAIN0) * PB_TILE,
-                         NC * PB_TILE * 8, bar);
-            tma_bulk_g2s(smem_u32(&s_forc[warp][0]), m.ft + (size_t)tile * 4 * PB_TILE, 4 * PB_TILE * 8, bar);
+    constexpr int SBS = MainCfg<FBR>::SBS, SBF = MainCfg<FBR>::SBF, SB = MainCfg<FBR>::SB;
+    constexpr int STAGES = MainCfg<FBR>::STAGES;
+    extern __shared__ __align__(128) unsigned char smem[];
+    typename MainCfg<FBR>::ring_t ring(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = gridDim.x, b = blockIdx.x;
+    const int gr = (ntile_r + PB_RING_GROUP - 1) / PB_RING_GROUP;
+    const int qe0 = (gr > b) ? (gr - b + G - 1) / G * PB_RING_GROUP : 0;
+    ring.init();
+    auto item = [&](int q) {
+        return ((long long)(q / PB_RING_GROUP) * G + b) * PB_RING_GROUP + q % PB_RING_GROUP;
+    };
+    // element tiles are walked from the last to the first: k_pre ran in ascending order, so
+    // its most recent tiles (columns shared by both kernels, neighbour records, y) are still in L2
+    auto request = [&](int q) {
+        const long long k = item(q) - (long long)gr * PB_RING_GROUP;
+        if (k < ntile_e) {
+            const size_t tile = (size_t)(ntile_e - 1 - k);
+            const int s = (q - qe0) % STAGES;
+            mbar_expect_tx(ring.bar(s), SB);
+            tma_bulk_g2s(smem_u32(ring.stage(s)), m.es + (tile * TS_NCOL + TS_MAIN0) * PB_TILE, SBS, ring.bar(s));
+            tma_bulk_g2s(smem_u32(ring.stage(s) + SBS), m.ft + tile * 4 * PB_TILE, SBF, ring.bar(s));
+        }
+    };
+    if (lane == 0)
+        for (int k = warp; k < STAGES; k += PB_RHS_WARPS) request(qe0 + k);
+    const long long r_end = (long long)gr * PB_RING_GROUP, e_end = r_end + ntile_e;
+    for (;;) {
+        const int q = ring.take(lane);
+        const long long g = item(q);
+        if (g >= e_end) break;
+        if (g < r_end) {
+            const int r = (int)g * PB_TILE + lane;
+            if (r < m.rown) river_main(m, dy, r);
+            continue;
+        }
+        const int k = q - qe0, s = k % STAGES, n = k / STAGES;
+        const unsigned phase = (unsigned)n & 1u;
+        ring.acquire(s, n);
+        const int i = (ntile_e - 1 - (int)(g - r_end)) * PB_TILE + lane;
+        const double *st = reinterpret_cast<const double *>(ring.stage(s)) + lane;
+        const double *f = reinterpret_cast<const double *>(ring.stage(s) + SBS) + lane;
+        if (i < m.nown) {
+            if (!elem_main<FBR, true>(m, y, dy, i, st, f, ring.bar(s), phase))
+                elem_main_exact<FBR>(m.self, y, dy, i, st, f, ring.bar(s), phase);
+        } else {
+            mbar_wait(ring.bar(s), phase);
         }
         __syncwarp();
-        const int i = tile * PB_TILE + lane;
-        if (i < m.nown) {
-            if (!elem_main<FBR, true>(m, y, dy, i, &s_tile[warp][lane], &s_forc[warp][lane], bar))
-                elem_main_exact<FBR>(m.self, y, dy, i, &s_tile[warp][lane], &s_forc[warp][lane], bar);
-        }
-    } else {
-        const int r = (blockIdx.x - elem_blocks) * PB_RHS_THREADS + threadIdx.x;
-        if (r < m.rown) river_main(m, dy, r);
+        if (lane == 0) { ring.release(s, n); request(q + STAGES); }
     }
 }
 
@@ -1161,7 +1317,9 @@ static __global__ void k_test_div(int n, const double *__restrict__ a, const dou
     fast[i] = q;
     ok[i] = ok1 ? 1.0 : 0.0;
     ref[i] = a[i] / b[i];
-    if (A.ok && bp > 0.0 && (q2 != a[i] / bp || q3 != a[n - 1 - i] / bp) && q2 == q2 && q3 == q3) ok[i] = -1.0;
+    const double a2 = a[n - 1 - i];
+    const bool dom = (fabs(a[i]) >= 1e-291 || a[i] == 0.0) && (fabs(a2) >= 1e-291 || a2 == 0.0);   // |a| >= 2^-969
+    if (A.ok && dom && (q2 != a[i] / bp || q3 != a2 / bp) && q2 == q2 && q3 == q3) ok[i] = -1.0;
     Arith<true> S;
     const double sq = S.sqrtp(bp);
     if (S.ok && sq != sqrt(bp)) ok[i] = -2.0;
