@@ -316,8 +316,8 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
         if (e == cudaSuccess)
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpre, k_pre, PB_RHS_THREADS, pre_smem);
         if (e == cudaSuccess)
-            e = dm.fbr ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bmain, k_main<true>, PB_RHS_THREADS, main_smem)
-                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bmain, k_main<false>, PB_RHS_THREADS, main_smem);
+            e = dm.fbr ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bmain, k_main<true>, MainCfg<true>::THREADS, main_smem)
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bmain, k_main<false>, MainCfg<false>::THREADS, main_smem);
         if (e != cudaSuccess || bpre < 1 || bmain < 1) {
             set_error(std::string("pihm_b200_create: RHS kernel configuration failed: ") + cudaGetErrorString(e));
             pihm_b200_destroy(ctx);
@@ -634,8 +634,8 @@ static int launch_rhs(pihm_b200_ctx *ctx, const double *y, double *dy)
     const int gpre = std::max(1, std::min(ctx->pre_grid, groups(te) + groups(tr)));
     const int gmain = std::max(1, std::min(ctx->main_grid, groups(te_own) + groups(tr_own)));
     k_pre<<<gpre, PB_RHS_THREADS, ctx->pre_smem, ctx->s()>>>(dm, y, te, tr);
-    if (dm.fbr) k_main<true><<<gmain, PB_RHS_THREADS, ctx->main_smem, ctx->s()>>>(dm, y, dy, te_own, tr_own);
-    else k_main<false><<<gmain, PB_RHS_THREADS, ctx->main_smem, ctx->s()>>>(dm, y, dy, te_own, tr_own);
+    if (dm.fbr) k_main<true><<<gmain, MainCfg<true>::THREADS, ctx->main_smem, ctx->s()>>>(dm, y, dy, te_own, tr_own);
+    else k_main<false><<<gmain, MainCfg<false>::THREADS, ctx->main_smem, ctx->s()>>>(dm, y, dy, te_own, tr_own);
     ctx->launches += 2;
     return 0;
 }

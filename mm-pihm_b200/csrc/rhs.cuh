@@ -1089,10 +1089,10 @@ __device__ __forceinline__ void river_main(const DevMesh &m, double *__restrict_
 #endif
 #define PB_RHS_THREADS (PB_RHS_WARPS * 32)
 #ifndef PB_PRE_STAGES
-#define PB_PRE_STAGES 13
+#define PB_PRE_STAGES 12
 #endif
 #ifndef PB_MAIN_STAGES
-#define PB_MAIN_STAGES 13
+#define PB_MAIN_STAGES 12
 #endif
 #ifndef PB_MAIN_STAGES_FBR
 #define PB_MAIN_STAGES_FBR 12
@@ -1105,6 +1105,9 @@ __device__ __forceinline__ void river_main(const DevMesh &m, double *__restrict_
 #endif
 #ifndef PB_MAIN_MINB_FBR
 #define PB_MAIN_MINB_FBR 2
+#endif
+#ifndef PB_MAIN_WARPS_FBR
+#define PB_MAIN_WARPS_FBR 8
 #endif
 #define PB_PATCH 128       // elements per locality patch of the internal ordering (reorder.h)
 
@@ -1152,6 +1155,8 @@ template <bool FBR> struct MainCfg {
     static constexpr int SBS = NC * PB_TILE * 8, SBF = 4 * PB_TILE * 8, SB = SBS + SBF;
     static constexpr int STAGES = FBR ? PB_MAIN_STAGES_FBR : PB_MAIN_STAGES;
     static constexpr int MINB = FBR ? PB_MAIN_MINB_FBR : PB_MAIN_MINB;
+    static constexpr int WARPS = FBR ? PB_MAIN_WARPS_FBR : PB_RHS_WARPS;   // fbr: 8 warps x 2 CTAs -> 128 registers
+    static constexpr int THREADS = WARPS * 32;
     typedef Ring<STAGES, SB> ring_t;
 };
 struct PreCfg {
@@ -1212,7 +1217,7 @@ k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r)
 }
 
 template <bool FBR>
-__global__ void __launch_bounds__(PB_RHS_THREADS, MainCfg<FBR>::MINB)
+__global__ void __launch_bounds__(MainCfg<FBR>::THREADS, MainCfg<FBR>::MINB)
 k_main(const DevMesh m, const double *__restrict__ y, double *__restrict__ dy, int ntile_e, int ntile_r)
 {
     constexpr int SBS = MainCfg<FBR>::SBS, SBF = MainCfg<FBR>::SBF, SB = MainCfg<FBR>::SB;
@@ -1240,7 +1245,7 @@ k_main(const DevMesh m, const double *__restrict__ y, double *__restrict__ dy, i
         }
     };
     if (lane == 0)
-        for (int k = warp; k < STAGES; k += PB_RHS_WARPS) request(qe0 + k);
+        for (int k = warp; k < STAGES; k += MainCfg<FBR>::WARPS) request(qe0 + k);
     const long long r_end = (long long)gr * PB_RING_GROUP, e_end = r_end + ntile_e;
     for (;;) {
         const int q = ring.take(lane);
