@@ -1095,7 +1095,7 @@ __device__ __forceinline__ void river_main(const DevMesh &m, double *__restrict_
 #define PB_MAIN_STAGES 12
 #endif
 #ifndef PB_MAIN_STAGES_FBR
-#define PB_MAIN_STAGES_FBR 12
+#define PB_MAIN_STAGES_FBR 10
 #endif
 #ifndef PB_PRE_MINB
 #define PB_PRE_MINB 3      // CTAs of 10 warps per SM: 3 -> 64 registers
