@@ -168,13 +168,18 @@ def run_ours(args):
         model.set_forcing(forcing_at(tb, 0), np.zeros(nr))
         cv.SetCVodeParam(y)
 
+    # forcing tables of every LSM step (15 model steps) the run crosses, generated before any
+    # timed region: the synthetic generator is numpy on the host and not part of the hot path
+    forc_host = {k: forcing_at(tb, k) for k in range(0, Wu + K + 15, 15)}
+    rivbc0 = np.zeros(nr)
+
     def step(k, e2e=False, host_forc=None, host_y=None):
         if e2e:
             # the drop-in driver's per-step traffic: forcing columns in, state out
             for c in (W.F_PCPDRP, W.F_EDIR, W.F_ETT):
                 model.set_forcing_col(c, host_forc[c])
         elif k % 15 == 0:
-            model.set_forcing(forcing_at(tb, k), np.zeros(nr))
+            model.set_forcing(forc_host[k], rivbc0)
         model.Summary(y)
         cv.SolveCVode((k + 1) * STEP, y)
         if e2e:
@@ -209,7 +214,7 @@ def run_ours(args):
     host_y = torch.empty(model.nsv, dtype=torch.float64).pin_memory().numpy()
     forc_tabs = {}
     for k in range(0, Wu + K + 15, 15):
-        t = torch.from_numpy(forcing_at(tb, k)).pin_memory()
+        t = torch.from_numpy(forc_host[k]).pin_memory()
         forc_tabs[k] = t.numpy()
         forc_tabs[("keep", k)] = t
     for k in range(Wu):

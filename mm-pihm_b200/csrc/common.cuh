@@ -72,7 +72,8 @@ struct DevMesh {
     const double *ft;    // [ntile][4][32]     hot forcing columns (pcpdrp, edir, ett, ws0.surf), warp-tiled
     const double4 *snb;  // [nes] static neighbour record  {zmin, zmax, rough, zbed}
     double4 *dnb;        // [nes] dynamic neighbour record {surfh, EffKh, |grad h|, (surfh-D)^(2/3)}, written by k_pre
-    double2 *vg;         // [nes] {KrFunc(beta, satn), Psi(satn)} of the unsaturated zone, written by k_pre
+    const double *cls;   // [nclass][CC_STRIDE] dictionary of the soil / land-cover / geology parameter rows
+    const int *cid;      // [nes] class id of each element (also inside the tile slab)
     const int *nb;       // [3][nes]           neighbour codes
     const int *bct;      // [3][nes]           bc_type
     const int *fbct;     // [3][nes]           fbrbc_type
@@ -123,7 +124,8 @@ struct pihm_b200_ctx {
     // device allocations
     double *d_es = nullptr, *d_ft = nullptr, *d_forc = nullptr, *d_rf = nullptr, *d_rivbc = nullptr;
     double4 *d_snb = nullptr, *d_dnb = nullptr;
-    double2 *d_vg = nullptr;
+    double *d_cls = nullptr;
+    int *d_cid = nullptr, nclass = 0;
     double *d_fbr_dist = nullptr;
     int *d_nb = nullptr, *d_bct = nullptr, *d_fbct = nullptr, *d_ri = nullptr;
     int *d_up_ptr = nullptr, *d_up_idx = nullptr;

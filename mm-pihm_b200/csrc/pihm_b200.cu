@@ -4,6 +4,8 @@
 #include <cmath>
 #include <cstring>
 #include <numeric>
+#include <string>
+#include <unordered_map>
 #include "common.cuh"
 #include "nvec.cuh"
 #include "reorder.h"
@@ -178,8 +180,47 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
     const int ntile = nes / 32;
     std::vector<double> es((size_t)ntile * TS_NCOL * 32, 1.0);
     for (int i = 0; i < ne; i++)
-        for (int c = 0; c < PB_E_NCOL; c++)
-            es[((size_t)(i >> 5) * TS_NCOL + tile_slot_of(c)) * 32 + (i & 31)] = EF(c, perm[i]);
+        for (int c = 0; c < PB_E_NCOL; c++) {
+            const int slot = tile_slot_of(c);
+            if (slot >= 0) es[((size_t)(i >> 5) * TS_NCOL + slot) * 32 + (i & 31)] = EF(c, perm[i]);
+        }
+    // ---- class dictionary of the soil / land-cover / geology columns (rhs.cuh: CC_*) ----------
+    std::vector<int> cid(nes, 0);
+    std::vector<double> cls;
+    {
+        std::vector<int> ccols;
+        for (int c = 0; c < PB_E_NCOL; c++) {
+            const int slot = class_slot_of(c);
+            if (slot >= 0 && (dm.fbr || slot < CC_GALPHA)) ccols.push_back(c);
+        }
+        std::unordered_map<std::string, int> seen;      // key = the row's bit patterns
+        std::string key(ccols.size() * sizeof(double), '\0');
+        for (int i = 0; i < ne; i++) {
+            for (size_t k = 0; k < ccols.size(); k++) {
+                const double v = EF(ccols[k], perm[i]);
+                std::memcpy(&key[k * sizeof(double)], &v, sizeof(double));
+            }
+            auto it = seen.find(key);
+            if (it == seen.end()) {
+                const int id = (int)seen.size();
+                it = seen.emplace(key, id).first;
+                cls.resize((size_t)(id + 1) * CC_STRIDE, 0.0);
+                double *row = &cls[(size_t)id * CC_STRIDE];
+                for (size_t k = 0; k < ccols.size(); k++) row[class_slot_of(ccols[k])] = EF(ccols[k], perm[i]);
+                // van Genuchten exponents, the divisions of soil.c:5-6 / vert_flow.c:276 done once
+                row[CC_M1] = row[CC_BETA] / (row[CC_BETA] - 1.0);
+                row[CC_M2] = (row[CC_BETA] - 1.0) / row[CC_BETA];
+                row[CC_M3] = 1.0 / row[CC_BETA];
+                if (dm.fbr) {
+                    row[CC_GM1] = row[CC_GBETA] / (row[CC_GBETA] - 1.0);
+                    row[CC_GM2] = (row[CC_GBETA] - 1.0) / row[CC_GBETA];
+                    row[CC_GM3] = 1.0 / row[CC_GBETA];
+                }
+            }
+            cid[i] = it->second;
+        }
+        ctx->nclass = (int)seen.size();
+    }
     std::vector<double4> snb(nes, make_double4(0.0, 0.0, 1.0, 0.0));
     for (int i = 0; i < ne; i++)
         snb[i] = make_double4(EF(PB_E_ZMIN, perm[i]), EF(PB_E_ZMAX, perm[i]), EF(PB_E_ROUGH, perm[i]),
@@ -204,12 +245,12 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
             fbct[(size_t)j * nes + i] = EI(PB_EI_FBRBC0 + j, e);
         }
     }
-    // the neighbour codes ride in the tile slab as int32 [3][32] (pseudo-columns TS_NB0/1)
+    // the neighbour codes and the class id ride in the tile slab as int32 [4][32] (pseudo-columns TS_NB0/1)
     for (int t = 0; t < ntile; t++) {
         int *dst = reinterpret_cast<int *>(&es[((size_t)t * TS_NCOL + TS_NB0) * 32]);
         for (int j = 0; j < 3; j++)
             for (int l = 0; l < 32; l++) dst[j * 32 + l] = nb[(size_t)j * nes + (size_t)t * 32 + l];
-        for (int l = 96; l < 128; l++) dst[l] = 0;
+        for (int l = 0; l < 32; l++) dst[96 + l] = cid[(size_t)t * 32 + l];
     }
     // ---- river columns --------------------------------------------------------
     std::vector<double> rf((size_t)PB_R_NCOL * nrs, 0.0), fbr_dist(nrs, 0.0);
@@ -245,6 +286,8 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
     int rc = 0;
     rc |= upload(&ctx->d_es, es);
     rc |= upload(&ctx->d_nb, nb);
+    rc |= upload(&ctx->d_cls, cls);
+    rc |= upload(&ctx->d_cid, cid);
     rc |= upload(&ctx->d_bct, bct);
     rc |= upload(&ctx->d_fbct, fbct);
     rc |= upload(&ctx->d_rf, rf);
@@ -267,7 +310,6 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
         ctx->d_snb = ctx->d_dnb + nes;
         if (cudaMemcpy(ctx->d_snb, snb.data(), sizeof(double4) * nes, cudaMemcpyHostToDevice) != cudaSuccess) rc = -1;
     }
-    zalloc((void **)&ctx->d_vg, sizeof(double2) * nes);
     zalloc((void **)&ctx->d_rivflow, sizeof(double) * PIHM_B200_NUM_RIVFLX * nrs);
     zalloc((void **)&ctx->d_stale, sizeof(double) * 2 * nrs);
     zalloc((void **)&ctx->d_nan, sizeof(int) * 4);
@@ -287,7 +329,7 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
         pihm_b200_destroy(ctx);
         return nullptr;
     }
-    dm.es = ctx->d_es; dm.ft = ctx->d_ft; dm.snb = ctx->d_snb; dm.dnb = ctx->d_dnb; dm.vg = ctx->d_vg; dm.nb = ctx->d_nb; dm.bct = ctx->d_bct; dm.fbct = ctx->d_fbct;
+    dm.es = ctx->d_es; dm.ft = ctx->d_ft; dm.snb = ctx->d_snb; dm.dnb = ctx->d_dnb; dm.cls = ctx->d_cls; dm.cid = ctx->d_cid; dm.nb = ctx->d_nb; dm.bct = ctx->d_bct; dm.fbct = ctx->d_fbct;
     dm.forc = ctx->d_forc; dm.rf = ctx->d_rf; dm.ri = ctx->d_ri; dm.rivbc = ctx->d_rivbc;
     dm.fbr_dist = ctx->d_fbr_dist; dm.up_ptr = ctx->d_up_ptr; dm.up_idx = ctx->d_up_idx;
     dm.rivflow = ctx->d_rivflow; dm.s2c_stale = ctx->d_stale;
@@ -372,7 +414,7 @@ void pihm_b200_destroy(pihm_b200_ctx *ctx)
     if (ctx->l2_on) cudaCtxResetPersistingL2Cache();   // hand the set-aside lines back
     pihm_b200_vec_free(ctx->y_tmp);
     pihm_b200_vec_free(ctx->yd_tmp);
-    void *dev[] = {ctx->d_es, ctx->d_ft, ctx->d_dnb, ctx->d_vg, ctx->d_forc, ctx->d_rf, ctx->d_rivbc, ctx->d_fbr_dist, ctx->d_nb,
+    void *dev[] = {ctx->d_es, ctx->d_ft, ctx->d_dnb, ctx->d_cls, ctx->d_cid, ctx->d_forc, ctx->d_rf, ctx->d_rivbc, ctx->d_fbr_dist, ctx->d_nb,
                    ctx->d_bct, ctx->d_fbct, ctx->d_ri, ctx->d_up_ptr, ctx->d_up_idx,
                    ctx->d_rivflow, ctx->d_stale, ctx->d_xflux, ctx->d_nan, ctx->d_perm,
                    ctx->d_iperm, ctx->d_stage, ctx->d_red, ctx->d_gel, ctx->d_gri, ctx->d_send_e, ctx->d_send_r,

@@ -34,23 +34,29 @@ namespace pb {
 // warps compute -- the loads no longer sit at the head of every warp's
 // dependency chain (ncu r01: both kernels were latency-, not bandwidth-bound).
 #define PB_TILE 32
-// PB_VG_IN_PRE: KrFunc/Psi of the unsaturated zone are evaluated by k_pre (which has
-// issue slots to spare) and handed to k_main through m.vg; otherwise k_main does it.
+// Soil / land-cover / geology parameters are CLASS data in MM-PIHM (soil, lc and geol tables
+// indexed by type; ReadSoil/ReadLc/ReadGeol, calibrated by global multipliers): the create
+// call deduplicates their rows into a dictionary `cls[ncls][CC_STRIDE]` (a few dozen rows, L1
+// resident) and the tiles carry a 4-byte class id per element instead of 12 (fbr: 17) doubles.
+// The dictionary also holds the van Genuchten exponents derived from beta, computed once on
+// the host with the same IEEE divisions.  dmac / dinf stay per element (clipped to the soil
+// depth, init_soil.c:57-59).  A table without repeated rows still works (one class per element).
 enum {   // k_pre reads [TS_PRE0, TS_PRE1), k_main [TS_MAIN0, TS_MAIN1 / TS_FBR1)
-    TS_NABRX0 = 0, TS_NABRX1, TS_NABRX2, TS_NABRY0, TS_NABRY1, TS_NABRY2, TS_KMACH, TS_AREAFV, TS_KSATH,
-#ifdef PB_VG_IN_PRE
-    TS_ALPHA, TS_BETA,
-    TS_ZMAX, TS_DEPTH, TS_DMAC, TS_DINF, TS_NB0, TS_NB1,
-    TS_AREA,
-#else
-    TS_ZMAX, TS_DEPTH, TS_DMAC, TS_NB0, TS_NB1,
-    TS_AREA, TS_DINF, TS_ALPHA, TS_BETA,
-#endif
-    TS_ZMIN, TS_EDGE0, TS_EDGE1, TS_EDGE2, TS_NABRDIST0, TS_NABRDIST1, TS_NABRDIST2,
-    TS_KINFV, TS_KMACV, TS_AREAFH, TS_KSATV, TS_POROSITY, TS_ROUGH, TS_RZD,
-    TS_ZBED, TS_GDEPTH, TS_GKSATH, TS_GKSATV, TS_GALPHA, TS_GBETA, TS_GPOROSITY,
+    TS_NABRX0 = 0, TS_NABRX1, TS_NABRX2, TS_NABRY0, TS_NABRY1, TS_NABRY2,
+    TS_ZMAX, TS_DEPTH, TS_DMAC, TS_NB0, TS_NB1,     // NB0/NB1: int32 [4][32] = 3 neighbour codes + class id
+    TS_AREA, TS_DINF, TS_ZMIN, TS_EDGE0, TS_EDGE1, TS_EDGE2, TS_NABRDIST0, TS_NABRDIST1, TS_NABRDIST2,
+    TS_ZBED, TS_GDEPTH,
     TS_NCOL,
     TS_PRE0 = TS_NABRX0, TS_PRE1 = TS_AREA, TS_MAIN0 = TS_ZMAX, TS_MAIN1 = TS_ZBED, TS_FBR1 = TS_NCOL
+};
+enum {   // dictionary row; pairs are fetched as double2
+    CC_ALPHA = 0, CC_M1, CC_M2, CC_M3,              // m1 = beta/(beta-1), m2 = (beta-1)/beta, m3 = 1/beta
+    CC_KINFV, CC_KMACV, CC_AREAFH, CC_KSATV,
+    CC_POROSITY, CC_ROUGH, CC_RZD, CC_BETA,
+    CC_KMACH, CC_AREAFV, CC_KSATH, CC_PAD,
+    CC_GALPHA, CC_GM1, CC_GM2, CC_GM3,
+    CC_GKSATV, CC_GKSATH, CC_GPOROSITY, CC_GBETA,
+    CC_STRIDE
 };
 // ABI column (include/pihm_b200.h) -> tile slot; used by the host packer
 __host__ __device__ inline int tile_slot_of(int abi_col)
@@ -63,18 +69,28 @@ __host__ __device__ inline int tile_slot_of(int abi_col)
         case PB_E_NABRDIST2: return TS_NABRDIST2;
         case PB_E_NABRX0: return TS_NABRX0; case PB_E_NABRX1: return TS_NABRX1; case PB_E_NABRX2: return TS_NABRX2;
         case PB_E_NABRY0: return TS_NABRY0; case PB_E_NABRY1: return TS_NABRY1; case PB_E_NABRY2: return TS_NABRY2;
-        case PB_E_DEPTH: return TS_DEPTH; case PB_E_KSATH: return TS_KSATH; case PB_E_KSATV: return TS_KSATV;
-        case PB_E_KINFV: return TS_KINFV; case PB_E_DINF: return TS_DINF; case PB_E_ALPHA: return TS_ALPHA;
-        case PB_E_BETA: return TS_BETA; case PB_E_POROSITY: return TS_POROSITY; case PB_E_DMAC: return TS_DMAC;
-        case PB_E_KMACH: return TS_KMACH; case PB_E_KMACV: return TS_KMACV; case PB_E_AREAFV: return TS_AREAFV;
-        case PB_E_AREAFH: return TS_AREAFH; case PB_E_ROUGH: return TS_ROUGH; case PB_E_RZD: return TS_RZD;
-        case PB_E_GDEPTH: return TS_GDEPTH; case PB_E_GKSATH: return TS_GKSATH; case PB_E_GKSATV: return TS_GKSATV;
-        case PB_E_GALPHA: return TS_GALPHA; case PB_E_GBETA: return TS_GBETA; case PB_E_GPOROSITY: return TS_GPOROSITY;
+        case PB_E_DEPTH: return TS_DEPTH; case PB_E_DINF: return TS_DINF; case PB_E_DMAC: return TS_DMAC;
+        case PB_E_GDEPTH: return TS_GDEPTH;
+    }
+    return -1;
+}
+// ABI column -> dictionary slot (-1: per-element column)
+__host__ __device__ inline int class_slot_of(int abi_col)
+{
+    switch (abi_col) {
+        case PB_E_ALPHA: return CC_ALPHA; case PB_E_BETA: return CC_BETA; case PB_E_KINFV: return CC_KINFV;
+        case PB_E_KMACV: return CC_KMACV; case PB_E_AREAFH: return CC_AREAFH; case PB_E_KSATV: return CC_KSATV;
+        case PB_E_POROSITY: return CC_POROSITY; case PB_E_ROUGH: return CC_ROUGH; case PB_E_RZD: return CC_RZD;
+        case PB_E_KMACH: return CC_KMACH; case PB_E_AREAFV: return CC_AREAFV; case PB_E_KSATH: return CC_KSATH;
+        case PB_E_GALPHA: return CC_GALPHA; case PB_E_GBETA: return CC_GBETA; case PB_E_GKSATV: return CC_GKSATV;
+        case PB_E_GKSATH: return CC_GKSATH; case PB_E_GPOROSITY: return CC_GPOROSITY;
     }
     return -1;
 }
 // global-memory access to a tile slot of an arbitrary element (river kernels, fbr gathers)
 #define TSC(slot, i) (m.es[((size_t)((i) >> 5) * TS_NCOL + (slot)) * PB_TILE + ((i) & 31)])
+// dictionary entry c of an arbitrary element (river kernels, fbr gathers)
+#define CLE(c, i) (m.cls[(size_t)m.cid[i] * CC_STRIDE + (c)])
 #define FTC(c, i) (m.ft[((size_t)((i) >> 5) * 4 + (c)) * PB_TILE + ((i) & 31)])
 
 // ---- TMA bulk copy + mbarrier (PTX; no CUTLASS dependency) ---------------------
@@ -97,6 +113,15 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned phase)
 {
     asm volatile("{\n .reg .pred P1;\n LAB_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
                  " @P1 bra DONE;\n bra LAB_WAIT;\n DONE:\n }" ::"r"(bar), "r"(phase) : "memory");
+}
+
+// dictionary fetches pinned at their point of use (asm volatile): the rows are L1-resident, so
+// the ~40 cycles are cheaper than holding a dozen doubles in registers from the top of the kernel
+__device__ __forceinline__ double2 ldg2_here(const double2 *p)
+{
+    double2 v;
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
 }
 
 #define RFC(c, r) (m.rf[(size_t)(c) * m.nrs + (r)])
@@ -213,8 +238,8 @@ __device__ __forceinline__ double eff_kh(double depth, double dmac, double kmach
 
 __device__ __forceinline__ double eff_kh_elem(const DevMesh &m, int e, double gw)
 {
-    return eff_kh(TSC(TS_DEPTH, e), TSC(TS_DMAC, e), TSC(TS_KMACH, e),
-                  TSC(TS_AREAFV, e), TSC(TS_KSATH, e), gw);
+    const double *row = m.cls + (size_t)m.cid[e] * CC_STRIDE;
+    return eff_kh(TSC(TS_DEPTH, e), TSC(TS_DMAC, e), row[CC_KMACH], row[CC_AREAFV], row[CC_KSATH], gw);
 }
 
 // OverLandFlow, src/lat_flow.c:267-271.  pow(0, 0.6666667) == 0 exactly, so the
@@ -238,13 +263,14 @@ __device__ __forceinline__ double kr_func(double beta, double satn)
 // element: the four pow() form two independent pairs, pow(s, m) / pow(1/s, m) and
 // pow(1 - A, (b-1)/b) / pow(C - 1, 1/b), each evaluated as one interleaved
 // straight-line block (pow_pos2).  Values are those of kr_func() / psi_func().
-__device__ __forceinline__ void vg_kr_psi(double satn, double alpha, double beta, double &kr, double &psi)
+// m1 = beta/(beta-1), m2 = (beta-1)/beta, m3 = 1/beta come from the class dictionary.
+__device__ __forceinline__ void vg_kr_psi(double satn, double alpha, double m1, double m2, double m3,
+                                          double &kr, double &psi)
 {
-    const double m1 = beta / (beta - 1.0);
     const double sp = (satn < PB_SATMIN) ? PB_SATMIN : satn;
     double A, C, B, D;
     pow_pos2(satn, m1, 1.0 / sp, m1, A, C);
-    pow_pos2(1.0 - A, (beta - 1.0) / beta, C - 1.0, 1.0 / beta, B, D);
+    pow_pos2(1.0 - A, m2, C - 1.0, m3, B, D);
     const double a = 1.0 - B;
     kr = sqrt(satn) * a * a;
     psi = -D / alpha;
@@ -572,14 +598,10 @@ __device__ __forceinline__ double dh_by_dl_a(Arith<FAST> &A, const double *l1, c
 // straight-line block and the pairs interleave.  Values are those of kr_func() /
 // psi_func().
 template <bool FAST>
-__device__ __forceinline__ void vg_kr_psi_a(Arith<FAST> &A, double satn, double alpha, double beta,
-                                            double &kr, double &psi)
+__device__ __forceinline__ void vg_kr_psi_a(Arith<FAST> &A, double satn, double alpha, double m1, double m2,
+                                            double m3, double &kr, double &psi)
 {
-    if (!FAST) { vg_kr_psi(satn, alpha, beta, kr, psi); return; }
-    const double rb = A.rcp(beta);
-    const double m1 = A.quo(beta, beta - 1.0);
-    const double m2 = A.div(beta - 1.0, beta, rb);
-    const double m3 = A.div(1.0, beta, rb);
+    if (!FAST) { vg_kr_psi(satn, alpha, m1, m2, m3, kr, psi); return; }
     const double sp = (satn < PB_SATMIN) ? PB_SATMIN : satn;
     const double Av = A.powp(satn, m1);
     const double Cv = A.powp(A.div(1.0, sp), m1);
@@ -601,7 +623,7 @@ __device__ __forceinline__ bool elem_pre(const DevMesh &m, const double *__restr
     mbar_wait(bar, phase);      // the tile slab has landed (it was requested STAGES tiles ago)
     // neighbour codes first, then every gather unconditionally (non-element
     // edges gather the element itself) so the loads are in flight together
-    int code[3], nn[3];
+    int code[3], nn[3], cid;
     {
         const int *nbs = reinterpret_cast<const int *>(st - (i & 31) + (TS_NB0 - TS_PRE0) * PB_TILE);
 #pragma unroll
@@ -609,7 +631,11 @@ __device__ __forceinline__ bool elem_pre(const DevMesh &m, const double *__restr
             code[j] = nbs[j * PB_TILE + (i & 31)];
             nn[j] = (code[j] >= 0) ? code[j] : i;
         }
+        cid = nbs[3 * PB_TILE + (i & 31)];
     }
+    const double2 *crow = reinterpret_cast<const double2 *>(m.cls + (size_t)cid * CC_STRIDE);
+    const double2 c_mach = __ldg(crow + CC_KMACH / 2);      // {kmach, areafv}
+    const double c_ksath = __ldg(m.cls + (size_t)cid * CC_STRIDE + CC_KSATH);
     double ysn[3], zmaxn[3];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
@@ -618,8 +644,7 @@ __device__ __forceinline__ bool elem_pre(const DevMesh &m, const double *__restr
     }
     const double surfh = surf_h_a<FAST>(A, max0(y_surf(m, y, i)));
     const double gw = max0(y_gw(m, y, i));
-    const double effkh = eff_kh_a<FAST>(A, EC(TS_DEPTH), EC(TS_DMAC), EC(TS_KMACH), EC(TS_AREAFV),
-                                        EC(TS_KSATH), gw);
+    const double effkh = eff_kh_a<FAST>(A, EC(TS_DEPTH), EC(TS_DMAC), c_mach.x, c_mach.y, c_ksath, gw);
     double sf = 0.0;
     if (m.surf_mode == PB_DIFF_WAVE) {
         const double zmax = EC(TS_ZMAX);
@@ -652,25 +677,8 @@ __device__ __forceinline__ bool elem_pre(const DevMesh &m, const double *__restr
     // per-element quantity -- evaluated once here instead of once per edge side
     const double hd = (surfh > PB_DEPRSTG) ? 1.0 * (surfh - PB_DEPRSTG) : 0.0;
     const double p23 = A.powp(hd, 0.6666667);
-    // KrFunc / Psi of the unsaturated zone (Infil vert_flow.c:84-91, Recharge :157-160): they
-    // depend on the element's own state only, and this kernel has FP64 issue slots to spare
-    // while its gathers are in flight.  Ghost elements need none (k_main runs on owned ones).
-#ifdef PB_VG_IN_PRE
-    double kr = 1.0, psi = 0.0;
-    const bool vg_on = (i < m.nown) && !(gw > EC(TS_DEPTH) - EC(TS_DINF));
-    if (__any_sync(__activemask(), vg_on)) {
-        const double unsat = max0(y[m.o_unsat + ((i < m.nown) ? i : 0)]);
-        double satn = A.div(unsat, vg_on ? EC(TS_DEPTH) - gw : 1.0);
-        satn = (satn > 1.0) ? 1.0 : satn;
-        satn = (satn < PB_SATMIN) ? PB_SATMIN : satn;
-        vg_kr_psi_a<FAST>(A, vg_on ? satn : 1.0, EC(TS_ALPHA), EC(TS_BETA), kr, psi);
-    }
-#endif
     if (FAST && !A.ok) return false;
     m.dnb[i] = make_double4(surfh, effkh, sf, p23);
-#ifdef PB_VG_IN_PRE
-    if (i < m.nown) m.vg[i] = make_double2(kr, psi);
-#endif
     return true;
 #undef EC
 }
@@ -701,7 +709,7 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
     Arith<FAST> A;
     mbar_wait(bar, phase);      // static + forcing slabs have landed
     // ---- loads: neighbour codes, then all gathers (unconditional) ---------------
-    int code[3], nn[3];
+    int code[3], nn[3], cid;
     {
         const int *nbs = reinterpret_cast<const int *>(st - (i & 31) + (TS_NB0 - TS_MAIN0) * PB_TILE);
 #pragma unroll
@@ -709,7 +717,12 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
             code[j] = nbs[j * PB_TILE + (i & 31)];
             nn[j] = (code[j] >= 0) ? code[j] : i;
         }
+        cid = nbs[3 * PB_TILE + (i & 31)];
     }
+    // the element's class row (soil / land cover / geology parameters and derived exponents)
+    const double2 *crow = reinterpret_cast<const double2 *>(m.cls + (size_t)cid * CC_STRIDE);
+    const double2 c_por = __ldg(crow + CC_POROSITY / 2);    // {porosity, rough}
+    const double c_rzd = __ldg(m.cls + (size_t)cid * CC_STRIDE + CC_RZD);
     double4 dn[3], sn[3];     // {surfh, effkh, sf, p23} and {zmin, zmax, rough, zbed} of the neighbours
     double gwn[3];
 #pragma unroll
@@ -719,9 +732,6 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
         gwn[j] = max0(y_gw(m, y, nn[j]));
     }
     const double4 own = m.dnb[i];
-#ifdef PB_VG_IN_PRE
-    const double2 vg = m.vg[i];         // {KrFunc, Psi} of the unsaturated zone (k_pre)
-#endif
     // ode.c:25-49
     const double unsat = max0(y[m.o_unsat + i]);
     const double gw = max0(y[m.o_gw + i]);
@@ -730,7 +740,7 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
     const double area = EC(TS_AREA);
     const double zmin = EC(TS_ZMIN), zmax = EC(TS_ZMAX);
     const double depth = EC(TS_DEPTH), dinf = EC(TS_DINF);
-    const double rough = EC(TS_ROUGH);
+    const double rough = c_por.y;
     const double pcpdrp = f[0 * PB_TILE];
     const double r_area = A.rcp(area);
 
@@ -741,7 +751,7 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
         if (surfh >= PB_DEPRSTG) edir_surf = edir;
         else if (gw > depth - dinf) edir_gw = edir;
         else edir_unsat = edir;
-        if (gw > depth - EC(TS_RZD)) ett_gw = ett;
+        if (gw > depth - c_rzd) ett_gw = ett;
         else ett_unsat = ett;
     }
 
@@ -828,8 +838,10 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
     // use the same satn / KrFunc / Psi in the unsaturated branch.
     double infil, rechg;
     {
-        const double kinfv = EC(TS_KINFV), kmacv = EC(TS_KMACV);
-        const double areafh = EC(TS_AREAFH);
+        const double2 c_kinf = ldg2_here(crow + CC_KINFV / 2);      // {kinfv, kmacv}
+        const double2 c_afh = ldg2_here(crow + CC_AREAFH / 2);      // {areafh, ksatv}
+        const double kinfv = c_kinf.x, kmacv = c_kinf.y;
+        const double areafh = c_afh.x;
         const bool sat = gw > depth - dinf;
         double satn = 1.0, satkfunc = 1.0, psi_u = 0.0, deficit = 0.0;
         if (!sat) {
@@ -837,12 +849,9 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
             satn = A.div(unsat, deficit);
             satn = (satn > 1.0) ? 1.0 : satn;
             satn = (satn < PB_SATMIN) ? PB_SATMIN : satn;
-#ifdef PB_VG_IN_PRE
-            satkfunc = vg.x;
-            psi_u = vg.y;
-#else
-            vg_kr_psi_a<FAST>(A, satn, EC(TS_ALPHA), EC(TS_BETA), satkfunc, psi_u);
-#endif
+            const double2 c_vg0 = ldg2_here(crow + CC_ALPHA / 2);   // {alpha, m1}
+            const double2 c_vg1 = ldg2_here(crow + CC_M2 / 2);      // {m2, m3}
+            vg_kr_psi_a<FAST>(A, satn, c_vg0.x, c_vg0.y, c_vg1.x, c_vg1.y, satkfunc, psi_u);
         }
         if (unsat + gw > depth) {
             infil = 0.0;
@@ -880,7 +889,7 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
             rechg = infil;
         } else {
             // AvgKv (_ARITH_), vert_flow.c:172-209
-            const double ksatv = EC(TS_KSATV), dmac = EC(TS_DMAC);
+            const double ksatv = c_afh.y, dmac = EC(TS_DMAC);
             double k1, k2, k3, d1, d2, d3;
             if (deficit > dmac) {
                 k1 = satkfunc * ksatv; d1 = dmac;
@@ -909,9 +918,12 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
     double fbr_infil = 0.0, fbr_rechg = 0.0, dfu = 0.0, dfg = 0.0, fbrflow[3] = {0.0, 0.0, 0.0};
     if (FBR) {
         const double fu = max0(y[m.o_fu + i]), fg = max0(y[m.o_fg + i]);
-        const double gdepth = EC(TS_GDEPTH), gksatv = EC(TS_GKSATV);
-        const double galpha = EC(TS_GALPHA), gbeta = EC(TS_GBETA);
-        const double zbed = EC(TS_ZBED), gksath = EC(TS_GKSATH);
+        const double2 c_g0 = ldg2_here(crow + CC_GALPHA / 2);   // {galpha, gm1}
+        const double2 c_g1 = ldg2_here(crow + CC_GM2 / 2);      // {gm2, gm3}
+        const double2 c_gk = ldg2_here(crow + CC_GKSATV / 2);   // {gksatv, gksath}
+        const double ksatv_s = ldg2_here(crow + CC_AREAFH / 2).y;   // soil ksatv
+        const double gdepth = EC(TS_GDEPTH), gksatv = c_gk.x;
+        const double zbed = EC(TS_ZBED), gksath = c_gk.y;
         const bool full = fg >= gdepth;
         double deficit = 0.0, satkfunc = 1.0, psi_c = 0.0;
         if (!full) {
@@ -919,18 +931,18 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
             double satn = A.div(fu, deficit);
             satn = (satn > 1.0) ? 1.0 : satn;
             satn = (satn < PB_SATMIN) ? PB_SATMIN : satn;
-            vg_kr_psi_a<FAST>(A, satn, galpha, gbeta, satkfunc, psi_c);
+            vg_kr_psi_a<FAST>(A, satn, c_g0.x, c_g0.y, c_g1.x, c_g1.y, satkfunc, psi_c);
             psi_c = (psi_c > PB_PSIMIN) ? psi_c : PB_PSIMIN;
         }
         // FbrInfil, vert_flow.c:284-330
         if (full) {
-            fbr_infil = -EC(TS_KSATV);
+            fbr_infil = -ksatv_s;
         } else if (fu + fg > gdepth || gw <= 0.0) {
             fbr_infil = 0.0;
         } else {
             double h_u = psi_c + zmin - 0.5 * deficit;
             double dh_by_dz = A.quo(zmin + gw - h_u, 0.5 * (gw + deficit));
-            double kavg = A.quo(gw + deficit, A.quo(gw, EC(TS_KSATV)) + A.quo(deficit, gksatv * satkfunc));
+            double kavg = A.quo(gw + deficit, A.quo(gw, ksatv_s) + A.quo(deficit, gksatv * satkfunc));
             fbr_infil = kavg * dh_by_dz;
         }
         // FbrRecharge, vert_flow.c:332-373
@@ -978,7 +990,7 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
                 double diff_h = (fg + zbed) - (fg_n + m.snb[n].w);
                 double avgh = avg_h(diff_h, fg, fg_n);
                 double grad_h = A.div(diff_h, dist);
-                double avg_ksat = 0.5 * (gksath + TSC(TS_GKSATH, n));
+                double avg_ksat = 0.5 * (gksath + CLE(CC_GKSATH, n));
                 fbrflow[j] = avg_ksat * grad_h * avgh * EC(TS_EDGE0 + j);
             }
         }
@@ -993,12 +1005,12 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
         dgw -= A.div(sub[j], area, r_area);
         if (FBR) dfg -= A.div(fbrflow[j], area, r_area);
     }
-    const double porosity = EC(TS_POROSITY);
+    const double porosity = c_por.x;
     const double r_por = A.rcp(porosity);
     dunsat = A.div(dunsat, porosity, r_por);
     dgw = A.div(dgw, porosity, r_por);
     if (FBR) {
-        const double gporosity = EC(TS_GPOROSITY);
+        const double gporosity = __ldg(m.cls + (size_t)cid * CC_STRIDE + CC_GPOROSITY);
         const double r_gpor = A.rcp(gporosity);
         dfu = A.div(dfu, gporosity, r_gpor);
         dfg = A.div(dfg, gporosity, r_gpor);
