@@ -6,6 +6,7 @@
 // dependency and loads on machines without NCCL.
 #include <dlfcn.h>
 #include <cstring>
+#include <vector>
 #include "common.cuh"
 
 namespace {
@@ -21,6 +22,7 @@ struct Nccl {
     int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
@@ -37,7 +39,7 @@ Nccl &nccl()
     for (const char *nm : names) { n.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (n.h) break; }
     if (!n.h) return n;
 #define PB_SYM(f) *(void **)(&n.f) = dlsym(n.h, "nccl" #f)
-    PB_SYM(GetUniqueId); PB_SYM(CommInitRank); PB_SYM(CommDestroy); PB_SYM(AllReduce);
+    PB_SYM(GetUniqueId); PB_SYM(CommInitRank); PB_SYM(CommDestroy); PB_SYM(AllReduce); PB_SYM(AllGather);
     PB_SYM(Send); PB_SYM(Recv); PB_SYM(GroupStart); PB_SYM(GroupEnd); PB_SYM(GetErrorString);
 #undef PB_SYM
     n.ok = n.GetUniqueId && n.CommInitRank && n.AllReduce && n.Send && n.Recv && n.GroupStart && n.GroupEnd;
@@ -83,6 +85,45 @@ int comm_allreduce(pihm_b200_ctx *ctx, double *dev_ptr, int count, int op)
     Nccl &n = nccl();
     const int nop = (op == 0) ? ncclSum : (op == 1 ? ncclMin : ncclMax);
     return check(n.AllReduce(dev_ptr, dev_ptr, (size_t)count, ncclFloat64, nop, ctx->comm, ctx->s()), "ncclAllReduce");
+}
+
+// Map one small device buffer of every rank into every other rank (CUDA IPC over NVLink peer
+// access): peers[r] = this process's pointer to rank r's buffer, peers[rank] = local.  The
+// integrator's reduction kernels use it to all-reduce their scalars themselves (cvode_kernels.cuh).
+// Collective; returns 0 only if it worked on ALL ranks (the handles travel by ncclAllGather).
+int comm_share_buffer(pihm_b200_ctx *ctx, void *local, void **peers)
+{
+    Nccl &n = nccl();
+    if (ctx->nranks <= 1 || !ctx->comm || !n.AllGather) return -1;
+    const int R = ctx->nranks;
+    cudaIpcMemHandle_t mine;
+    int good = (cudaIpcGetMemHandle(&mine, local) == cudaSuccess) ? 1 : 0;
+    unsigned char *d_h = nullptr;
+    std::vector<cudaIpcMemHandle_t> all(R);
+    if (cudaMalloc((void **)&d_h, sizeof(mine) * (R + 1)) != cudaSuccess) return -1;
+    cudaMemcpyAsync(d_h + sizeof(mine) * R, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->s());
+    int rc = n.AllGather(d_h + sizeof(mine) * R, d_h, sizeof(mine), /*ncclInt8*/ 0, ctx->comm, ctx->s());
+    cudaMemcpyAsync(all.data(), d_h, sizeof(mine) * R, cudaMemcpyDeviceToHost, ctx->s());
+    if (cudaStreamSynchronize(ctx->s()) != cudaSuccess || rc != 0) good = 0;
+    for (int r = 0; r < R && good; r++) {
+        if (r == ctx->rank) { peers[r] = local; continue; }
+        if (cudaIpcOpenMemHandle(&peers[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) good = 0;
+    }
+    cudaGetLastError();
+    // agree: every rank must have every mapping, otherwise nobody uses them
+    double v = (double)good, *d = reinterpret_cast<double *>(d_h);
+    cudaMemcpyAsync(d, &v, sizeof(double), cudaMemcpyHostToDevice, ctx->s());
+    n.AllReduce(d, d, 1, ncclFloat64, ncclMin, ctx->comm, ctx->s());
+    cudaMemcpyAsync(&v, d, sizeof(double), cudaMemcpyDeviceToHost, ctx->s());
+    cudaStreamSynchronize(ctx->s());
+    cudaFree(d_h);
+    return (v > 0.5) ? 0 : -1;
+}
+
+void comm_unshare_buffer(pihm_b200_ctx *ctx, void **peers)
+{
+    for (int r = 0; r < ctx->nranks; r++)
+        if (r != ctx->rank && peers[r]) { cudaIpcCloseMemHandle(peers[r]); peers[r] = nullptr; }
 }
 
 void comm_destroy(pihm_b200_ctx *ctx)

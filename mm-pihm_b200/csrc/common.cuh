@@ -100,6 +100,8 @@ namespace pb {
 int comm_halo_exchange(pihm_b200_ctx *ctx);
 int comm_allreduce(pihm_b200_ctx *ctx, double *dev_ptr, int count, int op /*0 sum, 1 min, 2 max*/);
 void comm_destroy(pihm_b200_ctx *ctx);
+int comm_share_buffer(pihm_b200_ctx *ctx, void *local, void **peers /*[nranks]*/);
+void comm_unshare_buffer(pihm_b200_ctx *ctx, void **peers);
 }  // namespace pb
 
 // opaque handle types of the C ABI

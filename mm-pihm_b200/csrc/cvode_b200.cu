@@ -99,13 +99,27 @@ struct pihm_b200_cvode {
     // Multi-GPU: kernels leave rank-local partial sums in d_sc; red() all-reduces
     // the slots in stream order and sync() then fetches the global values.
     double *h_sc_map = nullptr;          // mapped mirror the kernels write (single GPU: == h_sc)
+    // p2p: the fused reduction kernels all-reduce their scalars themselves over peer memory
+    // (red_exchange, cvode_kernels.cuh) and write the GLOBAL values to the mapped mirror, like
+    // on one GPU; otherwise NCCL does it after the kernel.
+    bool p2p = false;
+    double *d_xbuf = nullptr;            // this rank's exchange buffer
+    double **d_peer = nullptr;           // device array of the ranks' exchange buffers
+    void *h_peer[PB_MAX_RANKS] = {};
     void sync()
     {
-        if (ctx->nranks > 1)
+        if (ctx->nranks > 1 && !p2p)
             cudaMemcpyAsync(h_sc, d_sc, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, ctx->s());
         cudaStreamSynchronize(ctx->s());
     }
-    void red(int slot, int n = 1, int op = 0) { if (ctx->nranks > 1) comm_allreduce(ctx, d_sc + slot, n, op); }
+    void red(int slot, int n = 1, int op = 0) { if (ctx->nranks > 1 && !p2p) comm_allreduce(ctx, d_sc + slot, n, op); }
+    // a plain k_reduce launch (N_Vector kernel, rank-local result): always NCCL
+    void red_nccl(int slot)
+    {
+        if (ctx->nranks <= 1) return;
+        comm_allreduce(ctx, d_sc + slot, 1, 0);
+        if (p2p) cudaMemcpyAsync(h_sc + slot, d_sc + slot, sizeof(double), cudaMemcpyDeviceToHost, ctx->s());
+    }
     // Every reduction kernel gets a ticket; the kernel's finishing thread stores it to the
     // mapped host mirror after its results.  sync_spin() waits for the newest ticket by polling
     // that word (~2 us) instead of cudaStreamSynchronize (~15 us); use it only when the last
@@ -134,7 +148,7 @@ struct pihm_b200_cvode {
     }
     void sync_spin_()
     {
-        if (ctx->nranks > 1) { sync(); return; }
+        if (ctx->nranks > 1 && !p2p) { sync(); return; }
         volatile double *tk = h_sc_map + SC_SEQ;
         const double want = (double)seq_ctr;
         for (long long it = 0; *tk != want; it++) {
@@ -415,7 +429,7 @@ int pihm_b200_cvode::spgmrSolve(bool *b_is_zero)
                     k_reduce<RD_DOT, 0><<<blocks, PB_VEC_THREADS, 0, s()>>>(
                         N, V[i], V[l_plus_1], d_part, d_counter, d_sc + SC_TMP, h_sc_map + SC_TMP);
                     count();
-                    red(SC_TMP);
+                    red_nccl(SC_TMP);
                     sync();
                     const double new_product = h_sc[SC_TMP];
                     temp = 1000.0 * Hes[i][lk];
@@ -1153,7 +1167,24 @@ pihm_b200_cvode *pihm_b200_cvode_create(pihm_b200_ctx *ctx)
             for (cudaEvent_t &ev : cv->prof_ev) cudaEventCreate(&ev);
         }
     }
-    if (ctx->nranks > 1) {
+    cv->rb.peer = nullptr;
+    cv->rb.nranks = ctx->nranks;
+    cv->rb.rank = ctx->rank;
+    if (ctx->nranks > 1 && ctx->nranks <= PB_MAX_RANKS && !(getenv("PIHM_B200_NO_P2P") && atoi(getenv("PIHM_B200_NO_P2P")))) {
+        // exchange buffers of all ranks mapped into each other (collective; all or nobody)
+        bool got = cudaMalloc((void **)&cv->d_xbuf, sizeof(double) * PB_XB_DOUBLES) == cudaSuccess &&
+                   cudaMalloc((void **)&cv->d_peer, sizeof(double *) * PB_MAX_RANKS) == cudaSuccess;
+        if (got) {
+            cudaMemsetAsync(cv->d_xbuf, 0, sizeof(double) * PB_XB_DOUBLES, ctx->s());
+            cudaStreamSynchronize(ctx->s());
+        }
+        if (comm_share_buffer(ctx, got ? (void *)cv->d_xbuf : nullptr, cv->h_peer) == 0 && got) {
+            cudaMemcpy(cv->d_peer, cv->h_peer, sizeof(double *) * PB_MAX_RANKS, cudaMemcpyHostToDevice);
+            cv->rb.peer = cv->d_peer;
+            cv->p2p = true;
+        }
+    }
+    if (ctx->nranks > 1 && !cv->p2p) {
         // kernels keep writing their (rank-local) values to the mapped mirror; the host
         // reads a separate pinned copy that sync() fills after the all-reduces
         double *pinned = nullptr;
@@ -1193,6 +1224,9 @@ void pihm_b200_cvode_destroy(pihm_b200_cvode *cv)
                      cv->tempv, cv->ftemp, cv->V[0], cv->V[1], cv->V[2], cv->V[3], cv->V[4], cv->V[5],
                      cv->vtemp, cv->ytemp, cv->d_part, cv->d_sc};
     for (double *p : all) if (p) cudaFree(p);
+    if (cv->p2p) comm_unshare_buffer(cv->ctx, cv->h_peer);
+    if (cv->d_xbuf) cudaFree(cv->d_xbuf);
+    if (cv->d_peer) cudaFree(cv->d_peer);
     if (cv->d_counter) cudaFree(cv->d_counter);
     if (cv->h_sc_map && cv->h_sc_map != cv->h_sc) cudaFreeHost(cv->h_sc_map);
     if (cv->h_sc) cudaFreeHost(cv->h_sc);

@@ -40,6 +40,7 @@ enum {
     SC_COUNT = 32
 };
 
+#define PB_MAX_RANKS 8
 struct RedBuf {
     double *part;            // [SC_COUNT][max_blocks]
     unsigned int *counter;
@@ -47,7 +48,51 @@ struct RedBuf {
     volatile double *hsc;    // mapped host mirror
     int max_blocks;
     double seq;              // ticket written to hsc[SC_SEQ] after the results
+    // partitioned run: the exchange buffer of every rank, mapped into this one (comm_share_buffer);
+    // null = single GPU, or the scalars are all-reduced by NCCL after the kernel
+    double *const *peer;
+    int nranks, rank;
 };
+// exchange buffer: [parity of the ticket][slot][rank]{value, ticket}
+#define PB_XB_DOUBLES (2 * SC_COUNT * PB_MAX_RANKS * 2)
+__device__ __forceinline__ int xb_index(int par, int slot, int r) { return ((par * SC_COUNT + slot) * PB_MAX_RANKS + r) * 2; }
+
+// All-reduce of the finishing thread's raw sums over the ranks, inside the reduction kernel:
+// the value and then (after a system-scope fence) the kernel's ticket are stored straight into
+// every rank's exchange buffer over NVLink; the thread then waits for the ticket of every rank
+// in its own buffer and combines the values in rank order, so all ranks hold the same bits.
+// Consecutive tickets alternate between two copies of the buffer: a rank can be at most one
+// reduction ahead of the slowest one, so a value is never overwritten before it has been read.
+template <bool MIN_A>
+__device__ __forceinline__ void red_exchange(const RedBuf &rb, double &a, int slotA, double &b, int slotB)
+{
+    const int par = (int)((long long)rb.seq & 1);
+    for (int p = 0; p < rb.nranks; p++) {
+        volatile double *x = rb.peer[p];
+        x[xb_index(par, slotA, rb.rank)] = a;
+        if (slotB >= 0) x[xb_index(par, slotB, rb.rank)] = b;
+    }
+    __threadfence_system();
+    for (int p = 0; p < rb.nranks; p++) {
+        volatile double *x = rb.peer[p];
+        x[xb_index(par, slotA, rb.rank) + 1] = rb.seq;
+    }
+    const volatile double *mine = rb.peer[rb.rank];
+    for (int r = 0; r < rb.nranks; r++) {
+        long long spins = 0;
+        while (mine[xb_index(par, slotA, r) + 1] != rb.seq)
+            if (++spins > (1LL << 31)) break;       // a lost rank must not hang the GPU forever
+    }
+    __threadfence_system();
+    double sa = MIN_A ? __longlong_as_double(0x7ff0000000000000LL) : 0.0, sb = 0.0;
+    for (int r = 0; r < rb.nranks; r++) {
+        const double va = mine[xb_index(par, slotA, r)];
+        sa = MIN_A ? ((va < sa) ? va : sa) : sa + va;
+        if (slotB >= 0) sb += mine[xb_index(par, slotB, r)];
+    }
+    a = sa;
+    b = sb;
+}
 
 template <bool IS_MIN>
 __device__ __forceinline__ double red_block(double v)
@@ -100,6 +145,7 @@ __device__ __forceinline__ void red_finish(const RedBuf &rb, double a, int slotA
     sa = red_block<MIN_A>(sa);
     if (slotB >= 0) sb = red_block<false>(sb);
     if (threadIdx.x == 0) {
+        if (rb.peer) red_exchange<MIN_A>(rb, sa, slotA, sb, slotB);
         rb.sc[slotA] = sa;
         rb.hsc[slotA] = sa;
         if (slotB >= 0) { rb.sc[slotB] = sb; rb.hsc[slotB] = sb; }
