@@ -5,6 +5,7 @@
 // process uses torch.distributed), so the library itself has no link-time
 // dependency and loads on machines without NCCL.
 #include <dlfcn.h>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "common.cuh"
@@ -126,8 +127,86 @@ void comm_unshare_buffer(pihm_b200_ctx *ctx, void **peers)
         if (r != ctx->rank && peers[r]) { cudaIpcCloseMemHandle(peers[r]); peers[r] = nullptr; }
 }
 
+// Peer-memory halo exchange: every rank allocates [2 parities][ghost element records | ghost
+// river records] + arrival flags, maps it into all ranks, and learns from each neighbour where
+// its own records go in the neighbour's buffer (one grouped ncclSend/ncclRecv of 3 doubles).
+// Collective over all ranks; on any failure everybody keeps the NCCL send/recv path.
+int comm_setup_halo_p2p(pihm_b200_ctx *ctx)
+{
+    Nccl &n = nccl();
+    if (ctx->nranks <= 1 || ctx->nranks > PB_MAX_RANKS_H || !ctx->comm) return -1;
+    const int nn = (int)ctx->nbr_rank.size();
+    const int gs = ctx->dm.gs;
+    const long long ng = ctx->dm.ne - ctx->dm.nown, nrg = ctx->dm.nr - ctx->dm.rown;
+    const long long stride = ((gs * ng + 2 * nrg + 3) / 4) * 4 + 4;
+    int good = (nn <= PB_MAX_NBR) ? 1 : 0;
+    const size_t bytes = sizeof(double) * (size_t)(2 * stride + 2 * PB_MAX_RANKS_H);
+    if (cudaMalloc((void **)&ctx->d_hx, bytes) != cudaSuccess) { ctx->d_hx = nullptr; good = 0; }
+    else cudaMemset(ctx->d_hx, 0, bytes);
+    if (!ctx->d_hcount && cudaMalloc((void **)&ctx->d_hcount, sizeof(unsigned int)) == cudaSuccess)
+        cudaMemset(ctx->d_hcount, 0, sizeof(unsigned int));
+    if (comm_share_buffer(ctx, ctx->d_hx, ctx->hx_peer) != 0) good = 0;
+    // tell every neighbour where its records land here: {stride, element offset, river offset}
+    double *d_x = nullptr;
+    std::vector<double> mine(3 * (size_t)std::max(nn, 1)), theirs(3 * (size_t)std::max(nn, 1), 0.0);
+    long long roff_e = 0, roff_r = 0;
+    for (int k = 0; k < nn; k++) {
+        mine[3 * k] = (double)stride;
+        mine[3 * k + 1] = (double)(roff_e * gs);
+        mine[3 * k + 2] = (double)(gs * ng + roff_r * 2);
+        roff_e += ctx->recv_e_cnt[k];
+        roff_r += ctx->recv_r_cnt[k];
+    }
+    if (cudaMalloc((void **)&d_x, sizeof(double) * 6 * (size_t)std::max(nn, 1)) != cudaSuccess) return -1;
+    cudaMemcpyAsync(d_x, mine.data(), sizeof(double) * 3 * nn, cudaMemcpyHostToDevice, ctx->s());
+    n.GroupStart();
+    for (int k = 0; k < nn; k++) {
+        n.Send(d_x + 3 * k, 3, ncclFloat64, ctx->nbr_rank[k], ctx->comm, ctx->s());
+        n.Recv(d_x + 3 * nn + 3 * k, 3, ncclFloat64, ctx->nbr_rank[k], ctx->comm, ctx->s());
+    }
+    if (n.GroupEnd() != 0) good = 0;
+    cudaMemcpyAsync(theirs.data(), d_x + 3 * nn, sizeof(double) * 3 * nn, cudaMemcpyDeviceToHost, ctx->s());
+    if (cudaStreamSynchronize(ctx->s()) != cudaSuccess) good = 0;
+    // agree
+    double v = (double)good;
+    cudaMemcpyAsync(d_x, &v, sizeof(double), cudaMemcpyHostToDevice, ctx->s());
+    n.AllReduce(d_x, d_x, 1, ncclFloat64, ncclMin, ctx->comm, ctx->s());
+    cudaMemcpyAsync(&v, d_x, sizeof(double), cudaMemcpyDeviceToHost, ctx->s());
+    cudaStreamSynchronize(ctx->s());
+    cudaFree(d_x);
+    cudaGetLastError();
+    if (v < 0.5) return -1;
+    HaloPeers &hp = ctx->hpeers;
+    hp.nn = nn;
+    hp.myrank = ctx->rank;
+    for (int k = 0; k < nn; k++) {
+        hp.base[k] = static_cast<double *>(ctx->hx_peer[ctx->nbr_rank[k]]);
+        hp.pstride[k] = (long long)theirs[3 * k];
+        hp.gel_off[k] = (long long)theirs[3 * k + 1];
+        hp.gri_off[k] = (long long)theirs[3 * k + 2];
+        hp.flag_off[k] = 2 * hp.pstride[k];
+    }
+    for (int k = 0; k <= nn; k++) { hp.e_ptr[k] = ctx->send_e_ptr[k]; hp.r_ptr[k] = ctx->send_r_ptr[k]; }
+    ctx->hx_stride = stride;
+    // device copies of the mesh view whose ghost pointers select a parity (the rare exact paths read them)
+    for (int p = 0; p < 2; p++) {
+        DevMesh dm = ctx->dm;
+        dm.gel = ctx->d_hx + p * stride;
+        dm.gri = ctx->d_hx + p * stride + gs * ng;
+        if (cudaMalloc((void **)&ctx->d_dm_par[p], sizeof(DevMesh)) != cudaSuccess) return -1;
+        dm.self = ctx->d_dm_par[p];
+        cudaMemcpy(ctx->d_dm_par[p], &dm, sizeof(DevMesh), cudaMemcpyHostToDevice);
+    }
+    ctx->halo_p2p = 1;
+    return 0;
+}
+
 void comm_destroy(pihm_b200_ctx *ctx)
 {
+    if (ctx->halo_p2p) { comm_unshare_buffer(ctx, ctx->hx_peer); ctx->halo_p2p = 0; }
+    if (ctx->d_hx) { cudaFree(ctx->d_hx); ctx->d_hx = nullptr; }
+    if (ctx->d_hcount) { cudaFree(ctx->d_hcount); ctx->d_hcount = nullptr; }
+    for (int p = 0; p < 2; p++) if (ctx->d_dm_par[p]) { cudaFree(ctx->d_dm_par[p]); ctx->d_dm_par[p] = nullptr; }
     if (ctx->comm) {
         Nccl &n = nccl();
         if (n.CommDestroy) n.CommDestroy(ctx->comm);
@@ -170,6 +249,8 @@ int pihm_b200_comm_init(pihm_b200_ctx *ctx, int rank, int nranks, const void *id
     PB_CUDA(cudaMemcpyAsync(&v, d, sizeof(double), cudaMemcpyDeviceToHost, ctx->s()));
     PB_CUDA(cudaStreamSynchronize(ctx->s()));
     ctx->nsv_global = (long long)(v + 0.5);
+    // neighbours' ghost buffers over NVLink peer memory (falls back to ncclSend/ncclRecv)
+    if (!(std::getenv("PIHM_B200_NO_P2P") && std::atoi(std::getenv("PIHM_B200_NO_P2P")))) pb::comm_setup_halo_p2p(ctx);
     return 0;
 }
 

@@ -94,6 +94,28 @@ struct DevMesh {
 
 }  // namespace pb
 
+namespace pb {
+// Peer-memory halo exchange (partitioned run): what k_halo_put needs to store this rank's
+// boundary states straight into its neighbours' ghost buffers, and what k_pre waits for.
+#define PB_MAX_NBR 8
+struct HaloPeers {
+    double *base[PB_MAX_NBR];        // neighbour k's halo buffer, mapped into this process
+    long long pstride[PB_MAX_NBR];   // doubles per parity copy of that buffer
+    long long gel_off[PB_MAX_NBR];   // where this rank's element records start in it
+    long long gri_off[PB_MAX_NBR];   // ... river records
+    long long flag_off[PB_MAX_NBR];  // arrival flags [2][PB_MAX_RANKS_H]
+    int e_ptr[PB_MAX_NBR + 1], r_ptr[PB_MAX_NBR + 1];   // send segments per neighbour
+    int nn, myrank;
+};
+struct HaloWait {
+    const volatile double *flags;    // this rank's arrival flags of the current parity
+    int nn;
+    int rank[PB_MAX_NBR];
+    double seq;
+};
+#define PB_MAX_RANKS_H 8
+}  // namespace pb
+
 struct pihm_b200_ctx;
 namespace pb {
 // comm.cu: NCCL (dlopen'ed) halo exchange and scalar all-reduce
@@ -102,6 +124,7 @@ int comm_allreduce(pihm_b200_ctx *ctx, double *dev_ptr, int count, int op /*0 su
 void comm_destroy(pihm_b200_ctx *ctx);
 int comm_share_buffer(pihm_b200_ctx *ctx, void *local, void **peers /*[nranks]*/);
 void comm_unshare_buffer(pihm_b200_ctx *ctx, void **peers);
+int comm_setup_halo_p2p(pihm_b200_ctx *ctx);
 }  // namespace pb
 
 // opaque handle types of the C ABI
@@ -141,6 +164,15 @@ struct pihm_b200_ctx {
     int *d_send_e_idx = nullptr, *d_send_r_idx = nullptr;
     std::vector<int> nbr_rank, send_e_ptr, recv_e_cnt, send_r_ptr, recv_r_cnt;
     int nse = 0, nsr = 0;
+    // peer-memory halo exchange (comm.cu: comm_setup_halo_p2p)
+    int halo_p2p = 0;
+    double *d_hx = nullptr;            // [2][gel | gri] + flags, mapped into the neighbours
+    long long hx_stride = 0;           // doubles per parity copy
+    void *hx_peer[8] = {};             // all ranks' buffers mapped here (PB_MAX_RANKS_H)
+    pb::HaloPeers hpeers{};
+    pb::DevMesh *d_dm_par[2] = {nullptr, nullptr};   // device copies of dm with the parity's ghost pointers
+    unsigned int *d_hcount = nullptr;
+    long long halo_seq = 0;
     void *comm = nullptr;              // ncclComm_t
     int rank = 0, nranks = 1;
     long long nsv_global = 0;

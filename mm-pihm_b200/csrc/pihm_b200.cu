@@ -650,6 +650,14 @@ int pihm_b200_set_flux_recording(pihm_b200_ctx *ctx, int on)
     ctx->dm.xflux = ctx->d_xflux;
     ctx->dm.record = on ? 1 : 0;
     PB_CUDA(cudaMemcpy(ctx->d_dm, &ctx->dm, sizeof(DevMesh), cudaMemcpyHostToDevice));
+    for (int p = 0; p < 2; p++) {       // the parity views of a peer-memory halo exchange
+        if (!ctx->d_dm_par[p]) continue;
+        DevMesh dm = ctx->dm;
+        dm.gel = ctx->d_hx + p * ctx->hx_stride;
+        dm.gri = dm.gel + (size_t)dm.gs * (dm.ne - dm.nown);
+        dm.self = ctx->d_dm_par[p];
+        PB_CUDA(cudaMemcpy(ctx->d_dm_par[p], &dm, sizeof(DevMesh), cudaMemcpyHostToDevice));
+    }
     return 0;
 }
 
@@ -658,8 +666,27 @@ int pihm_b200_set_flux_recording(pihm_b200_ctx *ctx, int on)
 // ---------------------------------------------------------------------------
 static int launch_rhs(pihm_b200_ctx *ctx, const double *y, double *dy)
 {
-    const DevMesh &dm = ctx->dm;
-    if (ctx->nranks > 1) {
+    DevMesh dm = ctx->dm;
+    HaloWait hw{};
+    if (ctx->nranks > 1 && ctx->halo_p2p) {
+        // halo exchange over peer memory: stores into the neighbours' ghost buffers + arrival flags
+        const long long seq = ++ctx->halo_seq;
+        const int par = (int)(seq & 1);
+        const int n = ctx->nse + ctx->nsr;
+        if (ctx->hpeers.nn > 0) {
+            k_halo_put<<<std::max(1, (n + 255) / 256), 256, 0, ctx->s()>>>(dm, y, ctx->nse, ctx->d_send_e_idx, ctx->nsr,
+                                                                            ctx->d_send_r_idx, ctx->hpeers, par,
+                                                                            (double)seq, ctx->d_hcount);
+            ctx->launches++;
+        }
+        dm.gel = ctx->d_hx + par * ctx->hx_stride;
+        dm.gri = dm.gel + (size_t)dm.gs * (dm.ne - dm.nown);
+        dm.self = ctx->d_dm_par[par];
+        hw.flags = ctx->d_hx + 2 * ctx->hx_stride + par * PB_MAX_RANKS_H;
+        hw.nn = ctx->hpeers.nn;
+        for (int k = 0; k < hw.nn; k++) hw.rank[k] = ctx->nbr_rank[k];
+        hw.seq = (double)seq;
+    } else if (ctx->nranks > 1) {
         // one-ring(+) halo exchange of neighbour and river states before the RHS
         const int n = ctx->nse + ctx->nsr;
         if (n > 0) {
@@ -675,7 +702,7 @@ static int launch_rhs(pihm_b200_ctx *ctx, const double *y, double *dy)
     const auto groups = [](int t) { return (t + PB_RING_GROUP - 1) / PB_RING_GROUP; };
     const int gpre = std::max(1, std::min(ctx->pre_grid, groups(te) + groups(tr)));
     const int gmain = std::max(1, std::min(ctx->main_grid, groups(te_own) + groups(tr_own)));
-    k_pre<<<gpre, PB_RHS_THREADS, ctx->pre_smem, ctx->s()>>>(dm, y, te, tr);
+    k_pre<<<gpre, PB_RHS_THREADS, ctx->pre_smem, ctx->s()>>>(dm, y, te, tr, hw);
     if (dm.fbr) k_main<true><<<gmain, MainCfg<true>::THREADS, ctx->main_smem, ctx->s()>>>(dm, y, dy, te_own, tr_own);
     else k_main<false><<<gmain, MainCfg<false>::THREADS, ctx->main_smem, ctx->s()>>>(dm, y, dy, te_own, tr_own);
     ctx->launches += 2;

@@ -1178,9 +1178,18 @@ struct PreCfg {
 };
 
 static __global__ void __launch_bounds__(PB_RHS_THREADS, PB_PRE_MINB)
-k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r)
+k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r, const HaloWait hw)
 {
     constexpr int SB = PreCfg::SB;
+    if (hw.nn > 0) {        // partitioned run: the neighbours' halo records of this RHS have arrived
+        if ((int)threadIdx.x < hw.nn) {
+            long long spins = 0;
+            while (hw.flags[hw.rank[threadIdx.x]] != hw.seq)
+                if (++spins > (1LL << 31)) break;
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
     extern __shared__ __align__(128) unsigned char smem[];
     PreCfg::ring_t ring(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1301,6 +1310,48 @@ k_halo_pack(const DevMesh m, const double *__restrict__ y, int nse, const int *_
         const int r = send_r[k - nse];
         buf_r[(size_t)(k - nse) * 2] = y[m.o_stg + r];
         buf_r[(size_t)(k - nse) * 2 + 1] = y[m.o_rgw + r];
+    }
+}
+
+// Halo exchange over peer memory: the records go straight into the neighbours' ghost buffers
+// (NVLink stores), then the last block to finish raises this rank's arrival flag in each of
+// them.  k_pre of the neighbour waits for the flags of its neighbours (HaloWait).  Two parity
+// copies of the ghost buffers alternate per RHS: a neighbour can start the exchange of RHS n+2
+// only after this rank has sent n+1, i.e. after it has finished reading the copy of RHS n.
+static __global__ void __launch_bounds__(256)
+k_halo_put(const DevMesh m, const double *__restrict__ y, int nse, const int *__restrict__ send_e,
+           int nsr, const int *__restrict__ send_r, const HaloPeers hp, int par, double seq,
+           unsigned int *counter)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nse) {
+        int kk = 0;
+        while (kk + 1 < hp.nn && k >= hp.e_ptr[kk + 1]) kk++;
+        const int i = send_e[k];
+        double *dst = hp.base[kk] + par * hp.pstride[kk] + hp.gel_off[kk] + (size_t)(k - hp.e_ptr[kk]) * m.gs;
+        dst[0] = y[i];
+        dst[1] = y[m.o_gw + i];
+        if (m.gs == 3) dst[2] = y[m.o_fg + i];
+    } else if (k < nse + nsr) {
+        const int kr = k - nse;
+        int kk = 0;
+        while (kk + 1 < hp.nn && kr >= hp.r_ptr[kk + 1]) kk++;
+        const int r = send_r[kr];
+        double *dst = hp.base[kk] + par * hp.pstride[kk] + hp.gri_off[kk] + (size_t)(kr - hp.r_ptr[kk]) * 2;
+        dst[0] = y[m.o_stg + r];
+        dst[1] = y[m.o_rgw + r];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(counter, 1u) == gridDim.x - 1) {
+            *counter = 0u;
+            __threadfence_system();
+            for (int kk = 0; kk < hp.nn; kk++) {
+                volatile double *f = hp.base[kk] + hp.flag_off[kk] + par * PB_MAX_RANKS_H + hp.myrank;
+                *f = seq;
+            }
+        }
     }
 }
 
