@@ -260,8 +260,9 @@ def run_ours(args):
         "config": {"workload": f"pihm{'-fbr' if fbr else ''} synthetic {size}-triangle watershed "
                                f"({ne_glob} elements, {nr_glob} river segments), 60 s model steps in the rain pulse "
                                f"(t0 = 2 h), reltol 1e-3 abstol 1e-4"
-                               + (f"; mesh partitioned over {world} GPUs (1M triangles each), NCCL halo exchange "
-                                  f"per RHS + scalar all-reduce per norm; value = sim-days/s x (triangles / 1M)"
+                               + (f"; mesh partitioned over {world} GPUs (1M triangles each), halo exchange per RHS "
+                                  f"and scalar all-reduce per norm over NVLink peer memory inside our kernels (NCCL: setup, "
+                                  f"fallback); value = sim-days/s x (triangles / 1M)"
                                   if world > 1 else ""),
                    "nelem": ne_glob, "nriver": nr_glob, "nsv": model.nsv_global if world > 1 else model.nsv,
                    "reorder": args.reorder, "parallelism": f"mesh-partition x{world}",
