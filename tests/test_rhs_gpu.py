@@ -116,6 +116,36 @@ def test_rhs_no_river_and_ragged_sizes():
         model.close()
 
 
+@pytest.mark.parametrize("fbr", [False, True])
+@pytest.mark.parametrize("mode", ["unique", "single"])
+def test_rhs_class_dictionary_extremes(fbr, mode):
+    """The soil / land-cover / geology columns travel as a class dictionary (rhs.cuh CC_*).
+    Degenerate tables must give the same answers: every element its own class (nothing
+    repeats), and one class for the whole mesh."""
+    tb = W.make_named("small", fbr=fbr, dirichlet_edges=True)
+    ef = tb["elem_f64"]
+    ne = tb["nelem"]
+    cls_cols = [W.E_KSATH, W.E_KSATV, W.E_KINFV, W.E_ALPHA, W.E_BETA, W.E_POROSITY, W.E_KMACH,
+                W.E_KMACV, W.E_AREAFV, W.E_AREAFH, W.E_ROUGH, W.E_RZD]
+    if fbr:
+        cls_cols += [W.E_GKSATH, W.E_GKSATV, W.E_GALPHA, W.E_GBETA, W.E_GPOROSITY]
+    if mode == "unique":
+        wiggle = 1.0 + 1e-7 * np.arange(ne)
+        for c in (W.E_KSATV, W.E_BETA, W.E_ROUGH):
+            ef[c] = ef[c] * wiggle
+    else:
+        for c in cls_cols:
+            ef[c] = ef[c][0]
+    om = oraclelib.OracleModel(tb)
+    model = lib.Model(tb)
+    y = W.wet_state(tb, seed=21)
+    forc = W.storm_forcing(tb, 3 * 3600.0, ws0_surf=np.maximum(y[:ne], 0))
+    c = _oracle_case(tb, om, y, forc, np.zeros(tb["nriver"]), np.zeros((3, ne)))
+    worst, exact = check_case(model, tb, c, f"dictionary {mode} fbr={fbr}")
+    print(f"dictionary {mode} fbr={fbr}: max rel err {worst:.2e}, bit-exact {exact:.4f}")
+    model.close()
+
+
 def test_rhs_nan_flag():
     """CheckDy: a NaN in dy must raise the device flag (the reference exits,
     ode.c:305-310).  A NaN *state* is clamped to 0 by `y >= 0 ? y : 0` in both
