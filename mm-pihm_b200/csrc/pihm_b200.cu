@@ -29,7 +29,7 @@ static int upload(T **dst, const std::vector<T> &src)
 static int vec_blocks(const pihm_b200_ctx *ctx, long long n)
 {
     long long b = (n + PB_VEC_THREADS - 1) / PB_VEC_THREADS;
-    const long long cap = (long long)ctx->red_blocks;     // SMs x 8 resident CTAs
+    const long long cap = (long long)ctx->red_blocks;     // SMs x 4 resident CTAs
     return (int)std::max<long long>(1, std::min(b, cap));
 }
 template <int OP, int POST>
@@ -320,7 +320,9 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
     zalloc((void **)&ctx->d_gri, sizeof(double) * 2 * (size_t)std::max(nr - nown_riv, 1));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    ctx->red_blocks = sms * 8;
+    ctx->red_blocks = sms * 4;     // one resident wave of the batched vector kernels (<= 64 registers, 4 CTAs / SM)
+    if (const char *ov = std::getenv("PIHM_B200_VEC_CTAS"))      // tuning knob: CTAs per SM of the vector kernels
+        ctx->red_blocks = sms * std::max(1, std::min(16, std::atoi(ov)));
     zalloc((void **)&ctx->d_red, sizeof(double) * (ctx->red_blocks + 64));
     if (cudaHostAlloc((void **)&ctx->h_red, sizeof(double) * 64, cudaHostAllocMapped) != cudaSuccess) rc = -1;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) rc = -1;
