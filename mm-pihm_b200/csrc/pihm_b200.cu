@@ -358,7 +358,7 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
             e = dm.fbr ? cudaFuncSetAttribute(k_main<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, main_smem)
                        : cudaFuncSetAttribute(k_main<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, main_smem);
         if (e == cudaSuccess)
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpre, k_pre, PB_RHS_THREADS, pre_smem);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpre, k_pre, PB_PRE_THREADS, pre_smem);
         if (e == cudaSuccess)
             e = dm.fbr ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bmain, k_main<true>, MainCfg<true>::THREADS, main_smem)
                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bmain, k_main<false>, MainCfg<false>::THREADS, main_smem);
@@ -704,7 +704,7 @@ static int launch_rhs(pihm_b200_ctx *ctx, const double *y, double *dy)
     const auto groups = [](int t) { return (t + PB_RING_GROUP - 1) / PB_RING_GROUP; };
     const int gpre = std::max(1, std::min(ctx->pre_grid, groups(te) + groups(tr)));
     const int gmain = std::max(1, std::min(ctx->main_grid, groups(te_own) + groups(tr_own)));
-    k_pre<<<gpre, PB_RHS_THREADS, ctx->pre_smem, ctx->s()>>>(dm, y, te, tr, hw);
+    k_pre<<<gpre, PB_PRE_THREADS, ctx->pre_smem, ctx->s()>>>(dm, y, te, tr, hw);
     if (dm.fbr) k_main<true><<<gmain, MainCfg<true>::THREADS, ctx->main_smem, ctx->s()>>>(dm, y, dy, te_own, tr_own);
     else k_main<false><<<gmain, MainCfg<false>::THREADS, ctx->main_smem, ctx->s()>>>(dm, y, dy, te_own, tr_own);
     ctx->launches += 2;

@@ -1100,6 +1100,10 @@ __device__ __forceinline__ void river_main(const DevMesh &m, double *__restrict_
 #define PB_RHS_WARPS 10
 #endif
 #define PB_RHS_THREADS (PB_RHS_WARPS * 32)
+#ifndef PB_PRE_WARPS
+#define PB_PRE_WARPS PB_RHS_WARPS
+#endif
+#define PB_PRE_THREADS (PB_PRE_WARPS * 32)
 #ifndef PB_PRE_STAGES
 #define PB_PRE_STAGES 12
 #endif
@@ -1177,7 +1181,7 @@ struct PreCfg {
     typedef Ring<PB_PRE_STAGES, SB> ring_t;
 };
 
-static __global__ void __launch_bounds__(PB_RHS_THREADS, PB_PRE_MINB)
+static __global__ void __launch_bounds__(PB_PRE_THREADS, PB_PRE_MINB)
 k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r, const HaloWait hw)
 {
     constexpr int SB = PreCfg::SB;
@@ -1210,7 +1214,7 @@ k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r, c
         }
     };
     if (lane == 0)
-        for (int k = warp; k < PB_PRE_STAGES; k += PB_RHS_WARPS) request(qe0 + k);
+        for (int k = warp; k < PB_PRE_STAGES; k += PB_PRE_WARPS) request(qe0 + k);
     const long long r_end = (long long)gr * PB_RING_GROUP, e_end = r_end + ntile_e;
     for (;;) {
         const int q = ring.take(lane);

@@ -9,7 +9,7 @@ from mm_pihm_b200 import lib, watershed as W
 size = sys.argv[1] if len(sys.argv) > 1 else "1M"
 fbr = len(sys.argv) > 2 and sys.argv[2] == "fbr"
 n = int(os.environ.get("NREP", "5"))
-tb = W.make_named(size, fbr=fbr)
+tb = W.make_named(size, fbr=fbr) if os.environ.get("RIVER", "1") == "1" else W.make_watershed(*W.SIZES[size], fbr=fbr, river=False)
 m = lib.Model(tb, reorder=int(os.environ.get("REORDER", "1")))
 y = W.wet_state(tb, seed=11) if os.environ.get("STATE", "wet") == "wet" else tb["y0"]
 m.set_forcing(W.storm_forcing(tb, 3 * 3600.0, ws0_surf=np.maximum(y[:tb["nelem"]], 0)), np.zeros(tb["nriver"]))
