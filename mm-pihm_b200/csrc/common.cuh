@@ -74,7 +74,6 @@ struct DevMesh {
     double4 *dnb;        // [nes] dynamic neighbour record {surfh, EffKh, |grad h|, (surfh-D)^(2/3)}, written by k_pre
     const double *cls;   // [nclass][CC_STRIDE] dictionary of the soil / land-cover / geology parameter rows
     const int *cid;      // [nes] class id of each element (also inside the tile slab)
-    const int *nb;       // [3][nes]           neighbour codes
     const int *bct;      // [3][nes]           bc_type
     const int *fbct;     // [3][nes]           fbrbc_type
     const double *forc;  // [PB_F_NCOL][nes]   flat forcing table; the kernels read only its bc columns
@@ -152,7 +151,7 @@ struct pihm_b200_ctx {
     double *d_cls = nullptr;
     int *d_cid = nullptr, nclass = 0;
     double *d_fbr_dist = nullptr;
-    int *d_nb = nullptr, *d_bct = nullptr, *d_fbct = nullptr, *d_ri = nullptr;
+    int *d_bct = nullptr, *d_fbct = nullptr, *d_ri = nullptr;
     int *d_up_ptr = nullptr, *d_up_idx = nullptr;
     double *d_rivflow = nullptr, *d_stale = nullptr, *d_xflux = nullptr;
     int *d_nan = nullptr;

@@ -285,7 +285,6 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
 
     int rc = 0;
     rc |= upload(&ctx->d_es, es);
-    rc |= upload(&ctx->d_nb, nb);
     rc |= upload(&ctx->d_cls, cls);
     rc |= upload(&ctx->d_cid, cid);
     rc |= upload(&ctx->d_bct, bct);
@@ -331,7 +330,7 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
         pihm_b200_destroy(ctx);
         return nullptr;
     }
-    dm.es = ctx->d_es; dm.ft = ctx->d_ft; dm.snb = ctx->d_snb; dm.dnb = ctx->d_dnb; dm.cls = ctx->d_cls; dm.cid = ctx->d_cid; dm.nb = ctx->d_nb; dm.bct = ctx->d_bct; dm.fbct = ctx->d_fbct;
+    dm.es = ctx->d_es; dm.ft = ctx->d_ft; dm.snb = ctx->d_snb; dm.dnb = ctx->d_dnb; dm.cls = ctx->d_cls; dm.cid = ctx->d_cid; dm.bct = ctx->d_bct; dm.fbct = ctx->d_fbct;
     dm.forc = ctx->d_forc; dm.rf = ctx->d_rf; dm.ri = ctx->d_ri; dm.rivbc = ctx->d_rivbc;
     dm.fbr_dist = ctx->d_fbr_dist; dm.up_ptr = ctx->d_up_ptr; dm.up_idx = ctx->d_up_idx;
     dm.rivflow = ctx->d_rivflow; dm.s2c_stale = ctx->d_stale;
@@ -416,7 +415,7 @@ void pihm_b200_destroy(pihm_b200_ctx *ctx)
     if (ctx->l2_on) cudaCtxResetPersistingL2Cache();   // hand the set-aside lines back
     pihm_b200_vec_free(ctx->y_tmp);
     pihm_b200_vec_free(ctx->yd_tmp);
-    void *dev[] = {ctx->d_es, ctx->d_ft, ctx->d_dnb, ctx->d_cls, ctx->d_cid, ctx->d_forc, ctx->d_rf, ctx->d_rivbc, ctx->d_fbr_dist, ctx->d_nb,
+    void *dev[] = {ctx->d_es, ctx->d_ft, ctx->d_dnb, ctx->d_cls, ctx->d_cid, ctx->d_forc, ctx->d_rf, ctx->d_rivbc, ctx->d_fbr_dist,
                    ctx->d_bct, ctx->d_fbct, ctx->d_ri, ctx->d_up_ptr, ctx->d_up_idx,
                    ctx->d_rivflow, ctx->d_stale, ctx->d_xflux, ctx->d_nan, ctx->d_perm,
                    ctx->d_iperm, ctx->d_stage, ctx->d_red, ctx->d_gel, ctx->d_gri, ctx->d_send_e, ctx->d_send_r,
