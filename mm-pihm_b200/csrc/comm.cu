@@ -157,7 +157,11 @@ int comm_setup_halo_p2p(pihm_b200_ctx *ctx)
         roff_e += ctx->recv_e_cnt[k];
         roff_r += ctx->recv_r_cnt[k];
     }
-    if (cudaMalloc((void **)&d_x, sizeof(double) * 6 * (size_t)std::max(nn, 1)) != cudaSuccess) return -1;
+    if (cudaMalloc((void **)&d_x, sizeof(double) * 6 * (size_t)std::max(nn, 1)) != cudaSuccess) d_x = nullptr;
+    if (!d_x) {     // stay collective: the neighbours are waiting in their group call
+        set_error("halo p2p setup: allocation failed");
+        return -1;
+    }
     cudaMemcpyAsync(d_x, mine.data(), sizeof(double) * 3 * nn, cudaMemcpyHostToDevice, ctx->s());
     n.GroupStart();
     for (int k = 0; k < nn; k++) {

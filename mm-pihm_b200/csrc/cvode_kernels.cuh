@@ -78,10 +78,11 @@ __device__ __forceinline__ void red_exchange(const RedBuf &rb, double &a, int sl
         x[xb_index(par, slotA, rb.rank) + 1] = rb.seq;
     }
     const volatile double *mine = rb.peer[rb.rank];
+    bool lost = false;
     for (int r = 0; r < rb.nranks; r++) {
         long long spins = 0;
         while (mine[xb_index(par, slotA, r) + 1] != rb.seq)
-            if (++spins > (1LL << 31)) break;       // a lost rank must not hang the GPU forever
+            if (++spins > (1LL << 31)) { lost = true; break; }   // a lost rank must not hang the GPU forever
     }
     __threadfence_system();
     double sa = MIN_A ? __longlong_as_double(0x7ff0000000000000LL) : 0.0, sb = 0.0;
@@ -90,8 +91,9 @@ __device__ __forceinline__ void red_exchange(const RedBuf &rb, double &a, int sl
         sa = MIN_A ? ((va < sa) ? va : sa) : sa + va;
         if (slotB >= 0) sb += mine[xb_index(par, slotB, r)];
     }
-    a = sa;
-    b = sb;
+    // a rank that never arrived: poison the result so that the integrator stops (NaN norm)
+    a = lost ? __longlong_as_double(0x7ff8000000000000LL) : sa;
+    b = lost ? __longlong_as_double(0x7ff8000000000000LL) : sb;
 }
 
 template <bool IS_MIN>

@@ -1189,7 +1189,7 @@ k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r, c
         if ((int)threadIdx.x < hw.nn) {
             long long spins = 0;
             while (hw.flags[hw.rank[threadIdx.x]] != hw.seq)
-                if (++spins > (1LL << 31)) break;
+                if (++spins > (1LL << 31)) { atomicOr(m.nan_flag, 2); break; }   // lost neighbour: flag, do not hang
             __threadfence_system();
         }
         __syncthreads();
