@@ -141,6 +141,7 @@ struct pihm_b200_ctx {
     int pre_smem = 0, main_smem = 0;   // dynamic shared memory of the stage rings
     cudaAccessPolicyWindow l2_window{}; // persisting-L2 window over the neighbour records
     int l2_on = 0;
+    int pdl = 1;                       // launch k_main with programmatic stream serialization
     // host copies kept for permutation / validation
     std::vector<int> perm;             // internal element -> reference element
     std::vector<int> iperm;            // reference element -> internal element

@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <utility>
 #include "common.cuh"
 #include "cvode_kernels.cuh"
 
@@ -59,6 +60,25 @@ inline double rpowerR(double base, double exponent) { return (base <= 0.0) ? 0.0
 inline double rsqrt_s(double x) { return (x <= 0.0) ? 0.0 : std::sqrt(x); }
 
 }  // namespace
+
+// Every integrator kernel is launched with programmatic stream serialization (PDL): it may
+// become resident while its predecessor drains; all of them start with pdl_enter()
+// (cvode_kernels.cuh: launch_dependents + wait), so nothing is read or written early.
+template <typename... ExpTypes, typename... ActTypes>
+static inline void launch_pdl(cudaStream_t st, int pdl, int grid, int block, void (*kernel)(ExpTypes...),
+                              ActTypes &&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, std::forward<ActTypes>(args)...);
+}
 
 struct pihm_b200_cvode {
     pihm_b200_ctx *ctx = nullptr;
@@ -179,22 +199,22 @@ struct pihm_b200_cvode {
     ZnPtrs znp() const { ZnPtrs p; for (int j = 0; j < 6; j++) p.z[j] = zn[j]; return p; }
     void scale_inplace(double c, double *v)
     {
-        k_elementwise<EW_SCALE><<<blocks, PB_VEC_THREADS, 0, s()>>>(N, c, v, nullptr, v);
+        launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_elementwise<EW_SCALE>, N, c, v, nullptr, v);
         count();
     }
     void copy(const double *src, double *dst)
     {
-        k_elementwise<EW_COPY><<<blocks, PB_VEC_THREADS, 0, s()>>>(N, 0.0, src, nullptr, dst);
+        launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_elementwise<EW_COPY>, N, 0.0, src, nullptr, dst);
         count();
     }
     void axpy(double a, const double *x, double *yv)     // Vaxpy: y += a*x
     {
-        k_linearsum_alias<LS_GENERAL><<<blocks, PB_VEC_THREADS, 0, s()>>>(N, a, x, 1.0, yv, yv);
+        launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_linearsum_alias<LS_GENERAL>, N, a, x, 1.0, yv, yv);
         count();
     }
     void launch_ewt()                                    // efun + tolsf norm (cvode.c:1349,1376)
     {
-        k_ewt<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, reltol, abstol, zn[0], ewt, R());
+        launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_ewt, N, reltol, abstol, zn[0], ewt, R());
         count();
         red(SC_EWT_MIN, 1, 1);
         red(SC_EWT_NRM);
@@ -231,7 +251,7 @@ void pihm_b200_cvode::cvRescale()
     Coef6 f{};
     double factor = eta;
     for (int j = 1; j <= q; j++) { f.c[j] = factor; factor *= eta; }
-    k_rescale<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, q, znp(), f);
+    launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_rescale, N, q, znp(), f);
     count();
     h = hscale * eta;
     next_h = h;
@@ -246,7 +266,7 @@ void pihm_b200_cvode::cvPredict()
     if (tstopset) {
         if ((tn - tstop) * h > 0.0) tn = tstop;
     }
-    k_predict<1><<<blocks, PB_VEC_THREADS, 0, s()>>>(N, q, znp());
+    launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_predict<1>, N, q, znp());
     count();
 }
 
@@ -254,7 +274,7 @@ void pihm_b200_cvode::cvPredict()
 void pihm_b200_cvode::cvRestore(double saved_t)
 {
     tn = saved_t;
-    k_predict<-1><<<blocks, PB_VEC_THREADS, 0, s()>>>(N, q, znp());
+    launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_predict<-1>, N, q, znp());
     count();
 }
 
@@ -281,7 +301,7 @@ void pihm_b200_cvode::cvAdjustOrder(int deltaq)
         }
         A1 = (-alpha0 - alpha1) / prod;
         // zn[L] = A1 * zn[indx_acor]
-        k_elementwise<EW_SCALE><<<blocks, PB_VEC_THREADS, 0, s()>>>(N, A1, zn[indx_acor], nullptr, zn[L]);
+        launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_elementwise<EW_SCALE>, N, A1, zn[indx_acor], nullptr, zn[L]);
         count();
         for (int j = 2; j <= q; j++) axpy(l[j], zn[L], zn[j]);
     } else if (deltaq == -1) {
@@ -396,14 +416,14 @@ int pihm_b200_cvode::spgmrSolve(bool *b_is_zero)
             const int l_plus_1 = lk + 1;
             krydim = l_plus_1;
             // A-tilde V[l]: right scaling, DQ J*v, I - gamma J, left scaling, first MGS dot
-            k_krylov_a<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, cnorm, V[lk], ewt, vtemp, R());
+            launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_krylov_a, N, cnorm, V[lk], ewt, vtemp, R());
             red(SC_VNRM);
-            k_krylov_b<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, n_global, d_sc, vtemp, y, ytemp);
+            launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_krylov_b, N, n_global, d_sc, vtemp, y, ytemp);
             count(2);
             rhs(ytemp, V[l_plus_1]);     // Jv = f(tn, y + sig*v)   (cvode_spils.c:687)
             nfes++;
             njtimes++;
-            k_krylov_c<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, n_global, gamma, d_sc, vtemp, ftemp, ewt,
+            launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_krylov_c, N, n_global, gamma, d_sc, vtemp, ftemp, ewt,
                                                             V[0], V[l_plus_1], R());
             count();
             red(SC_VK2);
@@ -412,7 +432,7 @@ int pihm_b200_cvode::spgmrSolve(bool *b_is_zero)
             for (int i = 0; i < l_plus_1; i++) {
                 const double *vnext = (i + 1 < l_plus_1) ? V[i + 1] : V[l_plus_1];
                 const int slot_next = (i + 1 < l_plus_1) ? SC_H0 + i + 1 : SC_NEW2;
-                k_mgs_step<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, d_sc, SC_H0 + i, V[i], vnext,
+                launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_mgs_step, N, d_sc, SC_H0 + i, V[i], vnext,
                                                                 V[l_plus_1], slot_next, R());
                 count();
                 red(slot_next);
@@ -426,7 +446,7 @@ int pihm_b200_cvode::spgmrSolve(bool *b_is_zero)
                 // re-orthogonalisation branch (sundials_iterative.c:73-88); rare
                 double new_norm_2 = 0.0;
                 for (int i = 0; i < l_plus_1; i++) {
-                    k_reduce<RD_DOT, 0><<<blocks, PB_VEC_THREADS, 0, s()>>>(
+                    launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_reduce<RD_DOT, 0>, 
                         N, V[i], V[l_plus_1], d_part, d_counter, d_sc + SC_TMP, h_sc_map + SC_TMP);
                     count();
                     red_nccl(SC_TMP);
@@ -540,10 +560,10 @@ int pihm_b200_cvode::cvNewtonIteration()
     mnewt = 0;
     for (;;) {
         if (m == 0)
-            k_newton_res<true><<<blocks, PB_VEC_THREADS, 0, s()>>>(N, rl1, gamma, zn[0], zn[1], ftemp, ewt,
+            launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_newton_res<true>, N, rl1, gamma, zn[0], zn[1], ftemp, ewt,
                                                                    acor, y, tempv, V[0], R());
         else
-            k_newton_res<false><<<blocks, PB_VEC_THREADS, 0, s()>>>(N, rl1, gamma, zn[0], zn[1], ftemp, ewt,
+            launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_newton_res<false>, N, rl1, gamma, zn[0], zn[1], ftemp, ewt,
                                                                     acor, y, tempv, V[0], R());
         count();
         red(SC_BSUM);
@@ -560,9 +580,9 @@ int pihm_b200_cvode::cvNewtonIteration()
         if (bnorm <= deltar) {
             // x = b (first iteration) or x = 0
             if (mnewt > 0)
-                k_newton_update<true><<<blocks, PB_VEC_THREADS, 0, s()>>>(N, tempv, ewt, zn[0], acor, y, R());
+                launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_newton_update<true>, N, tempv, ewt, zn[0], acor, y, R());
             else
-                k_newton_update<false><<<blocks, PB_VEC_THREADS, 0, s()>>>(N, tempv, ewt, zn[0], acor, y, R());
+                launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_newton_update<false>, N, tempv, ewt, zn[0], acor, y, R());
             count();
             retval = 0;
         } else {
@@ -571,12 +591,12 @@ int pihm_b200_cvode::cvNewtonIteration()
             retval = spgmrSolve(&zero);
             if (retval == 0) {
                 if (zero || krydim_last == 0) {
-                    k_newton_update<true><<<blocks, PB_VEC_THREADS, 0, s()>>>(N, tempv, ewt, zn[0], acor, y, R());
+                    launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_newton_update<true>, N, tempv, ewt, zn[0], acor, y, R());
                 } else {
                     KryPtrs kp{};
                     Coef6 c{};
                     for (int k = 0; k < krydim_last; k++) { kp.v[k] = V[k]; c.c[k] = yg[k]; }
-                    k_spgmr_final<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, krydim_last, kp, c, ewt, zn[0], acor, y, R());
+                    launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_spgmr_final, N, krydim_last, kp, c, ewt, zn[0], acor, y, R());
                 }
                 count();
             }
@@ -594,7 +614,7 @@ int pihm_b200_cvode::cvNewtonIteration()
             if (m == 0) {
                 acnrm = del;
             } else {
-                k_wsq<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, acor, nullptr, ewt, SC_ACNRM, -1, R());
+                launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_wsq, N, acor, nullptr, ewt, SC_ACNRM, -1, R());
                 count();
                 red(SC_ACNRM);
                 sync_spin();
@@ -677,7 +697,7 @@ int pihm_b200_cvode::cvDoErrorTest(int *nflagPtr, double saved_t, int *nefPtr, d
     nscon = 0;
     rhs(zn[0], tempv);
     nfe++;
-    k_elementwise<EW_SCALE><<<blocks, PB_VEC_THREADS, 0, s()>>>(N, h, tempv, nullptr, zn[1]);
+    launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_elementwise<EW_SCALE>, N, h, tempv, nullptr, zn[1]);
     count();
     return TRY_AGAIN;
 }
@@ -701,7 +721,7 @@ void pihm_b200_cvode::cvCompleteStep()
         saved_tq5 = tq[5];
         indx_acor = qmax;
     }
-    k_complete<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, q, znp(), lc, acor, save);
+    launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_complete, N, q, znp(), lc, acor, save);
     count();
 }
 
@@ -766,7 +786,7 @@ void pihm_b200_cvode::cvPrepareNextStep(double dsm)
     etaqm1 = 0.0;
     etaqp1 = 0.0;
     if (do_m1 || do_p1) {
-        k_eta<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, do_m1, do_p1, cquot, zn[q], zn[qmax], acor, ewt, R());
+        launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_eta, N, do_m1, do_p1, cquot, zn[q], zn[qmax], acor, ewt, R());
         count();
         red(SC_ETA_M1, 2);
         sync_spin();
@@ -791,7 +811,7 @@ void pihm_b200_cvode::cvBDFStab()
             for (int i = 5; i >= 2; i--) ssdat[i][k] = ssdat[i - 1][k];
         int factorial = 1;
         for (int i = 1; i <= q - 1; i++) factorial *= i;
-        k_wsq<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, zn[q], zn[q - 1], ewt, SC_STAB1, SC_STAB2, R());
+        launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_wsq, N, zn[q], zn[q - 1], ewt, SC_STAB1, SC_STAB2, R());
         count();
         red(SC_STAB1, 2);
         sync_spin();
@@ -1003,7 +1023,7 @@ int pihm_b200_cvode::getDky(double t, double *dky)
     const double tn1 = tn + tfuzz;
     if ((t - tp) * (t - tn1) > 0.0) return CV_BAD_T;
     const double sv = (t - tn) / h;
-    k_dky<<<blocks, PB_VEC_THREADS, 0, s()>>>(N, q, sv, znp(), dky);
+    launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_dky, N, q, sv, znp(), dky);
     count();
     return CV_SUCCESS;
 }

@@ -188,6 +188,7 @@ static __global__ void __launch_bounds__(PB_VEC_THREADS, PB_VB_MINB)
 k_ewt(long long n, double reltol, double abstol, const double *__restrict__ y,
       double *__restrict__ ewt, RedBuf rb)
 {
+    pdl_enter();
     double mn = __longlong_as_double(0x7ff0000000000000LL), s = 0.0;
     PB_GRID_STRIDE_BATCH(i0, n) {
         double yv[PB_VB];
@@ -215,6 +216,7 @@ template <int SIGN>
 __global__ void __launch_bounds__(PB_VEC_THREADS)
 k_predict(long long n, int q, ZnPtrs zn)
 {
+    pdl_enter();
     PB_GRID_STRIDE(i, n) {
         double z[6];
 #pragma unroll
@@ -234,6 +236,7 @@ struct Coef6 { double c[6]; };
 static __global__ void __launch_bounds__(PB_VEC_THREADS)
 k_rescale(long long n, int q, ZnPtrs zn, Coef6 f)
 {
+    pdl_enter();
     PB_GRID_STRIDE(i, n) {
 #pragma unroll
         for (int j = 1; j < 6; j++) if (j <= q) zn.z[j][i] = f.c[j] * zn.z[j][i];
@@ -253,6 +256,7 @@ k_newton_res(long long n, double rl1, double gamma, const double *__restrict__ z
              const double *__restrict__ ewt, double *__restrict__ acor, double *__restrict__ y,
              double *__restrict__ b, double *__restrict__ V0, RedBuf rb)
 {
+    pdl_enter();
     double s = 0.0;
     PB_GRID_STRIDE_BATCH(i0, n) {
         double z0[PB_VB], z1[PB_VB], a0[PB_VB], ft[PB_VB], ew[PB_VB];
@@ -282,6 +286,7 @@ static __global__ void __launch_bounds__(PB_VEC_THREADS, PB_VB_MINB)
 k_krylov_a(long long n, double c, double *__restrict__ Vl, const double *__restrict__ ewt,
            double *__restrict__ vtemp, RedBuf rb)
 {
+    pdl_enter();
     double s = 0.0;
     PB_GRID_STRIDE_BATCH(i0, n) {
         double vl[PB_VB], ew[PB_VB];
@@ -305,6 +310,7 @@ k_krylov_b(long long n, double n_global, const double *__restrict__ sc,
            const double *__restrict__ vtemp, const double *__restrict__ y,
            double *__restrict__ work)
 {
+    pdl_enter();
     const double sig = 1.0 / sqrt(sc[SC_VNRM] / n_global);
     PB_GRID_STRIDE(i, n) work[i] = sig * vtemp[i] + y[i];
 }
@@ -318,6 +324,7 @@ k_krylov_c(long long n, double n_global, double gamma, const double *__restrict_
            const double *__restrict__ ewt, const double *__restrict__ V0,
            double *__restrict__ Vk, RedBuf rb)
 {
+    pdl_enter();
     const double sig = 1.0 / sqrt(sc[SC_VNRM] / n_global);
     const double siginv = 1.0 / sig;
     const double mg = -gamma;
@@ -346,6 +353,7 @@ k_mgs_step(long long n, const double *__restrict__ sc, int slot_prev,
            const double *__restrict__ Vprev, const double *Vnext, double *Vk,
            int slot_next, RedBuf rb)
 {
+    pdl_enter();
     const double mh = -sc[slot_prev];
     const bool self = (Vnext == Vk);
     double s = 0.0;
@@ -372,6 +380,7 @@ k_spgmr_final(long long n, int krydim, KryPtrs V, Coef6 yg, const double *__rest
               const double *__restrict__ zn0, double *__restrict__ acor, double *__restrict__ y,
               RedBuf rb)
 {
+    pdl_enter();
     double s = 0.0;
     constexpr int VB2 = 2;      // 8 input streams: two steps at a time
     for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x,
@@ -416,6 +425,7 @@ k_newton_update(long long n, const double *__restrict__ bvec, const double *__re
                 const double *__restrict__ zn0, double *__restrict__ acor, double *__restrict__ y,
                 RedBuf rb)
 {
+    pdl_enter();
     double s = 0.0;
     PB_GRID_STRIDE(i, n) {
         const double b = ZERO_B ? 0.0 : bvec[i];
@@ -434,6 +444,7 @@ static __global__ void __launch_bounds__(PB_VEC_THREADS)
 k_wsq(long long n, const double *__restrict__ x1, const double *x2, const double *__restrict__ w,
       int slot1, int slot2, RedBuf rb)
 {
+    pdl_enter();
     double s1 = 0.0, s2 = 0.0;
     PB_GRID_STRIDE(i, n) {
         const double wi = w[i];
@@ -449,6 +460,7 @@ k_wsq(long long n, const double *__restrict__ x1, const double *x2, const double
 static __global__ void __launch_bounds__(PB_VEC_THREADS)
 k_complete(long long n, int q, ZnPtrs zn, Coef6 l, const double *__restrict__ acor, double *save)
 {
+    pdl_enter();
     PB_GRID_STRIDE(i, n) {
         const double a = acor[i];
 #pragma unroll
@@ -463,6 +475,7 @@ static __global__ void __launch_bounds__(PB_VEC_THREADS)
 k_eta(long long n, int do_m1, int do_p1, double cquot, const double *znq, const double *znmax,
       const double *__restrict__ acor, const double *__restrict__ ewt, RedBuf rb)
 {
+    pdl_enter();
     double s1 = 0.0, s2 = 0.0;
     const double mc = -cquot;
     PB_GRID_STRIDE(i, n) {
@@ -477,6 +490,7 @@ k_eta(long long n, int do_m1, int do_p1, double cquot, const double *znq, const 
 static __global__ void __launch_bounds__(PB_VEC_THREADS)
 k_dky(long long n, int q, double s, ZnPtrs zn, double *__restrict__ dky)
 {
+    pdl_enter();
     PB_GRID_STRIDE(i, n) {
         double d = 0.0;
 #pragma unroll

@@ -13,6 +13,15 @@
 
 namespace pb {
 
+// programmatic dependent launch: let the next kernel of the stream start launching, then wait
+// until everything the previous one wrote is visible (both are no-ops for a plain launch)
+__device__ __forceinline__ void pdl_enter()
+{
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+
 #define PB_VEC_THREADS 256
 
 enum { LS_GENERAL = 0, LS_SCALESUM = 1, LS_SCALEDIFF = 2 };
@@ -22,6 +31,7 @@ __global__ void __launch_bounds__(PB_VEC_THREADS)
 k_linearsum(long long n, double a, const double *__restrict__ x, double b,
             const double *__restrict__ y, double *__restrict__ z)
 {
+    pdl_enter();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
@@ -36,6 +46,7 @@ template <int MODE>
 __global__ void __launch_bounds__(PB_VEC_THREADS)
 k_linearsum_alias(long long n, double a, const double *x, double b, const double *y, double *z)
 {
+    pdl_enter();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
@@ -52,6 +63,7 @@ template <int OP>
 __global__ void __launch_bounds__(PB_VEC_THREADS)
 k_elementwise(long long n, double c, const double *x, const double *y, double *z)
 {
+    pdl_enter();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
@@ -113,6 +125,7 @@ __global__ void __launch_bounds__(PB_VEC_THREADS)
 k_reduce(long long n, const double *__restrict__ x, const double *__restrict__ y,
          double *part, unsigned int *counter, double *out_dev, volatile double *out_host)
 {
+    pdl_enter();
     double v = rd_identity<OP>();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -149,6 +162,7 @@ static __global__ void __launch_bounds__(PB_VEC_THREADS)
 k_permute_state(int ne, int nr, int fbr, const int *__restrict__ perm,
                 const double *__restrict__ src, double *__restrict__ dst, int to_internal)
 {
+    pdl_enter();
     const long long n = (long long)(fbr ? 5 : 3) * ne + 2LL * nr;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -170,6 +184,7 @@ static __global__ void __launch_bounds__(256)
 k_scatter_forcing(int ne, int nes, int col, const int *__restrict__ perm, const double *__restrict__ src,
                   double *__restrict__ ft, double *__restrict__ forc)
 {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ne) return;
     const double v = src[perm[i]];

@@ -372,6 +372,7 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
         ctx->main_grid = prop.multiProcessorCount * bmain;
         ctx->pre_smem = pre_smem;
         ctx->main_smem = main_smem;
+        if (const char *ov = std::getenv("PIHM_B200_PDL")) ctx->pdl = std::atoi(ov);
         // B200's 126 MB L2 as a scratchpad: the 64 B / element of neighbour records (written by
         // k_pre, gathered three times per element by k_main, 64 MB at 1M triangles) are marked
         // persisting, everything else that passes through the RHS stream keeps normal priority --
@@ -704,8 +705,23 @@ static int launch_rhs(pihm_b200_ctx *ctx, const double *y, double *dy)
     const int gpre = std::max(1, std::min(ctx->pre_grid, groups(te) + groups(tr)));
     const int gmain = std::max(1, std::min(ctx->main_grid, groups(te_own) + groups(tr_own)));
     k_pre<<<gpre, PB_PRE_THREADS, ctx->pre_smem, ctx->s()>>>(dm, y, te, tr, hw);
-    if (dm.fbr) k_main<true><<<gmain, MainCfg<true>::THREADS, ctx->main_smem, ctx->s()>>>(dm, y, dy, te_own, tr_own);
-    else k_main<false><<<gmain, MainCfg<false>::THREADS, ctx->main_smem, ctx->s()>>>(dm, y, dy, te_own, tr_own);
+    {
+        // k_main right behind k_pre with programmatic stream serialization (PDL): its launch
+        // latency and prologue overlap k_pre's tail
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(gmain);
+        cfg.blockDim = dim3(dm.fbr ? MainCfg<true>::THREADS : MainCfg<false>::THREADS);
+        cfg.dynamicSmemBytes = ctx->main_smem;
+        cfg.stream = ctx->s();
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = ctx->pdl ? 1 : 0;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        const cudaError_t e = dm.fbr ? cudaLaunchKernelEx(&cfg, k_main<true>, dm, y, dy, te_own, tr_own)
+                                     : cudaLaunchKernelEx(&cfg, k_main<false>, dm, y, dy, te_own, tr_own);
+        if (e != cudaSuccess) { set_error(std::string("k_main launch: ") + cudaGetErrorString(e)); return -1; }
+    }
     ctx->launches += 2;
     return 0;
 }

@@ -1185,6 +1185,10 @@ static __global__ void __launch_bounds__(PB_PRE_THREADS, PB_PRE_MINB)
 k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r, const HaloWait hw)
 {
     constexpr int SB = PreCfg::SB;
+    // programmatic dependent launch: k_main's CTAs may become resident as this kernel's CTAs
+    // retire and run their prologue (ring set-up, first slab requests); they wait for the
+    // completion of this grid (griddepcontrol.wait) before they touch what it writes
+    asm volatile("griddepcontrol.launch_dependents;");
     if (hw.nn > 0) {        // partitioned run: the neighbours' halo records of this RHS have arrived
         if ((int)threadIdx.x < hw.nn) {
             long long spins = 0;
@@ -1215,6 +1219,7 @@ k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r, c
     };
     if (lane == 0)
         for (int k = warp; k < PB_PRE_STAGES; k += PB_PRE_WARPS) request(qe0 + k);
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // y comes from the previous kernel of the stream
     const long long r_end = (long long)gr * PB_RING_GROUP, e_end = r_end + ntile_e;
     for (;;) {
         const int q = ring.take(lane);
@@ -1247,6 +1252,7 @@ k_main(const DevMesh m, const double *__restrict__ y, double *__restrict__ dy, i
 {
     constexpr int SBS = MainCfg<FBR>::SBS, SBF = MainCfg<FBR>::SBF, SB = MainCfg<FBR>::SB;
     constexpr int STAGES = MainCfg<FBR>::STAGES;
+    asm volatile("griddepcontrol.launch_dependents;");
     extern __shared__ __align__(128) unsigned char smem[];
     typename MainCfg<FBR>::ring_t ring(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1271,6 +1277,9 @@ k_main(const DevMesh m, const double *__restrict__ y, double *__restrict__ dy, i
     };
     if (lane == 0)
         for (int k = warp; k < STAGES; k += MainCfg<FBR>::WARPS) request(qe0 + k);
+    // the static slabs above do not depend on k_pre; everything below does (no-op when the
+    // kernel was not launched with the programmatic-serialization attribute)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const long long r_end = (long long)gr * PB_RING_GROUP, e_end = r_end + ntile_e;
     for (;;) {
         const int q = ring.take(lane);
@@ -1327,6 +1336,8 @@ k_halo_put(const DevMesh m, const double *__restrict__ y, int nse, const int *__
            int nsr, const int *__restrict__ send_r, const HaloPeers hp, int par, double seq,
            unsigned int *counter)
 {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < nse) {
         int kk = 0;
