@@ -159,9 +159,11 @@ int             pihm_b200_set_halo(pihm_b200_ctx *ctx, int n_neighbours,
                     const int32_t *send_r_ptr, const int32_t *send_r_idx,
                     const int32_t *recv_r_cnt);
 /* NCCL communicator: rank 0 makes the 128-byte id, the launcher broadcasts it.
- * After comm_init every RHS call starts with the halo exchange (grouped
- * ncclSend/ncclRecv of {surf, gw[, fbr_gw]} / {stage, gw} records) and every
- * reduction of the integrator is followed by a scalar ncclAllReduce. */
+ * After comm_init every RHS call starts with the halo exchange of {surf, gw[, fbr_gw]} /
+ * {stage, gw} records and every reduction of the integrator is all-reduced over the
+ * ranks.  Both run inside the library's own kernels over NVLink peer memory (buffers
+ * mapped with CUDA IPC; set_halo must have been called before comm_init); if the mapping
+ * is not available on every rank, grouped ncclSend/ncclRecv and ncclAllReduce do it. */
 int             pihm_b200_comm_unique_id(void *out128);
 int             pihm_b200_comm_init(pihm_b200_ctx *ctx, int rank, int nranks,
                                     const void *id128);
