@@ -213,20 +213,34 @@ struct ZnPtrs { double *z[6]; };
 // cvPredict (cvode.c:2285-2287) / cvRestore (:2887-2889): the q(q+1)/2 in-place
 // N_VLinearSum(1, zn[j-1], +-1, zn[j], zn[j-1]) per component, in registers
 template <int SIGN>
-__global__ void __launch_bounds__(PB_VEC_THREADS)
+__global__ void __launch_bounds__(PB_VEC_THREADS, PB_VB_MINB)
 k_predict(long long n, int q, ZnPtrs zn)
 {
     pdl_enter();
-    PB_GRID_STRIDE(i, n) {
-        double z[6];
+    // two grid-stride steps at a time: all loads of both before the first in-place store
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x,
+                   stride_ = (long long)gridDim.x * blockDim.x; i0 < n; i0 += 2 * stride_) {
+        double z[2][6];
 #pragma unroll
-        for (int j = 0; j < 6; j++) if (j <= q) z[j] = zn.z[j][i];
-        for (int k = 1; k <= q; k++)
+        for (int u = 0; u < 2; u++) {
+            const long long i = i0 + u * stride_;
+            if (i < n) {
 #pragma unroll
-            for (int j = 5; j >= 1; j--)
-                if (j <= q && j >= k) z[j - 1] = (SIGN > 0) ? z[j - 1] + z[j] : z[j - 1] - z[j];
+                for (int j = 0; j < 6; j++) if (j <= q) z[u][j] = zn.z[j][i];
+            }
+        }
 #pragma unroll
-        for (int j = 0; j < 5; j++) if (j < q) zn.z[j][i] = z[j];
+        for (int u = 0; u < 2; u++) {
+            const long long i = i0 + u * stride_;
+            if (i < n) {
+                for (int k = 1; k <= q; k++)
+#pragma unroll
+                    for (int j = 5; j >= 1; j--)
+                        if (j <= q && j >= k) z[u][j - 1] = (SIGN > 0) ? z[u][j - 1] + z[u][j] : z[u][j - 1] - z[u][j];
+#pragma unroll
+                for (int j = 0; j < 5; j++) if (j < q) zn.z[j][i] = z[u][j];
+            }
+        }
     }
 }
 
@@ -457,15 +471,31 @@ k_wsq(long long n, const double *__restrict__ x1, const double *x2, const double
 
 // cvCompleteStep (cvode.c:3010-3016): zn[j] += l[j]*acor (Vaxpy), j = 0..q,
 // and the optional save zn[qmax] = acor
-static __global__ void __launch_bounds__(PB_VEC_THREADS)
+static __global__ void __launch_bounds__(PB_VEC_THREADS, PB_VB_MINB)
 k_complete(long long n, int q, ZnPtrs zn, Coef6 l, const double *__restrict__ acor, double *save)
 {
     pdl_enter();
-    PB_GRID_STRIDE(i, n) {
-        const double a = acor[i];
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x,
+                   stride_ = (long long)gridDim.x * blockDim.x; i0 < n; i0 += 2 * stride_) {
+        double z[2][6], a[2];
 #pragma unroll
-        for (int j = 0; j < 6; j++) if (j <= q) zn.z[j][i] = zn.z[j][i] + l.c[j] * a;
-        if (save) save[i] = a;
+        for (int u = 0; u < 2; u++) {
+            const long long i = i0 + u * stride_;
+            if (i < n) {
+                a[u] = acor[i];
+#pragma unroll
+                for (int j = 0; j < 6; j++) if (j <= q) z[u][j] = zn.z[j][i];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const long long i = i0 + u * stride_;
+            if (i < n) {
+#pragma unroll
+                for (int j = 0; j < 6; j++) if (j <= q) zn.z[j][i] = z[u][j] + l.c[j] * a[u];
+                if (save) save[i] = a[u];
+            }
+        }
     }
 }
 
