@@ -66,6 +66,7 @@ struct DevMesh {
     int fbr, surf_mode, riv_mode;
     int record;          // write the PB_X_* flux columns
     double dt;
+    double r_deprstg, r_dt;   // refined reciprocals of DEPRSTG and dt (k_class_rcp)
     // offsets of the state blocks inside y / ydot (pihm_func.h:7-15)
     long long o_unsat, o_gw, o_stg, o_rgw, o_fu, o_fg;
     const double *es;    // [ntile][PB_E_NCOL][32] static element columns, warp-tiled

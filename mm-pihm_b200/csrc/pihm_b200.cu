@@ -334,6 +334,22 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
     dm.forc = ctx->d_forc; dm.rf = ctx->d_rf; dm.ri = ctx->d_ri; dm.rivbc = ctx->d_rivbc;
     dm.fbr_dist = ctx->d_fbr_dist; dm.up_ptr = ctx->d_up_ptr; dm.up_idx = ctx->d_up_idx;
     dm.rivflow = ctx->d_rivflow; dm.s2c_stale = ctx->d_stale;
+    {   // reciprocals of the dictionary's divisors and of DEPRSTG / dt, computed on the device
+        double *d_c = nullptr, h_c[2] = {0.0, 0.0};
+        bool good = cudaMalloc((void **)&d_c, sizeof(h_c)) == cudaSuccess;
+        if (good) {
+            k_class_rcp<<<(ctx->nclass + 127) / 128, 128>>>(ctx->d_cls, ctx->nclass, dm.dt, d_c);
+            good = cudaMemcpy(h_c, d_c, sizeof(h_c), cudaMemcpyDeviceToHost) == cudaSuccess;
+            cudaFree(d_c);
+        }
+        if (!good) {
+            set_error("pihm_b200_create: class dictionary set-up failed");
+            pihm_b200_destroy(ctx);
+            return nullptr;
+        }
+        dm.r_deprstg = h_c[0];
+        dm.r_dt = h_c[1];
+    }
     dm.gel = ctx->d_gel; dm.gri = ctx->d_gri;
     dm.xflux = nullptr; dm.record = 0;
     dm.nan_flag = ctx->d_nan;

@@ -53,9 +53,10 @@ enum {   // dictionary row; pairs are fetched as double2
     CC_ALPHA = 0, CC_M1, CC_M2, CC_M3,              // m1 = beta/(beta-1), m2 = (beta-1)/beta, m3 = 1/beta
     CC_KINFV, CC_KMACV, CC_AREAFH, CC_KSATV,
     CC_POROSITY, CC_ROUGH, CC_RZD, CC_BETA,
-    CC_KMACH, CC_AREAFV, CC_KSATH, CC_PAD,
+    CC_KMACH, CC_AREAFV, CC_KSATH, CC_RALPHA,       // R*: refined reciprocals (k_class_rcp), shared by divisions
     CC_GALPHA, CC_GM1, CC_GM2, CC_GM3,
     CC_GKSATV, CC_GKSATH, CC_GPOROSITY, CC_GBETA,
+    CC_RPOR, CC_RGALPHA, CC_RGPOR, CC_PAD,
     CC_STRIDE
 };
 // ABI column (include/pihm_b200.h) -> tile slot; used by the host packer
@@ -598,18 +599,30 @@ __device__ __forceinline__ double dh_by_dl_a(Arith<FAST> &A, const double *l1, c
 // straight-line block and the pairs interleave.  Values are those of kr_func() /
 // psi_func().
 template <bool FAST>
-__device__ __forceinline__ void vg_kr_psi_a(Arith<FAST> &A, double satn, double alpha, double m1, double m2,
-                                            double m3, double &kr, double &psi)
+__device__ __forceinline__ void vg_kr_psi_a(Arith<FAST> &A, double satn, double alpha, double r_alpha, double m1,
+                                            double m2, double m3, double &kr, double &psi)
 {
     if (!FAST) { vg_kr_psi(satn, alpha, m1, m2, m3, kr, psi); return; }
     const double sp = (satn < PB_SATMIN) ? PB_SATMIN : satn;
+#ifndef PB_POW_NO_SHARE
+    // pow(s, m1) and pow(1/s, m1): one logarithm.  q = fl(1/s) satisfies s q = 1 - e with
+    // e = fma(-s, q, 1) exact, so log q = -log s + log(1 - e) = -log s - e (e^2 < 2^-106): the
+    // double-double logarithm of q at the accuracy the pow algorithm works with.  (The callers
+    // clamp satn to [SATMIN, 1], so sp == satn.)
+    const LogDD Ls = A.logp(sp);
+    const double Av = A.expy(Ls.H, Ls.Lo, m1);
+    const double q = A.div(1.0, sp);
+    const double e = __fma_rn(-sp, q, 1.0);
+    const double Cv = A.expy(-Ls.H, -Ls.Lo - e, m1);
+#else
     const double Av = A.powp(satn, m1);
     const double Cv = A.powp(A.div(1.0, sp), m1);
+#endif
     const double Bv = A.powp(1.0 - Av, m2);
     const double Dv = A.powp(Cv - 1.0, m3);
     const double a = 1.0 - Bv;
     kr = A.sqrtp(satn) * a * a;
-    psi = A.div(-Dv, alpha);
+    psi = A.div(-Dv, alpha, r_alpha);
 }
 
 // returns false (nothing written) when FAST arithmetic left its domain
@@ -851,7 +864,8 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
             satn = (satn < PB_SATMIN) ? PB_SATMIN : satn;
             const double2 c_vg0 = ldg2_here(crow + CC_ALPHA / 2);   // {alpha, m1}
             const double2 c_vg1 = ldg2_here(crow + CC_M2 / 2);      // {m2, m3}
-            vg_kr_psi_a<FAST>(A, satn, c_vg0.x, c_vg0.y, c_vg1.x, c_vg1.y, satkfunc, psi_u);
+            const double r_alpha = ldg2_here(crow + CC_KSATH / 2).y;
+            vg_kr_psi_a<FAST>(A, satn, c_vg0.x, r_alpha, c_vg0.y, c_vg1.x, c_vg1.y, satkfunc, psi_u);
         }
         if (unsat + gw > depth) {
             infil = 0.0;
@@ -861,7 +875,7 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
             for (int j = 0; j < 3; j++) applrate += A.div(-ovl_infil[j], area, r_area);
             applrate = (applrate > 0.0) ? applrate : 0.0;
             applrate += pcpdrp;
-            double wetfrac = A.div(surfh, PB_DEPRSTG);
+            double wetfrac = A.div(surfh, PB_DEPRSTG, m.r_deprstg);
             wetfrac = (wetfrac > 0.0) ? wetfrac : 0.0;
             wetfrac = (wetfrac < 1.0) ? wetfrac : 1.0;
             double dh_by_dz;
@@ -881,7 +895,7 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
                 infil = (infil > 0.0) ? infil : 0.0;
             }
             const double ws0surf = f[3 * PB_TILE];
-            double infil_max = applrate + ((ws0surf > 0.0) ? A.quo(ws0surf, m.dt) : 0.0);
+            double infil_max = applrate + ((ws0surf > 0.0) ? A.div(ws0surf, m.dt, m.r_dt) : 0.0);
             infil = (infil > infil_max) ? infil_max : infil;
             infil *= wetfrac;
         }
@@ -922,6 +936,7 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
         const double2 c_g1 = ldg2_here(crow + CC_GM2 / 2);      // {gm2, gm3}
         const double2 c_gk = ldg2_here(crow + CC_GKSATV / 2);   // {gksatv, gksath}
         const double ksatv_s = ldg2_here(crow + CC_AREAFH / 2).y;   // soil ksatv
+        const double2 c_rg = ldg2_here(crow + CC_RPOR / 2);         // {1/porosity, 1/galpha}
         const double gdepth = EC(TS_GDEPTH), gksatv = c_gk.x;
         const double zbed = EC(TS_ZBED), gksath = c_gk.y;
         const bool full = fg >= gdepth;
@@ -931,7 +946,7 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
             double satn = A.div(fu, deficit);
             satn = (satn > 1.0) ? 1.0 : satn;
             satn = (satn < PB_SATMIN) ? PB_SATMIN : satn;
-            vg_kr_psi_a<FAST>(A, satn, c_g0.x, c_g0.y, c_g1.x, c_g1.y, satkfunc, psi_c);
+            vg_kr_psi_a<FAST>(A, satn, c_g0.x, c_rg.y, c_g0.y, c_g1.x, c_g1.y, satkfunc, psi_c);
             psi_c = (psi_c > PB_PSIMIN) ? psi_c : PB_PSIMIN;
         }
         // FbrInfil, vert_flow.c:284-330
@@ -1006,12 +1021,12 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
         if (FBR) dfg -= A.div(fbrflow[j], area, r_area);
     }
     const double porosity = c_por.x;
-    const double r_por = A.rcp(porosity);
+    const double r_por = ldg2_here(crow + CC_RPOR / 2).x;
     dunsat = A.div(dunsat, porosity, r_por);
     dgw = A.div(dgw, porosity, r_por);
     if (FBR) {
         const double gporosity = __ldg(m.cls + (size_t)cid * CC_STRIDE + CC_GPOROSITY);
-        const double r_gpor = A.rcp(gporosity);
+        const double r_gpor = ldg2_here(crow + CC_RGPOR / 2).x;
         dfu = A.div(dfu, gporosity, r_gpor);
         dfg = A.div(dfg, gporosity, r_gpor);
     }
@@ -1304,6 +1319,24 @@ k_main(const DevMesh m, const double *__restrict__ y, double *__restrict__ dy, i
         }
         __syncwarp();
         if (lane == 0) { ring.release(s, n); request(q + STAGES); }
+    }
+}
+
+// One-off: the refined reciprocals of the dictionary's divisors and of the model constants
+// (same instruction sequence as Arith<true>::rcp, so div(a, b, r) stays bitwise `a / b`)
+static __global__ void k_class_rcp(double *cls, int ncls, double dt, double *consts)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < ncls) {
+        double *row = cls + (size_t)c * CC_STRIDE;
+        row[CC_RALPHA] = rcp_or_nan(row[CC_ALPHA]);
+        row[CC_RPOR] = rcp_or_nan(row[CC_POROSITY]);
+        row[CC_RGALPHA] = rcp_or_nan(row[CC_GALPHA]);
+        row[CC_RGPOR] = rcp_or_nan(row[CC_GPOROSITY]);
+    }
+    if (c == 0) {
+        consts[0] = rcp_or_nan(PB_DEPRSTG);
+        consts[1] = rcp_or_nan(dt);
     }
 }
 
