@@ -39,6 +39,9 @@ def lib():
         for f in ("oracle_set_forcing", "oracle_set_river_bc", "oracle_set_stale_ovlflow"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_get_fluxes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        for f in ("oracle_set_ws0", "oracle_get_ws0"):
+            getattr(L, f).argtypes = [C.c_void_p, C.c_void_p]
+        L.oracle_summary.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         L.oracle_ode.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
         L.oracle_nv_linearsum.argtypes = [C.c_int64, C.c_double, C.c_void_p, C.c_double,
                                           C.c_void_p, C.c_void_p]
@@ -117,6 +120,22 @@ class OracleModel:
         rf = np.zeros((NUM_RIVFLX, max(self.nriver, 1)))
         self.L.oracle_get_fluxes(self.h, _ptr(xf), _ptr(rf))
         return xf, rf[:, :self.nriver]
+
+
+    # -- Summary() + MassBalance(), src/update.c ---------------------------------
+    def set_ws0(self, y):
+        y = np.ascontiguousarray(y, np.float64); assert y.shape == (self.nsv,)
+        self.L.oracle_set_ws0(self.h, _ptr(y))
+
+    def get_ws0(self):
+        y = np.zeros(self.nsv); self.L.oracle_get_ws0(self.h, _ptr(y)); return y
+
+    def summary(self, y, stepsize):
+        """-> subrunoff [nelem]; get_fluxes() then shows the mass-balance infil."""
+        y = np.ascontiguousarray(y, np.float64); assert y.shape == (self.nsv,)
+        sr = np.zeros(self.nelem)
+        self.L.oracle_summary(self.h, _ptr(y), float(stepsize), _ptr(sr))
+        return sr
 
 
 # serial N_Vector arithmetic -------------------------------------------------

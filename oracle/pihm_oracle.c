@@ -57,6 +57,8 @@ typedef struct oracle_model
     double         *xf;     /* [PB_X_NCOL][ne]; OVL*, SUB* persist across calls */
     double         *rivflow;/* [11][nr] */
     double         *dhbydx, *dhbydy;
+    double         *ws0;    /* [nsv] elem/river ws0 (block layout of y)  */
+    double         *subrunoff; /* [ne] MassBalance's local, update.c:131 */
 } oracle_model;
 
 #define E(c, i)   (om->ef[(size_t)(c) * om->ne + (i)])
@@ -100,6 +102,8 @@ oracle_model *oracle_create(const pihm_b200_mesh *m)
     om->rivflow = (double *)calloc(PIHM_B200_NUM_RIVFLX * nr + 1, sizeof(double));
     om->dhbydx = (double *)calloc(ne + 1, sizeof(double));
     om->dhbydy = (double *)calloc(ne + 1, sizeof(double));
+    om->ws0 = (double *)calloc(5 * ne + 2 * nr + 1, sizeof(double));
+    om->subrunoff = (double *)calloc(ne + 1, sizeof(double));
     return om;
 }
 
@@ -110,7 +114,7 @@ void oracle_destroy(oracle_model *om)
     free(om->rivbc); free(om->surf); free(om->unsat); free(om->gw);
     free(om->fbr_unsat); free(om->fbr_gw); free(om->surfh); free(om->stage);
     free(om->rgw); free(om->xf); free(om->rivflow); free(om->dhbydx);
-    free(om->dhbydy); free(om);
+    free(om->dhbydy); free(om->ws0); free(om->subrunoff); free(om);
 }
 
 int64_t oracle_num_state_var(const oracle_model *om)   /* ode.c:313-339 */
@@ -139,6 +143,82 @@ void oracle_get_fluxes(const oracle_model *om, double *xf, double *rivflow)
     if (xf) memcpy(xf, om->xf, sizeof(double) * PB_X_NCOL * (size_t)om->ne);
     if (rivflow) memcpy(rivflow, om->rivflow,
         sizeof(double) * PIHM_B200_NUM_RIVFLX * (size_t)om->nr);
+}
+
+/* ---- Summary() + MassBalance(), src/update.c:3-160 ---------------------
+ * ws0 is kept as a vector in the block layout of y (pihm_func.h:7-15). */
+void oracle_set_ws0(oracle_model *om, const double *y)  /* initialize.c:598,612 */
+{
+    memcpy(om->ws0, y, sizeof(double) * (size_t)oracle_num_state_var(om));
+}
+
+void oracle_get_ws0(const oracle_model *om, double *y)
+{
+    memcpy(y, om->ws0, sizeof(double) * (size_t)oracle_num_state_var(om));
+}
+
+/* y = CV_Y after SolveCVode; the wf.* fields are those of the last oracle_ode
+ * call.  Overwrites X(INFIL) (and X(FBR_INFIL)) like update.c:135,150-152 and
+ * keeps the local `subrunoff` (update.c:128-133,154-158) for inspection. */
+void oracle_summary(oracle_model *om, const double *y, double stepsize,
+    double *subrunoff_out)
+{
+    const size_t    ne = (size_t)om->ne, nr = (size_t)om->nr;
+    const size_t    o_unsat = ne, o_gw = 2 * ne, o_fu = 3 * ne + 2 * nr,
+                    o_fg = 4 * ne + 2 * nr;
+    size_t          i;
+    int             j;
+
+    for (i = 0; i < ne; i++)
+    {
+        /* update.c:19-25: ws = y (not clamped) */
+        const double    unsat = y[o_unsat + i], gw = y[o_gw + i];
+        const double    unsat0 = om->ws0[o_unsat + i], gw0 = om->ws0[o_gw + i];
+        const double    depth = E(PB_E_DEPTH, i), area = E(PB_E_AREA, i);
+        double          soilw0, soilw1, subrunoff, infil;
+
+        /* MassBalance, update.c:103-160 */
+        soilw0 = gw0 + unsat0;
+        soilw0 = (soilw0 > depth) ? depth : soilw0;
+        soilw0 = (soilw0 < 0.0) ? 0.0 : soilw0;
+
+        soilw1 = gw + unsat;
+        soilw1 = (soilw1 > depth) ? depth : soilw1;
+        soilw1 = (soilw1 < 0.0) ? 0.0 : soilw1;
+
+        subrunoff = 0.0;
+        for (j = 0; j < 3; j++) subrunoff += X(PB_X_SUB0 + j, i) / area;
+
+        infil = (soilw1 - soilw0) * E(PB_E_POROSITY, i) / stepsize + subrunoff +
+            X(PB_X_EDIR_UNSAT, i) + X(PB_X_EDIR_GW, i) + X(PB_X_ETT_UNSAT, i) +
+            X(PB_X_ETT_GW, i);
+
+        if (om->fbr)
+        {
+            const double    fbrw0 = om->ws0[o_fg + i] + om->ws0[o_fu + i];
+            const double    fbrw1 = y[o_fg + i] + y[o_fu + i];
+            double          fbrrunoff = 0.0, fbr_infil;
+
+            for (j = 0; j < 3; j++) fbrrunoff += X(PB_X_FBRFLOW0 + j, i) / area;
+            fbr_infil = (fbrw1 - fbrw0) * E(PB_E_GPOROSITY, i) / stepsize +
+                fbrrunoff;
+            X(PB_X_FBR_INFIL, i) = fbr_infil;
+            infil += fbr_infil;
+        }
+
+        if (infil < 0.0)
+        {
+            subrunoff -= infil;
+            infil = 0.0;
+        }
+        X(PB_X_INFIL, i) = infil;
+        om->subrunoff[i] = subrunoff;
+        /* update.c:47: ws0 = ws; ws0.surf is what Infil() reads next step */
+        F(PB_F_WS0SURF, i) = y[i];
+    }
+    /* update.c:47,94 */
+    memcpy(om->ws0, y, sizeof(double) * (size_t)oracle_num_state_var(om));
+    if (subrunoff_out) memcpy(subrunoff_out, om->subrunoff, sizeof(double) * ne);
 }
 
 /* ---- small physics helpers ------------------------------------------- */

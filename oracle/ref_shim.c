@@ -656,6 +656,38 @@ void ref_get_stats(long int *s, double *d)
     CVodeGetCurrentTime(H.cvode_mem, &d[2]);
 }
 
+/* Summary() (src/update.c:3-98) on caller data: y plays CV_Y after SolveCVode,
+ * the wf.* fields are those the last ODE() call left behind.  Afterwards
+ * ref_get_fluxes() shows the mass-balance wf.infil / wf.fbr_infil. */
+void ref_summary(const double *y)
+{
+    ref_set_y(y);
+    Summary(H.pihm->elem, H.pihm->river, H.CV_Y,
+        (double)H.pihm->ctrl.stepsize);
+}
+
+/* ws0 of elements and rivers in the block layout of y */
+void ref_get_ws0(double *y)
+{
+    int             i;
+
+    for (i = 0; i < nelem; i++)
+    {
+        y[SURF(i)] = H.pihm->elem[i].ws0.surf;
+        y[UNSAT(i)] = H.pihm->elem[i].ws0.unsat;
+        y[GW(i)] = H.pihm->elem[i].ws0.gw;
+#if defined(_FBR_)
+        y[FBRUNSAT(i)] = H.pihm->elem[i].ws0.fbr_unsat;
+        y[FBRGW(i)] = H.pihm->elem[i].ws0.fbr_gw;
+#endif
+    }
+    for (i = 0; i < nriver; i++)
+    {
+        y[RIVSTG(i)] = H.pihm->river[i].ws0.stage;
+        y[RIVGW(i)] = H.pihm->river[i].ws0.gw;
+    }
+}
+
 /* element/river water states after Summary() (ws), for trajectory checks */
 void ref_get_ws(double *y)
 {

@@ -178,6 +178,14 @@ class RefModel:
     def get_ws(self):
         y = np.zeros(self.nsv); self.lib.ref_get_ws(_ptr(y)); return y
 
+    def summary(self, y):
+        """Summary() of src/update.c on y (= CV_Y after SolveCVode)."""
+        y = np.ascontiguousarray(y, np.float64); assert y.shape == (self.nsv,)
+        self.lib.ref_summary(_ptr(y))
+
+    def get_ws0(self):
+        y = np.zeros(self.nsv); self.lib.ref_get_ws0(_ptr(y)); return y
+
     # -- RHS -------------------------------------------------------------------
     def ode(self, y, t=0.0):
         y = np.ascontiguousarray(y, np.float64); assert y.shape == (self.nsv,)

@@ -20,6 +20,11 @@ reference on machines where /root/reference does not exist (the GPU box).
       same for watershed.make_named('small', dirichlet_edges=True) driven by
       watershed.storm_forcing: RHS cases on wet/branch-rich states and a
       2-hour trajectory through the rain pulse.
+  summary_small_{pihm,fbr}.npz
+      Summary() + MassBalance() (src/update.c:3-160) known-answer cases on the
+      same synthetic watershed: ws0, the RHS call that leaves the wf.* fields
+      behind, the new state y -> wf.infil / wf.fbr_infil after Summary and the
+      new ws0 (two consecutive model steps per case).
   nvec_serial.npz
       outputs of nvector_serial.c for the special-case table of N_VLinearSum /
       N_VScale and the four reductions.
@@ -186,6 +191,49 @@ def synth(fbr: bool):
     m.close()
 
 
+def summary(fbr: bool):
+    tb = W.make_named("small", fbr=fbr, dirichlet_edges=True)
+    m = reflib.RefModel(fbr=fbr).create_from_tables(tb)
+    ne, nr = tb["nelem"], tb["nriver"]
+    depth = tb["elem_f64"][W.E_DEPTH]
+    rng = np.random.default_rng(123 + fbr)
+    cases = []
+    for k, (seed, t) in enumerate([(11, 3 * 3600.0), (13, 600.0)]):
+        y0 = W.wet_state(tb, seed=seed, ponded_frac=0.3)
+        m.init_state(y0)                       # ws = ws0 = y0 (initialize.c:598,612)
+        m.set_ovlflow(np.zeros((3, ne)))
+        c = dict(ws0=y0.copy())
+        y_prev = y0
+        for step in range(2):
+            # the RHS call whose fluxes Summary sees: a state near the step's end state
+            y_rhs = y_prev * (1 + 1e-3 * rng.standard_normal(y_prev.shape))
+            forc = W.storm_forcing(tb, t + 60.0 * step, ws0_surf=np.maximum(y_prev[:ne], 0.0))
+            stale = m.get_ovlflow()
+            m.set_forcing(forc, np.zeros(nr))
+            dy = m.ode(y_rhs)
+            xf_rhs, rf = m.get_fluxes()
+            # end-of-step state: drift by dy*60 s, plus cases that hit the clamps of
+            # MassBalance (storage above the soil depth, negative storage, infil < 0)
+            y_new = y_rhs + 60.0 * dy
+            sel = rng.permutation(ne)
+            y_new[2 * ne + sel[:ne // 10]] = depth[sel[:ne // 10]] * 1.05       # gw + unsat > depth
+            y_new[ne + sel[ne // 10:ne // 5]] = -1e-3                            # negative unsat
+            y_new[2 * ne + sel[ne // 5:3 * ne // 10]] *= 0.9                     # storage drops: infil < 0
+            m.summary(y_new)
+            xf_sum, _ = m.get_fluxes()
+            c.update({f"s{step}_y_rhs": y_rhs, f"s{step}_forc": forc, f"s{step}_stale": stale,
+                      f"s{step}_infil_rhs": xf_rhs[[W.X_INFIL, W.X_FBR_INFIL]], f"s{step}_y_new": y_new,
+                      f"s{step}_xflux_sum": xf_sum, f"s{step}_ws0": m.get_ws0()})
+            y_prev = y_new
+        cases.append(c)
+    out = pack_cases(cases, prefix="sum")
+    name = "summary_small_fbr.npz" if fbr else "summary_small_pihm.npz"
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    neg = [(c[f"s{s_}_xflux_sum"][W.X_INFIL] == 0).mean() for c in cases for s_ in range(2)]
+    print(name, "cases", len(cases), "share of infil clipped at 0:", np.round(neg, 3))
+    m.close()
+
+
 def nvec():
     m = reflib.RefModel(fbr=False)
     rng = np.random.default_rng(5)
@@ -215,8 +263,14 @@ def nvec():
 
 
 if __name__ == "__main__":
+    if sys.argv[1:] == ["summary"]:     # only the files added for SURVEY 8(f) f1
+        summary(False)
+        summary(True)
+        sys.exit(0)
     example(False)
     example(True)
     synth(False)
     synth(True)
     nvec()
+    summary(False)
+    summary(True)

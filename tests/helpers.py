@@ -27,6 +27,18 @@ def golden_cases(g, prefix="rhs"):
     return [{k: g[f"{prefix}{i}_{k}"] for k in keys} for i in range(n)]
 
 
+def summary_cases(g):
+    """Summary()/MassBalance() known-answer cases (make_golden.py summary)."""
+    out = []
+    for i in range(int(g["sum_n"])):
+        steps = []
+        for s in range(2):
+            keys = ("y_rhs", "forc", "stale", "infil_rhs", "y_new", "xflux_sum", "ws0")
+            steps.append({k: g[f"sum{i}_s{s}_{k}"] for k in keys})
+        out.append(dict(ws0=g[f"sum{i}_ws0"], steps=steps))
+    return out
+
+
 def dy_scale(tables, case_forc, xflux, rivflow):
     """Per-component magnitude of the flux terms that are summed into dy
     (SURVEY 8(d) 'Parity acceptance'): the 1e-12 bound is relative to
