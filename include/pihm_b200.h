@@ -241,6 +241,34 @@ int             pihm_b200_get_fluxes(pihm_b200_ctx *ctx, double *elem_flux,
                                      double *rivflow);
 
 /* ------------------------------------------------------------------------
+ * Summary() + MassBalance() on the device.
+ *   replaces: void Summary(elem_struct *, river_struct *, N_Vector CV_Y,
+ *             double stepsize) and MassBalance() (src/update.c:3-160), called
+ *             after every SolveCVode (src/pihm.c:57).
+ * The reference reads the wf.* fields the LAST ODE() call left in the structs
+ *  -- usually a difference-quotient call of the Krylov solver.
+ * With diagnostics on, the library remembers the input vector of the last RHS
+ * call (and saves a copy if that vector is about to be overwritten by one of
+ * its own vector kernels); pihm_b200_summary_mb evaluates that call once more
+ * with the PB_X_* columns switched on (hidden state untouched), then
+ *   wf.infil / wf.fbr_infil <- mass balance (PB_X_INFIL, PB_X_FBR_INFIL are
+ *   overwritten like update.c:135,150), subrunoff, ws0 <- y (all components;
+ *   also the ws0.surf column Infil() reads, like pihm_b200_summary).
+ * Costs one extra RHS evaluation per model step instead of 144 B/element per
+ * RHS call (pihm_b200_set_flux_recording) or a D2H of y plus a host loop.
+ * ---------------------------------------------------------------------- */
+int             pihm_b200_set_diagnostics(pihm_b200_ctx *ctx, int on);
+/* ws0 = y: InitVar (src/initialize.c:598,612); also sets the ws0.surf column */
+int             pihm_b200_set_ws0(pihm_b200_ctx *ctx, const pihm_b200_vec *y);
+int             pihm_b200_summary_mb(pihm_b200_ctx *ctx, const pihm_b200_vec *y,
+                                     double stepsize);
+/* D2H, reference order; either may be NULL.  subrunoff [nelem] (the local of
+ * MassBalance, update.c:128-133,154-158; Noah's runoff2), ws0 [N] in the block
+ * layout of y.  The fluxes themselves: pihm_b200_get_fluxes. */
+int             pihm_b200_get_summary(pihm_b200_ctx *ctx, double *subrunoff,
+                                      double *ws0);
+
+/* ------------------------------------------------------------------------
  * Device-resident N_Vector.
  *   replaces: cvode/src/nvec_ser/nvector_serial.c:421-770 (ops) and
  *             :76-419 (constructors), same arithmetic per component.

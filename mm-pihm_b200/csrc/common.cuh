@@ -65,6 +65,7 @@ struct DevMesh {
     int nes, nrs;        // column strides (padded)
     int fbr, surf_mode, riv_mode;
     int record;          // write the PB_X_* flux columns
+    int replay;          // re-evaluation of the last call for its fluxes: keep s2c_stale as it is
     double dt;
     double r_deprstg, r_dt;   // refined reciprocals of DEPRSTG and dt (k_class_rcp)
     // offsets of the state blocks inside y / ydot (pihm_func.h:7-15)
@@ -185,7 +186,31 @@ struct pihm_b200_ctx {
     double *h_red = nullptr;           // pinned scalars
     int red_blocks = 0;
     long long launches = 0;            // total kernel launches (for gpu_launches)
+    // Summary()/MassBalance() on the device (pihm_b200_set_diagnostics): the wf.* fields of the
+    // LAST RHS call are produced on demand by evaluating that call once more with record = 1.
+    int diag = 0;
+    const double *last_in = nullptr;   // input vector of the last RHS call (device pointer)
+    int flux_fresh = 0;                // d_xflux holds the fluxes of the last RHS call
+    double *d_last_snap = nullptr;     // copy of *last_in, taken just before that vector is overwritten
+    double *d_rec_dy = nullptr;        // ydot scratch of the re-evaluation
+    double *d_ws0 = nullptr;           // [nsv] ws0 of elements and rivers, block layout of y
+    double *d_subrunoff = nullptr;     // [nes] MassBalance's subrunoff (update.c:128-133,154-158)
+    pb::DevMesh *d_dm_rec = nullptr;   // device copy of the record/replay view (rare exact paths)
 };
+
+namespace pb {
+inline void snapshot_last_in(pihm_b200_ctx *ctx)
+{
+    cudaMemcpyAsync(ctx->d_last_snap, ctx->last_in, sizeof(double) * ctx->nsv, cudaMemcpyDeviceToDevice, ctx->s());
+    ctx->last_in = ctx->d_last_snap;
+}
+// Call BEFORE launching anything that overwrites device vector p: if p is the input of the last
+// RHS call and the diagnostics are on, its contents are saved first (stream order).
+inline void note_write(pihm_b200_ctx *ctx, const double *p)
+{
+    if (ctx->diag && p == ctx->last_in) snapshot_last_in(ctx);
+}
+}  // namespace pb
 
 struct pihm_b200_vec {
     pihm_b200_ctx *ctx = nullptr;

@@ -196,6 +196,9 @@ struct pihm_b200_cvode {
         }
         pihm_b200_ode(ctx, tn, &wrap_a, &wrap_b);
     }
+    // diagnostics (pihm_b200_set_diagnostics): say so BEFORE a kernel overwrites a vector that
+    // can be the input of the last RHS call (zn[0], y, ytemp), see common.cuh note_write
+    void clobber(const double *p) { pb::note_write(ctx, p); }
     ZnPtrs znp() const { ZnPtrs p; for (int j = 0; j < 6; j++) p.z[j] = zn[j]; return p; }
     void scale_inplace(double c, double *v)
     {
@@ -204,6 +207,7 @@ struct pihm_b200_cvode {
     }
     void copy(const double *src, double *dst)
     {
+        clobber(dst);
         launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_elementwise<EW_COPY>, N, 0.0, src, nullptr, dst);
         count();
     }
@@ -266,6 +270,7 @@ void pihm_b200_cvode::cvPredict()
     if (tstopset) {
         if ((tn - tstop) * h > 0.0) tn = tstop;
     }
+    clobber(zn[0]);
     launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_predict<1>, N, q, znp());
     count();
 }
@@ -274,6 +279,7 @@ void pihm_b200_cvode::cvPredict()
 void pihm_b200_cvode::cvRestore(double saved_t)
 {
     tn = saved_t;
+    clobber(zn[0]);
     launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_predict<-1>, N, q, znp());
     count();
 }
@@ -418,6 +424,7 @@ int pihm_b200_cvode::spgmrSolve(bool *b_is_zero)
             // A-tilde V[l]: right scaling, DQ J*v, I - gamma J, left scaling, first MGS dot
             launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_krylov_a, N, cnorm, V[lk], ewt, vtemp, R());
             red(SC_VNRM);
+            clobber(ytemp);
             launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_krylov_b, N, n_global, d_sc, vtemp, y, ytemp);
             count(2);
             rhs(ytemp, V[l_plus_1]);     // Jv = f(tn, y + sig*v)   (cvode_spils.c:687)
@@ -559,6 +566,7 @@ int pihm_b200_cvode::cvNewtonIteration()
     double del = 0.0, delp = 0.0, dcon;
     mnewt = 0;
     for (;;) {
+        clobber(y);
         if (m == 0)
             launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_newton_res<true>, N, rl1, gamma, zn[0], zn[1], ftemp, ewt,
                                                                    acor, y, tempv, V[0], R());
@@ -577,6 +585,7 @@ int pihm_b200_cvode::cvNewtonIteration()
         deltar = eplifac * tq[4];
         const double bnorm = wrms(SC_BSUM);
         int retval;
+        clobber(y);                      // k_newton_update / k_spgmr_final: y = zn[0] + acor
         if (bnorm <= deltar) {
             // x = b (first iteration) or x = 0
             if (mnewt > 0)
@@ -721,6 +730,7 @@ void pihm_b200_cvode::cvCompleteStep()
         saved_tq5 = tq[5];
         indx_acor = qmax;
     }
+    clobber(zn[0]);
     launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_complete, N, q, znp(), lc, acor, save);
     count();
 }
@@ -1023,6 +1033,7 @@ int pihm_b200_cvode::getDky(double t, double *dky)
     const double tn1 = tn + tfuzz;
     if ((t - tp) * (t - tn1) > 0.0) return CV_BAD_T;
     const double sv = (t - tn) / h;
+    clobber(dky);
     launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_dky, N, q, sv, znp(), dky);
     count();
     return CV_SUCCESS;
@@ -1226,6 +1237,8 @@ pihm_b200_cvode *pihm_b200_cvode_create(pihm_b200_ctx *ctx)
 void pihm_b200_cvode_destroy(pihm_b200_cvode *cv)
 {
     if (!cv) return;
+    cv->clobber(cv->zn[0]);             // the vectors go away: keep the last RHS input if it is one of them
+    cv->clobber(cv->ytemp);
     cudaStreamSynchronize(cv->ctx->s());
     if (cv->prof) {
         double rhs_ms = 0.0;

@@ -436,7 +436,8 @@ void pihm_b200_destroy(pihm_b200_ctx *ctx)
                    ctx->d_bct, ctx->d_fbct, ctx->d_ri, ctx->d_up_ptr, ctx->d_up_idx,
                    ctx->d_rivflow, ctx->d_stale, ctx->d_xflux, ctx->d_nan, ctx->d_perm,
                    ctx->d_iperm, ctx->d_stage, ctx->d_red, ctx->d_gel, ctx->d_gri, ctx->d_send_e, ctx->d_send_r,
-                   ctx->d_send_e_idx, ctx->d_send_r_idx, ctx->d_slow, ctx->d_dm};
+                   ctx->d_send_e_idx, ctx->d_send_r_idx, ctx->d_slow, ctx->d_dm,
+                   ctx->d_last_snap, ctx->d_rec_dy, ctx->d_ws0, ctx->d_subrunoff, ctx->d_dm_rec};
     pb::comm_destroy(ctx);
     for (void *p : dev) if (p) cudaFree(p);
     if (ctx->h_red) cudaFreeHost(ctx->h_red);
@@ -682,11 +683,24 @@ int pihm_b200_set_flux_recording(pihm_b200_ctx *ctx, int on)
 // ---------------------------------------------------------------------------
 // RHS
 // ---------------------------------------------------------------------------
-static int launch_rhs(pihm_b200_ctx *ctx, const double *y, double *dy)
+// replay: evaluate the LAST call once more (same input, same ghosts, same stale river-edge
+// flows) with the flux columns switched on -- no halo exchange, hidden state left as it is.
+static int launch_rhs(pihm_b200_ctx *ctx, const double *y, double *dy, bool replay = false)
 {
     DevMesh dm = ctx->dm;
     HaloWait hw{};
-    if (ctx->nranks > 1 && ctx->halo_p2p) {
+    if (replay) {
+        if (ctx->nranks > 1 && ctx->halo_p2p) {     // the ghost records of the last exchange
+            const int par = (int)(ctx->halo_seq & 1);
+            dm.gel = ctx->d_hx + par * ctx->hx_stride;
+            dm.gri = dm.gel + (size_t)dm.gs * (dm.ne - dm.nown);
+        }
+        dm.record = 1;
+        dm.replay = 1;
+        dm.xflux = ctx->d_xflux;
+        dm.self = ctx->d_dm_rec;
+        PB_CUDA(cudaMemcpyAsync(ctx->d_dm_rec, &dm, sizeof(DevMesh), cudaMemcpyHostToDevice, ctx->s()));
+    } else if (ctx->nranks > 1 && ctx->halo_p2p) {
         // halo exchange over peer memory: stores into the neighbours' ghost buffers + arrival flags
         const long long seq = ++ctx->halo_seq;
         const int par = (int)(seq & 1);
@@ -739,6 +753,86 @@ static int launch_rhs(pihm_b200_ctx *ctx, const double *y, double *dy)
         if (e != cudaSuccess) { set_error(std::string("k_main launch: ") + cudaGetErrorString(e)); return -1; }
     }
     ctx->launches += 2;
+    if (!replay) ctx->last_in = y;
+    ctx->flux_fresh = dm.record;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Summary() + MassBalance() on the device (src/update.c:3-160)
+// ---------------------------------------------------------------------------
+int pihm_b200_set_diagnostics(pihm_b200_ctx *ctx, int on)
+{
+    if (!ctx) return -1;
+    PB_CUDA(cudaStreamSynchronize(ctx->s()));
+    if (on && !ctx->d_ws0) {
+        const size_t nb = sizeof(double) * std::max<int64_t>(ctx->nsv, 1);
+        if (!ctx->d_xflux) {
+            PB_CUDA(cudaMalloc((void **)&ctx->d_xflux, sizeof(double) * PB_X_NCOL * ctx->dm.nes));
+            PB_CUDA(cudaMemset(ctx->d_xflux, 0, sizeof(double) * PB_X_NCOL * ctx->dm.nes));
+        }
+        PB_CUDA(cudaMalloc((void **)&ctx->d_last_snap, nb));
+        PB_CUDA(cudaMalloc((void **)&ctx->d_rec_dy, nb));
+        PB_CUDA(cudaMalloc((void **)&ctx->d_ws0, nb));
+        PB_CUDA(cudaMemset(ctx->d_ws0, 0, nb));
+        PB_CUDA(cudaMalloc((void **)&ctx->d_subrunoff, sizeof(double) * ctx->dm.nes));
+        PB_CUDA(cudaMemset(ctx->d_subrunoff, 0, sizeof(double) * ctx->dm.nes));
+        PB_CUDA(cudaMalloc((void **)&ctx->d_dm_rec, sizeof(DevMesh)));
+    }
+    if (on && !ctx->dm.xflux) {
+        // the column pointer travels with every launch; record stays as it is (0: no writes)
+        ctx->dm.xflux = ctx->d_xflux;
+        PB_CUDA(cudaMemcpy(ctx->d_dm, &ctx->dm, sizeof(DevMesh), cudaMemcpyHostToDevice));
+    }
+    if (!on && ctx->last_in == ctx->d_last_snap) ctx->last_in = nullptr;
+    ctx->diag = on ? 1 : 0;
+    return 0;
+}
+
+int pihm_b200_set_ws0(pihm_b200_ctx *ctx, const pihm_b200_vec *y)
+{
+    if (!ctx || !y || y->n != ctx->nsv) { set_error("pihm_b200_set_ws0: bad argument"); return -1; }
+    if (!ctx->d_ws0) { set_error("pihm_b200_set_ws0: call pihm_b200_set_diagnostics(ctx, 1) first"); return -1; }
+    PB_CUDA(cudaMemcpyAsync(ctx->d_ws0, y->d, sizeof(double) * ctx->nsv, cudaMemcpyDeviceToDevice, ctx->s()));
+    return pihm_b200_summary(ctx, y);      // ws0.surf of Infil()
+}
+
+int pihm_b200_summary_mb(pihm_b200_ctx *ctx, const pihm_b200_vec *y, double stepsize)
+{
+    if (!ctx || !y || y->n != ctx->nsv || !(stepsize > 0.0)) { set_error("pihm_b200_summary_mb: bad argument"); return -1; }
+    if (!ctx->diag) { set_error("pihm_b200_summary_mb: call pihm_b200_set_diagnostics(ctx, 1) first"); return -1; }
+    if (!ctx->flux_fresh) {
+        // wf.* of the last ODE() call: evaluate that call again with the columns on
+        if (!ctx->last_in) { set_error("pihm_b200_summary_mb: no RHS call to take the fluxes from"); return -1; }
+        if (launch_rhs(ctx, ctx->last_in, ctx->d_rec_dy, true) != 0) return -1;
+        ctx->flux_fresh = 1;
+    }
+    const int ne = ctx->dm.nown;
+    if (ne > 0) {
+        k_summary_mb<<<(ne + 255) / 256, 256, 0, ctx->s()>>>(ctx->dm, y->d, ctx->d_ws0, ctx->d_subrunoff, stepsize);
+        ctx->launches++;
+    }
+    // update.c:47,94: ws0 = ws
+    PB_CUDA(cudaMemcpyAsync(ctx->d_ws0, y->d, sizeof(double) * ctx->nsv, cudaMemcpyDeviceToDevice, ctx->s()));
+    PB_CUDA(cudaGetLastError());
+    return pihm_b200_summary(ctx, y);
+}
+
+int pihm_b200_get_summary(pihm_b200_ctx *ctx, double *subrunoff, double *ws0)
+{
+    if (!ctx || !ctx->d_ws0) { set_error("pihm_b200_get_summary: diagnostics are off"); return -1; }
+    if (subrunoff) {
+        const int ne = ctx->dm.nown, nes = ctx->dm.nes;
+        std::vector<double> h((size_t)nes);
+        PB_CUDA(cudaStreamSynchronize(ctx->s()));
+        PB_CUDA(cudaMemcpy(h.data(), ctx->d_subrunoff, sizeof(double) * nes, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < ne; i++) subrunoff[ctx->perm[i]] = h[i];
+    }
+    if (ws0) {
+        pihm_b200_vec w;
+        w.ctx = ctx; w.d = ctx->d_ws0; w.n = ctx->nsv; w.owns = false;
+        if (pihm_b200_vec_download(&w, ws0) != 0) return -1;
+    }
     return 0;
 }
 
@@ -777,7 +871,10 @@ int pihm_b200_get_fluxes(pihm_b200_ctx *ctx, double *elem_flux, double *rivflow)
     const int ne = ctx->dm.ne, nes = ctx->dm.nes, nr = ctx->dm.nr, nrs = ctx->dm.nrs;
     PB_CUDA(cudaStreamSynchronize(ctx->s()));
     if (elem_flux) {
-        if (!ctx->dm.record) { set_error("get_fluxes: enable pihm_b200_set_flux_recording first"); return -1; }
+        if (!ctx->d_xflux || !(ctx->dm.record || ctx->diag)) {
+            set_error("get_fluxes: enable pihm_b200_set_flux_recording or pihm_b200_set_diagnostics first");
+            return -1;
+        }
         std::vector<double> h((size_t)PB_X_NCOL * nes);
         PB_CUDA(cudaMemcpy(h.data(), ctx->d_xflux, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
         for (int c = 0; c < PB_X_NCOL; c++)
@@ -813,7 +910,11 @@ pihm_b200_vec *pihm_b200_vec_new(pihm_b200_ctx *ctx)
 void pihm_b200_vec_free(pihm_b200_vec *v)
 {
     if (!v) return;
-    if (v->owns && v->d) { cudaStreamSynchronize(v->ctx->s()); cudaFree(v->d); }
+    if (v->owns && v->d) {
+        pb::note_write(v->ctx, v->d);
+        cudaStreamSynchronize(v->ctx->s());
+        cudaFree(v->d);
+    }
     delete v;
 }
 
@@ -823,6 +924,7 @@ void *pihm_b200_vec_devptr(pihm_b200_vec *v) { return v ? v->d : nullptr; }
 int pihm_b200_vec_upload(pihm_b200_vec *v, const double *host)
 {
     pihm_b200_ctx *ctx = v->ctx;
+    pb::note_write(ctx, v->d);
     if (!ctx->reorder) {
         PB_CUDA(cudaMemcpyAsync(v->d, host, sizeof(double) * v->n, cudaMemcpyHostToDevice, ctx->s()));
     } else {
@@ -864,6 +966,7 @@ void pihm_b200_nv_linearsum(double a, const pihm_b200_vec *x, double b, const pi
     const int mode = (!unit && a == b) ? LS_SCALESUM : ((!unit && a == -b) ? LS_SCALEDIFF : LS_GENERAL);
     const bool alias = (z->d == x->d) || (z->d == y->d);
     cudaStream_t s = ctx->s();
+    pb::note_write(ctx, z->d);
     if (alias) {
         if (mode == LS_GENERAL) k_linearsum_alias<LS_GENERAL><<<g, PB_VEC_THREADS, 0, s>>>(n, a, x->d, b, y->d, z->d);
         else if (mode == LS_SCALESUM) k_linearsum_alias<LS_SCALESUM><<<g, PB_VEC_THREADS, 0, s>>>(n, a, x->d, b, y->d, z->d);
@@ -879,6 +982,7 @@ void pihm_b200_nv_linearsum(double a, const pihm_b200_vec *x, double b, const pi
 #define PB_EW(OP, c, xp, yp)                                                                     \
     do {                                                                                         \
         pihm_b200_ctx *ctx = z->ctx;                                                             \
+        pb::note_write(ctx, z->d);                                                               \
         k_elementwise<OP><<<vec_blocks(ctx, z->n), PB_VEC_THREADS, 0, ctx->s()>>>(z->n, c, xp, yp, z->d); \
         ctx->launches++;                                                                         \
     } while (0)

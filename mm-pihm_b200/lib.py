@@ -88,6 +88,10 @@ _SIGS = {
     "pihm_b200_test_div": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pihm_b200_set_flux_recording": (C.c_int, [C.c_void_p, C.c_int]),
     "pihm_b200_get_fluxes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pihm_b200_set_diagnostics": (C.c_int, [C.c_void_p, C.c_int]),
+    "pihm_b200_set_ws0": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pihm_b200_summary_mb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double]),
+    "pihm_b200_get_summary": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pihm_b200_vec_new": (C.c_void_p, [C.c_void_p]),
     "pihm_b200_vec_free": (None, [C.c_void_p]),
     "pihm_b200_vec_length": (C.c_int64, [C.c_void_p]),
@@ -303,6 +307,25 @@ class Model:
     def Summary(self, y: "Vec"):
         """ws0.surf <- y[SURF] on the device (the RHS-relevant part of Summary, src/update.c:47)"""
         _check(self.L, self.L.pihm_b200_summary(self.h, y.h), "summary")
+
+    # Summary() + MassBalance() on the device (src/update.c:3-160) ---------------
+    def set_diagnostics(self, on: bool = True):
+        _check(self.L, self.L.pihm_b200_set_diagnostics(self.h, int(on)), "set_diagnostics")
+
+    def set_ws0(self, y: "Vec"):
+        """elem[i].ws0 = elem[i].ws of InitVar (src/initialize.c:598,612)"""
+        _check(self.L, self.L.pihm_b200_set_ws0(self.h, y.h), "set_ws0")
+
+    def SummaryMB(self, y: "Vec", stepsize: float):
+        """void Summary(elem, river, CV_Y, stepsize) (src/update.c:3): mass-balance wf.infil /
+        wf.fbr_infil from the fluxes of the last RHS call, ws0 <- y; everything stays on the device."""
+        _check(self.L, self.L.pihm_b200_summary_mb(self.h, y.h, float(stepsize)), "summary_mb")
+
+    def get_summary(self):
+        """-> (subrunoff [nelem], ws0 [N]) in reference order"""
+        sr = np.zeros(self.nelem); w = np.zeros(self.nsv)
+        _check(self.L, self.L.pihm_b200_get_summary(self.h, _ptr(sr), _ptr(w)), "get_summary")
+        return sr, w
 
     def set_flux_recording(self, on: bool):
         _check(self.L, self.L.pihm_b200_set_flux_recording(self.h, int(on)), "set_flux_recording")

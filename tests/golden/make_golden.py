@@ -227,6 +227,25 @@ def summary(fbr: bool):
             y_prev = y_new
         cases.append(c)
     out = pack_cases(cases, prefix="sum")
+    # the wf.* fields after SolveCVode + Summary along the reference's own run (the quiet first
+    # 15 model steps of synth()'s trajectory, where both integrators walk in lock step)
+    m.init_state(tb["y0"])
+    m.set_ovlflow(np.zeros((3, ne)))
+    m.set_cvode_param()
+    tx, ty, ts = [], [], []
+    for k in range(15):
+        ws = m.get_ws()
+        if k % 15 == 0:
+            f = W.storm_forcing(tb, k * 60.0)
+        f[W.F_WS0SURF] = ws[:ne]
+        m.set_forcing(f, np.zeros(nr))
+        m.model_step(k)
+        if (k + 1) in (1, 15):
+            tx.append(m.get_fluxes()[0]); ty.append(m.get_y())
+            s = m.stats()
+            ts.append([s[key] for key in ("nst", "nfe", "nni", "ncfn", "netf", "nli", "ncfl", "nfeLS")])
+    out["traj_steps"] = np.array([1, 15]); out["traj_xflux"] = np.array(tx)
+    out["traj_y"] = np.array(ty); out["traj_stats"] = np.array(ts)
     name = "summary_small_fbr.npz" if fbr else "summary_small_pihm.npz"
     np.savez_compressed(os.path.join(HERE, name), **out)
     neg = [(c[f"s{s_}_xflux_sum"][W.X_INFIL] == 0).mean() for c in cases for s_ in range(2)]

@@ -82,6 +82,41 @@ def test_reference_cvode_on_device_nvector_matches_our_integrator_bitwise(size, 
     cv.close(); mA.close(); mB.close()
 
 
+def dropin_run(tb, steps, t0, diagnostics=False):
+    """Route 1 model steps (reference CVODE on our N_Vector / RHS) -> per step dict(y[, xf, sr]);
+    with diagnostics the device Summary()/MassBalance() follows every solve (tests/test_summary_gpu.py)."""
+    nr = tb["nriver"]
+    L = lib.load_library()
+    m = lib.Model(tb, reorder=1)
+    nv = L.N_VNew_PihmB200(m.h)
+    y_host = host_mirror(nv, m.nsv)
+    y_host[:] = tb["y0"]
+    assert L.N_VPihmB200_Push(nv) == 0
+    ext = reflib.RefCvodeExternal(nv, C.cast(L.PihmB200_ODE, C.c_void_p).value, m.h)
+    yv = lib.Vec(m, handle=L.N_VPihmB200_Device(nv))
+    if diagnostics:
+        m.set_diagnostics(True)
+        m.set_ws0(yv)
+    out = []
+    for k in range(steps):
+        if k % 15 == 0:
+            m.set_forcing(W.storm_forcing(tb, t0 + k * 60.0), np.zeros(nr))
+        m.Summary(yv)
+        assert ext.solve((k + 1) * 60.0) == (k + 1) * 60.0
+        r = {}
+        if diagnostics:
+            m.SummaryMB(yv, tb["stepsize"])
+            r["xf"] = m.get_fluxes()[0]
+            r["sr"] = m.get_summary()[0]
+        assert L.N_VPihmB200_Pull(nv) == 0
+        r["y"] = np.array(y_host)
+        out.append(r)
+    ext.free()
+    L.N_VDestroy_PihmB200(nv)
+    m.close()
+    return out
+
+
 def test_nvector_ops_table_and_mirror():
     """clone/destroy through the ops table and Serial-compatible content prefix"""
     tb = W.make_named("tiny")
