@@ -91,6 +91,30 @@ enum pihm_b200_elem_flux_col {
     PB_X_NCOL
 };
 
+/* interception / snow / ET: static double columns read by
+ * IntcpSnowEt (src/is_sm_et.c:4-225) besides those of pihm_b200_elem_col:
+ * lc_struct (elem_struct.h:113-137), epc_struct, soil smc*, ps.zlvl_wind */
+enum pihm_b200_et_col {
+    PB_ET_ALBEDOMIN = 0, PB_ET_ALBEDOMAX, PB_ET_CMCFACTR, PB_ET_SHDFAC,
+    PB_ET_CFACTR, PB_ET_RGL, PB_ET_RSMIN, PB_ET_RSMAX, PB_ET_TOPT,
+    PB_ET_SMCMIN, PB_ET_SMCWLT, PB_ET_SMCREF, PB_ET_ZLVL_WIND,
+    PB_ET_NCOL
+};
+/* attrib.meteo_type / lai_type / lc_type (elem_struct.h:5-25), 1-based;
+ * lai_type 0 = monthly table by land cover (forcing.c:249-257) */
+enum pihm_b200_et_icol {
+    PB_ETI_METEO_TYPE = 0, PB_ETI_LAI_TYPE, PB_ETI_LC_TYPE,
+    PB_ETI_NCOL
+};
+/* what pihm_b200_et_get returns per element: the three forcing columns of the
+ * RHS, the two canopy fluxes, the two storages IntcpSnowEt integrates */
+enum pihm_b200_et_out_col {
+    PB_EO_PCPDRP = 0, PB_EO_EDIR, PB_EO_ETT, PB_EO_EC, PB_EO_DRIP,
+    PB_EO_SNEQV, PB_EO_CMC,
+    PB_EO_NCOL
+};
+#define PIHM_B200_NUM_METEO_VAR 7  /* src/include/pihm_const.h:48-55 */
+
 #define PIHM_B200_NUM_RIVFLX 11   /* src/include/pihm_const.h:71,130-140 */
 
 typedef struct pihm_b200_mesh {
@@ -267,6 +291,46 @@ int             pihm_b200_summary_mb(pihm_b200_ctx *ctx, const pihm_b200_vec *y,
  * layout of y.  The fluxes themselves: pihm_b200_get_fluxes. */
 int             pihm_b200_get_summary(pihm_b200_ctx *ctx, double *subrunoff,
                                       double *ws0);
+
+/* ------------------------------------------------------------------------
+ * Forcing scatter + interception / snow / ET on the device.
+ *   replaces: the per-element loops of ApplyMeteoForc and ApplyLai
+ *             (src/forcing.c:134-160, 242-258) and
+ *             void IntcpSnowEt(int t, double stepsize, elem_struct *elem,
+ *             const calib_struct *cal) (src/is_sm_et.c:4-225), run every
+ *             ctrl.etstep (src/pihm.c:27-48).
+ * The host keeps the time-series interpolation (IntrplForc, a handful of
+ * stations) and the month-of-year lookups, and passes their results by type;
+ * the device gathers them per element, runs the element physics and writes
+ * wf.pcpdrp / wf.edir / wf.ett straight into the forcing columns the RHS
+ * reads -- no [nelem] array crosses PCIe.  ws.sneqv and ws.cmc live on the
+ * device (zero after et_create, like Initialize without an .ic file).
+ * ---------------------------------------------------------------------- */
+/* et_f64 [PB_ET_NCOL][nelem], et_i32 [PB_ETI_NCOL][nelem], reference order */
+int             pihm_b200_et_create(pihm_b200_ctx *ctx, const double *et_f64,
+                                    const int32_t *et_i32);
+typedef struct pihm_b200_et_step {
+    double          stepsize;    /* (double)ctrl.etstep (pihm.c:41)          */
+    double          cal_edir, cal_ec, cal_ett;   /* calib_struct             */
+    double          meltf;       /* MonthlyMf(t) (forcing.c:603)             */
+    int32_t         nmeteo, nlai, nlc;
+    int32_t         reserved;
+    const double   *meteo;       /* [nmeteo][PIHM_B200_NUM_METEO_VAR]:
+                                    forc->meteo[k].value[] after IntrplForc  */
+    const double   *lai;         /* [nlai] forc->lai[k].value[0]; may be NULL */
+    const double   *lai_lc;      /* [nlc] MonthlyLai(t, lc) for lc = 1..nlc  */
+    const double   *z0_lc;       /* [nlc] MonthlyRl(t, lc)                   */
+} pihm_b200_et_step;
+/* y: the state Summary() left in elem.ws (= CV_Y after the last model step,
+ * or the initial condition); only its UNSAT and GW blocks are read */
+int             pihm_b200_intcp_snow_et(pihm_b200_ctx *ctx,
+                                        const pihm_b200_et_step *step,
+                                        const pihm_b200_vec *y);
+/* ws.sneqv / ws.cmc (e.g. from an .ic file): [nelem] each, reference order */
+int             pihm_b200_et_set_state(pihm_b200_ctx *ctx, const double *sneqv,
+                                       const double *cmc);
+/* D2H of [PB_EO_NCOL][nelem], reference order (print / restart only) */
+int             pihm_b200_et_get(pihm_b200_ctx *ctx, double *out);
 
 /* ------------------------------------------------------------------------
  * Device-resident N_Vector.

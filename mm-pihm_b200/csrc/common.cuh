@@ -196,6 +196,13 @@ struct pihm_b200_ctx {
     double *d_ws0 = nullptr;           // [nsv] ws0 of elements and rivers, block layout of y
     double *d_subrunoff = nullptr;     // [nes] MassBalance's subrunoff (update.c:128-133,154-158)
     pb::DevMesh *d_dm_rec = nullptr;   // device copy of the record/replay view (rare exact paths)
+    // interception / snow / ET on the device (pihm_b200_et_create)
+    double *d_etf = nullptr;           // [PB_ET_NCOL][nes] static columns, internal order
+    int *d_eti = nullptr;              // [PB_ETI_NCOL][nes]
+    double *d_eto = nullptr;           // [PB_EO_NCOL][nes] outputs + the two storages
+    double *d_et_tab = nullptr;        // per-step tables by type: meteo | lai | lai_lc | z0_lc
+    size_t et_tab_cap = 0;             // doubles
+    int et_max_meteo = 0, et_max_lai = 0, et_max_lc = 0;   // largest type index used by an element
 };
 
 namespace pb {

@@ -10,6 +10,7 @@
 #include "nvec.cuh"
 #include "reorder.h"
 #include "rhs.cuh"
+#include "et.cuh"
 
 namespace pb {
 static thread_local std::string g_err;
@@ -437,7 +438,8 @@ void pihm_b200_destroy(pihm_b200_ctx *ctx)
                    ctx->d_rivflow, ctx->d_stale, ctx->d_xflux, ctx->d_nan, ctx->d_perm,
                    ctx->d_iperm, ctx->d_stage, ctx->d_red, ctx->d_gel, ctx->d_gri, ctx->d_send_e, ctx->d_send_r,
                    ctx->d_send_e_idx, ctx->d_send_r_idx, ctx->d_slow, ctx->d_dm,
-                   ctx->d_last_snap, ctx->d_rec_dy, ctx->d_ws0, ctx->d_subrunoff, ctx->d_dm_rec};
+                   ctx->d_last_snap, ctx->d_rec_dy, ctx->d_ws0, ctx->d_subrunoff, ctx->d_dm_rec,
+                   ctx->d_etf, ctx->d_eti, ctx->d_eto, ctx->d_et_tab};
     pb::comm_destroy(ctx);
     for (void *p : dev) if (p) cudaFree(p);
     if (ctx->h_red) cudaFreeHost(ctx->h_red);
@@ -833,6 +835,107 @@ int pihm_b200_get_summary(pihm_b200_ctx *ctx, double *subrunoff, double *ws0)
         w.ctx = ctx; w.d = ctx->d_ws0; w.n = ctx->nsv; w.owns = false;
         if (pihm_b200_vec_download(&w, ws0) != 0) return -1;
     }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Forcing scatter + IntcpSnowEt on the device (src/forcing.c:134-160,242-258; src/is_sm_et.c:4-225)
+// ---------------------------------------------------------------------------
+int pihm_b200_et_create(pihm_b200_ctx *ctx, const double *et_f64, const int32_t *et_i32)
+{
+    if (!ctx || !et_f64 || !et_i32) { set_error("et_create: bad argument"); return -1; }
+    const int ne = ctx->dm.ne, nes = ctx->dm.nes;
+    std::vector<double> f((size_t)PB_ET_NCOL * nes, 0.0);
+    std::vector<int> ii((size_t)PB_ETI_NCOL * nes, 1);
+    ctx->et_max_meteo = ctx->et_max_lai = ctx->et_max_lc = 0;
+    for (int i = 0; i < ne; i++) {
+        const int r = ctx->perm[i];
+        for (int c = 0; c < PB_ET_NCOL; c++) f[(size_t)c * nes + i] = et_f64[(size_t)c * ne + r];
+        for (int c = 0; c < PB_ETI_NCOL; c++) ii[(size_t)c * nes + i] = et_i32[(size_t)c * ne + r];
+        const int mt = et_i32[(size_t)PB_ETI_METEO_TYPE * ne + r], lt = et_i32[(size_t)PB_ETI_LAI_TYPE * ne + r],
+                  lc = et_i32[(size_t)PB_ETI_LC_TYPE * ne + r];
+        if (mt < 1 || lt < 0 || lc < 1) { set_error("et_create: meteo_type / lc_type must be >= 1, lai_type >= 0"); return -1; }
+        ctx->et_max_meteo = std::max(ctx->et_max_meteo, mt);
+        ctx->et_max_lai = std::max(ctx->et_max_lai, lt);
+        ctx->et_max_lc = std::max(ctx->et_max_lc, lc);
+    }
+    PB_CUDA(cudaStreamSynchronize(ctx->s()));
+    if (!ctx->d_etf) {
+        PB_CUDA(cudaMalloc((void **)&ctx->d_etf, sizeof(double) * f.size()));
+        PB_CUDA(cudaMalloc((void **)&ctx->d_eti, sizeof(int) * ii.size()));
+        PB_CUDA(cudaMalloc((void **)&ctx->d_eto, sizeof(double) * PB_EO_NCOL * nes));
+    }
+    PB_CUDA(cudaMemcpy(ctx->d_etf, f.data(), sizeof(double) * f.size(), cudaMemcpyHostToDevice));
+    PB_CUDA(cudaMemcpy(ctx->d_eti, ii.data(), sizeof(int) * ii.size(), cudaMemcpyHostToDevice));
+    PB_CUDA(cudaMemset(ctx->d_eto, 0, sizeof(double) * PB_EO_NCOL * nes));
+    return 0;
+}
+
+int pihm_b200_intcp_snow_et(pihm_b200_ctx *ctx, const pihm_b200_et_step *st, const pihm_b200_vec *y)
+{
+    if (!ctx || !st || !y || y->n != ctx->nsv) { set_error("intcp_snow_et: bad argument"); return -1; }
+    if (!ctx->d_etf) { set_error("intcp_snow_et: call pihm_b200_et_create first"); return -1; }
+    if (!(st->stepsize > 0.0) || !st->meteo || !st->lai_lc || !st->z0_lc || st->nmeteo < ctx->et_max_meteo ||
+        st->nlc < ctx->et_max_lc || st->nlai < ctx->et_max_lai || (ctx->et_max_lai > 0 && !st->lai)) {
+        set_error("intcp_snow_et: a type table is missing or shorter than the largest type index in use");
+        return -1;
+    }
+    // the by-type tables of this step: a few hundred bytes, one staged copy
+    const size_t nm = (size_t)st->nmeteo * PIHM_B200_NUM_METEO_VAR, nl = (size_t)std::max(st->nlai, 0), nc = (size_t)st->nlc;
+    std::vector<double> tab(nm + nl + 2 * nc);
+    std::copy(st->meteo, st->meteo + nm, tab.begin());
+    if (nl) std::copy(st->lai, st->lai + nl, tab.begin() + nm);
+    std::copy(st->lai_lc, st->lai_lc + nc, tab.begin() + nm + nl);
+    std::copy(st->z0_lc, st->z0_lc + nc, tab.begin() + nm + nl + nc);
+    if (tab.size() > ctx->et_tab_cap) {
+        PB_CUDA(cudaStreamSynchronize(ctx->s()));
+        if (ctx->d_et_tab) cudaFree(ctx->d_et_tab);
+        PB_CUDA(cudaMalloc((void **)&ctx->d_et_tab, sizeof(double) * tab.size()));
+        ctx->et_tab_cap = tab.size();
+    }
+    PB_CUDA(cudaMemcpyAsync(ctx->d_et_tab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice, ctx->s()));
+    PB_CUDA(cudaStreamSynchronize(ctx->s()));      // `tab` goes out of scope
+    EtStepDev d{};
+    d.stepsize = st->stepsize; d.cal_edir = st->cal_edir; d.cal_ec = st->cal_ec; d.cal_ett = st->cal_ett;
+    d.meltf = st->meltf;
+    d.nmeteo = st->nmeteo; d.nlai = st->nlai; d.nlc = st->nlc;
+    d.meteo = ctx->d_et_tab; d.lai = ctx->d_et_tab + nm; d.lai_lc = ctx->d_et_tab + nm + nl;
+    d.z0_lc = ctx->d_et_tab + nm + nl + nc;
+    const int ne = ctx->dm.nown;
+    if (ne > 0) {
+        k_intcp_snow_et<<<(ne + 127) / 128, 128, 0, ctx->s()>>>(ctx->dm, d, ctx->d_etf, ctx->d_eti, y->d, ctx->d_eto,
+                                                                  ctx->d_ft);
+        ctx->launches++;
+    }
+    PB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int pihm_b200_et_set_state(pihm_b200_ctx *ctx, const double *sneqv, const double *cmc)
+{
+    if (!ctx || !ctx->d_eto) { set_error("et_set_state: call pihm_b200_et_create first"); return -1; }
+    const int ne = ctx->dm.ne, nes = ctx->dm.nes;
+    std::vector<double> h((size_t)nes, 0.0);
+    PB_CUDA(cudaStreamSynchronize(ctx->s()));
+    const double *src[2] = {sneqv, cmc};
+    const int col[2] = {PB_EO_SNEQV, PB_EO_CMC};
+    for (int k = 0; k < 2; k++) {
+        if (!src[k]) continue;
+        for (int i = 0; i < ne; i++) h[i] = src[k][ctx->perm[i]];
+        PB_CUDA(cudaMemcpy(ctx->d_eto + (size_t)col[k] * nes, h.data(), sizeof(double) * nes, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+int pihm_b200_et_get(pihm_b200_ctx *ctx, double *out)
+{
+    if (!ctx || !ctx->d_eto || !out) { set_error("et_get: call pihm_b200_et_create first"); return -1; }
+    const int ne = ctx->dm.ne, nes = ctx->dm.nes;
+    std::vector<double> h((size_t)PB_EO_NCOL * nes);
+    PB_CUDA(cudaStreamSynchronize(ctx->s()));
+    PB_CUDA(cudaMemcpy(h.data(), ctx->d_eto, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+    for (int c = 0; c < PB_EO_NCOL; c++)
+        for (int i = 0; i < ne; i++) out[(size_t)c * ne + ctx->perm[i]] = h[(size_t)c * nes + i];
     return 0;
 }
 

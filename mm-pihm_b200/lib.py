@@ -36,6 +36,27 @@ class CvodeParam(C.Structure):
                 ("stab_lim_det", C.c_int32), ("maxl", C.c_int32)]
 
 
+class EtStep(C.Structure):
+    """struct pihm_b200_et_step"""
+    _fields_ = [("stepsize", C.c_double), ("cal_edir", C.c_double), ("cal_ec", C.c_double),
+                ("cal_ett", C.c_double), ("meltf", C.c_double),
+                ("nmeteo", C.c_int32), ("nlai", C.c_int32), ("nlc", C.c_int32), ("reserved", C.c_int32),
+                ("meteo", C.c_void_p), ("lai", C.c_void_p), ("lai_lc", C.c_void_p), ("z0_lc", C.c_void_p)]
+
+
+def make_et_step(stepsize, cal, meltf, meteo, lai, lai_lc, z0_lc):
+    """-> (EtStep, keepalive).  meteo [nmeteo, 7], lai [nlai], lai_lc / z0_lc [nlc]; cal = (edir, ec, ett)"""
+    meteo = np.ascontiguousarray(meteo, np.float64).reshape(-1, W.NUM_METEO_VAR)
+    lai = np.ascontiguousarray(lai if lai is not None else [], np.float64).reshape(-1)
+    lai_lc = np.ascontiguousarray(lai_lc, np.float64); z0_lc = np.ascontiguousarray(z0_lc, np.float64)
+    assert lai_lc.shape == z0_lc.shape
+    st = EtStep(stepsize=float(stepsize), cal_edir=float(cal[0]), cal_ec=float(cal[1]), cal_ett=float(cal[2]),
+                meltf=float(meltf), nmeteo=meteo.shape[0], nlai=lai.shape[0], nlc=lai_lc.shape[0], reserved=0,
+                meteo=meteo.ctypes.data, lai=lai.ctypes.data if lai.size else None,
+                lai_lc=lai_lc.ctypes.data, z0_lc=z0_lc.ctypes.data)
+    return st, (meteo, lai, lai_lc, z0_lc)
+
+
 class CvodeStats(C.Structure):
     """struct pihm_b200_cvode_stats"""
     _fields_ = [(k, C.c_int64) for k in ("nst", "nfe", "nni", "ncfn", "netf", "nli", "ncfl",
@@ -88,6 +109,10 @@ _SIGS = {
     "pihm_b200_test_div": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pihm_b200_set_flux_recording": (C.c_int, [C.c_void_p, C.c_int]),
     "pihm_b200_get_fluxes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pihm_b200_et_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pihm_b200_intcp_snow_et": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pihm_b200_et_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pihm_b200_et_get": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pihm_b200_set_diagnostics": (C.c_int, [C.c_void_p, C.c_int]),
     "pihm_b200_set_ws0": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pihm_b200_summary_mb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double]),
@@ -326,6 +351,27 @@ class Model:
         sr = np.zeros(self.nelem); w = np.zeros(self.nsv)
         _check(self.L, self.L.pihm_b200_get_summary(self.h, _ptr(sr), _ptr(w)), "get_summary")
         return sr, w
+
+    # ApplyMeteoForc/ApplyLai scatter + IntcpSnowEt on the device (src/forcing.c, src/is_sm_et.c) ---
+    def et_create(self, et_f64, et_i32):
+        f = np.ascontiguousarray(et_f64, np.float64); ii = np.ascontiguousarray(et_i32, np.int32)
+        assert f.shape == (W.ET_NCOL, self.nelem) and ii.shape == (W.ETI_NCOL, self.nelem)
+        _check(self.L, self.L.pihm_b200_et_create(self.h, _ptr(f), _ptr(ii)), "et_create")
+
+    def IntcpSnowEt(self, step: "EtStep", y: "Vec"):
+        """void IntcpSnowEt(t, stepsize, elem, cal) (src/is_sm_et.c:4) incl. the per-element forcing
+        assignments; writes wf.pcpdrp / edir / ett into the forcing columns of the RHS on the device"""
+        _check(self.L, self.L.pihm_b200_intcp_snow_et(self.h, C.byref(step), y.h), "intcp_snow_et")
+
+    def et_set_state(self, sneqv, cmc):
+        a = np.ascontiguousarray(sneqv, np.float64); b = np.ascontiguousarray(cmc, np.float64)
+        assert a.shape == b.shape == (self.nelem,)
+        _check(self.L, self.L.pihm_b200_et_set_state(self.h, _ptr(a), _ptr(b)), "et_set_state")
+
+    def et_get(self):
+        out = np.zeros((W.EO_NCOL, self.nelem))
+        _check(self.L, self.L.pihm_b200_et_get(self.h, _ptr(out)), "et_get")
+        return out
 
     def set_flux_recording(self, on: bool):
         _check(self.L, self.L.pihm_b200_set_flux_recording(self.h, int(on)), "set_flux_recording")

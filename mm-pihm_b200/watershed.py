@@ -38,6 +38,12 @@ import numpy as np
 (X_OVL0, X_OVL1, X_OVL2, X_SUB0, X_SUB1, X_SUB2, X_INFIL, X_RECHG,
  X_EDIR_SURF, X_EDIR_UNSAT, X_EDIR_GW, X_ETT_UNSAT, X_ETT_GW, X_FBR_INFIL,
  X_FBR_RECHG, X_FBRFLOW0, X_FBRFLOW1, X_FBRFLOW2, X_NCOL) = range(19)
+# include/pihm_b200.h: pihm_b200_et_col / et_icol / et_out_col
+(ET_ALBEDOMIN, ET_ALBEDOMAX, ET_CMCFACTR, ET_SHDFAC, ET_CFACTR, ET_RGL, ET_RSMIN, ET_RSMAX, ET_TOPT,
+ ET_SMCMIN, ET_SMCWLT, ET_SMCREF, ET_ZLVL_WIND, ET_NCOL) = range(14)
+(ETI_METEO_TYPE, ETI_LAI_TYPE, ETI_LC_TYPE, ETI_NCOL) = range(4)
+(EO_PCPDRP, EO_EDIR, EO_ETT, EO_EC, EO_DRIP, EO_SNEQV, EO_CMC, EO_NCOL) = range(8)
+NUM_METEO_VAR = 7
 NUM_RIVFLX = 11
 
 # ksath ksatv kinfv dinf alpha beta porosity kmach kmacv areafv areafh

@@ -42,6 +42,7 @@ def lib():
         for f in ("oracle_set_ws0", "oracle_get_ws0"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_summary.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+        L.oracle_intcp_snow_et.argtypes = [C.c_void_p] * 6
         L.oracle_ode.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
         L.oracle_nv_linearsum.argtypes = [C.c_int64, C.c_double, C.c_void_p, C.c_double,
                                           C.c_void_p, C.c_void_p]
@@ -121,6 +122,16 @@ class OracleModel:
         self.L.oracle_get_fluxes(self.h, _ptr(xf), _ptr(rf))
         return xf, rf[:, :self.nriver]
 
+
+    # -- IntcpSnowEt + per-element forcing assignment, src/is_sm_et.c / src/forcing.c --
+    def intcp_snow_et(self, step, et_f64, et_i32, y, state):
+        """step: ctypes struct pihm_b200_et_step (by reference); state [EO_NCOL, nelem] carries
+        sneqv / cmc in; returns the updated [EO_NCOL, nelem] table"""
+        f = np.ascontiguousarray(et_f64, np.float64); ii = np.ascontiguousarray(et_i32, np.int32)
+        y = np.ascontiguousarray(y, np.float64)
+        out = np.array(state, np.float64, order="C")
+        self.L.oracle_intcp_snow_et(self.h, C.byref(step), _ptr(f), _ptr(ii), _ptr(y), _ptr(out))
+        return out
 
     # -- Summary() + MassBalance(), src/update.c ---------------------------------
     def set_ws0(self, y):

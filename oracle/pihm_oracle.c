@@ -221,6 +221,167 @@ void oracle_summary(oracle_model *om, const double *y, double stepsize,
     if (subrunoff_out) memcpy(subrunoff_out, om->subrunoff, sizeof(double) * ne);
 }
 
+/* ---- ApplyMeteoForc/ApplyLai per-element part + IntcpSnowEt ------------
+ * forcing.c:134-160, 242-258; is_sm_et.c:4-225.  etf [PB_ET_NCOL][ne], eti
+ * [PB_ETI_NCOL][ne]; out [PB_EO_NCOL][ne] carries ws.sneqv / ws.cmc in and
+ * everything out; y supplies elem.ws.unsat / ws.gw (Summary, update.c:19-21).
+ * Also writes wf.pcpdrp/edir/ett into the forcing table of the RHS. */
+void oracle_intcp_snow_et(oracle_model *om, const pihm_b200_et_step *st,
+    const double *etf, const int32_t *eti, const double *y, double *out)
+{
+    const double    CP = 1004.0, LVH2O = 2.501e6, SIGMA = 5.67e-8, RD = 287.04,
+                    RV = 461.5;                      /* pihm_const.h:8-14 */
+    const double    TSNOW = -3.0, TRAIN = 1.0, T0 = 0.0;
+    const size_t    ne = (size_t)om->ne;
+    const double    stepsize = st->stepsize;
+    size_t          i;
+
+#define TF(c) (etf[(size_t)(c) * ne + i])
+#define TI(c) (eti[(size_t)(c) * ne + i])
+#define O(c)  (out[(size_t)(c) * ne + i])
+    for (i = 0; i < ne; i++)
+    {
+        const double   *mv = st->meteo +
+            (size_t)(TI(PB_ETI_METEO_TYPE) - 1) * PIHM_B200_NUM_METEO_VAR;
+        double          prcp = mv[0] / 1000.0, sfctmp = mv[1], rh = mv[2];
+        double          wind = mv[3], soldn = (mv[4] > 0.0) ? mv[4] : 0.0;
+        int             lc = TI(PB_ETI_LC_TYPE) - 1;
+        double          lai = (TI(PB_ETI_LAI_TYPE) > 0) ?
+            st->lai[TI(PB_ETI_LAI_TYPE) - 1] : st->lai_lc[lc];
+        double          shdfac = TF(PB_ET_SHDFAC), cfactr = TF(PB_ET_CFACTR);
+        double          depth = E(PB_E_DEPTH, i), rzd = E(PB_E_RZD, i);
+        double          unsat = y[ne + i], gw = y[2 * ne + i];
+        double          sneqv = O(PB_EO_SNEQV), cmc = O(PB_EO_CMC);
+        double          albedo, radnet, vp, pres, qv, qvsat, frac_snow,
+                        snow_rate, melt_rate, intcp_max, z0, zlvl, ra, gamma,
+                        delta, etp, satn, betas, edir, ec, ett, drip, isval;
+
+        albedo = 0.5 * (TF(PB_ET_ALBEDOMIN) + TF(PB_ET_ALBEDOMAX));
+        radnet = soldn * (1.0 - albedo);
+        sfctmp = sfctmp - 273.15;
+        rh = rh / 100.0;
+        vp = 611.2 * exp(17.67 * sfctmp / (sfctmp + 243.5)) * rh;
+        pres = 101.325 * 1.0e3 *
+            pow((293.0 - 0.0065 * E(PB_E_ZMAX, i)) / 293.0, 5.26);
+        qv = 0.622 * vp / pres;
+        qvsat = 0.622 * (vp / rh) / pres;
+
+        frac_snow = (sfctmp < TSNOW) ? 1.0 :
+            ((sfctmp > TRAIN) ? 0.0 : (TRAIN - sfctmp) / (TRAIN - TSNOW));
+        snow_rate = frac_snow * prcp;
+        sneqv += snow_rate * stepsize;
+        melt_rate = (sfctmp > T0) ? (sfctmp - T0) * st->meltf : 0.0;
+        if (sneqv > melt_rate * stepsize)
+        {
+            sneqv -= melt_rate * stepsize;
+        }
+        else
+        {
+            melt_rate = sneqv / stepsize;
+            sneqv = 0.0;
+        }
+
+        intcp_max = TF(PB_ET_CMCFACTR) * lai * shdfac;
+        z0 = st->z0_lc[lc];
+        zlvl = TF(PB_ET_ZLVL_WIND);
+        ra = log(zlvl / z0) * log(10.0 * zlvl / z0) / (wind * 0.16);
+        gamma = 4.0 * 0.7 * SIGMA * RD / CP * pow(sfctmp + 273.15, 4) /
+            (pres / ra) + 1.0;
+        delta = LVH2O * LVH2O * 0.622 / RV / CP / pow(sfctmp + 273.15, 2) *
+            qvsat;
+        etp = (radnet * delta + gamma * (1.2 * LVH2O * (qvsat - qv) / ra)) /
+            (1000.0 * LVH2O * (delta + gamma));
+
+        if (depth - gw < rzd)
+        {
+            satn = 1.0;
+        }
+        else
+        {
+            double          ratio = unsat / (depth - gw);
+
+            satn = (ratio > 1.0) ? 1.0 : ((ratio < 0.0) ? 0.0 :
+                0.5 * (1.0 - cos(3.14 * ratio)));
+        }
+        betas = (satn * E(PB_E_POROSITY, i) + TF(PB_ET_SMCMIN) -
+            TF(PB_ET_SMCWLT)) / (TF(PB_ET_SMCREF) - TF(PB_ET_SMCWLT));
+        betas = (betas < 0.0001) ? 0.0001 : ((betas > 1.0) ? 1.0 : betas);
+        edir = (1.0 - shdfac) * pow(betas, 2) * etp;
+        edir *= st->cal_edir;
+        edir = (edir < 0.0) ? 0.0 : edir;
+
+        if (lai > 0.0)
+        {
+            double          cmc_c = (cmc < 0.0) ? 0.0 :
+                ((cmc > intcp_max) ? intcp_max : cmc);
+            double          cfrac = (cmc < 0.0) ? 0.0 :
+                ((cmc > intcp_max) ? intcp_max : cmc) / intcp_max;
+            double          rsmin = TF(PB_ET_RSMIN), rsmax = TF(PB_ET_RSMAX);
+            double          fr, alphar, etas, gammas, rs, pc;
+
+            ec = shdfac * pow(cmc_c / intcp_max, cfactr) * etp;
+            ec *= st->cal_ec;
+            ec = (ec < 0.0) ? 0.0 : ec;
+            fr = 1.1 * radnet / (TF(PB_ET_RGL) * lai);
+            fr = (fr < 0.0) ? 0.0 : fr;
+            alphar = (1.0 + fr) / (fr + (rsmin / rsmax));
+            alphar = (alphar > 10000.0) ? 10000.0 : alphar;
+            etas = 1.0 - 0.0016 * (pow((TF(PB_ET_TOPT) - 273.15 - sfctmp), 2));
+            etas = (etas < 0.0001) ? 0.0001 : etas;
+            gammas = 1.0 / (1.0 + 0.00025 * (vp / rh - vp));
+            gammas = (gammas < 0.01) ? 0.01 : gammas;
+            rs = rsmin * alphar / (betas * lai * etas * gammas);
+            rs = (rs > rsmax) ? rsmax : rs;
+            pc = (1.0 + delta / gamma) / (1.0 + rs / ra + delta / gamma);
+            ett = shdfac * pc * (1.0 - pow(cfrac, cfactr)) * etp;
+            ett *= st->cal_ett;
+            ett = (ett < 0.0) ? 0.0 : ett;
+            ett = ((gw < (depth - rzd)) && unsat <= 0.0) ? 0.0 : ett;
+            drip = (cmc <= 0.0) ? 0.0 :
+                6.52E-7 * intcp_max * exp(3.89 * cmc / intcp_max);
+        }
+        else
+        {
+            ett = 0.0; ec = 0.0; drip = 0.0;
+        }
+
+        if (drip < 0.0) drip = 0.0;
+        if (drip * stepsize > cmc) drip = cmc / stepsize;
+        isval = cmc + (1.0 - frac_snow) * prcp * shdfac * stepsize -
+            ec * stepsize - drip * stepsize;
+        if (isval > intcp_max)
+        {
+            cmc = intcp_max;
+            drip += (isval - intcp_max) / stepsize;
+        }
+        else if (isval < 0.0)
+        {
+            cmc = 0.0;
+            if (ec + drip > 0.0)
+            {
+                ec = ec / (ec + drip) *
+                    (cmc + (1.0 - frac_snow) * prcp * shdfac * stepsize);
+                drip = drip / (ec + drip) *
+                    (cmc + (1.0 - frac_snow) * prcp * shdfac * stepsize);
+            }
+        }
+        else
+        {
+            cmc = isval;
+        }
+        O(PB_EO_PCPDRP) = (1.0 - shdfac) * (1.0 - frac_snow) * prcp + drip +
+            melt_rate;
+        O(PB_EO_EDIR) = edir; O(PB_EO_ETT) = ett; O(PB_EO_EC) = ec;
+        O(PB_EO_DRIP) = drip; O(PB_EO_SNEQV) = sneqv; O(PB_EO_CMC) = cmc;
+        F(PB_F_PCPDRP, i) = O(PB_EO_PCPDRP);
+        F(PB_F_EDIR, i) = edir;
+        F(PB_F_ETT, i) = ett;
+    }
+#undef TF
+#undef TI
+#undef O
+}
+
 /* ---- small physics helpers ------------------------------------------- */
 
 static double surf_h(double surfeqv)                 /* hydrol.c:92-126 */

@@ -688,6 +688,167 @@ void ref_get_ws0(double *y)
     }
 }
 
+/*
+ * Interception / snow / ET, files mode only (the land-cover
+ * and vegetation fields come from Initialize()).
+ */
+/* dims[4] = {nmeteo, nlai, 40 (rows of the monthly tables, forcing.c:359), etstep} */
+int ref_et_dims(int *dims)
+{
+    if (!H.from_files) return -1;
+    dims[0] = H.pihm->forc.nmeteo;
+    dims[1] = H.pihm->forc.nlai;
+    dims[2] = 40;
+    dims[3] = H.pihm->ctrl.etstep;
+    return 0;
+}
+
+/* the static columns IntcpSnowEt reads: [PB_ET_NCOL][nelem], [PB_ETI_NCOL][nelem] */
+void ref_pack_et_tables(double *etf, int32_t *eti)
+{
+    int             i;
+
+#define TF(c) (etf[(size_t)(c) * nelem + i])
+#define TI(c) (eti[(size_t)(c) * nelem + i])
+    for (i = 0; i < nelem; i++)
+    {
+        const elem_struct *e = &H.pihm->elem[i];
+
+        TF(PB_ET_ALBEDOMIN) = e->lc.albedomin;
+        TF(PB_ET_ALBEDOMAX) = e->lc.albedomax;
+        TF(PB_ET_CMCFACTR) = e->lc.cmcfactr;
+        TF(PB_ET_SHDFAC) = e->lc.shdfac;
+        TF(PB_ET_CFACTR) = e->lc.cfactr;
+        TF(PB_ET_RGL) = e->epc.rgl;
+        TF(PB_ET_RSMIN) = e->epc.rsmin;
+        TF(PB_ET_RSMAX) = e->epc.rsmax;
+        TF(PB_ET_TOPT) = e->epc.topt;
+        TF(PB_ET_SMCMIN) = e->soil.smcmin;
+        TF(PB_ET_SMCWLT) = e->soil.smcwlt;
+        TF(PB_ET_SMCREF) = e->soil.smcref;
+        TF(PB_ET_ZLVL_WIND) = e->ps.zlvl_wind;
+        TI(PB_ETI_METEO_TYPE) = e->attrib.meteo_type;
+        TI(PB_ETI_LAI_TYPE) = e->attrib.lai_type;
+        TI(PB_ETI_LC_TYPE) = e->attrib.lc_type;
+    }
+#undef TF
+#undef TI
+}
+
+/* month-of-year lookups of the reference at model time t (forcing.c:351-618) */
+void ref_et_monthly(int t, int nlc, double *lai_lc, double *z0_lc,
+    double *meltf)
+{
+    int             k;
+
+    for (k = 0; k < nlc; k++)
+    {
+        lai_lc[k] = MonthlyLai(t, k + 1);
+        z0_lc[k] = MonthlyRl(t, k + 1);
+    }
+    *meltf = MonthlyMf(t);
+}
+
+/* forc->meteo[k].value[] / forc->lai[k].value[0] as the last ApplyForc left them */
+void ref_et_get_forc(double *meteo, double *lai)
+{
+    int             k, j;
+
+    for (k = 0; k < H.pihm->forc.nmeteo; k++)
+        for (j = 0; j < NUM_METEO_VAR; j++)
+            meteo[k * NUM_METEO_VAR + j] = H.pihm->forc.meteo[k].value[j];
+    for (k = 0; k < H.pihm->forc.nlai; k++)
+        lai[k] = H.pihm->forc.lai[k].value[0];
+}
+
+void ref_et_get_cal(double *cal3)
+{
+    cal3[0] = H.pihm->cal.edir;
+    cal3[1] = H.pihm->cal.ec;
+    cal3[2] = H.pihm->cal.ett;
+}
+
+/* out[PB_EO_NCOL][nelem] */
+void ref_et_get(double *out)
+{
+    int             i;
+
+    for (i = 0; i < nelem; i++)
+    {
+        const elem_struct *e = &H.pihm->elem[i];
+
+        out[(size_t)PB_EO_PCPDRP * nelem + i] = e->wf.pcpdrp;
+        out[(size_t)PB_EO_EDIR * nelem + i] = e->wf.edir;
+        out[(size_t)PB_EO_ETT * nelem + i] = e->wf.ett;
+        out[(size_t)PB_EO_EC * nelem + i] = e->wf.ec;
+        out[(size_t)PB_EO_DRIP * nelem + i] = e->wf.drip;
+        out[(size_t)PB_EO_SNEQV * nelem + i] = e->ws.sneqv;
+        out[(size_t)PB_EO_CMC * nelem + i] = e->ws.cmc;
+    }
+}
+
+void ref_et_set_state(const double *sneqv, const double *cmc)
+{
+    int             i;
+
+    for (i = 0; i < nelem; i++)
+    {
+        H.pihm->elem[i].ws.sneqv = sneqv[i];
+        H.pihm->elem[i].ws.cmc = cmc[i];
+    }
+}
+
+/*
+ * The reference's IntcpSnowEt (src/is_sm_et.c:4) on caller data: station
+ * values meteo[nmeteo][NUM_METEO_VAR] and lai[nlai] take the place of
+ * IntrplForc's results, the per-element assignments of ApplyMeteoForc /
+ * ApplyLai (forcing.c:134-160, 242-258) are made as there, y supplies
+ * elem.ws.unsat / ws.gw as Summary() would have left them.
+ */
+int ref_et_run(int t, double stepsize, const double *meteo, const double *lai,
+    const double *y)
+{
+    int             i, k, j;
+    pihm_struct     pihm = H.pihm;
+
+    if (!H.from_files) return -1;
+    for (k = 0; k < pihm->forc.nmeteo; k++)
+        for (j = 0; j < NUM_METEO_VAR; j++)
+            pihm->forc.meteo[k].value[j] = meteo[k * NUM_METEO_VAR + j];
+    for (k = 0; k < pihm->forc.nlai; k++)
+        pihm->forc.lai[k].value[0] = lai[k];
+    for (i = 0; i < nelem; i++)
+    {
+        elem_struct    *e = &pihm->elem[i];
+        int             ind = e->attrib.meteo_type - 1;
+
+        e->wf.prcp = pihm->forc.meteo[ind].value[PRCP_TS] / 1000.0;
+        e->es.sfctmp = pihm->forc.meteo[ind].value[SFCTMP_TS];
+        e->ps.rh = pihm->forc.meteo[ind].value[RH_TS];
+        e->ps.sfcspd = pihm->forc.meteo[ind].value[SFCSPD_TS];
+        e->ef.soldn = pihm->forc.meteo[ind].value[SOLAR_TS];
+        e->ef.soldn = (e->ef.soldn > 0.0) ? e->ef.soldn : 0.0;
+        if (e->attrib.lai_type > 0)
+        {
+            e->ps.proj_lai = pihm->forc.lai[e->attrib.lai_type - 1].value[0];
+        }
+        else
+        {
+            e->ps.proj_lai = MonthlyLai(t, e->attrib.lc_type);
+        }
+        e->ws.unsat = y[UNSAT(i)];
+        e->ws.gw = y[GW(i)];
+    }
+    IntcpSnowEt(t, stepsize, pihm->elem, &pihm->cal);
+    return 0;
+}
+
+/* model time of step k (ctrl.tout[k]) */
+int ref_tout(int cstep)
+{
+    return H.from_files ? H.pihm->ctrl.tout[cstep] : 0;
+}
+
 /* element/river water states after Summary() (ws), for trajectory checks */
 void ref_get_ws(double *y)
 {

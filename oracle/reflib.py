@@ -178,6 +178,49 @@ class RefModel:
     def get_ws(self):
         y = np.zeros(self.nsv); self.lib.ref_get_ws(_ptr(y)); return y
 
+    # -- interception / snow / ET (files mode) -----------------------------------
+    def et_dims(self):
+        d = (C.c_int * 4)()
+        if self.lib.ref_et_dims(d) != 0:
+            raise RuntimeError("ET hooks need a project opened from files")
+        return dict(nmeteo=d[0], nlai=d[1], nlc=d[2], etstep=d[3])
+
+    def pack_et_tables(self):
+        f = np.zeros((13, self.nelem)); ii = np.zeros((3, self.nelem), np.int32)
+        self.lib.ref_pack_et_tables(_ptr(f), _ptr(ii))
+        return f, ii
+
+    def et_monthly(self, t, nlc=40):
+        a = np.zeros(nlc); b = np.zeros(nlc); mf = C.c_double()
+        self.lib.ref_et_monthly(int(t), int(nlc), _ptr(a), _ptr(b), C.byref(mf))
+        return a, b, mf.value
+
+    def et_get_forc(self):
+        d = self.et_dims()
+        m = np.zeros((d["nmeteo"], 7)); l = np.zeros(max(d["nlai"], 1))
+        self.lib.ref_et_get_forc(_ptr(m), _ptr(l))
+        return m, l[:d["nlai"]]
+
+    def et_get_cal(self):
+        c = np.zeros(3); self.lib.ref_et_get_cal(_ptr(c)); return c
+
+    def et_get(self):
+        o = np.zeros((7, self.nelem)); self.lib.ref_et_get(_ptr(o)); return o
+
+    def et_set_state(self, sneqv, cmc):
+        a = np.ascontiguousarray(sneqv, np.float64); b = np.ascontiguousarray(cmc, np.float64)
+        self.lib.ref_et_set_state(_ptr(a), _ptr(b))
+
+    def et_run(self, t, stepsize, meteo, lai, y):
+        m = np.ascontiguousarray(meteo, np.float64); l = np.ascontiguousarray(lai if len(lai) else [0.0], np.float64)
+        y = np.ascontiguousarray(y, np.float64)
+        self.lib.ref_et_run.argtypes = [C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+        if self.lib.ref_et_run(int(t), float(stepsize), _ptr(m), _ptr(l), _ptr(y)) != 0:
+            raise RuntimeError("ref_et_run: files mode only")
+
+    def tout(self, cstep):
+        return int(self.lib.ref_tout(int(cstep)))
+
     def summary(self, y):
         """Summary() of src/update.c on y (= CV_Y after SolveCVode)."""
         y = np.ascontiguousarray(y, np.float64); assert y.shape == (self.nsv,)

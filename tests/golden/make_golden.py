@@ -25,6 +25,12 @@ reference on machines where /root/reference does not exist (the GPU box).
       same synthetic watershed: ws0, the RHS call that leaves the wf.* fields
       behind, the new state y -> wf.infil / wf.fbr_infil after Summary and the
       new ws0 (two consecutive model steps per case).
+  et_example.npz
+      IntcpSnowEt (src/is_sm_et.c) with the per-element forcing assignments of
+      ApplyMeteoForc/ApplyLai on input/example: the static columns, the
+      reference's own ApplyForc + IntcpSnowEt calls of the first simulated hour,
+      and calls on made-up station values / canopy and snow storages / months
+      that reach the other branches (rain, melt, lai = 0, full canopy ...).
   nvec_serial.npz
       outputs of nvector_serial.c for the special-case table of N_VLinearSum /
       N_VScale and the four reductions.
@@ -253,6 +259,67 @@ def summary(fbr: bool):
     m.close()
 
 
+def et():
+    m = reflib.RefModel(fbr=False).open_project(REF_ROOT, "example")
+    ne = m.nelem
+    d = m.et_dims()
+    etf, eti = m.pack_et_tables()
+    tb = m.pack_tables()
+    out = {k: tb[k] for k in TABLE_KEYS}
+    out.update(et_f64=etf, et_i32=eti, cal=m.et_get_cal(), etstep=np.float64(d["etstep"]))
+    cases = []
+
+    def record(t, state_in, y, meteo, lai, res):
+        lai_lc, z0_lc, meltf = m.et_monthly(t, d["nlc"])
+        cases.append(dict(t=np.int64(t), state_in=state_in, y=y.copy(), meteo=meteo.copy(), lai=np.array(lai, float),
+                          lai_lc=lai_lc, z0_lc=z0_lc, meltf=np.float64(meltf), out=res))
+
+    # (a) the reference's own calls: ApplyForc + IntcpSnowEt at the etsteps of the first hour,
+    #     with the model advancing in between (elem.ws changes, snow accumulates)
+    m.set_cvode_param()
+    for k in range(60):
+        if k % 15 == 0:
+            state_in = m.et_get()[[W.EO_SNEQV, W.EO_CMC]]
+            y = m.get_ws()
+            m.apply_forcing(k)
+            meteo, lai = m.et_get_forc()
+            record(m.tout(k), state_in, y, meteo, lai, m.et_get())
+        m.model_step(k, skip_forcing=True)
+    # (b) made-up inputs through the same IntcpSnowEt
+    rng = np.random.default_rng(77)
+    y0 = m.get_ws()
+    depth = tb["elem_f64"][W.E_DEPTH]
+    month_t = [1230768000 + int(86400 * 30.5 * k) for k in range(12)]
+    for k in range(14):
+        t = month_t[k % 12] + 3600 * int(rng.integers(0, 24))
+        temp_c = [-8.0, -2.0, 0.5, 3.0, 12.0, 25.0, 33.0][k % 7] + rng.uniform(-0.4, 0.4)
+        meteo = np.array([[rng.choice([0.0, 0.8, 6.0]), temp_c + 273.15, rng.uniform(25, 100), rng.uniform(0.3, 9.0),
+                           rng.choice([-5.0, 0.0, 150.0, 700.0]), 300.0, 98000.0]])
+        lai = [[0.0, 0.4, 2.5, 5.0][k % 4]]
+        intcp_max = etf[W.ET_CMCFACTR] * lai[0] * etf[W.ET_SHDFAC]
+        cmc = rng.choice([0.0, 0.3, 0.9, 1.0, 1.4], ne) * np.maximum(intcp_max, 1e-5) - 1e-6 * (rng.random(ne) < 0.05)
+        sneqv = rng.choice([0.0, 1e-5, 2e-3, 0.05], ne)
+        y = y0.copy()
+        y[ne:2 * ne] = rng.choice([-1e-3, 0.0, 0.05, 0.3, 1.5], ne) * rng.random(ne)          # unsat
+        y[2 * ne:3 * ne] = depth * rng.choice([0.0, 0.2, 0.7, 0.97, 1.02], ne)               # gw
+        m.et_set_state(sneqv, cmc)
+        m.et_run(t, [900.0, 3600.0][k % 2], meteo, lai, y)
+        cases.append(dict(t=np.int64(t), state_in=np.array([sneqv, cmc]), y=y, meteo=meteo, lai=np.array(lai[:1]),
+                          stepsize=np.float64([900.0, 3600.0][k % 2]), out=m.et_get(),
+                          **dict(zip(("lai_lc", "z0_lc", "meltf"), m.et_monthly(t, d["nlc"])))))
+        cases[-1]["meltf"] = np.float64(cases[-1]["meltf"])
+    for c in cases:
+        c.setdefault("stepsize", np.float64(d["etstep"]))
+    out.update(pack_cases(cases, prefix="et"))
+    np.savez_compressed(os.path.join(HERE, "et_example.npz"), **out)
+    o = np.array([c["out"] for c in cases])
+    print("et_example.npz cases", len(cases), "pcpdrp>0:", (o[:, W.EO_PCPDRP] > 0).mean().round(3),
+          "ett>0:", (o[:, W.EO_ETT] > 0).mean().round(3), "snow>0:", (o[:, W.EO_SNEQV] > 0).mean().round(3),
+          "cmc at max:", np.mean([np.mean(c["out"][W.EO_CMC] >= etf[W.ET_CMCFACTR] * c["lai"][0] * etf[W.ET_SHDFAC])
+                                  for c in cases[4:]]).round(3))
+    m.close()
+
+
 def nvec():
     m = reflib.RefModel(fbr=False)
     rng = np.random.default_rng(5)
@@ -282,6 +349,9 @@ def nvec():
 
 
 if __name__ == "__main__":
+    if sys.argv[1:] == ["et"]:          # only the file added for SURVEY 8(f) f2
+        et()
+        sys.exit(0)
     if sys.argv[1:] == ["summary"]:     # only the files added for SURVEY 8(f) f1
         summary(False)
         summary(True)
@@ -293,3 +363,4 @@ if __name__ == "__main__":
     nvec()
     summary(False)
     summary(True)
+    et()

@@ -39,6 +39,12 @@ def summary_cases(g):
     return out
 
 
+def et_cases(g):
+    """IntcpSnowEt known-answer cases (make_golden.py et)"""
+    keys = ("t", "state_in", "y", "meteo", "lai", "lai_lc", "z0_lc", "meltf", "stepsize", "out")
+    return [{k: g[f"et{i}_{k}"] for k in keys} for i in range(int(g["et_n"]))]
+
+
 def dy_scale(tables, case_forc, xflux, rivflow):
     """Per-component magnitude of the flux terms that are summed into dy
     (SURVEY 8(d) 'Parity acceptance'): the 1e-12 bound is relative to
