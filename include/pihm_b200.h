@@ -410,6 +410,21 @@ int             pihm_b200_cvode_solve(pihm_b200_cvode *cv, double tout,
                                       pihm_b200_vec *y, double *tret);
 int             pihm_b200_cvode_get_stats(const pihm_b200_cvode *cv,
                                           pihm_b200_cvode_stats *st);
+/* The linear solver alone: the lsolve hook for a CVODE that keeps its own BDF /
+ * Newton stepper (cv_mem->cv_lsolve, cvode_impl.h:198-211).
+ *   replaces: CVSpgmrSolve (cvode/src/cvode/cvode_spgmr.c:355-441) and under it
+ *   SpgmrSolve, ModifiedGS, QRfact/QRsol, CVSpilsAtimes, CVSpilsDQJtimes.
+ * cv: an engine from pihm_b200_cvode_create (no cvode_init needed); tn, gamma,
+ * tq4 = cv_mem->cv_tn, cv_gamma, cv_tq[4]; mnewt = cv_mem->cv_mnewt; b, weight,
+ * ycur, fcur as handed to lsolve.  Returns 0, >0 (recoverable) or <0; the
+ * solution overwrites b.  Counters: pihm_b200_cvode_get_stats (nli, ncfl,
+ * nfeLS, njtimes).  The attach code is in INTEGRATION.md 3a'. */
+int             pihm_b200_spgmr_solve(pihm_b200_cvode *cv, double tn,
+                                      double gamma, double tq4, int mnewt,
+                                      pihm_b200_vec *b,
+                                      const pihm_b200_vec *weight,
+                                      const pihm_b200_vec *ycur,
+                                      const pihm_b200_vec *fcur);
 /* AdjCVodeMaxStep (ode.c:500-560) on the integrator's own counters */
 typedef struct pihm_b200_maxstep_ctrl {
     double          maxstep, stepsize, stmin, nncfn, nnimax, nnimin, decr, incr;

@@ -1301,6 +1301,69 @@ int pihm_b200_cvode_init(pihm_b200_cvode *cv, const pihm_b200_cvode_param *p, do
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// The linear solver alone, as the lsolve hook of a CVODE that keeps its own stepper
+// (SURVEY 8(b) "Linear-solver plug-in"): CVSpgmrSolve (cvode_spgmr.c:355-441) with SpgmrSolve,
+// CVSpilsAtimes and CVSpilsDQJtimes underneath -- the same fused kernels the integrator uses.
+// b, weight, ycur, fcur are the caller's vectors (cv_mem->cv_tempv, cv_ewt, cv_y, cv_ftemp).
+// Returns 0 / >0 recoverable / <0 fatal like cv_lsolve; the solution overwrites b.
+// ---------------------------------------------------------------------------
+int pihm_b200_spgmr_solve(pihm_b200_cvode *cv, double tn, double gamma, double tq4, int mnewt, pihm_b200_vec *b,
+                          const pihm_b200_vec *weight, const pihm_b200_vec *ycur, const pihm_b200_vec *fcur)
+{
+    if (!cv || !b || !weight || !ycur || !fcur || b->n != cv->N || weight->n != cv->N || ycur->n != cv->N ||
+        fcur->n != cv->N) {
+        set_error("spgmr_solve: bad argument");
+        return -1;
+    }
+    cudaSetDevice(cv->ctx->device);
+    // the integrator's own ewt / y / ftemp step aside for the caller's vectors
+    double *ewt0 = cv->ewt, *y0 = cv->y, *ft0 = cv->ftemp;
+    cv->ewt = weight->d; cv->y = ycur->d; cv->ftemp = fcur->d;
+    cv->tn = tn; cv->gamma = gamma; cv->mnewt = mnewt;
+    if (cv->maxl <= 0 || cv->maxl > 5) cv->maxl = CVSPILS_MAXL;
+    cv->sqrtN = std::sqrt(cv->n_global);            // cvode_spgmr.c:195-196
+    int ret;
+    {
+        cv->clobber(cv->V[0]);
+        launch_pdl(cv->s(), cv->ctx->pdl, cv->blocks, PB_VEC_THREADS, k_lsolve_head, cv->N, (const double *)b->d,
+                   (const double *)weight->d, cv->V[0], cv->R());
+        cv->count();
+        cv->red(SC_BSUM);
+        cv->sync_spin();
+        cv->deltar = cv->eplifac * tq4;
+        const double bnorm = cv->wrms(SC_BSUM);
+        KryPtrs kp{};
+        Coef6 c{};
+        int krydim = 0;
+        bool write_b = false;
+        if (bnorm <= cv->deltar) {
+            ret = 0;                                 // x = b, or x = 0 after the first Newton iteration
+            write_b = mnewt > 0;
+        } else {
+            cv->delta = cv->deltar * cv->sqrtN;
+            bool zero = false;
+            ret = cv->spgmrSolve(&zero);
+            if (ret == 0) {
+                write_b = true;
+                if (!zero) {
+                    krydim = cv->krydim_last;
+                    for (int k = 0; k < krydim; k++) { kp.v[k] = cv->V[k]; c.c[k] = cv->yg[k]; }
+                }
+            }
+        }
+        if (write_b) {
+            cv->clobber(b->d);
+            launch_pdl(cv->s(), cv->ctx->pdl, cv->blocks, PB_VEC_THREADS, k_lsolve_tail, cv->N, krydim, kp, c,
+                       (const double *)weight->d, b->d);
+            cv->count();
+        }
+    }
+    cv->ewt = ewt0; cv->y = y0; cv->ftemp = ft0;
+    if (cudaGetLastError() != cudaSuccess) { set_error("spgmr_solve: kernel launch failed"); return -1; }
+    return ret;
+}
+
 int pihm_b200_cvode_set_max_step(pihm_b200_cvode *cv, double hmax)
 {
     if (!cv || hmax < 0.0) { set_error("set_max_step: bad argument"); return -1; }

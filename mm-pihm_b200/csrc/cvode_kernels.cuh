@@ -293,6 +293,24 @@ k_newton_res(long long n, double rl1, double gamma, const double *__restrict__ z
     red_finish<false>(rb, s, SC_BSUM, 0.0, -1);
 }
 
+// Head of CVSpgmrSolve when it is used as the lsolve hook of an external CVODE
+// (pihm_b200_spgmr_solve): the part of k_newton_res that belongs to the linear solver,
+//   V0 = weight * b ;  S = sum (b*weight)^2   [bnorm = sqrt(S/N), beta = sqrt(S)]
+// (cvode_spgmr.c:370, sundials_spgmr.c:209-233 with x0 = 0, no preconditioner)
+static __global__ void __launch_bounds__(PB_VEC_THREADS)
+k_lsolve_head(long long n, const double *__restrict__ b, const double *__restrict__ w,
+              double *__restrict__ V0, RedBuf rb)
+{
+    pdl_enter();
+    double s = 0.0;
+    PB_GRID_STRIDE(i, n) {
+        const double p = w[i] * b[i];
+        V0[i] = p;
+        s += p * p;
+    }
+    red_finish<false>(rb, s, SC_BSUM, 0.0, -1);
+}
+
 // Krylov step, part a (sundials_spgmr.c:264 or :341, then :278):
 //   V[l] = c * V[l]   (normalisation, c = 1/r_norm or 1/Hes[l][l-1])
 //   vtemp = V[l] / ewt ;  SC_VNRM = sum (vtemp*ewt)^2   (cvode_spils.c:679)
@@ -428,6 +446,22 @@ k_spgmr_final(long long n, int krydim, KryPtrs V, Coef6 yg, const double *__rest
         }
     }
     red_finish<false>(rb, s, SC_DEL, 0.0, -1);
+}
+
+// Tail of the lsolve hook: the solver part of k_spgmr_final,
+//   xcor = sum_k yg[k]*V[k] ; xcor /= weight ; x = 0 + xcor ; b = x
+// (sundials_spgmr.c:348-378, cvode_spgmr.c:389); krydim == 0: b = 0 (x stayed 0)
+static __global__ void __launch_bounds__(PB_VEC_THREADS)
+k_lsolve_tail(long long n, int krydim, KryPtrs V, Coef6 yg, const double *__restrict__ w, double *__restrict__ b)
+{
+    pdl_enter();
+    PB_GRID_STRIDE(i, n) {
+        double xc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 5; k++) if (k < krydim) xc = xc + yg.c[k] * V.v[k][i];
+        if (krydim > 0) xc = xc / w[i];
+        b[i] = 0.0 + xc;
+    }
 }
 
 // Newton update when the linear solve returned b itself (early outs of

@@ -141,6 +141,8 @@ _SIGS = {
     "pihm_b200_cvode_set_max_step": (C.c_int, [C.c_void_p, C.c_double]),
     "pihm_b200_cvode_solve": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "pihm_b200_cvode_get_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pihm_b200_spgmr_solve": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pihm_b200_adj_cvode_max_step": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 # include/pihm_b200_sundials.h

@@ -19,7 +19,9 @@
  */
 #include "pihm.h"
 #include "cvode_spils.h"
+#include "cvode_impl.h"      /* CVodeMem: the linear-solver hooks (cvode/src/cvode/cvode_impl.h:198-226) */
 #include "pihm_b200.h"
+#include "pihm_b200_sundials.h"
 
 /* globals that src/main.c:4-16 defines (main.c itself is not compiled) */
 int             verbose_mode;
@@ -963,6 +965,66 @@ int ref_ext_cvode_init(void *nv_y, void *rhs_fn, void *user_data, double reltol,
     CVodeSetMaxStep(X_mem, (realtype)maxstep);
     CVodeSetMaxNumSteps(X_mem, mxsteps);
     return CVSpgmr(X_mem, PREC_NONE, 0);
+}
+
+/*
+ * Linear-solver plug-in: attach a device SPGMR to the reference
+ * CVODE the way CVSpgmr() attaches its own (cvode_spgmr.c:135-138,174,220).
+ * This is the binding a maintainer adds (INTEGRATION.md 3a'); `solve` is
+ * pihm_b200_spgmr_solve, `engine` a pihm_b200_cvode from pihm_b200_cvode_create.
+ */
+typedef int     (*b200_lsolve_fn)(void *engine, double tn, double gamma,
+    double tq4, int mnewt, void *b, void *weight, void *ycur, void *fcur);
+static b200_lsolve_fn X_lsolve;
+static void    *X_engine;
+
+#define DEVVEC(v) ((void *)((N_VectorContent_PihmB200)((v)->content))->dev)
+
+static int x_linit(CVodeMem cv_mem)
+{
+    (void)cv_mem;
+    return 0;
+}
+
+static int x_lsolve(CVodeMem cv_mem, N_Vector b, N_Vector weight, N_Vector ycur,
+    N_Vector fcur)
+{
+    return X_lsolve(X_engine, cv_mem->cv_tn, cv_mem->cv_gamma,
+        cv_mem->cv_tq[4], cv_mem->cv_mnewt, DEVVEC(b), DEVVEC(weight),
+        DEVVEC(ycur), DEVVEC(fcur));
+}
+
+static int x_lfree(CVodeMem cv_mem)
+{
+    cv_mem->cv_lmem = NULL;
+    return 0;
+}
+
+int ref_ext_cvode_attach_lsolve(void *solve, void *engine)
+{
+    CVodeMem        cv_mem = (CVodeMem)X_mem;
+
+    if (cv_mem == NULL || solve == NULL) return -1;
+    if (cv_mem->cv_lfree != NULL) cv_mem->cv_lfree(cv_mem);   /* drop CVSPGMR */
+    X_lsolve = (b200_lsolve_fn)solve;
+    X_engine = engine;
+    cv_mem->cv_linit = x_linit;
+    cv_mem->cv_lsetup = NULL;
+    cv_mem->cv_lsolve = x_lsolve;
+    cv_mem->cv_lfree = x_lfree;
+    cv_mem->cv_lmem = engine;
+    cv_mem->cv_setupNonNull = FALSE;
+    return 0;
+}
+
+/* nst nfe nni ncfn netf of the stepper only (the plug-in keeps its own nli, ncfl, nfeLS) */
+void ref_ext_cvode_stepper_stats(long int *s)
+{
+    CVodeGetNumSteps(X_mem, &s[0]);
+    CVodeGetNumRhsEvals(X_mem, &s[1]);
+    CVodeGetNumNonlinSolvIters(X_mem, &s[2]);
+    CVodeGetNumNonlinSolvConvFails(X_mem, &s[3]);
+    CVodeGetNumErrTestFails(X_mem, &s[4]);
 }
 
 int ref_ext_cvode_solve(double tout, double *tret)

@@ -293,6 +293,18 @@ class RefCvodeExternal:
         if rc != 0:
             raise RuntimeError(f"ref_ext_cvode_init failed ({rc})")
 
+    def attach_lsolve(self, solve_fn_ptr: int, engine_ptr: int):
+        """swap CVSPGMR for a device linear solver (pihm_b200_spgmr_solve) through cv_mem->cv_lsolve"""
+        L = self.model.lib
+        L.ref_ext_cvode_attach_lsolve.argtypes = [C.c_void_p, C.c_void_p]
+        if L.ref_ext_cvode_attach_lsolve(solve_fn_ptr, engine_ptr) != 0:
+            raise RuntimeError("ref_ext_cvode_attach_lsolve failed")
+
+    def stepper_stats(self):
+        s = (C.c_long * 5)()
+        self.model.lib.ref_ext_cvode_stepper_stats(s)
+        return {k: int(s[i]) for i, k in enumerate(["nst", "nfe", "nni", "ncfn", "netf"])}
+
     def solve(self, tout: float) -> float:
         t = C.c_double()
         rc = self.model.lib.ref_ext_cvode_solve(float(tout), C.byref(t))

@@ -82,6 +82,50 @@ def test_reference_cvode_on_device_nvector_matches_our_integrator_bitwise(size, 
     cv.close(); mA.close(); mB.close()
 
 
+@pytest.mark.parametrize("size,steps,t0", [("small", 40, 0.0), ("small", 30, 3 * 3600.0)])
+def test_device_spgmr_plugged_into_reference_cvode(size, steps, t0):
+    """SURVEY 8(b) 'Linear-solver plug-in': the reference CVODE keeps its BDF/Newton stepper and gets
+    N_VNew_PihmB200, PihmB200_ODE and -- through cv_mem->cv_lsolve, attached the way CVSpgmr attaches
+    itself -- pihm_b200_spgmr_solve.  Same bits and counters as the all-device integrator."""
+    if not reflib.available(False):
+        pytest.skip("oracle/_ref not present")
+    tb = W.make_named(size, dirichlet_edges=True)
+    nr = tb["nriver"]
+    L = lib.load_library()
+    mA = lib.Model(tb, reorder=1)
+    nv = L.N_VNew_PihmB200(mA.h)
+    y_host = host_mirror(nv, mA.nsv)
+    y_host[:] = tb["y0"]
+    assert L.N_VPihmB200_Push(nv) == 0
+    ext = reflib.RefCvodeExternal(nv, C.cast(L.PihmB200_ODE, C.c_void_p).value, mA.h)
+    engine = lib.Cvode(mA)                                  # vectors + scalar buffers of the solver
+    ext.attach_lsolve(C.cast(L.pihm_b200_spgmr_solve, C.c_void_p).value, engine.h)
+    yA_vec = lib.Vec(mA, handle=L.N_VPihmB200_Device(nv))
+
+    mB = lib.Model(tb, reorder=1)
+    cv = lib.Cvode(mB)
+    yB = mB.N_VNew(tb["y0"])
+    cv.SetCVodeParam(yB)
+    for k in range(steps):
+        if k % 15 == 0:
+            f = W.storm_forcing(tb, t0 + k * 60.0)
+            mA.set_forcing(f, np.zeros(nr)); mB.set_forcing(f, np.zeros(nr))
+        mA.Summary(yA_vec); mB.Summary(yB)
+        assert ext.solve((k + 1) * 60.0) == cv.SolveCVode((k + 1) * 60.0, yB) == (k + 1) * 60.0
+        assert L.N_VPihmB200_Pull(nv) == 0
+        sA, sE, sB = ext.stepper_stats(), engine.stats(), cv.stats()
+        assert {k_: sB[k_] for k_ in sA} == sA, f"step {k + 1}: stepper counters {sA} vs {sB}"
+        assert [sE[k_] for k_ in ("nli", "ncfl", "nfeLS", "njtimes")] == [sB[k_] for k_ in ("nli", "ncfl", "nfeLS", "njtimes")]
+        a, b = np.array(y_host), yB.download()
+        assert np.array_equal(a, b), f"step {k + 1}: max |diff| {np.abs(a - b).max():.3e}"
+    print(f"{size}: {steps} model steps with the plugged-in device SPGMR, {sA['nst']} CVODE steps, "
+          f"{sE['nli']} Krylov iterations -- bit-identical")
+    ext.free()
+    engine.close()
+    L.N_VDestroy_PihmB200(nv)
+    cv.close(); mA.close(); mB.close()
+
+
 def dropin_run(tb, steps, t0, diagnostics=False):
     """Route 1 model steps (reference CVODE on our N_Vector / RHS) -> per step dict(y[, xf, sr]);
     with diagnostics the device Summary()/MassBalance() follows every solve (tests/test_summary_gpu.py)."""
