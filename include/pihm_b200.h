@@ -333,6 +333,36 @@ int             pihm_b200_et_set_state(pihm_b200_ctx *ctx, const double *sneqv,
 int             pihm_b200_et_get(pihm_b200_ctx *ctx, double *out);
 
 /* ------------------------------------------------------------------------
+ * Print accumulation on the device.
+ *   replaces: UpdPrintVar (src/print.c:171-190: buffer[j] += *var[j];
+ *             counter++) and the averaging of PrintData (src/print.c:192-251:
+ *             buffer[j] / counter, then buffer[j] = 0, counter = 0).
+ * The reference keeps one pointer per element and variable into its structs
+ * (map_output.c) and therefore needs every printed field on the host every
+ * step; here a print variable is (source, column) and its running sum lives
+ * on the device: nothing is copied until PrintNow() (src/print.c:578, host
+ * time logic, unchanged) says a record is due.
+ * ---------------------------------------------------------------------- */
+enum pihm_b200_print_src {
+    PB_PS_STATE = 0,     /* column = block of y: 0 SURF 1 UNSAT 2 GW 3 RIVSTG 4 RIVGW
+                            5 FBRUNSAT 6 FBRGW (elem.ws / river.ws after Summary) */
+    PB_PS_ELEM_FLUX,     /* column = PB_X_*  (needs diagnostics or flux recording)  */
+    PB_PS_RIV_FLUX,      /* column = 0..10, river.wf.rivflow[k]                     */
+    PB_PS_ET             /* column = PB_EO_* (needs pihm_b200_et_create)            */
+};
+/* -> id >= 0 of the new print variable (one varctrl_struct), or < 0 */
+int             pihm_b200_print_add(pihm_b200_ctx *ctx, int src, int column);
+/* UpdPrintVar for the listed variables (the caller groups them by
+ * upd_intvl like print.c:180); y = CV_Y, read by PB_PS_STATE variables */
+int             pihm_b200_print_update(pihm_b200_ctx *ctx, const int32_t *ids,
+                                       int n, const pihm_b200_vec *y);
+/* PrintData for one variable: out[j] = buffer[j] / counter (buffer[j] when
+ * counter == 0), reference order, [nelem] or [nriver]; then reset.
+ * *counter_out (may be NULL) = number of updates averaged. */
+int             pihm_b200_print_data(pihm_b200_ctx *ctx, int id, double *out,
+                                     int32_t *counter_out);
+
+/* ------------------------------------------------------------------------
  * Device-resident N_Vector.
  *   replaces: cvode/src/nvec_ser/nvector_serial.c:421-770 (ops) and
  *             :76-419 (constructors), same arithmetic per component.

@@ -128,6 +128,17 @@ void comm_unshare_buffer(pihm_b200_ctx *ctx, void **peers);
 int comm_setup_halo_p2p(pihm_b200_ctx *ctx);
 }  // namespace pb
 
+namespace pb {
+// one varctrl_struct of the reference's print system (pihm_struct.h:193-216) on the device
+struct PrintVar {
+    int src = 0, col = 0;      // pihm_b200_print_src, column within it
+    int len = 0;               // owned elements or river segments
+    int is_river = 0;
+    double *acc = nullptr;     // running sum (varctrl.buffer), internal order
+    int counter = 0;           // varctrl.counter
+};
+}  // namespace pb
+
 // opaque handle types of the C ABI
 struct pihm_b200_ctx {
     pb::DevMesh dm{};
@@ -203,6 +214,7 @@ struct pihm_b200_ctx {
     double *d_et_tab = nullptr;        // per-step tables by type: meteo | lai | lai_lc | z0_lc
     size_t et_tab_cap = 0;             // doubles
     int et_max_meteo = 0, et_max_lai = 0, et_max_lc = 0;   // largest type index used by an element
+    std::vector<pb::PrintVar> pvars;   // pihm_b200_print_add
 };
 
 namespace pb {

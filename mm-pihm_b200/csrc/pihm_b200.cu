@@ -442,6 +442,7 @@ void pihm_b200_destroy(pihm_b200_ctx *ctx)
                    ctx->d_etf, ctx->d_eti, ctx->d_eto, ctx->d_et_tab};
     pb::comm_destroy(ctx);
     for (void *p : dev) if (p) cudaFree(p);
+    for (pb::PrintVar &v : ctx->pvars) if (v.acc) cudaFree(v.acc);
     if (ctx->h_red) cudaFreeHost(ctx->h_red);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -936,6 +937,93 @@ int pihm_b200_et_get(pihm_b200_ctx *ctx, double *out)
     PB_CUDA(cudaMemcpy(h.data(), ctx->d_eto, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
     for (int c = 0; c < PB_EO_NCOL; c++)
         for (int i = 0; i < ne; i++) out[(size_t)c * ne + ctx->perm[i]] = h[(size_t)c * nes + i];
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Print accumulation (UpdPrintVar / PrintData averaging, src/print.c:171-251)
+// ---------------------------------------------------------------------------
+static __global__ void __launch_bounds__(256)
+k_print_accum(int n, const double *__restrict__ src, double *__restrict__ acc)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) acc[i] = acc[i] + src[i];        // buffer[j] += *var[j]
+}
+
+// where a print variable reads from (internal order, contiguous), nullptr if unavailable
+static const double *print_source(pihm_b200_ctx *ctx, const PrintVar &v, const pihm_b200_vec *y)
+{
+    const DevMesh &dm = ctx->dm;
+    switch (v.src) {
+    case PB_PS_STATE: {
+        if (!y) return nullptr;
+        const long long off[7] = {0, dm.o_unsat, dm.o_gw, dm.o_stg, dm.o_rgw, dm.o_fu, dm.o_fg};
+        return y->d + off[v.col];
+    }
+    case PB_PS_ELEM_FLUX: return ctx->d_xflux ? ctx->d_xflux + (size_t)v.col * dm.nes : nullptr;
+    case PB_PS_RIV_FLUX: return ctx->d_rivflow + (size_t)v.col * dm.nrs;
+    case PB_PS_ET: return ctx->d_eto ? ctx->d_eto + (size_t)v.col * dm.nes : nullptr;
+    }
+    return nullptr;
+}
+
+int pihm_b200_print_add(pihm_b200_ctx *ctx, int src, int column)
+{
+    if (!ctx) return -1;
+    const DevMesh &dm = ctx->dm;
+    PrintVar v;
+    v.src = src; v.col = column;
+    bool ok = false;
+    switch (src) {
+    case PB_PS_STATE:
+        ok = column >= 0 && column < (dm.fbr ? 7 : 5);
+        v.is_river = (column == 3 || column == 4);
+        break;
+    case PB_PS_ELEM_FLUX: ok = column >= 0 && column < PB_X_NCOL; break;
+    case PB_PS_RIV_FLUX: ok = column >= 0 && column < PIHM_B200_NUM_RIVFLX; v.is_river = 1; break;
+    case PB_PS_ET: ok = column >= 0 && column < PB_EO_NCOL; break;
+    }
+    if (!ok) { set_error("print_add: unknown source / column"); return -1; }
+    v.len = v.is_river ? dm.rown : dm.nown;
+    PB_CUDA(cudaMalloc((void **)&v.acc, sizeof(double) * std::max(v.len, 1)));
+    PB_CUDA(cudaMemsetAsync(v.acc, 0, sizeof(double) * std::max(v.len, 1), ctx->s()));
+    ctx->pvars.push_back(v);
+    return (int)ctx->pvars.size() - 1;
+}
+
+int pihm_b200_print_update(pihm_b200_ctx *ctx, const int32_t *ids, int n, const pihm_b200_vec *y)
+{
+    if (!ctx || (n > 0 && !ids) || (y && y->n != ctx->nsv)) { set_error("print_update: bad argument"); return -1; }
+    for (int k = 0; k < n; k++) {
+        if (ids[k] < 0 || ids[k] >= (int)ctx->pvars.size()) { set_error("print_update: unknown variable id"); return -1; }
+        PrintVar &v = ctx->pvars[ids[k]];
+        const double *src = print_source(ctx, v, y);
+        if (!src) { set_error("print_update: the variable's source is not available (y / diagnostics / et_create)"); return -1; }
+        if (v.len > 0) {
+            k_print_accum<<<(v.len + 255) / 256, 256, 0, ctx->s()>>>(v.len, src, v.acc);
+            ctx->launches++;
+        }
+        v.counter++;
+    }
+    PB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int pihm_b200_print_data(pihm_b200_ctx *ctx, int id, double *out, int32_t *counter_out)
+{
+    if (!ctx || id < 0 || id >= (int)ctx->pvars.size() || !out) { set_error("print_data: bad argument"); return -1; }
+    PrintVar &v = ctx->pvars[id];
+    std::vector<double> h((size_t)std::max(v.len, 1));
+    PB_CUDA(cudaMemcpyAsync(h.data(), v.acc, sizeof(double) * v.len, cudaMemcpyDeviceToHost, ctx->s()));
+    PB_CUDA(cudaMemsetAsync(v.acc, 0, sizeof(double) * std::max(v.len, 1), ctx->s()));
+    PB_CUDA(cudaStreamSynchronize(ctx->s()));
+    const double cnt = (double)v.counter;
+    for (int i = 0; i < v.len; i++) {
+        const double val = (v.counter > 0) ? h[i] / cnt : h[i];        // print.c:234-241
+        out[v.is_river ? i : ctx->perm[i]] = val;
+    }
+    if (counter_out) *counter_out = v.counter;
+    v.counter = 0;
     return 0;
 }
 

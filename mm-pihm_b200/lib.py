@@ -113,6 +113,9 @@ _SIGS = {
     "pihm_b200_intcp_snow_et": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pihm_b200_et_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pihm_b200_et_get": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pihm_b200_print_add": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "pihm_b200_print_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "pihm_b200_print_data": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "pihm_b200_set_diagnostics": (C.c_int, [C.c_void_p, C.c_int]),
     "pihm_b200_set_ws0": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pihm_b200_summary_mb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double]),
@@ -374,6 +377,23 @@ class Model:
         out = np.zeros((W.EO_NCOL, self.nelem))
         _check(self.L, self.L.pihm_b200_et_get(self.h, _ptr(out)), "et_get")
         return out
+
+    # print accumulation on the device (UpdPrintVar / PrintData, src/print.c:171-251) -----------
+    def print_add(self, src: int, column: int) -> int:
+        rc = self.L.pihm_b200_print_add(self.h, int(src), int(column))
+        _check(self.L, min(rc, 0), "print_add")
+        return rc
+
+    def UpdPrintVar(self, ids, y: "Vec" = None):
+        a = np.ascontiguousarray(ids, np.int32)
+        _check(self.L, self.L.pihm_b200_print_update(self.h, _ptr(a), len(a), y.h if y is not None else None),
+               "print_update")
+
+    def PrintData(self, vid: int, river: bool = False):
+        """-> (average over the updates since the last record, number of updates)"""
+        out = np.zeros(self.nriver if river else self.nelem); cnt = C.c_int32(0)
+        _check(self.L, self.L.pihm_b200_print_data(self.h, int(vid), _ptr(out), C.byref(cnt)), "print_data")
+        return out, cnt.value
 
     def set_flux_recording(self, on: bool):
         _check(self.L, self.L.pihm_b200_set_flux_recording(self.h, int(on)), "set_flux_recording")

@@ -44,6 +44,7 @@ import numpy as np
 (ETI_METEO_TYPE, ETI_LAI_TYPE, ETI_LC_TYPE, ETI_NCOL) = range(4)
 (EO_PCPDRP, EO_EDIR, EO_ETT, EO_EC, EO_DRIP, EO_SNEQV, EO_CMC, EO_NCOL) = range(8)
 NUM_METEO_VAR = 7
+(PS_STATE, PS_ELEM_FLUX, PS_RIV_FLUX, PS_ET) = range(4)     # pihm_b200_print_src
 NUM_RIVFLX = 11
 
 # ksath ksatv kinfv dinf alpha beta porosity kmach kmacv areafv areafh

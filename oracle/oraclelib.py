@@ -149,6 +149,27 @@ class OracleModel:
         return sr
 
 
+class PrintVarOracle:
+    """numpy restatement of one varctrl_struct of the reference's print system:
+    UpdPrintVar (src/print.c:171-190): buffer[j] += *var[j]; counter++
+    PrintData   (src/print.c:230-246): buffer[j] / (double)counter (buffer[j] if counter == 0), then reset."""
+
+    def __init__(self, n):
+        self.buffer = np.zeros(n)
+        self.counter = 0
+
+    def update(self, values):
+        self.buffer = self.buffer + np.asarray(values, np.float64)
+        self.counter += 1
+
+    def data(self):
+        out = self.buffer / float(self.counter) if self.counter > 0 else self.buffer.copy()
+        n = self.counter
+        self.buffer = np.zeros_like(self.buffer)
+        self.counter = 0
+        return out, n
+
+
 # serial N_Vector arithmetic -------------------------------------------------
 def nv_linearsum(a, x, b, y, inplace=None):
     """z = a x + b y with nvector_serial.c's special-case rounding.

@@ -851,6 +851,137 @@ int ref_tout(int cstep)
     return H.from_files ? H.pihm->ctrl.tout[cstep] : 0;
 }
 
+/*
+ * Print accumulation: a varctrl_struct over one field, fed to
+ * the reference's own UpdPrintVar() and PrintData() (src/print.c:171-251); the
+ * record PrintData writes goes to a temporary file and is read back.
+ * src / col as in enum pihm_b200_print_src.
+ */
+#define MAX_PV 64
+static varctrl_struct PV[MAX_PV];
+static int      npv;
+
+static const double *pv_field(int src, int col, int j)
+{
+    const elem_struct *e = &H.pihm->elem[(src == PB_PS_RIV_FLUX ||
+        (src == PB_PS_STATE && (col == 3 || col == 4))) ? 0 : j];
+    const river_struct *r = &H.pihm->river[(nriver > 0 && j < nriver) ? j : 0];
+
+    switch (src)
+    {
+        case PB_PS_STATE:
+            switch (col)
+            {
+                case 0: return &e->ws.surf;
+                case 1: return &e->ws.unsat;
+                case 2: return &e->ws.gw;
+                case 3: return &r->ws.stage;
+                case 4: return &r->ws.gw;
+#if defined(_FBR_)
+                case 5: return &e->ws.fbr_unsat;
+                case 6: return &e->ws.fbr_gw;
+#endif
+            }
+            return NULL;
+        case PB_PS_ELEM_FLUX:
+            if (col >= PB_X_OVL0 && col <= PB_X_OVL2) return &e->wf.ovlflow[col - PB_X_OVL0];
+            if (col >= PB_X_SUB0 && col <= PB_X_SUB2) return &e->wf.subsurf[col - PB_X_SUB0];
+            switch (col)
+            {
+                case PB_X_INFIL: return &e->wf.infil;
+                case PB_X_RECHG: return &e->wf.rechg;
+                case PB_X_EDIR_SURF: return &e->wf.edir_surf;
+                case PB_X_EDIR_UNSAT: return &e->wf.edir_unsat;
+                case PB_X_EDIR_GW: return &e->wf.edir_gw;
+                case PB_X_ETT_UNSAT: return &e->wf.ett_unsat;
+                case PB_X_ETT_GW: return &e->wf.ett_gw;
+#if defined(_FBR_)
+                case PB_X_FBR_INFIL: return &e->wf.fbr_infil;
+                case PB_X_FBR_RECHG: return &e->wf.fbr_rechg;
+#endif
+            }
+#if defined(_FBR_)
+            if (col >= PB_X_FBRFLOW0 && col <= PB_X_FBRFLOW2) return &e->wf.fbrflow[col - PB_X_FBRFLOW0];
+#endif
+            return NULL;
+        case PB_PS_RIV_FLUX:
+            return (col >= 0 && col < NUM_RIVFLX) ? &r->wf.rivflow[col] : NULL;
+        case PB_PS_ET:
+            switch (col)
+            {
+                case PB_EO_PCPDRP: return &e->wf.pcpdrp;
+                case PB_EO_EDIR: return &e->wf.edir;
+                case PB_EO_ETT: return &e->wf.ett;
+                case PB_EO_EC: return &e->wf.ec;
+                case PB_EO_DRIP: return &e->wf.drip;
+                case PB_EO_SNEQV: return &e->ws.sneqv;
+                case PB_EO_CMC: return &e->ws.cmc;
+            }
+            return NULL;
+    }
+    return NULL;
+}
+
+int ref_print_add(int src, int col, int upd_intvl, int intvl)
+{
+    varctrl_struct *v;
+    int             j, n;
+    int             river = (src == PB_PS_RIV_FLUX) ||
+        (src == PB_PS_STATE && (col == 3 || col == 4));
+
+    if (npv >= MAX_PV || pv_field(src, col, 0) == NULL) return -1;
+    v = &PV[npv];
+    memset(v, 0, sizeof(*v));
+    n = river ? nriver : nelem;
+    v->nvar = n;
+    v->intvl = intvl;
+    v->upd_intvl = upd_intvl;
+    v->var = (const double **)malloc(sizeof(double *) * (n > 0 ? n : 1));
+    v->buffer = (double *)calloc(n > 0 ? n : 1, sizeof(double));
+    for (j = 0; j < n; j++) v->var[j] = pv_field(src, col, j);
+    v->datfile = tmpfile();
+    return npv++;
+}
+
+/* UpdPrintVar(varctrl, nprint, module_step) over all variables made so far */
+void ref_print_update(int module_step)
+{
+    UpdPrintVar(PV, npv, module_step);
+}
+
+/* PrintData(varctrl, nprint, t, lapse, ascii = 0) for all variables; then the
+ * last record of variable id is read back: returns 1 and fills out[nvar] when
+ * a record was written by this call, 0 when PrintNow() said no */
+int ref_print_data(int id, int t, int lapse, double *out)
+{
+    varctrl_struct *v = &PV[id];
+    long            before, after;
+    double          tt;
+
+    before = ftell(v->datfile);
+    PrintData(v, 1, t, lapse, 0);
+    after = ftell(v->datfile);
+    if (after == before) return 0;
+    fseek(v->datfile, before, SEEK_SET);
+    if (fread(&tt, sizeof(double), 1, v->datfile) != 1) return -1;
+    if (fread(out, sizeof(double), v->nvar, v->datfile) != (size_t)v->nvar) return -1;
+    fseek(v->datfile, 0, SEEK_END);
+    return 1;
+}
+
+void ref_print_reset(void)
+{
+    int             i;
+
+    for (i = 0; i < npv; i++)
+    {
+        free((void *)PV[i].var);
+        free(PV[i].buffer);
+        if (PV[i].datfile) fclose(PV[i].datfile);
+    }
+    npv = 0;
+}
+
 /* element/river water states after Summary() (ws), for trajectory checks */
 void ref_get_ws(double *y)
 {

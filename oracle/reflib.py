@@ -221,6 +221,24 @@ class RefModel:
     def tout(self, cstep):
         return int(self.lib.ref_tout(int(cstep)))
 
+    # -- print accumulation: the reference's UpdPrintVar / PrintData on a field -----
+    def print_add(self, src, col, upd_intvl=0, intvl=60):
+        vid = self.lib.ref_print_add(int(src), int(col), int(upd_intvl), int(intvl))
+        if vid < 0:
+            raise RuntimeError("ref_print_add: unknown field")
+        return vid
+
+    def print_update(self, module_step=0):
+        self.lib.ref_print_update(int(module_step))
+
+    def print_data(self, vid, t, lapse, n):
+        out = np.zeros(max(n, 1))
+        rc = self.lib.ref_print_data(int(vid), int(t), int(lapse), _ptr(out))
+        return (out[:n] if rc == 1 else None)
+
+    def print_reset(self):
+        self.lib.ref_print_reset()
+
     def summary(self, y):
         """Summary() of src/update.c on y (= CV_Y after SolveCVode)."""
         y = np.ascontiguousarray(y, np.float64); assert y.shape == (self.nsv,)
