@@ -37,20 +37,38 @@ def main():
     forc = W.storm_forcing(tb, 3 * 3600.0, ws0_surf=np.maximum(yg[:ne], 0))
     model.set_forcing(forc[:, part["elem_gid"]], np.zeros(part["nriver"]))
     yv = model.N_VNew(yg[part["state_idx"]]); dv = model.N_VNew()
+    model.set_diagnostics(True)                # Summary()/MassBalance() on every rank
+    model.set_ws0(yv)
     outs = []
     for _ in range(2):                         # second call: stale river-edge flows
         model.ode_dev(0.0, yv, dv)
         outs.append(dv.download())
+    y1g = yg * (1 + 1e-3 * np.random.default_rng(0).standard_normal(yg.shape))
+    model.SummaryMB(model.N_VNew(y1g[part["state_idx"]]), tb["stepsize"])     # re-evaluates the last call on its ghosts
+    no = part["nown_elem"]
+    xf_own = model.get_fluxes()[0][:, :no]
+    sr_own = model.get_summary()[0][:no]
     gathered = [None] * world
-    dist.all_gather_object(gathered, (part["state_idx"], outs))
+    dist.all_gather_object(gathered, (part["state_idx"], outs, part["elem_gid"][:no], xf_own, sr_own))
     ok = True
     if rank == 0:
         single = lib.Model(tb, device=local, reorder=1)
         single.set_forcing(forc, np.zeros(nr))
+        single.set_diagnostics(True)
+        sv = single.N_VNew(yg); single.set_ws0(sv)
         ref = [single.ODE(0.0, yg), single.ODE(0.0, yg)]
+        single.SummaryMB(single.N_VNew(y1g), tb["stepsize"])
+        xf_ref, sr_ref = single.get_fluxes()[0], single.get_summary()[0]
+        xf = np.zeros_like(xf_ref); sr = np.zeros_like(sr_ref)
+        for _, _, own, x, s_ in gathered:
+            xf[:, own] = x
+            sr[own] = s_
+        same = np.array_equal(xf, xf_ref) and np.array_equal(sr, sr_ref)
+        print(f"[mgpu] Summary/MassBalance fluxes: partitioned == single GPU bitwise: {same}", flush=True)
+        ok = ok and same
         for k in range(2):
             dy = np.empty(nsv_glob)
-            for idx, o in gathered:
+            for idx, o, *_ in gathered:
                 dy[idx] = o[k]
             same = np.array_equal(dy, ref[k])
             print(f"[mgpu] RHS call {k}: partitioned == single GPU bitwise: {same}", flush=True)
