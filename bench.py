@@ -35,7 +35,7 @@ STEP = 60.0
 B_RHS = {False: 376.0, True: 476.0}     # algorithmic bytes / element / RHS
 # dram__bytes_read.sum + dram__bytes_write.sum of one RHS (k_pre + k_main) from the committed
 # ncu --set full capture (profiles/); None where no capture exists
-RHS_TRAFFIC_BYTES = {("1M", False): 413.6e6, ("1M", True): 460.3e6}
+RHS_TRAFFIC_BYTES = {("1M", False): 418.8e6, ("1M", True): 460.3e6}
 
 
 def forcing_at(tb, k):
@@ -274,7 +274,7 @@ def run_ours(args):
                      "kernel": "k_pre + k_main (one RHS evaluation, per GPU)",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": B_RHS[fbr] * model.nown_elem,
-                     "traffic_source": "profiles/r01d_rhs_1M_ncu_summary.md (ncu --set full, dram read+write)"},
+                     "traffic_source": "profiles/r01g_rhs_1M_ncu_summary.md (pihm) / r01d (fbr): ncu --set full, dram read+write"},
         "e2e": {"value": e2e_value, "unit": "sim-days/s", "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": 3 * 8 * ne, "d2h_bytes_per_step": 8 * model.nsv},
         "gpu_launches": int(l1 - l0),
