@@ -229,6 +229,14 @@ inline void note_write(pihm_b200_ctx *ctx, const double *p)
 {
     if (ctx->diag && p == ctx->last_in) snapshot_last_in(ctx);
 }
+// ... and before freeing it: without diagnostics there is nowhere to keep the contents, so the
+// library simply forgets the input (a later pihm_b200_summary_mb then asks for an RHS call first)
+inline void note_free(pihm_b200_ctx *ctx, const double *p)
+{
+    if (p != ctx->last_in) return;
+    if (ctx->diag) snapshot_last_in(ctx);
+    else ctx->last_in = nullptr;
+}
 }  // namespace pb
 
 struct pihm_b200_vec {

@@ -1237,8 +1237,8 @@ pihm_b200_cvode *pihm_b200_cvode_create(pihm_b200_ctx *ctx)
 void pihm_b200_cvode_destroy(pihm_b200_cvode *cv)
 {
     if (!cv) return;
-    cv->clobber(cv->zn[0]);             // the vectors go away: keep the last RHS input if it is one of them
-    cv->clobber(cv->ytemp);
+    pb::note_free(cv->ctx, cv->zn[0]);  // the vectors go away: keep the last RHS input if it is one of them
+    pb::note_free(cv->ctx, cv->ytemp);
     cudaStreamSynchronize(cv->ctx->s());
     if (cv->prof) {
         double rhs_ms = 0.0;

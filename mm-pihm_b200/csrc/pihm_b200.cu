@@ -1102,7 +1102,7 @@ void pihm_b200_vec_free(pihm_b200_vec *v)
 {
     if (!v) return;
     if (v->owns && v->d) {
-        pb::note_write(v->ctx, v->d);
+        pb::note_free(v->ctx, v->d);
         cudaStreamSynchronize(v->ctx->s());
         cudaFree(v->d);
     }

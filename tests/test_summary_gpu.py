@@ -214,3 +214,49 @@ def test_dropin_route_gives_same_fluxes():
         assert np.array_equal(a[k]["y"], b[k]["y"]), k
         assert np.array_equal(a[k]["xf"], b[k]["xf"]), k
         assert np.array_equal(a[k]["sr"], b[k]["sr"]), k
+
+
+@pytest.mark.parametrize("fbr", [False, True])
+def test_summary_ragged_sizes_and_no_river(fbr):
+    """element counts that are not multiples of a tile, meshes without rivers: Summary/MassBalance,
+    print accumulation of states and fluxes against the oracle port"""
+    for nx, ny in ((3, 2), (7, 5), (13, 9)):
+        tb = W.make_watershed(nx, ny, river=False, fbr=fbr)
+        ne = tb["nelem"]
+        assert tb["nriver"] == 0 and ne % 32 != 0
+        om = oraclelib.OracleModel(tb)
+        model = lib.Model(tb, reorder=1)
+        model.set_diagnostics(True)
+        rng = np.random.default_rng(nx)
+        y0 = W.wet_state(tb, seed=nx)
+        forc = W.storm_forcing(tb, 4 * 3600.0, ws0_surf=np.maximum(y0[:ne], 0))
+        model.set_forcing(forc, np.zeros(0)); om.set_forcing(forc, np.zeros(0))
+        v = model.N_VNew(y0)
+        model.set_ws0(v); om.set_ws0(y0)
+        pid = [model.print_add(W.PS_STATE, 2), model.print_add(W.PS_ELEM_FLUX, W.X_INFIL)]
+        acc = [oraclelib.PrintVarOracle(ne), oraclelib.PrintVarOracle(ne)]
+        y = y0
+        for step in range(3):
+            y_rhs = y * (1 + 1e-3 * rng.standard_normal(y.shape))
+            dy = model.ODE(0.0, y_rhs)
+            om.ode(y_rhs)
+            y = y_rhs + 60.0 * dy
+            v.upload(y)
+            model.SummaryMB(v, tb["stepsize"])
+            sro = om.summary(y, tb["stepsize"])
+            xf, _ = model.get_fluxes(); xo, _ = om.get_fluxes()
+            sr, ws0 = model.get_summary()
+            scale, scale_f = mb_scale(tb, xo, y_rhs, y)
+            for col in range(W.X_NCOL):
+                cs = max(np.abs(xo[col]).max(), 1e-300)
+                tol = 1e-12 * (np.maximum(scale, cs) if col in (W.X_INFIL, W.X_FBR_INFIL) else cs)
+                assert (np.abs(xf[col] - xo[col]) <= tol).all(), (nx, ny, step, col)
+            assert (np.abs(sr - sro) <= 1e-12 * np.maximum(scale, 1e-300)).all()
+            assert np.array_equal(ws0, y) and np.array_equal(om.get_ws0(), y)
+            model.UpdPrintVar(pid, v)
+            acc[0].update(y[2 * ne:3 * ne]); acc[1].update(xf[W.X_INFIL])
+        for p_, a_ in zip(pid, acc):
+            out, n = model.PrintData(p_)
+            ref, nref = a_.data()
+            assert n == nref == 3 and np.array_equal(out, ref)
+        model.close(); om.close()
