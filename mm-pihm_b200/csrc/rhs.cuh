@@ -1115,11 +1115,11 @@ __device__ __forceinline__ void river_main(const DevMesh &m, double *__restrict_
 // the element tiles.
 // ---------------------------------------------------------------------------
 #ifndef PB_RHS_WARPS
-#define PB_RHS_WARPS 10
-#endif
+#define PB_RHS_WARPS 8     // k_main: 8 warps x 2 CTAs -> 128 registers, no spills: 113.8 us against 116.6 us with
+#endif                     // 10 warps at 96 registers (7 / 6 / 5 warps: 121 / 122 / 133 us; 11 at 80: 121 us)
 #define PB_RHS_THREADS (PB_RHS_WARPS * 32)
 #ifndef PB_PRE_WARPS
-#define PB_PRE_WARPS PB_RHS_WARPS
+#define PB_PRE_WARPS 10    // k_pre: 3 x 10 (3 x 8, 2 x 12, 2 x 10, 4 x 6: 1.5-5 us slower)
 #endif
 #define PB_PRE_THREADS (PB_PRE_WARPS * 32)
 #ifndef PB_PRE_STAGES
@@ -1135,7 +1135,7 @@ __device__ __forceinline__ void river_main(const DevMesh &m, double *__restrict_
 #define PB_PRE_MINB 3      // CTAs of 10 warps per SM: 3 -> 64 registers
 #endif
 #ifndef PB_MAIN_MINB
-#define PB_MAIN_MINB 2      // 2 CTAs of 10 warps -> 96 registers, no spills
+#define PB_MAIN_MINB 2      // 2 CTAs of 8 warps -> 128 registers, no spills
 #endif
 #ifndef PB_MAIN_MINB_FBR
 #define PB_MAIN_MINB_FBR 2
