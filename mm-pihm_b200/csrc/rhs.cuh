@@ -1129,7 +1129,7 @@ __device__ __forceinline__ void river_main(const DevMesh &m, double *__restrict_
 #define PB_MAIN_STAGES 12
 #endif
 #ifndef PB_MAIN_STAGES_FBR
-#define PB_MAIN_STAGES_FBR 10
+#define PB_MAIN_STAGES_FBR 12
 #endif
 #ifndef PB_PRE_MINB
 #define PB_PRE_MINB 3      // CTAs of 10 warps per SM: 3 -> 64 registers
@@ -1141,7 +1141,7 @@ __device__ __forceinline__ void river_main(const DevMesh &m, double *__restrict_
 #define PB_MAIN_MINB_FBR 2
 #endif
 #ifndef PB_MAIN_WARPS_FBR
-#define PB_MAIN_WARPS_FBR 8
+#define PB_MAIN_WARPS_FBR 10   // fbr: 10 warps x 2 CTAs at 96 registers: 175.3 us (8 / 7 / 6 warps: 178.8 / 191 / 195 us)
 #endif
 #define PB_PATCH 128       // elements per locality patch of the internal ordering (reorder.h)
 
@@ -1189,7 +1189,7 @@ template <bool FBR> struct MainCfg {
     static constexpr int SBS = NC * PB_TILE * 8, SBF = 4 * PB_TILE * 8, SB = SBS + SBF;
     static constexpr int STAGES = FBR ? PB_MAIN_STAGES_FBR : PB_MAIN_STAGES;
     static constexpr int MINB = FBR ? PB_MAIN_MINB_FBR : PB_MAIN_MINB;
-    static constexpr int WARPS = FBR ? PB_MAIN_WARPS_FBR : PB_RHS_WARPS;   // fbr: 8 warps x 2 CTAs -> 128 registers
+    static constexpr int WARPS = FBR ? PB_MAIN_WARPS_FBR : PB_RHS_WARPS;
     static constexpr int THREADS = WARPS * 32;
     typedef Ring<STAGES, SB> ring_t;
 };
