@@ -1143,7 +1143,9 @@ __device__ __forceinline__ void river_main(const DevMesh &m, double *__restrict_
 #ifndef PB_MAIN_WARPS_FBR
 #define PB_MAIN_WARPS_FBR 10   // fbr: 10 warps x 2 CTAs at 96 registers: 175.3 us (8 / 7 / 6 warps: 178.8 / 191 / 195 us)
 #endif
+#ifndef PB_PATCH
 #define PB_PATCH 128       // elements per locality patch of the internal ordering (reorder.h)
+#endif
 
 #ifndef PB_RING_GROUP
 #define PB_RING_GROUP 1     // consecutive tiles a CTA takes at a time (1: tile t goes to CTA t mod grid)
