@@ -212,6 +212,8 @@ struct pihm_b200_ctx {
     int *d_eti = nullptr;              // [PB_ETI_NCOL][nes]
     double *d_eto = nullptr;           // [PB_EO_NCOL][nes] outputs + the two storages
     double *d_et_tab = nullptr;        // per-step tables by type: meteo | lai | lai_lc | z0_lc
+    double *h_et_tab = nullptr;        // pinned staging of the same
+    cudaEvent_t et_ev = nullptr;       // the last upload from h_et_tab has finished
     size_t et_tab_cap = 0;             // doubles
     int et_max_meteo = 0, et_max_lai = 0, et_max_lc = 0;   // largest type index used by an element
     std::vector<pb::PrintVar> pvars;   // pihm_b200_print_add

@@ -443,6 +443,8 @@ void pihm_b200_destroy(pihm_b200_ctx *ctx)
     pb::comm_destroy(ctx);
     for (void *p : dev) if (p) cudaFree(p);
     for (pb::PrintVar &v : ctx->pvars) if (v.acc) cudaFree(v.acc);
+    if (ctx->h_et_tab) cudaFreeHost(ctx->h_et_tab);
+    if (ctx->et_ev) cudaEventDestroy(ctx->et_ev);
     if (ctx->h_red) cudaFreeHost(ctx->h_red);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -881,21 +883,27 @@ int pihm_b200_intcp_snow_et(pihm_b200_ctx *ctx, const pihm_b200_et_step *st, con
         set_error("intcp_snow_et: a type table is missing or shorter than the largest type index in use");
         return -1;
     }
-    // the by-type tables of this step: a few hundred bytes, one staged copy
+    // the by-type tables of this step: a few hundred bytes through a pinned staging buffer
     const size_t nm = (size_t)st->nmeteo * PIHM_B200_NUM_METEO_VAR, nl = (size_t)std::max(st->nlai, 0), nc = (size_t)st->nlc;
-    std::vector<double> tab(nm + nl + 2 * nc);
-    std::copy(st->meteo, st->meteo + nm, tab.begin());
-    if (nl) std::copy(st->lai, st->lai + nl, tab.begin() + nm);
-    std::copy(st->lai_lc, st->lai_lc + nc, tab.begin() + nm + nl);
-    std::copy(st->z0_lc, st->z0_lc + nc, tab.begin() + nm + nl + nc);
-    if (tab.size() > ctx->et_tab_cap) {
+    const size_t ntab = nm + nl + 2 * nc;
+    if (ntab > ctx->et_tab_cap) {
         PB_CUDA(cudaStreamSynchronize(ctx->s()));
         if (ctx->d_et_tab) cudaFree(ctx->d_et_tab);
-        PB_CUDA(cudaMalloc((void **)&ctx->d_et_tab, sizeof(double) * tab.size()));
-        ctx->et_tab_cap = tab.size();
+        if (ctx->h_et_tab) cudaFreeHost(ctx->h_et_tab);
+        PB_CUDA(cudaMalloc((void **)&ctx->d_et_tab, sizeof(double) * ntab));
+        PB_CUDA(cudaHostAlloc((void **)&ctx->h_et_tab, sizeof(double) * ntab, cudaHostAllocDefault));
+        if (!ctx->et_ev) PB_CUDA(cudaEventCreateWithFlags(&ctx->et_ev, cudaEventDisableTiming));
+        ctx->et_tab_cap = ntab;
+    } else {
+        PB_CUDA(cudaEventSynchronize(ctx->et_ev));      // the previous call's upload (long finished)
     }
-    PB_CUDA(cudaMemcpyAsync(ctx->d_et_tab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice, ctx->s()));
-    PB_CUDA(cudaStreamSynchronize(ctx->s()));      // `tab` goes out of scope
+    double *tab = ctx->h_et_tab;
+    std::copy(st->meteo, st->meteo + nm, tab);
+    if (nl) std::copy(st->lai, st->lai + nl, tab + nm);
+    std::copy(st->lai_lc, st->lai_lc + nc, tab + nm + nl);
+    std::copy(st->z0_lc, st->z0_lc + nc, tab + nm + nl + nc);
+    PB_CUDA(cudaMemcpyAsync(ctx->d_et_tab, tab, sizeof(double) * ntab, cudaMemcpyHostToDevice, ctx->s()));
+    PB_CUDA(cudaEventRecord(ctx->et_ev, ctx->s()));
     EtStepDev d{};
     d.stepsize = st->stepsize; d.cal_edir = st->cal_edir; d.cal_ec = st->cal_ec; d.cal_ett = st->cal_ett;
     d.meltf = st->meltf;
