@@ -45,4 +45,4 @@ t_sum = timed(summary) - t_rhs
 t_et = timed(lambda: m.IntcpSnowEt(st, yv))
 t_pr = timed(lambda: m.UpdPrintVar(ids, yv))
 print(f"{size}: RHS {t_rhs:.1f} us; Summary/MassBalance incl. the re-evaluation {t_sum:.1f} us; "
-      f"IntcpSnowEt {t_et:.1f} us (incl. the by-type table upload and its sync); UpdPrintVar of {len(ids)} variables {t_pr:.1f} us")
+      f"IntcpSnowEt {t_et:.1f} us (incl. the by-type table upload); UpdPrintVar of {len(ids)} variables {t_pr:.1f} us")
