@@ -37,6 +37,7 @@ enum {
     SC_STAB2,         // sum (zn[q-1]*ewt)^2
     SC_TMP,
     SC_SEQ,           // ticket of the last finished reduction kernel (host spin-wait)
+    SC_GATE,          // device copy of that ticket for k_mgs_chain's CTAs (RedBuf::gate)
     SC_COUNT = 32
 };
 
@@ -52,6 +53,9 @@ struct RedBuf {
     // null = single GPU, or the scalars are all-reduced by NCCL after the kernel
     double *const *peer;
     int nranks, rank;
+    // device-side gate: when set, the finishing thread also publishes the ticket here, for the
+    // other CTAs of a cooperative kernel that runs several reductions in a row (k_mgs_chain)
+    double *gate;
 };
 // exchange buffer: [parity of the ticket][slot][rank]{value, ticket}
 #define PB_XB_DOUBLES (2 * SC_COUNT * PB_MAX_RANKS * 2)
@@ -154,6 +158,7 @@ __device__ __forceinline__ void red_finish(const RedBuf &rb, double a, int slotA
         *rb.counter = 0u;
         __threadfence_system();          // results visible to the host before the ticket
         rb.hsc[SC_SEQ] = rb.seq;
+        if (rb.gate) *reinterpret_cast<volatile double *>(rb.gate) = rb.seq;
     }
 }
 
@@ -402,6 +407,72 @@ k_mgs_step(long long n, const double *__restrict__ sc, int slot_prev,
 }
 
 struct KryPtrs { const double *v[5]; };
+
+// The whole modified Gram-Schmidt chain of one Krylov iteration (nsteps = l + 1 k_mgs_step
+// launches) in ONE cooperative launch: every thread keeps its elements of V[k] in shared memory
+// across the steps, so a step reads V[i] (for the update) and V[i+1] (for the next dot product)
+// and nothing else -- 1-2 vector passes instead of 4.  Same grid and block shape as k_mgs_step and
+// the same per-thread order of operations and of the summation, hence the same bits.  Between the
+// steps the CTAs wait at a device-side gate for the ticket of the reduction that produces the next
+// coefficient (red_finish publishes it; in a partitioned run after the exchange over peer memory).
+// Requires all CTAs to be resident (cooperative launch) and slice <= the shared memory given.
+static __global__ void __launch_bounds__(PB_VEC_THREADS, 4)
+k_mgs_chain(long long n, int nsteps, KryPtrs V, double *Vk, RedBuf rb, int per_thread)
+{
+    extern __shared__ double wsh[];
+    const long long stride_ = (long long)gridDim.x * blockDim.x;
+    const long long i_first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    {
+        int k = 0;
+        for (long long i = i_first; i < n; i += stride_, k++) wsh[k * PB_VEC_THREADS + threadIdx.x] = Vk[i];
+    }
+    const double seq0 = rb.seq;
+    const volatile double *gate = rb.gate;
+    const volatile double *sc = rb.sc;
+    for (int st = 0; st < nsteps; st++) {
+        if (st > 0) {
+            if (threadIdx.x == 0) {
+                const double want = seq0 + (double)(st - 1);
+                while (*gate != want) { }
+                __threadfence();
+            }
+            __syncthreads();
+        }
+        const double mh = -sc[SC_H0 + st];
+        const bool self = (st == nsteps - 1);
+        const double *__restrict__ Vprev = V.v[st];
+        const double *__restrict__ Vnext = self ? nullptr : V.v[st + 1];
+        double s = 0.0;
+        // PB_VB grid-stride steps at a time: all global loads of a batch first (see PB_GRID_STRIDE_BATCH)
+        int k0 = 0;
+        for (long long i0 = i_first; i0 < n; i0 += PB_VB * stride_, k0 += PB_VB) {
+            double p[PB_VB], x[PB_VB];
+#pragma unroll
+            for (int u = 0; u < PB_VB; u++) {
+                const long long i = i0 + u * stride_;
+                if (i < n) { p[u] = Vprev[i]; x[u] = self ? 0.0 : Vnext[i]; }
+            }
+#pragma unroll
+            for (int u = 0; u < PB_VB; u++) {
+                const long long i = i0 + u * stride_;
+                if (i < n) {
+                    double *wp = wsh + (k0 + u) * PB_VEC_THREADS + threadIdx.x;
+                    const double v = *wp + mh * p[u];
+                    *wp = v;
+                    s += (self ? v : x[u]) * v;
+                }
+            }
+        }
+        RedBuf r = rb;
+        r.seq = seq0 + (double)st;
+        red_finish<false>(r, s, self ? SC_NEW2 : SC_H0 + st + 1, 0.0, -1);
+    }
+    {
+        int k = 0;
+        for (long long i = i_first; i < n; i += stride_, k++) Vk[i] = wsh[k * PB_VEC_THREADS + threadIdx.x];
+    }
+    (void)per_thread;
+}
 
 // End of SpgmrSolve + CVSpgmrSolve + Newton update, fused:
 //   xcor = sum_k yg[k]*V[k]  (Vaxpy chain from 0, sundials_spgmr.c:348-357)
