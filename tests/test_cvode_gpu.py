@@ -161,3 +161,28 @@ def test_100k_lockstep_with_live_reference():
     assert err <= MULT
     assert abs(sg["nst"] - sr["nst"]) <= 0.25 * sr["nst"]
     ref.close(); cv.close(); model.close()
+
+
+@pytest.mark.parametrize("fbr", [False, True])
+def test_mgs_chain_cooperative_launch_is_bit_identical(fbr, monkeypatch):
+    """PIHM_B200_MGS_CHAIN=1: the Gram-Schmidt chain of a Krylov iteration as one cooperative launch
+    (k_mgs_chain, device-side ticket gate between the steps) against one k_mgs_step launch per step."""
+    tb = W.make_named("small", fbr=fbr, dirichlet_edges=True)
+    outs = []
+    for chain in ("0", "1"):
+        monkeypatch.setenv("PIHM_B200_MGS_CHAIN", chain)
+        model = lib.Model(tb, reorder=1)
+        cv = lib.Cvode(model)                    # reads the switch
+        y = model.N_VNew(tb["y0"])
+        cv.SetCVodeParam(y)
+        launches0 = model.launches
+        for k in range(25):
+            if k % 15 == 0:
+                model.set_forcing(W.storm_forcing(tb, 3600.0 + k * 60.0), np.zeros(tb["nriver"]))
+            model.Summary(y)
+            cv.SolveCVode((k + 1) * 60.0, y)
+        outs.append((y.download(), cv.stats(), model.launches - launches0))
+        cv.close(); model.close()
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert outs[0][1] == outs[1][1] and outs[0][1]["nli"] > 50
+    assert outs[1][2] < outs[0][2]               # the chain really ran: fewer launches
