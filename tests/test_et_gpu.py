@@ -142,3 +142,43 @@ def test_example_model_loop_entirely_on_device():
     xf, _ = model.get_fluxes()
     assert np.isfinite(xf).all() and model.check_nan() == 0
     cv.close(); model.close()
+
+
+def test_et_1m_reorder_invariance_and_oracle_sample():
+    """BASELINE's full size: the result does not depend on the internal element order (bitwise), the
+    forcing columns reach the RHS, and a 4096-element sample equals the oracle port within the bound."""
+    g = load_golden("et_example.npz")
+    tb = W.make_named("1M")
+    ne, nr = tb["nelem"], tb["nriver"]
+    rng = np.random.default_rng(12)
+    pick = rng.integers(0, g["et_f64"].shape[1], ne)                  # land-cover rows of input/example, shuffled
+    etf = np.ascontiguousarray(g["et_f64"][:, pick]); eti = np.ascontiguousarray(g["et_i32"][:, pick])
+    c = et_cases(g)[9]
+    st, keep = lib.make_et_step(c["stepsize"], g["cal"], c["meltf"], c["meteo"], c["lai"], c["lai_lc"], c["z0_lc"])
+    y = W.wet_state(tb, seed=3)
+    sneqv = rng.choice([0.0, 1e-3, 0.02], ne); cmc = rng.uniform(0, 8e-4, ne)
+    outs = []
+    for reorder in (0, 1):
+        model = lib.Model(tb, reorder=reorder)
+        model.et_create(etf, eti)
+        model.et_set_state(sneqv, cmc)
+        yv = model.N_VNew(y)
+        model.set_forcing(np.zeros((W.F_NCOL, ne)), np.zeros(nr))
+        model.IntcpSnowEt(st, yv)
+        outs.append(model.et_get())
+        if reorder:
+            dy = model.ODE(0.0, np.maximum(y, 0.0))
+            assert np.isfinite(dy).all() and np.abs(dy[:ne]).max() > 0
+        model.close()
+    assert np.array_equal(outs[0], outs[1])
+    # oracle port on a sample (its own small model: only the columns of the sampled elements matter)
+    idx = np.sort(rng.choice(ne, 4096, replace=False))
+    sub = dict(tb); sub["nelem"] = len(idx); sub["nriver"] = 0
+    sub["elem_f64"] = np.ascontiguousarray(tb["elem_f64"][:, idx]); sub["elem_i32"] = np.zeros((W.EI_NCOL, len(idx)), np.int32)
+    sub["riv_f64"] = np.zeros((W.R_NCOL, 0)); sub["riv_i32"] = np.zeros((W.RI_NCOL, 0), np.int32)
+    om = oraclelib.OracleModel(sub)
+    state = np.zeros((W.EO_NCOL, len(idx))); state[W.EO_SNEQV] = sneqv[idx]; state[W.EO_CMC] = cmc[idx]
+    ys = np.concatenate([y[idx], y[ne + idx], y[2 * ne + idx]])
+    ref = om.intcp_snow_et(st, etf[:, idx], eti[:, idx], ys, state)
+    check(outs[1][:, idx], ref, "1M sample")
+    om.close()

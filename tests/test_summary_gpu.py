@@ -260,3 +260,46 @@ def test_summary_ragged_sizes_and_no_river(fbr):
             ref, nref = a_.data()
             assert n == nref == 3 and np.array_equal(out, ref)
         model.close(); om.close()
+
+
+def test_summary_1m_properties():
+    """BASELINE's full size (1M triangles): size-independent properties of the device Summary --
+    re-evaluating the last RHS call gives the bits of recording every call; ws0 = y; the mass balance
+    closes: infil = max(0, d(storage) * porosity / dt + sum subsurf / area + ET terms) recomputed from
+    the outputs; subrunoff = sum subsurf / area + max(0, -that sum)."""
+    tb = W.make_named("1M")
+    ne, nr = tb["nelem"], tb["nriver"]
+    ef = tb["elem_f64"]
+    runs = {}
+    for mode in ("lazy", "eager"):
+        model = lib.Model(tb, reorder=1)
+        model.set_diagnostics(True)
+        if mode == "eager":
+            model.set_flux_recording(True)
+        y = model.N_VNew(tb["y0"]); model.set_ws0(y)
+        cv = lib.Cvode(model); cv.SetCVodeParam(y)
+        model.set_forcing(W.storm_forcing(tb, 2 * 3600.0), np.zeros(nr))
+        out = []
+        y_prev = tb["y0"]
+        for k in range(2):
+            model.Summary(y)
+            cv.SolveCVode((k + 1) * 60.0, y)
+            model.SummaryMB(y, tb["stepsize"])
+            xf, _ = model.get_fluxes(); sr, ws0 = model.get_summary(); yh = y.download()
+            out.append((yh, xf, sr, ws0, y_prev))
+            y_prev = yh
+        runs[mode] = out
+        cv.close(); model.close()
+    for a, b in zip(runs["lazy"], runs["eager"]):
+        for u, v in zip(a[:4], b[:4]):
+            assert np.array_equal(u, v)
+    area, depth, por = ef[W.E_AREA], ef[W.E_DEPTH], ef[W.E_POROSITY]
+    for yh, xf, sr, ws0, y_prev in runs["lazy"]:
+        assert np.array_equal(ws0, yh)
+        sw = lambda y: np.clip(y[2 * ne:3 * ne] + y[ne:2 * ne], 0.0, depth)
+        sub = xf[W.X_SUB0] / area + xf[W.X_SUB1] / area + xf[W.X_SUB2] / area
+        raw = (sw(yh) - sw(y_prev)) * por / tb["stepsize"] + sub + xf[W.X_EDIR_UNSAT] + xf[W.X_EDIR_GW] \
+            + xf[W.X_ETT_UNSAT] + xf[W.X_ETT_GW]
+        assert np.array_equal(xf[W.X_INFIL], np.where(raw < 0.0, 0.0, raw))      # same IEEE operations in numpy
+        assert np.array_equal(sr, np.where(raw < 0.0, sub - raw, sub))
+        assert (xf[W.X_INFIL] > 0).any()
