@@ -737,6 +737,20 @@ void ref_pack_et_tables(double *etf, int32_t *eti)
 #undef TI
 }
 
+/* overwrite attrib.lai_type / lc_type (test variety: input/example uses one LAI series and one
+ * land-cover class, so the monthly-table branches of forcing.c:249-257 / is_sm_et.c:58-65,92 would
+ * stay unvisited); eti as in ref_pack_et_tables, meteo_type is left alone */
+void ref_et_set_types(const int32_t *eti)
+{
+    int             i;
+
+    for (i = 0; i < nelem; i++)
+    {
+        H.pihm->elem[i].attrib.lai_type = eti[(size_t)PB_ETI_LAI_TYPE * nelem + i];
+        H.pihm->elem[i].attrib.lc_type = eti[(size_t)PB_ETI_LC_TYPE * nelem + i];
+    }
+}
+
 /* month-of-year lookups of the reference at model time t (forcing.c:351-618) */
 void ref_et_monthly(int t, int nlc, double *lai_lc, double *z0_lc,
     double *meltf)

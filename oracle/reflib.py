@@ -190,6 +190,10 @@ class RefModel:
         self.lib.ref_pack_et_tables(_ptr(f), _ptr(ii))
         return f, ii
 
+    def et_set_types(self, eti):
+        ii = np.ascontiguousarray(eti, np.int32); assert ii.shape == (3, self.nelem)
+        self.lib.ref_et_set_types(_ptr(ii))
+
     def et_monthly(self, t, nlc=40):
         a = np.zeros(nlc); b = np.zeros(nlc); mf = C.c_double()
         self.lib.ref_et_monthly(int(t), int(nlc), _ptr(a), _ptr(b), C.byref(mf))

@@ -311,6 +311,36 @@ def et():
     for c in cases:
         c.setdefault("stepsize", np.float64(d["etstep"]))
     out.update(pack_cases(cases, prefix="et"))
+    # (c) mixed types: half of the elements take their LAI from the monthly table of a random
+    #     land-cover class (lai_type 0), every element gets a random class for its roughness length
+    eti_b = eti.copy()
+    eti_b[W.ETI_LAI_TYPE] = np.where(rng.random(ne) < 0.5, 0, eti[W.ETI_LAI_TYPE])
+    # classes with a roughness length in every month (the table rows of unused classes are zero and
+    # make the reference itself divide by zero)
+    valid = np.array([c + 1 for c in range(d["nlc"]) if all(m.et_monthly(tt, d["nlc"])[1][c] > 0 for tt in month_t)])
+    eti_b[W.ETI_LC_TYPE] = rng.choice(valid, ne)
+    m.et_set_types(eti_b)
+    out["et_i32_b"] = eti_b
+    cases_b = []
+    for k in range(6):
+        t = month_t[(2 * k + 1) % 12] + 3600 * int(rng.integers(0, 24))
+        temp_c = [-5.0, 2.0, 9.0, 18.0, 27.0, 0.8][k] + rng.uniform(-0.4, 0.4)
+        meteo = np.array([[rng.choice([0.0, 1.5, 9.0]), temp_c + 273.15, rng.uniform(25, 100), rng.uniform(0.3, 9.0),
+                           rng.choice([0.0, 250.0, 800.0]), 300.0, 98000.0]])
+        lai = [[0.0, 1.2, 3.5][k % 3]]
+        cmc = rng.uniform(-1e-6, 9e-4, ne)
+        sneqv = rng.choice([0.0, 2e-3, 0.05], ne)
+        y = y0.copy()
+        y[ne:2 * ne] = rng.choice([-1e-3, 0.0, 0.05, 0.3, 1.5], ne) * rng.random(ne)
+        y[2 * ne:3 * ne] = depth * rng.choice([0.0, 0.2, 0.7, 0.97, 1.02], ne)
+        m.et_set_state(sneqv, cmc)
+        m.et_run(t, 900.0, meteo, lai, y)
+        lai_lc, z0_lc, meltf = m.et_monthly(t, d["nlc"])
+        cases_b.append(dict(t=np.int64(t), state_in=np.array([sneqv, cmc]), y=y, meteo=meteo, lai=np.array(lai[:1]),
+                            stepsize=np.float64(900.0), out=m.et_get(), lai_lc=lai_lc, z0_lc=z0_lc,
+                            meltf=np.float64(meltf)))
+    out.update(pack_cases(cases_b, prefix="etb"))
+    m.et_set_types(eti)
     np.savez_compressed(os.path.join(HERE, "et_example.npz"), **out)
     o = np.array([c["out"] for c in cases])
     print("et_example.npz cases", len(cases), "pcpdrp>0:", (o[:, W.EO_PCPDRP] > 0).mean().round(3),

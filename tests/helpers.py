@@ -39,10 +39,10 @@ def summary_cases(g):
     return out
 
 
-def et_cases(g):
-    """IntcpSnowEt known-answer cases (make_golden.py et)"""
+def et_cases(g, prefix="et"):
+    """IntcpSnowEt known-answer cases (make_golden.py et); prefix 'etb': the mixed-type table et_i32_b"""
     keys = ("t", "state_in", "y", "meteo", "lai", "lai_lc", "z0_lc", "meltf", "stepsize", "out")
-    return [{k: g[f"et{i}_{k}"] for k in keys} for i in range(int(g["et_n"]))]
+    return [{k: g[f"{prefix}{i}_{k}"] for k in keys} for i in range(int(g[f"{prefix}_n"]))]
 
 
 def dy_scale(tables, case_forc, xflux, rivflow):

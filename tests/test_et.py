@@ -34,6 +34,27 @@ def test_oracle_et_matches_golden():
     om.close()
 
 
+def test_oracle_et_matches_golden_mixed_types():
+    """lai_type 0 (monthly LAI table by land-cover class) and 40 roughness classes, forcing.c:249-257"""
+    g = load_golden("et_example.npz")
+    tb = golden_tables(g)
+    om = oraclelib.OracleModel(tb)
+    eti = g["et_i32_b"]
+    assert (eti[W.ETI_LAI_TYPE] == 0).any() and (eti[W.ETI_LAI_TYPE] > 0).any() and len(set(eti[W.ETI_LC_TYPE])) >= 10
+    cases = et_cases(g, "etb")
+    assert len(cases) == 6
+    nolai = False
+    for c in cases:
+        st, keep = lib.make_et_step(c["stepsize"], g["cal"], c["meltf"], c["meteo"], c["lai"], c["lai_lc"], c["z0_lc"])
+        state = np.zeros((W.EO_NCOL, tb["nelem"]))
+        state[[W.EO_SNEQV, W.EO_CMC]] = c["state_in"]
+        out = om.intcp_snow_et(st, g["et_f64"], eti, c["y"], state)
+        assert np.array_equal(out, c["out"])
+        nolai |= bool((c["lai_lc"][eti[W.ETI_LC_TYPE][eti[W.ETI_LAI_TYPE] == 0] - 1] == 0).any())
+    assert nolai                                  # a class whose monthly LAI is zero: the lai <= 0 branch per element
+    om.close()
+
+
 def test_oracle_et_matches_live_reference():
     if not reflib.available(False):
         pytest.skip("oracle/_ref not built (needs /root/reference)")

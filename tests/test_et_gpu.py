@@ -61,6 +61,25 @@ def test_et_matches_golden(reorder):
     model.close(); om.close()
 
 
+def test_et_matches_golden_mixed_types():
+    """per-element choice between the LAI series and the monthly table of the element's land-cover
+    class, 40 roughness classes (tests/golden: et_i32_b, cases etb*)"""
+    g = load_golden("et_example.npz")
+    tb = golden_tables(g)
+    model = lib.Model(tb, reorder=1)
+    model.et_create(g["et_f64"], g["et_i32_b"])
+    yv = model.N_VNew()
+    worst = 0.0
+    for k, c in enumerate(et_cases(g, "etb")):
+        st, keep = lib.make_et_step(c["stepsize"], g["cal"], c["meltf"], c["meteo"], c["lai"], c["lai_lc"], c["z0_lc"])
+        model.et_set_state(c["state_in"][0], c["state_in"][1])
+        yv.upload(c["y"])
+        model.IntcpSnowEt(st, yv)
+        worst = max(worst, check(model.et_get(), c["out"], f"mixed case {k}"))
+    print(f"mixed types: worst {worst:.2e}")
+    model.close()
+
+
 def test_et_sequence_keeps_storages_on_device():
     """the reference's own four etsteps of the first hour, storages carried on the device"""
     g = load_golden("et_example.npz")
