@@ -80,6 +80,34 @@ def test_et_matches_golden_mixed_types():
     model.close()
 
 
+def test_et_multiple_stations_vs_oracle():
+    """several meteorological stations and LAI series (input/example has one of each): the by-type
+    gather of forcing.c:141-149,249-253 against the oracle port"""
+    g = load_golden("et_example.npz")
+    tb = golden_tables(g)
+    ne = tb["nelem"]
+    rng = np.random.default_rng(21)
+    eti = g["et_i32_b"].copy()
+    eti[W.ETI_METEO_TYPE] = rng.integers(1, 4, ne)
+    eti[W.ETI_LAI_TYPE] = rng.integers(0, 3, ne)
+    c = et_cases(g, "etb")[3]
+    meteo = np.repeat(c["meteo"], 3, axis=0)
+    meteo[:, 0] = [0.0, 2.0, 11.0]; meteo[:, 1] += [-14.0, 0.0, 9.0]; meteo[:, 4] = [0.0, 300.0, 650.0]
+    lai = np.array([0.7, 3.9])
+    st, keep = lib.make_et_step(900.0, g["cal"], c["meltf"], meteo, lai, c["lai_lc"], c["z0_lc"])
+    model = lib.Model(tb, reorder=1)
+    model.et_create(g["et_f64"], eti)
+    model.et_set_state(c["state_in"][0], c["state_in"][1])
+    yv = model.N_VNew(c["y"])
+    model.IntcpSnowEt(st, yv)
+    om = oraclelib.OracleModel(tb)
+    state = np.zeros((W.EO_NCOL, ne)); state[[W.EO_SNEQV, W.EO_CMC]] = c["state_in"]
+    ref = om.intcp_snow_et(st, g["et_f64"], eti, c["y"], state)
+    assert len({tuple(r) for r in np.round(ref[[W.EO_PCPDRP, W.EO_SNEQV]].T, 12)}) > 3      # the stations differ
+    check(model.et_get(), ref, "3 stations, 2 LAI series")
+    model.close(); om.close()
+
+
 def test_et_sequence_keeps_storages_on_device():
     """the reference's own four etsteps of the first hour, storages carried on the device"""
     g = load_golden("et_example.npz")
