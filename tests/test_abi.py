@@ -59,7 +59,36 @@ def test_enums_match_python_mirror():
             assert getattr(W, pyprefix + name[len(prefix):]) == idx, name
 
 
+def test_new_enums_match_python_mirror():
+    txt = header_text()
+    for enum, prefix, pyprefix in (("pihm_b200_et_col", "PB_ET_", "ET_"), ("pihm_b200_et_icol", "PB_ETI_", "ETI_"),
+                                   ("pihm_b200_et_out_col", "PB_EO_", "EO_"), ("pihm_b200_print_src", "PB_PS_", "PS_")):
+        body = re.search(r"enum\s+%s\s*\{(.*?)\}" % enum, txt, flags=re.S).group(1)
+        names = [n.strip().split("=")[0].strip() for n in body.split(",") if n.strip()]
+        for idx, name in enumerate(names):
+            assert getattr(W, pyprefix + name[len(prefix):]) == idx, name
+    assert int(re.search(r"PIHM_B200_NUM_METEO_VAR\s+(\d+)", txt).group(1)) == W.NUM_METEO_VAR
+
+
+def test_null_handles_are_refused():
+    """every entry point added for SURVEY 8(f) / the lsolve hook fails cleanly on a null handle (no GPU needed)"""
+    L = lib.load_library()
+    assert L.pihm_b200_set_diagnostics(None, 1) < 0
+    assert L.pihm_b200_set_ws0(None, None) < 0
+    assert L.pihm_b200_summary_mb(None, None, 60.0) < 0
+    assert L.pihm_b200_get_summary(None, None, None) < 0
+    assert L.pihm_b200_et_create(None, None, None) < 0
+    assert L.pihm_b200_intcp_snow_et(None, None, None) < 0
+    assert L.pihm_b200_et_set_state(None, None, None) < 0
+    assert L.pihm_b200_et_get(None, None) < 0
+    assert L.pihm_b200_print_add(None, 0, 0) < 0
+    assert L.pihm_b200_print_update(None, None, 0, None) < 0
+    assert L.pihm_b200_print_data(None, 0, None, None) < 0
+    assert L.pihm_b200_spgmr_solve(None, 0.0, 0.0, 0.0, 0, None, None, None, None) < 0
+
+
 def test_struct_layouts():
+    assert ctypes.sizeof(lib.EtStep) == 5 * 8 + 4 * 4 + 4 * 8
     assert ctypes.sizeof(lib.MeshStruct) == 64
     assert ctypes.sizeof(lib.CvodeParam) == 48
     assert ctypes.sizeof(lib.MaxStepCtrl) == 64
