@@ -36,6 +36,25 @@ B_RHS = {False: 376.0, True: 476.0}     # algorithmic bytes / element / RHS (SUR
 # dram__bytes_read.sum + dram__bytes_write.sum of one RHS (k_pre + k_main) from the committed
 # ncu --set full capture (profiles/); None where no capture exists
 RHS_TRAFFIC_BYTES = {("1M", False): 418.8e6, ("1M", True): 460.3e6}
+# FP64 side figure: 2 x DFMA + DADD + DMUL thread instructions of k_pre + k_main from the same kind
+# of capture (profiles/r01i_rhs_1M_ncu_summary.md): 295.2 + 782.7 MFLOP per RHS at 1M triangles
+RHS_FP64_FLOP = {("1M", False): 1.078e9}
+FP64_LANES_PER_SM = 64      # sm__sass_thread_inst_executed_op_dfma_pred_on peak_sustained per SM and cycle
+
+
+def fp64_side(size, fbr, rhs_ms, clk):
+    """achieved FP64 rate of one RHS evaluation next to the HBM figure (the kernels are bound by
+    dependent FP64 chains, not by memory): counted flops / CUDA-event time; peak = SMs x 64 lanes x 2 x SM clock"""
+    flop = RHS_FP64_FLOP.get((size, fbr))
+    if flop is None or not rhs_ms:
+        return None
+    import torch
+    nsm = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    mhz = (clk or {}).get("sm_mhz") or (clk or {}).get("sm_max_mhz") or 1965.0
+    peak = nsm * FP64_LANES_PER_SM * 2 * mhz * 1e6 / 1e12
+    ach = flop / (rhs_ms * 1e-3) / 1e12
+    return {"flop_per_rhs": flop, "achieved_tflops": ach, "peak_tflops": peak, "frac": ach / peak,
+            "source": "profiles/r01i_rhs_1M_ncu_summary.md (2 x DFMA + DADD + DMUL thread instructions)"}
 
 
 def forcing_at(tb, k):
@@ -275,6 +294,7 @@ def run_ours(args):
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": B_RHS[fbr] * model.nown_elem,
                      "traffic_source": "profiles/r01g_rhs_1M_ncu_summary.md (pihm) / r01d (fbr): ncu --set full, dram read+write"},
+        "fp64": fp64_side(size, fbr, rhs_ms, clk),
         "e2e": {"value": e2e_value, "unit": "sim-days/s", "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": 3 * 8 * ne, "d2h_bytes_per_step": 8 * model.nsv},
         "gpu_launches": int(l1 - l0),
