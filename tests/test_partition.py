@@ -32,6 +32,21 @@ def _global_case(fbr, seed=5):
     return tb, y, forc, om.ode(y), om.ode(y)
 
 
+_SUMMARY_CACHE = {}
+
+
+def _summary_ref(fbr, tb, y, forc, y1):
+    """global Summary after two RHS calls on y (cached per variant): (xflux, subrunoff)"""
+    if fbr not in _SUMMARY_CACHE:
+        om = oraclelib.OracleModel(tb)
+        om.set_forcing(forc, np.zeros(tb["nriver"]))
+        om.set_ws0(y)
+        om.ode(y); om.ode(y)
+        sr = om.summary(y1, tb["stepsize"])
+        _SUMMARY_CACHE[fbr] = (om.get_fluxes()[0], sr)
+    return _SUMMARY_CACHE[fbr]
+
+
 @pytest.mark.parametrize("fbr", [False, True])
 @pytest.mark.parametrize("nparts", [2, 3, 8])
 def test_local_meshes_reproduce_global_rhs(fbr, nparts):
@@ -50,6 +65,14 @@ def test_local_meshes_reproduce_global_rhs(fbr, nparts):
         own = PT.state_index(p["nown_elem"], p["nown_riv"], fbr, np.arange(nl), np.arange(rl), nl, rl)
         assert np.array_equal(ol.ode(y[idx])[own], dy1[p["state_idx"]])
         assert np.array_equal(ol.ode(y[idx])[own], dy2[p["state_idx"]])   # stale river-edge flows carried locally
+        # Summary()/MassBalance() of the owned elements from the local fluxes = the global ones
+        y1 = y * 1.001
+        og = _summary_ref(fbr, tb, y, forc, y1)
+        ol.set_ws0(y[idx])
+        sr_l = ol.summary(y1[idx], tb["stepsize"])
+        no = p["nown_elem"]
+        assert np.array_equal(ol.get_fluxes()[0][:, :no], og[0][:, p["elem_gid"][:no]])
+        assert np.array_equal(sr_l[:no], og[1][p["elem_gid"][:no]])
         # exchange maps are consistent: what p sends to q is what q expects from p
         for k, q in enumerate(p["nbr_rank"]):
             pq = parts[q]
