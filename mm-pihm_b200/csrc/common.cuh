@@ -129,6 +129,14 @@ int comm_setup_halo_p2p(pihm_b200_ctx *ctx);
 }  // namespace pb
 
 namespace pb {
+// rhs_kernels.cu: the RHS kernels live in their own translation unit (own -fmad setting)
+int rhs_configure(pihm_b200_ctx *ctx, int sms);
+int rhs_class_rcp(pihm_b200_ctx *ctx);
+int rhs_halo_pack(pihm_b200_ctx *ctx, const double *y);
+int rhs_launch(pihm_b200_ctx *ctx, const double *y, double *dy, bool replay);
+}  // namespace pb
+
+namespace pb {
 // one varctrl_struct of the reference's print system (pihm_struct.h:193-216) on the device
 struct PrintVar {
     int src = 0, col = 0;      // pihm_b200_print_src, column within it

@@ -9,7 +9,8 @@
 #include "common.cuh"
 #include "nvec.cuh"
 #include "reorder.h"
-#include "rhs.cuh"
+#include "rhs_layout.cuh"
+#include "summary.cuh"
 #include "et.cuh"
 
 namespace pb {
@@ -335,21 +336,10 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
     dm.forc = ctx->d_forc; dm.rf = ctx->d_rf; dm.ri = ctx->d_ri; dm.rivbc = ctx->d_rivbc;
     dm.fbr_dist = ctx->d_fbr_dist; dm.up_ptr = ctx->d_up_ptr; dm.up_idx = ctx->d_up_idx;
     dm.rivflow = ctx->d_rivflow; dm.s2c_stale = ctx->d_stale;
-    {   // reciprocals of the dictionary's divisors and of DEPRSTG / dt, computed on the device
-        double *d_c = nullptr, h_c[2] = {0.0, 0.0};
-        bool good = cudaMalloc((void **)&d_c, sizeof(h_c)) == cudaSuccess;
-        if (good) {
-            k_class_rcp<<<(ctx->nclass + 127) / 128, 128>>>(ctx->d_cls, ctx->nclass, dm.dt, d_c);
-            good = cudaMemcpy(h_c, d_c, sizeof(h_c), cudaMemcpyDeviceToHost) == cudaSuccess;
-            cudaFree(d_c);
-        }
-        if (!good) {
-            set_error("pihm_b200_create: class dictionary set-up failed");
-            pihm_b200_destroy(ctx);
-            return nullptr;
-        }
-        dm.r_deprstg = h_c[0];
-        dm.r_dt = h_c[1];
+    if (pb::rhs_class_rcp(ctx) != 0) {      // reciprocals of the dictionary's divisors and of DEPRSTG / dt
+        set_error("pihm_b200_create: class dictionary set-up failed");
+        pihm_b200_destroy(ctx);
+        return nullptr;
     }
     dm.gel = ctx->d_gel; dm.gri = ctx->d_gri;
     dm.xflux = nullptr; dm.record = 0;
@@ -366,29 +356,10 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
     {
         cudaDeviceProp prop;
         cudaGetDeviceProperties(&prop, ctx->device);
-        const int pre_smem = PreCfg::ring_t::smem_bytes();
-        const int main_smem = dm.fbr ? MainCfg<true>::ring_t::smem_bytes() : MainCfg<false>::ring_t::smem_bytes();
-        int bpre = 0, bmain = 0;
-        cudaError_t e = cudaFuncSetAttribute(k_pre, cudaFuncAttributeMaxDynamicSharedMemorySize, pre_smem);
-        if (e == cudaSuccess)
-            e = dm.fbr ? cudaFuncSetAttribute(k_main<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, main_smem)
-                       : cudaFuncSetAttribute(k_main<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, main_smem);
-        if (e == cudaSuccess)
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpre, k_pre, PB_PRE_THREADS, pre_smem);
-        if (e == cudaSuccess)
-            e = dm.fbr ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bmain, k_main<true>, MainCfg<true>::THREADS, main_smem)
-                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bmain, k_main<false>, MainCfg<false>::THREADS, main_smem);
-        if (e != cudaSuccess || bpre < 1 || bmain < 1) {
-            set_error(std::string("pihm_b200_create: RHS kernel configuration failed: ") + cudaGetErrorString(e));
+        if (pb::rhs_configure(ctx, prop.multiProcessorCount) != 0) {
             pihm_b200_destroy(ctx);
             return nullptr;
         }
-        if (const char *ov = std::getenv("PIHM_B200_PRE_CTAS")) bpre = std::max(1, std::min(bpre, std::atoi(ov)));
-        if (const char *ov = std::getenv("PIHM_B200_MAIN_CTAS")) bmain = std::max(1, std::min(bmain, std::atoi(ov)));
-        ctx->pre_grid = prop.multiProcessorCount * bpre;
-        ctx->main_grid = prop.multiProcessorCount * bmain;
-        ctx->pre_smem = pre_smem;
-        ctx->main_smem = main_smem;
         if (const char *ov = std::getenv("PIHM_B200_PDL")) ctx->pdl = std::atoi(ov);
         // B200's 126 MB L2 as a scratchpad: the 64 B / element of neighbour records (written by
         // k_pre, gathered three times per element by k_main, 64 MB at 1M triangles) are marked
@@ -622,44 +593,13 @@ int pihm_b200_halo_pack_host(pihm_b200_ctx *ctx, const pihm_b200_vec *y, double 
     if (!ctx || !y) return -1;
     const int n = ctx->nse + ctx->nsr;
     if (n > 0) {
-        k_halo_pack<<<(n + 255) / 256, 256, 0, ctx->s()>>>(ctx->dm, y->d, ctx->nse, ctx->d_send_e_idx, ctx->d_send_e,
-                                                           ctx->nsr, ctx->d_send_r_idx, ctx->d_send_r);
-        ctx->launches++;
+        pb::rhs_halo_pack(ctx, y->d);
     }
     PB_CUDA(cudaStreamSynchronize(ctx->s()));
     if (ctx->nse && elem_rec)
         PB_CUDA(cudaMemcpy(elem_rec, ctx->d_send_e, sizeof(double) * ctx->dm.gs * ctx->nse, cudaMemcpyDeviceToHost));
     if (ctx->nsr && riv_rec)
         PB_CUDA(cudaMemcpy(riv_rec, ctx->d_send_r, sizeof(double) * 2 * ctx->nsr, cudaMemcpyDeviceToHost));
-    return 0;
-}
-
-// test hook (not part of the reference interface): pow_pos vs libdevice pow on n pairs
-int pihm_b200_test_pow(int n, const double *x, const double *y, double *fast, double *ref)
-{
-    double *d = nullptr;
-    PB_CUDA(cudaMalloc((void **)&d, sizeof(double) * 4 * (size_t)n));
-    PB_CUDA(cudaMemcpy(d, x, sizeof(double) * n, cudaMemcpyHostToDevice));
-    PB_CUDA(cudaMemcpy(d + n, y, sizeof(double) * n, cudaMemcpyHostToDevice));
-    k_test_pow<<<(n + 255) / 256, 256>>>(n, d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n);
-    PB_CUDA(cudaMemcpy(fast, d + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost));
-    PB_CUDA(cudaMemcpy(ref, d + 3 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost));
-    cudaFree(d);
-    return 0;
-}
-
-// test hook: the branch-free division of the RHS kernels vs the hardware division
-int pihm_b200_test_div(int n, const double *a, const double *b, double *fast, double *ok, double *ref)
-{
-    double *d = nullptr;
-    PB_CUDA(cudaMalloc((void **)&d, sizeof(double) * 5 * (size_t)n));
-    PB_CUDA(cudaMemcpy(d, a, sizeof(double) * n, cudaMemcpyHostToDevice));
-    PB_CUDA(cudaMemcpy(d + n, b, sizeof(double) * n, cudaMemcpyHostToDevice));
-    k_test_div<<<(n + 255) / 256, 256>>>(n, d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n, d + 4 * (size_t)n);
-    PB_CUDA(cudaMemcpy(fast, d + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost));
-    PB_CUDA(cudaMemcpy(ok, d + 3 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost));
-    PB_CUDA(cudaMemcpy(ref, d + 4 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost));
-    cudaFree(d);
     return 0;
 }
 
@@ -682,84 +622,6 @@ int pihm_b200_set_flux_recording(pihm_b200_ctx *ctx, int on)
         dm.self = ctx->d_dm_par[p];
         PB_CUDA(cudaMemcpy(ctx->d_dm_par[p], &dm, sizeof(DevMesh), cudaMemcpyHostToDevice));
     }
-    return 0;
-}
-
-// ---------------------------------------------------------------------------
-// RHS
-// ---------------------------------------------------------------------------
-// replay: evaluate the LAST call once more (same input, same ghosts, same stale river-edge
-// flows) with the flux columns switched on -- no halo exchange, hidden state left as it is.
-static int launch_rhs(pihm_b200_ctx *ctx, const double *y, double *dy, bool replay = false)
-{
-    DevMesh dm = ctx->dm;
-    HaloWait hw{};
-    if (replay) {
-        if (ctx->nranks > 1 && ctx->halo_p2p) {     // the ghost records of the last exchange
-            const int par = (int)(ctx->halo_seq & 1);
-            dm.gel = ctx->d_hx + par * ctx->hx_stride;
-            dm.gri = dm.gel + (size_t)dm.gs * (dm.ne - dm.nown);
-        }
-        dm.record = 1;
-        dm.replay = 1;
-        dm.xflux = ctx->d_xflux;
-        dm.self = ctx->d_dm_rec;
-        PB_CUDA(cudaMemcpyAsync(ctx->d_dm_rec, &dm, sizeof(DevMesh), cudaMemcpyHostToDevice, ctx->s()));
-    } else if (ctx->nranks > 1 && ctx->halo_p2p) {
-        // halo exchange over peer memory: stores into the neighbours' ghost buffers + arrival flags
-        const long long seq = ++ctx->halo_seq;
-        const int par = (int)(seq & 1);
-        const int n = ctx->nse + ctx->nsr;
-        if (ctx->hpeers.nn > 0) {
-            k_halo_put<<<std::max(1, (n + 255) / 256), 256, 0, ctx->s()>>>(dm, y, ctx->nse, ctx->d_send_e_idx, ctx->nsr,
-                                                                            ctx->d_send_r_idx, ctx->hpeers, par,
-                                                                            (double)seq, ctx->d_hcount);
-            ctx->launches++;
-        }
-        dm.gel = ctx->d_hx + par * ctx->hx_stride;
-        dm.gri = dm.gel + (size_t)dm.gs * (dm.ne - dm.nown);
-        dm.self = ctx->d_dm_par[par];
-        hw.flags = ctx->d_hx + 2 * ctx->hx_stride + par * PB_MAX_RANKS_H;
-        hw.nn = ctx->hpeers.nn;
-        for (int k = 0; k < hw.nn; k++) hw.rank[k] = ctx->nbr_rank[k];
-        hw.seq = (double)seq;
-    } else if (ctx->nranks > 1) {
-        // one-ring(+) halo exchange of neighbour and river states before the RHS
-        const int n = ctx->nse + ctx->nsr;
-        if (n > 0) {
-            k_halo_pack<<<(n + 255) / 256, 256, 0, ctx->s()>>>(dm, y, ctx->nse, ctx->d_send_e_idx, ctx->d_send_e,
-                                                               ctx->nsr, ctx->d_send_r_idx, ctx->d_send_r);
-            ctx->launches++;
-        }
-        if (pb::comm_halo_exchange(ctx) != 0) return -1;
-    }
-    // work items = 32-entity tiles; k_pre: owned + ghost, k_main: owned only
-    const int te = (dm.ne + PB_TILE - 1) / PB_TILE, tr = (dm.nr + PB_TILE - 1) / PB_TILE;
-    const int te_own = (dm.nown + PB_TILE - 1) / PB_TILE, tr_own = (dm.rown + PB_TILE - 1) / PB_TILE;
-    const auto groups = [](int t) { return (t + PB_RING_GROUP - 1) / PB_RING_GROUP; };
-    const int gpre = std::max(1, std::min(ctx->pre_grid, groups(te) + groups(tr)));
-    const int gmain = std::max(1, std::min(ctx->main_grid, groups(te_own) + groups(tr_own)));
-    k_pre<<<gpre, PB_PRE_THREADS, ctx->pre_smem, ctx->s()>>>(dm, y, te, tr, hw);
-    {
-        // k_main right behind k_pre with programmatic stream serialization (PDL): its launch
-        // latency and prologue overlap k_pre's tail
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(gmain);
-        cfg.blockDim = dim3(dm.fbr ? MainCfg<true>::THREADS : MainCfg<false>::THREADS);
-        cfg.dynamicSmemBytes = ctx->main_smem;
-        cfg.stream = ctx->s();
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = ctx->pdl ? 1 : 0;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        const cudaError_t e = dm.fbr ? cudaLaunchKernelEx(&cfg, k_main<true>, dm, y, dy, te_own, tr_own)
-                                     : cudaLaunchKernelEx(&cfg, k_main<false>, dm, y, dy, te_own, tr_own);
-        if (e != cudaSuccess) { set_error(std::string("k_main launch: ") + cudaGetErrorString(e)); return -1; }
-    }
-    ctx->launches += 2;
-    if (!replay) ctx->last_in = y;
-    ctx->flux_fresh = dm.record;
     return 0;
 }
 
@@ -809,7 +671,7 @@ int pihm_b200_summary_mb(pihm_b200_ctx *ctx, const pihm_b200_vec *y, double step
     if (!ctx->flux_fresh) {
         // wf.* of the last ODE() call: evaluate that call again with the columns on
         if (!ctx->last_in) { set_error("pihm_b200_summary_mb: no RHS call to take the fluxes from"); return -1; }
-        if (launch_rhs(ctx, ctx->last_in, ctx->d_rec_dy, true) != 0) return -1;
+        if (pb::rhs_launch(ctx, ctx->last_in, ctx->d_rec_dy, true) != 0) return -1;
         ctx->flux_fresh = 1;
     }
     const int ne = ctx->dm.nown;
@@ -1042,7 +904,7 @@ int pihm_b200_ode(pihm_b200_ctx *ctx, double t, const pihm_b200_vec *y, pihm_b20
         set_error("pihm_b200_ode: bad argument");
         return -1;
     }
-    return launch_rhs(ctx, y->d, ydot->d);
+    return pb::rhs_launch(ctx, y->d, ydot->d, false);
 }
 
 int pihm_b200_check_nan(pihm_b200_ctx *ctx)

@@ -16,78 +16,12 @@
 // (libdevice vs glibc) can differ, by <= 2 ulp.
 #pragma once
 #include "common.cuh"
+#include "rhs_layout.cuh"
 #include "fastpow.cuh"
 #include "fdiv.cuh"
 
 namespace pb {
 
-// Static element columns are stored warp-tiled ("AoSoA-32"): tile t = i >> 5
-// holds all columns of its 32 elements contiguously, 256 B per column, in the
-// slot order below; the three neighbour codes of the tile (int32 [3][32]) ride
-// along as two pseudo-columns.  One warp works on one tile at a time.  Both RHS
-// kernels are persistent: a CTA owns a ring of PB_*_STAGES shared-memory stages,
-// each filled by ONE bulk async copy (cp.async.bulk, the TMA engine; SASS UBLKCP)
-// of the contiguous slot range the kernel needs (+ one for the forcing columns),
-// completion signalled on the stage's mbarrier.  Warps take tiles by ticket; the
-// warp that finishes a tile re-arms its stage with the tile PB_*_STAGES tickets
-// ahead, so (STAGES - WARPS) tile loads per CTA are always in flight while the
-// warps compute -- the loads no longer sit at the head of every warp's
-// dependency chain (ncu r01: both kernels were latency-, not bandwidth-bound).
-#define PB_TILE 32
-// Soil / land-cover / geology parameters are CLASS data in MM-PIHM (soil, lc and geol tables
-// indexed by type; ReadSoil/ReadLc/ReadGeol, calibrated by global multipliers): the create
-// call deduplicates their rows into a dictionary `cls[ncls][CC_STRIDE]` (a few dozen rows, L1
-// resident) and the tiles carry a 4-byte class id per element instead of 12 (fbr: 17) doubles.
-// The dictionary also holds the van Genuchten exponents derived from beta, computed once on
-// the host with the same IEEE divisions.  dmac / dinf stay per element (clipped to the soil
-// depth, init_soil.c:57-59).  A table without repeated rows still works (one class per element).
-enum {   // k_pre reads [TS_PRE0, TS_PRE1), k_main [TS_MAIN0, TS_MAIN1 / TS_FBR1)
-    TS_NABRX0 = 0, TS_NABRX1, TS_NABRX2, TS_NABRY0, TS_NABRY1, TS_NABRY2,
-    TS_ZMAX, TS_DEPTH, TS_DMAC, TS_NB0, TS_NB1,     // NB0/NB1: int32 [4][32] = 3 neighbour codes + class id
-    TS_AREA, TS_DINF, TS_ZMIN, TS_EDGE0, TS_EDGE1, TS_EDGE2, TS_NABRDIST0, TS_NABRDIST1, TS_NABRDIST2,
-    TS_ZBED, TS_GDEPTH,
-    TS_NCOL,
-    TS_PRE0 = TS_NABRX0, TS_PRE1 = TS_AREA, TS_MAIN0 = TS_ZMAX, TS_MAIN1 = TS_ZBED, TS_FBR1 = TS_NCOL
-};
-enum {   // dictionary row; pairs are fetched as double2
-    CC_ALPHA = 0, CC_M1, CC_M2, CC_M3,              // m1 = beta/(beta-1), m2 = (beta-1)/beta, m3 = 1/beta
-    CC_KINFV, CC_KMACV, CC_AREAFH, CC_KSATV,
-    CC_POROSITY, CC_ROUGH, CC_RZD, CC_BETA,
-    CC_KMACH, CC_AREAFV, CC_KSATH, CC_RALPHA,       // R*: refined reciprocals (k_class_rcp), shared by divisions
-    CC_GALPHA, CC_GM1, CC_GM2, CC_GM3,
-    CC_GKSATV, CC_GKSATH, CC_GPOROSITY, CC_GBETA,
-    CC_RPOR, CC_RGALPHA, CC_RGPOR, CC_PAD,
-    CC_STRIDE
-};
-// ABI column (include/pihm_b200.h) -> tile slot; used by the host packer
-__host__ __device__ inline int tile_slot_of(int abi_col)
-{
-    switch (abi_col) {
-        case PB_E_AREA: return TS_AREA;  case PB_E_ZMIN: return TS_ZMIN;  case PB_E_ZMAX: return TS_ZMAX;
-        case PB_E_ZBED: return TS_ZBED;
-        case PB_E_EDGE0: return TS_EDGE0; case PB_E_EDGE1: return TS_EDGE1; case PB_E_EDGE2: return TS_EDGE2;
-        case PB_E_NABRDIST0: return TS_NABRDIST0; case PB_E_NABRDIST1: return TS_NABRDIST1;
-        case PB_E_NABRDIST2: return TS_NABRDIST2;
-        case PB_E_NABRX0: return TS_NABRX0; case PB_E_NABRX1: return TS_NABRX1; case PB_E_NABRX2: return TS_NABRX2;
-        case PB_E_NABRY0: return TS_NABRY0; case PB_E_NABRY1: return TS_NABRY1; case PB_E_NABRY2: return TS_NABRY2;
-        case PB_E_DEPTH: return TS_DEPTH; case PB_E_DINF: return TS_DINF; case PB_E_DMAC: return TS_DMAC;
-        case PB_E_GDEPTH: return TS_GDEPTH;
-    }
-    return -1;
-}
-// ABI column -> dictionary slot (-1: per-element column)
-__host__ __device__ inline int class_slot_of(int abi_col)
-{
-    switch (abi_col) {
-        case PB_E_ALPHA: return CC_ALPHA; case PB_E_BETA: return CC_BETA; case PB_E_KINFV: return CC_KINFV;
-        case PB_E_KMACV: return CC_KMACV; case PB_E_AREAFH: return CC_AREAFH; case PB_E_KSATV: return CC_KSATV;
-        case PB_E_POROSITY: return CC_POROSITY; case PB_E_ROUGH: return CC_ROUGH; case PB_E_RZD: return CC_RZD;
-        case PB_E_KMACH: return CC_KMACH; case PB_E_AREAFV: return CC_AREAFV; case PB_E_KSATH: return CC_KSATH;
-        case PB_E_GALPHA: return CC_GALPHA; case PB_E_GBETA: return CC_GBETA; case PB_E_GKSATV: return CC_GKSATV;
-        case PB_E_GKSATH: return CC_GKSATH; case PB_E_GPOROSITY: return CC_GPOROSITY;
-    }
-    return -1;
-}
 // global-memory access to a tile slot of an arbitrary element (river kernels, fbr gathers)
 #define TSC(slot, i) (m.es[((size_t)((i) >> 5) * TS_NCOL + (slot)) * PB_TILE + ((i) & 31)])
 // dictionary entry c of an arbitrary element (river kernels, fbr gathers)
@@ -1143,9 +1077,6 @@ __device__ __forceinline__ void river_main(const DevMesh &m, double *__restrict_
 #ifndef PB_MAIN_WARPS_FBR
 #define PB_MAIN_WARPS_FBR 10   // fbr: 10 warps x 2 CTAs at 96 registers: 175.3 us (8 / 7 / 6 warps: 178.8 / 191 / 195 us)
 #endif
-#ifndef PB_PATCH
-#define PB_PATCH 128       // elements per locality patch of the internal ordering (reorder.h)
-#endif
 
 #ifndef PB_RING_GROUP
 #define PB_RING_GROUP 1     // consecutive tiles a CTA takes at a time (1: tile t goes to CTA t mod grid)
@@ -1325,51 +1256,6 @@ k_main(const DevMesh m, const double *__restrict__ y, double *__restrict__ dy, i
         __syncwarp();
         if (lane == 0) { ring.release(s, n); request(q + STAGES); }
     }
-}
-
-// Summary() + MassBalance() (src/update.c:3-160): ws = y (not clamped), the mass-balance
-// infiltration from the change of soil storage and the wf.* fields of the last RHS call
-// (PB_X_* columns), subrunoff, fbr: wf.fbr_infil.  One thread per owned element; plain
-// IEEE operators (-fmad=false), so equal inputs give the reference's bits.  ws0 itself is
-// replaced by y afterwards (a copy on the same stream).
-static __global__ void __launch_bounds__(256)
-k_summary_mb(const DevMesh m, const double *__restrict__ y, const double *__restrict__ ws0,
-             double *__restrict__ subrunoff_out, double stepsize)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m.nown) return;
-    const double depth = TSC(TS_DEPTH, i), area = TSC(TS_AREA, i);
-    // update.c:122-128
-    double soilw0 = ws0[m.o_gw + i] + ws0[m.o_unsat + i];
-    soilw0 = (soilw0 > depth) ? depth : soilw0;
-    soilw0 = (soilw0 < 0.0) ? 0.0 : soilw0;
-    double soilw1 = y[m.o_gw + i] + y[m.o_unsat + i];
-    soilw1 = (soilw1 > depth) ? depth : soilw1;
-    soilw1 = (soilw1 < 0.0) ? 0.0 : soilw1;
-    // update.c:130-136
-    double subrunoff = 0.0;
-#pragma unroll
-    for (int j = 0; j < 3; j++) subrunoff += XFC(PB_X_SUB0 + j, i) / area;
-    double infil = (soilw1 - soilw0) * CLE(CC_POROSITY, i) / stepsize + subrunoff + XFC(PB_X_EDIR_UNSAT, i) +
-        XFC(PB_X_EDIR_GW, i) + XFC(PB_X_ETT_UNSAT, i) + XFC(PB_X_ETT_GW, i);
-    if (m.fbr) {
-        // update.c:138-152
-        const double fbrw0 = ws0[m.o_fg + i] + ws0[m.o_fu + i];
-        const double fbrw1 = y[m.o_fg + i] + y[m.o_fu + i];
-        double fbrrunoff = 0.0;
-#pragma unroll
-        for (int j = 0; j < 3; j++) fbrrunoff += XFC(PB_X_FBRFLOW0 + j, i) / area;
-        const double fbr_infil = (fbrw1 - fbrw0) * CLE(CC_GPOROSITY, i) / stepsize + fbrrunoff;
-        XFC(PB_X_FBR_INFIL, i) = fbr_infil;
-        infil += fbr_infil;
-    }
-    // update.c:154-158
-    if (infil < 0.0) {
-        subrunoff -= infil;
-        infil = 0.0;
-    }
-    XFC(PB_X_INFIL, i) = infil;
-    subrunoff_out[i] = subrunoff;
 }
 
 // One-off: the refined reciprocals of the dictionary's divisors and of the model constants
