@@ -31,6 +31,11 @@ void set_error(const std::string &msg);
         }                                                                      \
     } while (0)
 
+// Every state-sized device vector is allocated with PB_VEC_PAD extra doubles: the RHS kernels
+// fetch the own-state columns of a 32-element tile with bulk copies of a whole tile, which for
+// the last (partial) tile of a block reach past the end of the vector (read only, never used).
+#define PB_VEC_PAD 64
+
 // ---- physical constants (src/include/pihm_const.h:7,77-82) -----------------
 #define PB_GRAV 9.80665
 #define PB_PSIMIN (-70.0)
@@ -163,6 +168,7 @@ struct pihm_b200_ctx {
     cudaAccessPolicyWindow l2_window{}; // persisting-L2 window over the neighbour records
     int l2_on = 0;
     int pdl = 1;                       // launch k_main with programmatic stream serialization
+    int ystage = 1;                    // own-state columns of a tile travel with the TMA stage
     // host copies kept for permutation / validation
     std::vector<int> perm;             // internal element -> reference element
     std::vector<int> iperm;            // reference element -> internal element

@@ -1187,7 +1187,7 @@ pihm_b200_cvode *pihm_b200_cvode_create(pihm_b200_ctx *ctx)
     cv->n_global = (double)ctx->nsv_global;      // N of the WRMS norms: all ranks' unknowns
     cv->blocks = (int)std::max<long long>(1, std::min<long long>((cv->N + PB_VEC_THREADS - 1) / PB_VEC_THREADS,
                                                                   ctx->red_blocks));
-    const size_t bytes = sizeof(double) * (size_t)std::max<long long>(cv->N, 1);
+    const size_t bytes = sizeof(double) * ((size_t)std::max<long long>(cv->N, 1) + PB_VEC_PAD);
     double **all[] = {&cv->zn[0], &cv->zn[1], &cv->zn[2], &cv->zn[3], &cv->zn[4], &cv->zn[5], &cv->ewt,
                       &cv->acor, &cv->tempv, &cv->ftemp, &cv->V[0], &cv->V[1], &cv->V[2], &cv->V[3],
                       &cv->V[4], &cv->V[5], &cv->vtemp, &cv->ytemp};

@@ -633,7 +633,7 @@ int pihm_b200_set_diagnostics(pihm_b200_ctx *ctx, int on)
     if (!ctx) return -1;
     PB_CUDA(cudaStreamSynchronize(ctx->s()));
     if (on && !ctx->d_ws0) {
-        const size_t nb = sizeof(double) * std::max<int64_t>(ctx->nsv, 1);
+        const size_t nb = sizeof(double) * (std::max<int64_t>(ctx->nsv, 1) + PB_VEC_PAD);
         if (!ctx->d_xflux) {
             PB_CUDA(cudaMalloc((void **)&ctx->d_xflux, sizeof(double) * PB_X_NCOL * ctx->dm.nes));
             PB_CUDA(cudaMemset(ctx->d_xflux, 0, sizeof(double) * PB_X_NCOL * ctx->dm.nes));
@@ -959,12 +959,12 @@ pihm_b200_vec *pihm_b200_vec_new(pihm_b200_ctx *ctx)
     pihm_b200_vec *v = new pihm_b200_vec();
     v->ctx = ctx;
     v->n = ctx->nsv;
-    if (cudaMalloc((void **)&v->d, sizeof(double) * std::max<int64_t>(v->n, 1)) != cudaSuccess) {
+    if (cudaMalloc((void **)&v->d, sizeof(double) * (std::max<int64_t>(v->n, 1) + PB_VEC_PAD)) != cudaSuccess) {
         set_error("pihm_b200_vec_new: cudaMalloc failed");
         delete v;
         return nullptr;
     }
-    cudaMemsetAsync(v->d, 0, sizeof(double) * v->n, ctx->s());
+    cudaMemsetAsync(v->d, 0, sizeof(double) * (v->n + PB_VEC_PAD), ctx->s());
     return v;
 }
 

@@ -39,6 +39,12 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// more bytes for the current phase, without an arrival (the static part of a stage requested
+// in the prologue, before the dependency wait; the arrival comes with the dynamic part)
+__device__ __forceinline__ void mbar_expect_tx_only(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tma_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -518,14 +524,14 @@ __device__ __forceinline__ double eff_kh_a(Arith<FAST> &A, double depth, double 
     const double k1 = kmach * areafv + ksath * (1.0 - areafv);
     const double d2 = depth - dmac;
     const double d1 = (gw > depth) ? dmac : gw - (depth - dmac);
-    const double q = A.quo(mac ? k1 * d1 + ksath * d2 : 1.0, mac ? d1 + d2 : 1.0);
+    const double q = A.quor(mac ? k1 * d1 + ksath * d2 : 1.0, mac ? d1 + d2 : 1.0);
     return mac ? q : ksath;
 }
 template <bool FAST>
 __device__ __forceinline__ double dh_by_dl_a(Arith<FAST> &A, const double *l1, const double *l2, const double *h)
 {
     if (!FAST) return dh_by_dl(l1, l2, h);
-    return A.quo(-1.0 *
+    return A.quor(-1.0 *
         (l1[2] * (h[1] - h[0]) + l1[1] * (h[0] - h[2]) + l1[0] * (h[2] - h[1])),
         (l2[2] * (l1[1] - l1[0]) + l2[1] * (l1[0] - l1[2]) + l2[0] * (l1[2] - l1[1])));
 }
@@ -541,6 +547,31 @@ __device__ __forceinline__ void vg_kr_psi_a(Arith<FAST> &A, double satn, double 
 {
     if (!FAST) { vg_kr_psi(satn, alpha, m1, m2, m3, kr, psi); return; }
     const double sp = (satn < PB_SATMIN) ? PB_SATMIN : satn;
+#if PB_RELAX & 4
+    // With A = s^m1 the reference's C = (1/s)^m1 is 1/A, so C - 1 = (1 - A) / A and
+    //   B = (1 - A)^m2 = exp(m2 L1),  D = (C - 1)^m3 = exp(m3 (L1 - m1 Ls)),  L1 = log(1 - A), Ls = log s:
+    // two logarithms and three exponentials instead of three and four, no 1/s.  (The callers
+    // clamp satn to [SATMIN, 1], so sp == satn; satn = 1 gives A = 1, B = D = 0 exactly.)
+    {
+        const LogDD Ls = A.logp(sp);
+        const double Av = A.expy(Ls.H, Ls.Lo, m1);
+        const double oma = 1.0 - Av;
+        const bool nz = oma > 0.0;
+        const LogDD L1 = A.logp(nz ? oma : 1.0);
+        const double Bv = A.expy(L1.H, L1.Lo, m2);
+        // m1 * Ls as a double-double, then L1 - m1 Ls (two-sum of the heads)
+        const double P = __dmul_rn(Ls.H, m1);
+        const double Pl = __fma_rn(Ls.Lo, m1, __fma_rn(Ls.H, m1, -P));
+        const double Hs = __dsub_rn(L1.H, P);
+        const double bb = __dsub_rn(Hs, L1.H);
+        const double He = __dsub_rn(__dsub_rn(L1.H, __dsub_rn(Hs, bb)), __dadd_rn(P, bb));
+        const double Dv = A.expy(Hs, __dadd_rn(He, __dsub_rn(L1.Lo, Pl)), m3);
+        const double a = 1.0 - (nz ? Bv : 0.0);
+        kr = A.sqrtr(satn) * a * a;
+        psi = A.divs(nz ? -Dv : -0.0, alpha, r_alpha);
+        return;
+    }
+#endif
 #ifndef PB_POW_NO_SHARE
     // pow(s, m1) and pow(1/s, m1): one logarithm.  q = fl(1/s) satisfies s q = 1 - e with
     // e = fma(-s, q, 1) exact, so log q = -log s + log(1 - e) = -log s - e (e^2 < 2^-106): the
@@ -548,25 +579,26 @@ __device__ __forceinline__ void vg_kr_psi_a(Arith<FAST> &A, double satn, double 
     // clamp satn to [SATMIN, 1], so sp == satn.)
     const LogDD Ls = A.logp(sp);
     const double Av = A.expy(Ls.H, Ls.Lo, m1);
-    const double q = A.div(1.0, sp);
+    const double q = A.divs(1.0, sp);
     const double e = __fma_rn(-sp, q, 1.0);
     const double Cv = A.expy(-Ls.H, -Ls.Lo - e, m1);
 #else
     const double Av = A.powp(satn, m1);
-    const double Cv = A.powp(A.div(1.0, sp), m1);
+    const double Cv = A.powp(A.divs(1.0, sp), m1);
 #endif
     const double Bv = A.powp(1.0 - Av, m2);
     const double Dv = A.powp(Cv - 1.0, m3);
     const double a = 1.0 - Bv;
-    kr = A.sqrtp(satn) * a * a;
-    psi = A.div(-Dv, alpha, r_alpha);
+    kr = A.sqrtr(satn) * a * a;
+    psi = A.divs(-Dv, alpha, r_alpha);
 }
 
 // returns false (nothing written) when FAST arithmetic left its domain
 template <bool FAST>
 __device__ __forceinline__ bool elem_pre(const DevMesh &m, const double *__restrict__ y, int i,
-                                         const double *st, unsigned bar, unsigned phase)
+                                         const double *st, unsigned bar, unsigned phase, bool ys)
 {
+    // ys: the tile's own surf / gw columns arrived with the stage (behind the static slab)
     // st: this lane's column 0 of the stage's tile slab (slots TS_PRE0..TS_PRE1)
 #define EC(c) st[((c) - TS_PRE0) * PB_TILE]
     Arith<FAST> A;
@@ -592,9 +624,17 @@ __device__ __forceinline__ bool elem_pre(const DevMesh &m, const double *__restr
         ysn[j] = y_surf(m, y, nn[j]);
         zmaxn[j] = m.snb[nn[j]].y;
     }
-    const double surfh = surf_h_a<FAST>(A, max0(y_surf(m, y, i)));
-    const double gw = max0(y_gw(m, y, i));
+    const double *sy = st + (TS_PRE1 - TS_PRE0) * PB_TILE;
+    const double surfh = surf_h_a<FAST>(A, max0(ys ? sy[0] : y_surf(m, y, i)));
+    const double gw = max0(ys ? sy[PB_TILE] : y_gw(m, y, i));
     const double effkh = eff_kh_a<FAST>(A, EC(TS_DEPTH), EC(TS_DMAC), c_mach.x, c_mach.y, c_ksath, gw);
+    // pow(avg_h, 0.6666667) of OverLandFlow (lat_flow.c:270): AvgHsurf (lat_flow.c:175-203)
+    // returns the depth above DEPRSTG of the UPWIND element, so the power is a
+    // per-element quantity -- evaluated once here instead of once per edge side.  It needs
+    // the element's own state only: placed ahead of the friction slope, its FP64 chain runs
+    // while the neighbour gathers are in flight.
+    const double hd = (surfh > PB_DEPRSTG) ? 1.0 * (surfh - PB_DEPRSTG) : 0.0;
+    const double p23 = A.powp(hd, 0.6666667);
     double sf = 0.0;
     if (m.surf_mode == PB_DIFF_WAVE) {
         const double zmax = EC(TS_ZMAX);
@@ -620,13 +660,8 @@ __device__ __forceinline__ bool elem_pre(const DevMesh &m, const double *__restr
         }
         const double dx = dh_by_dl_a<FAST>(A, ny, nx, h);
         const double dy = dh_by_dl_a<FAST>(A, nx, ny, h);
-        sf = A.sqrtp(dx * dx + dy * dy);
+        sf = A.sqrtr(dx * dx + dy * dy);
     }
-    // pow(avg_h, 0.6666667) of OverLandFlow (lat_flow.c:270): AvgHsurf (lat_flow.c:175-203)
-    // returns the depth above DEPRSTG of the UPWIND element, so the power is a
-    // per-element quantity -- evaluated once here instead of once per edge side
-    const double hd = (surfh > PB_DEPRSTG) ? 1.0 * (surfh - PB_DEPRSTG) : 0.0;
-    const double p23 = A.powp(hd, 0.6666667);
     if (FAST && !A.ok) return false;
     m.dnb[i] = make_double4(surfh, effkh, sf, p23);
     return true;
@@ -635,10 +670,10 @@ __device__ __forceinline__ bool elem_pre(const DevMesh &m, const double *__restr
 
 template <int DUMMY>
 __device__ __noinline__ void elem_pre_exact(const DevMesh *gm, const double *__restrict__ y, int i,
-                                            const double *st, unsigned bar, unsigned phase)
+                                            const double *st, unsigned bar, unsigned phase, bool ys)
 {
     const DevMesh &m = *gm;
-    elem_pre<false>(m, y, i, st, bar, phase);
+    elem_pre<false>(m, y, i, st, bar, phase, ys);
     if (m.slow_count) atomicAdd(m.slow_count, 1ULL);
 }
 
@@ -651,10 +686,12 @@ __device__ __noinline__ void elem_pre_exact(const DevMesh *gm, const double *__r
 template <bool FBR, bool FAST>
 __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__restrict__ y,
                                           double *__restrict__ dy, int i, const double *st,
-                                          const double *f, unsigned bar, unsigned phase)
+                                          const double *f, unsigned bar, unsigned phase, int ys)
 {
     // st / f: this lane's column 0 of the stage's slabs (static slots TS_MAIN0.., hot
-    // forcing columns), filled by the bulk copies issued STAGES tiles ago in k_main
+    // forcing columns), filled by the bulk copies issued STAGES tiles ago in k_main; behind
+    // them the tile's own state columns (ys bit 0: gw [, fbr_gw], bit 1: unsat [, fbr_unsat]
+    // arrived with the stage; otherwise they are read from y) and its own dynamic records
 #define EC(c) st[((c) - TS_MAIN0) * PB_TILE]
     Arith<FAST> A;
     mbar_wait(bar, phase);      // static + forcing slabs have landed
@@ -681,10 +718,20 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
         sn[j] = m.snb[nn[j]];
         gwn[j] = max0(y_gw(m, y, nn[j]));
     }
-    const double4 own = m.dnb[i];
+    double fgn[3] = {0.0, 0.0, 0.0};
+    int cidn[3] = {0, 0, 0};
+    if (FBR && FAST) {      // bedrock: the neighbours' deep groundwater and geology class
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            fgn[j] = max0(y_fg(m, y, nn[j]));
+            cidn[j] = m.cid[nn[j]];
+        }
+    }
+    const double *sy = f + 4 * PB_TILE;
+    const double4 own = *reinterpret_cast<const double4 *>(sy - (i & 31) + (FBR ? 4 : 2) * PB_TILE + 4 * (i & 31));
     // ode.c:25-49
-    const double unsat = max0(y[m.o_unsat + i]);
-    const double gw = max0(y[m.o_gw + i]);
+    const double unsat = max0((ys & 2) ? sy[1 * PB_TILE] : y[m.o_unsat + i]);
+    const double gw = max0((ys & 1) ? sy[0] : y[m.o_gw + i]);
     const double surfh = own.x;
     const double effkh = own.y;
     const double area = EC(TS_AREA);
@@ -705,11 +752,54 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
         else ett_unsat = ett;
     }
 
+    // van Genuchten pair of the unsaturated zone (FAST): it depends on the element's own state
+    // only, so its long dependent FP64 chain is placed ahead of the lateral block and runs while
+    // the neighbour gathers are still in flight.  Branch-free: a saturated lane evaluates it for
+    // satn = 1 and its results are selected away below.
+    const bool sat = gw > depth - dinf;
+    double satn = 1.0, satkfunc = 1.0, psi_u = 0.0, deficit = 0.0;
+#if !defined(PB_VG_LATE)
+    if (FAST) {
+        deficit = depth - gw;
+        double sv = A.divs(sat ? 1.0 : unsat, sat ? 1.0 : deficit);
+        sv = (sv > 1.0) ? 1.0 : sv;
+        sv = (sv < PB_SATMIN) ? PB_SATMIN : sv;
+        satn = sv;
+        const double2 c_vg0 = ldg2_here(crow + CC_ALPHA / 2);   // {alpha, m1}
+        const double2 c_vg1 = ldg2_here(crow + CC_M2 / 2);      // {m2, m3}
+        const double r_alpha = ldg2_here(crow + CC_KSATH / 2).y;
+        double kr;
+        vg_kr_psi_a<FAST>(A, satn, c_vg0.x, r_alpha, c_vg0.y, c_vg1.x, c_vg1.y, kr, psi_u);
+        satkfunc = sat ? 1.0 : kr;
+    }
+#endif
+    // ... and the same for the bedrock layer (vert_flow.c:284-373), whose pair of pows is
+    // independent of the soil's: the two chains interleave
+    double fu = 0.0, fg = 0.0, g_deficit = 0.0, g_kr = 1.0, g_psi = 0.0;
+    bool full = true;
+    if (FBR && FAST) {
+        fu = max0((ys & 2) ? sy[3 * PB_TILE] : y[m.o_fu + i]);
+        fg = max0((ys & 1) ? sy[2 * PB_TILE] : y[m.o_fg + i]);
+        const double gdepth = EC(TS_GDEPTH);
+        full = fg >= gdepth;
+        g_deficit = gdepth - fg;
+        double sv = A.divs(full ? 1.0 : fu, full ? 1.0 : g_deficit);
+        sv = (sv > 1.0) ? 1.0 : sv;
+        sv = (sv < PB_SATMIN) ? PB_SATMIN : sv;
+        const double2 c_g0 = ldg2_here(crow + CC_GALPHA / 2);   // {galpha, gm1}
+        const double2 c_g1 = ldg2_here(crow + CC_GM2 / 2);      // {gm2, gm3}
+        const double r_galpha = ldg2_here(crow + CC_RPOR / 2).y;
+        double kr, ps;
+        vg_kr_psi_a<FAST>(A, sv, c_g0.x, r_galpha, c_g0.y, c_g1.x, c_g1.y, kr, ps);
+        g_kr = full ? 1.0 : kr;
+        g_psi = (ps > PB_PSIMIN) ? ps : PB_PSIMIN;
+    }
+
     // LateralFlow, lat_flow.c:17-51.  The element-to-element formulas run for all
     // three edges as one straight-line block (an edge without an element behind it
     // sees the element itself: every difference is zero); boundary and river edges
     // are patched afterwards.
-    double ovl[3], sub[3], ovl_infil[3];
+    double ovl[3], sub[3], ovl_infil[3], fbrflow[3] = {0.0, 0.0, 0.0};
     const double sf_i = own.z;
     {
         double num[3], den[3], p[3];
@@ -718,12 +808,20 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
             const double edge = EC(TS_EDGE0 + j);
             const double dist = (code[j] >= 0) ? EC(TS_NABRDIST0 + j) : 1.0;
             const double r_dist = A.rcp(dist);
+            if (FBR && FAST) {
+                // FbrFlowElemToElem, lat_flow.c:374-390 (an edge without an element behind it
+                // sees the element itself: zero; boundary and river edges are patched below)
+                const double gksath = __ldg(m.cls + (size_t)cid * CC_STRIDE + CC_GKSATH);
+                const double gk_n = __ldg(m.cls + (size_t)cidn[j] * CC_STRIDE + CC_GKSATH);
+                const double dfh = (fg + EC(TS_ZBED)) - (fgn[j] + sn[j].w);
+                fbrflow[j] = 0.5 * (gksath + gk_n) * A.divr(dfh, dist, r_dist) * avg_h(dfh, fg, fgn[j]) * edge;
+            }
             const double gw_n = gwn[j], surfh_n = dn[j].x;
             const double zmin_n = sn[j].x, zmax_n = sn[j].y;
             // SubFlowElemToElem, lat_flow.c:273-298
             double diff_h = (gw + zmin) - (gw_n + zmin_n);
             double avgh = avg_h(diff_h, gw, gw_n);
-            double grad_h = A.div(diff_h, dist, r_dist);
+            double grad_h = A.divr(diff_h, dist, r_dist);
             double avg_ksat = 0.5 * (effkh + dn[j].y);
             sub[j] = avg_ksat * grad_h * avgh * edge;
             // OvlFlowElemToElem, lat_flow.c:300-327 with avg_sf of :33-36
@@ -731,7 +829,7 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
             diff_h = (m.surf_mode == PB_KINEMATIC) ? zmax - zmax_n
                                                    : (surfh + zmax) - (surfh_n + zmax_n);
             avgh = avg_hsurf(diff_h, surfh, surfh_n);
-            grad_h = A.div(diff_h, dist, r_dist);
+            grad_h = A.divr(diff_h, dist, r_dist);
             if (m.surf_mode == PB_KINEMATIC) {
                 avg_sf = (grad_h > 0.0) ? grad_h : PB_GRADMIN;
             } else {
@@ -740,14 +838,14 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
             }
             const double avg_rough = 0.5 * (rough + sn[j].z);
             p[j] = (diff_h > 0.0) ? own.w : dn[j].w;   // pow(avgh, 0.6666667) of the upwind element (k_pre)
-            den[j] = A.sqrtp(avg_sf) * avg_rough;
+            den[j] = A.sqrtr(avg_sf) * avg_rough;
             num[j] = avgh * edge;                     // crossa; crossa * p * grad left to right (lat_flow.c:270)
             ovl_infil[j] = grad_h;                    // parked: grad_h of the overland flux
         }
         // OverLandFlow, lat_flow.c:267-271
 #pragma unroll
         for (int j = 0; j < 3; j++) {
-            ovl[j] = A.div(num[j] * p[j] * ovl_infil[j], den[j]);
+            ovl[j] = A.divr(num[j] * p[j] * ovl_infil[j], den[j]);
             ovl_infil[j] = ovl[j];
         }
     }
@@ -787,16 +885,59 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
     // VerticalFlow: Infil (vert_flow.c:33-130) and Recharge (:132-170).  Both
     // use the same satn / KrFunc / Psi in the unsaturated branch.
     double infil, rechg;
+#if !defined(PB_VG_LATE)
+    if (FAST) {
+        // straight-line form of the block below: both branches of Infil share the denominator
+        // of dh_by_dz, divisors of lanes that do not use a quotient are replaced by 1.0
+        const double2 c_kinf = ldg2_here(crow + CC_KINFV / 2);      // {kinfv, kmacv}
+        const double2 c_afh = ldg2_here(crow + CC_AREAFH / 2);      // {areafh, ksatv}
+        const double kinfv = c_kinf.x, kmacv = c_kinf.y;
+        const double areafh = c_afh.x;
+        double applrate = 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; j++) applrate += A.divs(-ovl_infil[j], area, r_area);
+        applrate = (applrate > 0.0) ? applrate : 0.0;
+        applrate += pcpdrp;
+        double wetfrac = A.divr(surfh, PB_DEPRSTG, m.r_deprstg);
+        wetfrac = (wetfrac > 0.0) ? wetfrac : 0.0;
+        wetfrac = (wetfrac < 1.0) ? wetfrac : 1.0;
+        const double psi_c = (psi_u > PB_PSIMIN) ? psi_u : PB_PSIMIN;
+        const double h_u = psi_c + zmax - 0.5 * dinf;
+        double dh_by_dz = A.quor(surfh + zmax - (sat ? (gw + zmin) : h_u), 0.5 * (surfh + dinf));
+        dh_by_dz = (surfh <= 0.0 && dh_by_dz > 0.0) ? 0.0 : dh_by_dz;
+        const double kinf = eff_kinf(kinfv, kmacv, areafh, dh_by_dz, satkfunc, satn, applrate, surfh);
+        double v = kinf * dh_by_dz;
+        v = (sat || v > 0.0) ? v : 0.0;          // the unsaturated branch clamps at zero (vert_flow.c:112)
+        const double ws0surf = f[3 * PB_TILE];
+        const double infil_max = applrate + ((ws0surf > 0.0) ? A.divr(ws0surf, m.dt, m.r_dt) : 0.0);
+        v = (v > infil_max) ? infil_max : v;
+        v *= wetfrac;
+        infil = (unsat + gw > depth) ? 0.0 : v;
+        // Recharge; AvgKv (_ARITH_), vert_flow.c:172-209
+        const double ksatv = c_afh.y, dmac = EC(TS_DMAC);
+        const bool deep = deficit > dmac;
+        const double k1 = satkfunc * ksatv;
+        const double kmid = (areafh > 0.0) ? kmacv * areafh + ksatv * (1.0 - areafh) : ksatv;
+        const double d1 = deep ? dmac : deficit;
+        const double k2 = deep ? k1 : kmid;
+        const double d2 = deep ? deficit - dmac : dmac - deficit;
+        const double d3 = deep ? gw : gw - (dmac - deficit);
+        const double kavg = A.quor(k1 * d1 + k2 * d2 + ksatv * d3, sat ? 1.0 : d1 + d2 + d3);
+        const double dh2 = A.quor(0.5 * deficit + psi_u, sat ? 1.0 : 0.5 * (deficit + gw));
+        double rc = kavg * dh2;
+        rc = (rc > 0.0 && unsat <= 0.0) ? 0.0 : rc;
+        rc = (rc < 0.0 && gw <= 0.0) ? 0.0 : rc;
+        rechg = sat ? infil : rc;
+    } else
+#endif
     {
         const double2 c_kinf = ldg2_here(crow + CC_KINFV / 2);      // {kinfv, kmacv}
         const double2 c_afh = ldg2_here(crow + CC_AREAFH / 2);      // {areafh, ksatv}
         const double kinfv = c_kinf.x, kmacv = c_kinf.y;
         const double areafh = c_afh.x;
-        const bool sat = gw > depth - dinf;
-        double satn = 1.0, satkfunc = 1.0, psi_u = 0.0, deficit = 0.0;
         if (!sat) {
             deficit = depth - gw;
-            satn = A.div(unsat, deficit);
+            satn = A.divs(unsat, deficit);
             satn = (satn > 1.0) ? 1.0 : satn;
             satn = (satn < PB_SATMIN) ? PB_SATMIN : satn;
             const double2 c_vg0 = ldg2_here(crow + CC_ALPHA / 2);   // {alpha, m1}
@@ -809,30 +950,30 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
         } else {
             double applrate = 0.0;
 #pragma unroll
-            for (int j = 0; j < 3; j++) applrate += A.div(-ovl_infil[j], area, r_area);
+            for (int j = 0; j < 3; j++) applrate += A.divs(-ovl_infil[j], area, r_area);
             applrate = (applrate > 0.0) ? applrate : 0.0;
             applrate += pcpdrp;
-            double wetfrac = A.div(surfh, PB_DEPRSTG, m.r_deprstg);
+            double wetfrac = A.divr(surfh, PB_DEPRSTG, m.r_deprstg);
             wetfrac = (wetfrac > 0.0) ? wetfrac : 0.0;
             wetfrac = (wetfrac < 1.0) ? wetfrac : 1.0;
             double dh_by_dz;
             if (sat) {
                 // KrFunc(beta, 1.0) == 1.0 exactly (pow(1,x) = 1, pow(0,x>0) = 0)
-                dh_by_dz = A.quo(surfh + zmax - (gw + zmin), 0.5 * (surfh + dinf));
+                dh_by_dz = A.quor(surfh + zmax - (gw + zmin), 0.5 * (surfh + dinf));
                 dh_by_dz = (surfh <= 0.0 && dh_by_dz > 0.0) ? 0.0 : dh_by_dz;
                 double kinf = eff_kinf(kinfv, kmacv, areafh, dh_by_dz, 1.0, 1.0, applrate, surfh);
                 infil = kinf * dh_by_dz;
             } else {
                 double psi_c = (psi_u > PB_PSIMIN) ? psi_u : PB_PSIMIN;
                 double h_u = psi_c + zmax - 0.5 * dinf;
-                dh_by_dz = A.quo(surfh + zmax - h_u, 0.5 * (surfh + dinf));
+                dh_by_dz = A.quor(surfh + zmax - h_u, 0.5 * (surfh + dinf));
                 dh_by_dz = (surfh <= 0.0 && dh_by_dz > 0.0) ? 0.0 : dh_by_dz;
                 double kinf = eff_kinf(kinfv, kmacv, areafh, dh_by_dz, satkfunc, satn, applrate, surfh);
                 infil = kinf * dh_by_dz;
                 infil = (infil > 0.0) ? infil : 0.0;
             }
             const double ws0surf = f[3 * PB_TILE];
-            double infil_max = applrate + ((ws0surf > 0.0) ? A.div(ws0surf, m.dt, m.r_dt) : 0.0);
+            double infil_max = applrate + ((ws0surf > 0.0) ? A.divr(ws0surf, m.dt, m.r_dt) : 0.0);
             infil = (infil > infil_max) ? infil_max : infil;
             infil *= wetfrac;
         }
@@ -852,8 +993,8 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
                 d2 = dmac - deficit;
                 k3 = ksatv; d3 = gw - (dmac - deficit);
             }
-            double kavg = A.quo(k1 * d1 + k2 * d2 + k3 * d3, d1 + d2 + d3);
-            double dh_by_dz = A.quo(0.5 * deficit + psi_u, 0.5 * (deficit + gw));
+            double kavg = A.quor(k1 * d1 + k2 * d2 + k3 * d3, d1 + d2 + d3);
+            double dh_by_dz = A.quor(0.5 * deficit + psi_u, 0.5 * (deficit + gw));
             rechg = kavg * dh_by_dz;
             rechg = (rechg > 0.0 && unsat <= 0.0) ? 0.0 : rechg;
             rechg = (rechg < 0.0 && gw <= 0.0) ? 0.0 : rechg;
@@ -866,9 +1007,65 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
     dunsat += infil - rechg - edir_unsat - ett_unsat;
     dgw += rechg - edir_gw - ett_gw;
 
-    double fbr_infil = 0.0, fbr_rechg = 0.0, dfu = 0.0, dfg = 0.0, fbrflow[3] = {0.0, 0.0, 0.0};
-    if (FBR) {
-        const double fu = max0(y[m.o_fu + i]), fg = max0(y[m.o_fg + i]);
+    double fbr_infil = 0.0, fbr_rechg = 0.0, dfu = 0.0, dfg = 0.0;
+    if (FBR && FAST) {
+        // straight-line form of the block below (FbrInfil, FbrRecharge): divisors of lanes that
+        // do not use a quotient are replaced by 1.0
+        const double2 c_gk = ldg2_here(crow + CC_GKSATV / 2);   // {gksatv, gksath}
+        const double ksatv_s = ldg2_here(crow + CC_AREAFH / 2).y;   // soil ksatv
+        const double gksatv = c_gk.x, gksath = c_gk.y;
+        const double zbed = EC(TS_ZBED);
+        const double gdepth = EC(TS_GDEPTH);
+        const bool none = (fu + fg > gdepth) || (gw <= 0.0);     // vert_flow.c:298-301
+        const bool calc = !full && !none;
+        const double h_u = g_psi + zmin - 0.5 * g_deficit;
+        const double dh1 = A.quor(zmin + gw - h_u, calc ? 0.5 * (gw + g_deficit) : 1.0);
+        const double q1 = A.quor(gw, ksatv_s), q2 = A.quor(g_deficit, calc ? gksatv * g_kr : 1.0);
+        const double kavg1 = A.quor(gw + g_deficit, calc ? q1 + q2 : 1.0);
+        fbr_infil = full ? -ksatv_s : (none ? 0.0 : kavg1 * dh1);
+        const double dh2 = A.quor(0.5 * g_deficit + g_psi, full ? 1.0 : 0.5 * (g_deficit + fg));
+        const double kavg2 = A.quor(fu * gksatv * g_kr + fg * gksatv, full ? 1.0 : fu + fg);
+        double rc = kavg2 * dh2;
+        rc = (rc > 0.0 && fu <= 0.0) ? 0.0 : rc;
+        rc = (rc < 0.0 && fg <= 0.0) ? 0.0 : rc;
+        fbr_rechg = full ? fbr_infil : rc;
+        if ((code[0] | code[1] | code[2]) < 0) {
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                if (code[j] == PB_NB_BOUNDARY) {
+                    // FbrBoundFluxElem, lat_flow.c:392-424
+                    const int bc = m.fbct[(size_t)j * m.nes + i];
+                    if (bc == 0) {
+                        fbrflow[j] = 0.0;
+                    } else if (bc > 0) {
+                        const double head = FOC(PB_F_FBRBC0 + j, i);
+                        double diff_h = fg + zbed - head;
+                        double avgh = avg_h(diff_h, fg, head - zbed);
+                        double grad_h = div_pos(diff_h, EC(TS_NABRDIST0 + j));
+                        fbrflow[j] = gksath * grad_h * avgh * EC(TS_EDGE0 + j);
+                    } else {
+                        fbrflow[j] = -FOC(PB_F_FBRBC0 + j, i);
+                    }
+                } else if (code[j] < 0) {
+                    // neighbour across the river, lat_flow.c:85-100
+                    const int r = (-code[j] - 2) >> 2;
+                    const int l = RIC(PB_RI_LEFTELE, r);
+                    const int n = (l == i) ? RIC(PB_RI_RIGHTELE, r) : l;
+                    const double fg_n = max0(y_fg(m, y, n));
+                    double diff_h = (fg + zbed) - (fg_n + m.snb[n].w);
+                    double avgh = avg_h(diff_h, fg, fg_n);
+                    double grad_h = div_any(diff_h, m.fbr_dist[r]);
+                    double avg_ksat = 0.5 * (gksath + CLE(CC_GKSATH, n));
+                    fbrflow[j] = avg_ksat * grad_h * avgh * EC(TS_EDGE0 + j);
+                }
+            }
+        }
+        dgw -= fbr_infil;
+        dfu += fbr_infil - fbr_rechg;
+        dfg += fbr_rechg;
+    } else if (FBR) {
+        const double fu = max0((ys & 2) ? sy[3 * PB_TILE] : y[m.o_fu + i]);
+        const double fg = max0((ys & 1) ? sy[2 * PB_TILE] : y[m.o_fg + i]);
         const double2 c_g0 = ldg2_here(crow + CC_GALPHA / 2);   // {galpha, gm1}
         const double2 c_g1 = ldg2_here(crow + CC_GM2 / 2);      // {gm2, gm3}
         const double2 c_gk = ldg2_here(crow + CC_GKSATV / 2);   // {gksatv, gksath}
@@ -880,7 +1077,7 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
         double deficit = 0.0, satkfunc = 1.0, psi_c = 0.0;
         if (!full) {
             deficit = gdepth - fg;
-            double satn = A.div(fu, deficit);
+            double satn = A.divs(fu, deficit);
             satn = (satn > 1.0) ? 1.0 : satn;
             satn = (satn < PB_SATMIN) ? PB_SATMIN : satn;
             vg_kr_psi_a<FAST>(A, satn, c_g0.x, c_rg.y, c_g0.y, c_g1.x, c_g1.y, satkfunc, psi_c);
@@ -893,16 +1090,16 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
             fbr_infil = 0.0;
         } else {
             double h_u = psi_c + zmin - 0.5 * deficit;
-            double dh_by_dz = A.quo(zmin + gw - h_u, 0.5 * (gw + deficit));
-            double kavg = A.quo(gw + deficit, A.quo(gw, ksatv_s) + A.quo(deficit, gksatv * satkfunc));
+            double dh_by_dz = A.quor(zmin + gw - h_u, 0.5 * (gw + deficit));
+            double kavg = A.quor(gw + deficit, A.quor(gw, ksatv_s) + A.quor(deficit, gksatv * satkfunc));
             fbr_infil = kavg * dh_by_dz;
         }
         // FbrRecharge, vert_flow.c:332-373
         if (full) {
             fbr_rechg = fbr_infil;
         } else {
-            double dh_by_dz = A.quo(0.5 * deficit + psi_c, 0.5 * (deficit + fg));
-            double kavg = A.quo(fu * gksatv * satkfunc + fg * gksatv, fu + fg);
+            double dh_by_dz = A.quor(0.5 * deficit + psi_c, 0.5 * (deficit + fg));
+            double kavg = A.quor(fu * gksatv * satkfunc + fg * gksatv, fu + fg);
             fbr_rechg = kavg * dh_by_dz;
             fbr_rechg = (fbr_rechg > 0.0 && fu <= 0.0) ? 0.0 : fbr_rechg;
             fbr_rechg = (fbr_rechg < 0.0 && fg <= 0.0) ? 0.0 : fbr_rechg;
@@ -941,7 +1138,7 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
                 const double fg_n = max0(y_fg(m, y, n));
                 double diff_h = (fg + zbed) - (fg_n + m.snb[n].w);
                 double avgh = avg_h(diff_h, fg, fg_n);
-                double grad_h = A.div(diff_h, dist);
+                double grad_h = A.divr(diff_h, dist);
                 double avg_ksat = 0.5 * (gksath + CLE(CC_GKSATH, n));
                 fbrflow[j] = avg_ksat * grad_h * avgh * EC(TS_EDGE0 + j);
             }
@@ -953,19 +1150,19 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
 
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-        dsurf -= A.div(ovl[j], area, r_area);
-        dgw -= A.div(sub[j], area, r_area);
-        if (FBR) dfg -= A.div(fbrflow[j], area, r_area);
+        dsurf -= A.divr(ovl[j], area, r_area);
+        dgw -= A.divr(sub[j], area, r_area);
+        if (FBR) dfg -= A.divr(fbrflow[j], area, r_area);
     }
     const double porosity = c_por.x;
     const double r_por = ldg2_here(crow + CC_RPOR / 2).x;
-    dunsat = A.div(dunsat, porosity, r_por);
-    dgw = A.div(dgw, porosity, r_por);
+    dunsat = A.divr(dunsat, porosity, r_por);
+    dgw = A.divr(dgw, porosity, r_por);
     if (FBR) {
         const double gporosity = __ldg(m.cls + (size_t)cid * CC_STRIDE + CC_GPOROSITY);
         const double r_gpor = ldg2_here(crow + CC_RGPOR / 2).x;
-        dfu = A.div(dfu, gporosity, r_gpor);
-        dfg = A.div(dfg, gporosity, r_gpor);
+        dfu = A.divr(dfu, gporosity, r_gpor);
+        dfg = A.divr(dfg, gporosity, r_gpor);
     }
     if (FAST && !A.ok) return false;        // nothing written yet: the caller recomputes this element
 
@@ -1005,10 +1202,10 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
 template <bool FBR>
 __device__ __noinline__ void elem_main_exact(const DevMesh *gm, const double *__restrict__ y,
                                              double *__restrict__ dy, int i, const double *st,
-                                             const double *f, unsigned bar, unsigned phase)
+                                             const double *f, unsigned bar, unsigned phase, int ys)
 {
     const DevMesh &m = *gm;
-    elem_main<FBR, false>(m, y, dy, i, st, f, bar, phase);
+    elem_main<FBR, false>(m, y, dy, i, st, f, bar, phase, ys);
     if (m.slow_count) atomicAdd(m.slow_count, 1ULL);
 }
 
@@ -1119,7 +1316,10 @@ template <int STAGES, int STAGE_BYTES> struct Ring {
 
 template <bool FBR> struct MainCfg {
     static constexpr int NC = (FBR ? TS_FBR1 : TS_MAIN1) - TS_MAIN0;
-    static constexpr int SBS = NC * PB_TILE * 8, SBF = 4 * PB_TILE * 8, SB = SBS + SBF;
+    // static slab | hot forcing columns | own state {gw, unsat[, fbr_gw, fbr_unsat]} | own dynamic record
+    static constexpr int SBS = NC * PB_TILE * 8, SBF = 4 * PB_TILE * 8;
+    static constexpr int NY = FBR ? 4 : 2, SBY = NY * PB_TILE * 8, SBD = PB_TILE * 32;
+    static constexpr int SB = SBS + SBF + SBY + SBD;
     static constexpr int STAGES = FBR ? PB_MAIN_STAGES_FBR : PB_MAIN_STAGES;
     static constexpr int MINB = FBR ? PB_MAIN_MINB_FBR : PB_MAIN_MINB;
     static constexpr int WARPS = FBR ? PB_MAIN_WARPS_FBR : PB_RHS_WARPS;
@@ -1128,14 +1328,15 @@ template <bool FBR> struct MainCfg {
 };
 struct PreCfg {
     static constexpr int NC = TS_PRE1 - TS_PRE0;
-    static constexpr int SB = NC * PB_TILE * 8;
+    static constexpr int SBS = NC * PB_TILE * 8, SBY = 2 * PB_TILE * 8;     // static slab | own {surf, gw}
+    static constexpr int SB = SBS + SBY;
     typedef Ring<PB_PRE_STAGES, SB> ring_t;
 };
 
 static __global__ void __launch_bounds__(PB_PRE_THREADS, PB_PRE_MINB)
-k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r, const HaloWait hw)
+k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r, const HaloWait hw, int ys)
 {
-    constexpr int SB = PreCfg::SB;
+    constexpr int SBS = PreCfg::SBS;
     // programmatic dependent launch: k_main's CTAs may become resident as this kernel's CTAs
     // retire and run their prologue (ring set-up, first slab requests); they wait for the
     // completion of this grid (griddepcontrol.wait) before they touch what it writes
@@ -1159,18 +1360,34 @@ k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r, c
     auto item = [&](int q) {    // tile index in [river groups | element tiles]
         return ((long long)(q / PB_RING_GROUP) * G + b) * PB_RING_GROUP + q % PB_RING_GROUP;
     };
-    // request the tile of element ticket q (no-op past the end)
-    auto request = [&](int q) {
+    // request the tile of element ticket q (no-op past the end): the static slab does not depend
+    // on the previous kernel (prologue), the own surf / gw columns of a tile of owned elements do
+    // (after the dependency wait; the arrival travels with this part)
+    const int ntile_own = ys ? m.nown / PB_TILE : 0;        // tiles whose 32 elements all live in y
+    auto request = [&](int q, bool stat, bool dyn) {
         const long long tile = item(q) - (long long)gr * PB_RING_GROUP;
         if (tile < ntile_e) {
             const int s = (q - qe0) % PB_PRE_STAGES;
-            mbar_expect_tx(ring.bar(s), SB);
-            tma_bulk_g2s(smem_u32(ring.stage(s)), m.es + ((size_t)tile * TS_NCOL + TS_PRE0) * PB_TILE, SB, ring.bar(s));
+            if (stat) {
+                mbar_expect_tx_only(ring.bar(s), SBS);
+                tma_bulk_g2s(smem_u32(ring.stage(s)), m.es + ((size_t)tile * TS_NCOL + TS_PRE0) * PB_TILE, SBS, ring.bar(s));
+            }
+            if (dyn) {
+                if (tile < ntile_own) {
+                    mbar_expect_tx(ring.bar(s), 2 * PB_TILE * 8);
+                    tma_bulk_g2s(smem_u32(ring.stage(s) + SBS), y + tile * PB_TILE, PB_TILE * 8, ring.bar(s));
+                    tma_bulk_g2s(smem_u32(ring.stage(s) + SBS + PB_TILE * 8), y + m.o_gw + tile * PB_TILE, PB_TILE * 8, ring.bar(s));
+                } else {
+                    mbar_expect_tx(ring.bar(s), 0);
+                }
+            }
         }
     };
     if (lane == 0)
-        for (int k = warp; k < PB_PRE_STAGES; k += PB_PRE_WARPS) request(qe0 + k);
+        for (int k = warp; k < PB_PRE_STAGES; k += PB_PRE_WARPS) request(qe0 + k, true, false);
     asm volatile("griddepcontrol.wait;" ::: "memory");      // y comes from the previous kernel of the stream
+    if (lane == 0)
+        for (int k = warp; k < PB_PRE_STAGES; k += PB_PRE_WARPS) request(qe0 + k, false, true);
     const long long r_end = (long long)gr * PB_RING_GROUP, e_end = r_end + ntile_e;
     for (;;) {
         const int q = ring.take(lane);
@@ -1187,21 +1404,22 @@ k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r, c
         const int i = (int)(g - r_end) * PB_TILE + lane;
         const double *st = reinterpret_cast<const double *>(ring.stage(s)) + lane;
         if (i < m.ne) {
-            if (!elem_pre<true>(m, y, i, st, ring.bar(s), phase))
-                elem_pre_exact<0>(m.self, y, i, st, ring.bar(s), phase);
+            const bool tys = (g - r_end) < ntile_own;
+            if (!elem_pre<true>(m, y, i, st, ring.bar(s), phase, tys))
+                elem_pre_exact<0>(m.self, y, i, st, ring.bar(s), phase, tys);
         } else {
             mbar_wait(ring.bar(s), phase);
         }
         __syncwarp();           // every lane is done with the stage: hand it to the tile STAGES tickets ahead
-        if (lane == 0) { ring.release(s, n); request(q + PB_PRE_STAGES); }
+        if (lane == 0) { ring.release(s, n); request(q + PB_PRE_STAGES, true, true); }
     }
 }
 
 template <bool FBR>
 __global__ void __launch_bounds__(MainCfg<FBR>::THREADS, MainCfg<FBR>::MINB)
-k_main(const DevMesh m, const double *__restrict__ y, double *__restrict__ dy, int ntile_e, int ntile_r)
+k_main(const DevMesh m, const double *__restrict__ y, double *__restrict__ dy, int ntile_e, int ntile_r, int ys)
 {
-    constexpr int SBS = MainCfg<FBR>::SBS, SBF = MainCfg<FBR>::SBF, SB = MainCfg<FBR>::SB;
+    constexpr int SBS = MainCfg<FBR>::SBS, SBF = MainCfg<FBR>::SBF, SBY = MainCfg<FBR>::SBY, SBD = MainCfg<FBR>::SBD;
     constexpr int STAGES = MainCfg<FBR>::STAGES;
     asm volatile("griddepcontrol.launch_dependents;");
     extern __shared__ __align__(128) unsigned char smem[];
@@ -1216,21 +1434,42 @@ k_main(const DevMesh m, const double *__restrict__ y, double *__restrict__ dy, i
     };
     // element tiles are walked from the last to the first: k_pre ran in ascending order, so
     // its most recent tiles (columns shared by both kernels, neighbour records, y) are still in L2
-    auto request = [&](int q) {
+    // A stage = the tile's static slab and forcing columns (they do not depend on the kernels
+    // before this one: requested in the prologue) + the tile's own state columns and dynamic
+    // records (written by the predecessors: requested after the dependency wait).  The arrival
+    // travels with the dynamic part; the static part only announces its bytes.
+    const unsigned dyn_bytes = ((ys & 1) ? (FBR ? 2 : 1) * PB_TILE * 8 : 0) + ((ys & 2) ? (FBR ? 2 : 1) * PB_TILE * 8 : 0) + SBD;
+    auto request = [&](int q, bool stat, bool dyn) {
         const long long k = item(q) - (long long)gr * PB_RING_GROUP;
         if (k < ntile_e) {
             const size_t tile = (size_t)(ntile_e - 1 - k);
             const int s = (q - qe0) % STAGES;
-            mbar_expect_tx(ring.bar(s), SB);
-            tma_bulk_g2s(smem_u32(ring.stage(s)), m.es + (tile * TS_NCOL + TS_MAIN0) * PB_TILE, SBS, ring.bar(s));
-            tma_bulk_g2s(smem_u32(ring.stage(s) + SBS), m.ft + tile * 4 * PB_TILE, SBF, ring.bar(s));
+            unsigned char *sp = ring.stage(s);
+            if (stat) {
+                mbar_expect_tx_only(ring.bar(s), SBS + SBF);
+                tma_bulk_g2s(smem_u32(sp), m.es + (tile * TS_NCOL + TS_MAIN0) * PB_TILE, SBS, ring.bar(s));
+                tma_bulk_g2s(smem_u32(sp + SBS), m.ft + tile * 4 * PB_TILE, SBF, ring.bar(s));
+            }
+            if (dyn) {
+                sp += SBS + SBF;
+                mbar_expect_tx(ring.bar(s), dyn_bytes);
+                if (ys & 1) tma_bulk_g2s(smem_u32(sp), y + m.o_gw + tile * PB_TILE, PB_TILE * 8, ring.bar(s));
+                if (ys & 2) tma_bulk_g2s(smem_u32(sp + PB_TILE * 8), y + m.o_unsat + tile * PB_TILE, PB_TILE * 8, ring.bar(s));
+                if (FBR) {
+                    if (ys & 1) tma_bulk_g2s(smem_u32(sp + 2 * PB_TILE * 8), y + m.o_fg + tile * PB_TILE, PB_TILE * 8, ring.bar(s));
+                    if (ys & 2) tma_bulk_g2s(smem_u32(sp + 3 * PB_TILE * 8), y + m.o_fu + tile * PB_TILE, PB_TILE * 8, ring.bar(s));
+                }
+                tma_bulk_g2s(smem_u32(sp + SBY), m.dnb + tile * PB_TILE, SBD, ring.bar(s));
+            }
         }
     };
     if (lane == 0)
-        for (int k = warp; k < STAGES; k += MainCfg<FBR>::WARPS) request(qe0 + k);
+        for (int k = warp; k < STAGES; k += MainCfg<FBR>::WARPS) request(qe0 + k, true, false);
     // the static slabs above do not depend on k_pre; everything below does (no-op when the
     // kernel was not launched with the programmatic-serialization attribute)
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (lane == 0)
+        for (int k = warp; k < STAGES; k += MainCfg<FBR>::WARPS) request(qe0 + k, false, true);
     const long long r_end = (long long)gr * PB_RING_GROUP, e_end = r_end + ntile_e;
     for (;;) {
         const int q = ring.take(lane);
@@ -1248,13 +1487,13 @@ k_main(const DevMesh m, const double *__restrict__ y, double *__restrict__ dy, i
         const double *st = reinterpret_cast<const double *>(ring.stage(s)) + lane;
         const double *f = reinterpret_cast<const double *>(ring.stage(s) + SBS) + lane;
         if (i < m.nown) {
-            if (!elem_main<FBR, true>(m, y, dy, i, st, f, ring.bar(s), phase))
-                elem_main_exact<FBR>(m.self, y, dy, i, st, f, ring.bar(s), phase);
+            if (!elem_main<FBR, true>(m, y, dy, i, st, f, ring.bar(s), phase, ys))
+                elem_main_exact<FBR>(m.self, y, dy, i, st, f, ring.bar(s), phase, ys);
         } else {
             mbar_wait(ring.bar(s), phase);
         }
         __syncwarp();
-        if (lane == 0) { ring.release(s, n); request(q + STAGES); }
+        if (lane == 0) { ring.release(s, n); request(q + STAGES, true, true); }
     }
 }
 

@@ -36,6 +36,7 @@ int rhs_configure(pihm_b200_ctx *ctx, int sms)
     ctx->main_grid = sms * bmain;
     ctx->pre_smem = pre_smem;
     ctx->main_smem = main_smem;
+    ctx->ystage = std::getenv("PIHM_B200_NO_YSTAGE") ? 0 : 1;
     return 0;
 }
 
@@ -121,7 +122,10 @@ int rhs_launch(pihm_b200_ctx *ctx, const double *y, double *dy, bool replay)
     const auto groups = [](int t) { return (t + PB_RING_GROUP - 1) / PB_RING_GROUP; };
     const int gpre = std::max(1, std::min(ctx->pre_grid, groups(te) + groups(tr)));
     const int gmain = std::max(1, std::min(ctx->main_grid, groups(te_own) + groups(tr_own)));
-    k_pre<<<gpre, PB_PRE_THREADS, ctx->pre_smem, ctx->s()>>>(dm, y, te, tr, hw);
+    // own-state columns of a tile by bulk copy: needs 16-byte alignment of each block inside y
+    int ys = 0;
+    if (ctx->ystage && ((uintptr_t)y & 15) == 0) ys = 1 | ((dm.nown % 2 == 0) ? 2 : 0);
+    k_pre<<<gpre, PB_PRE_THREADS, ctx->pre_smem, ctx->s()>>>(dm, y, te, tr, hw, ys & 1);
     {
         // k_main right behind k_pre with programmatic stream serialization (PDL): its launch
         // latency and prologue overlap k_pre's tail
@@ -135,8 +139,8 @@ int rhs_launch(pihm_b200_ctx *ctx, const double *y, double *dy, bool replay)
         at[0].val.programmaticStreamSerializationAllowed = ctx->pdl ? 1 : 0;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        const cudaError_t e = dm.fbr ? cudaLaunchKernelEx(&cfg, k_main<true>, dm, y, dy, te_own, tr_own)
-                                     : cudaLaunchKernelEx(&cfg, k_main<false>, dm, y, dy, te_own, tr_own);
+        const cudaError_t e = dm.fbr ? cudaLaunchKernelEx(&cfg, k_main<true>, dm, y, dy, te_own, tr_own, ys)
+                                     : cudaLaunchKernelEx(&cfg, k_main<false>, dm, y, dy, te_own, tr_own, ys);
         if (e != cudaSuccess) { set_error(std::string("k_main launch: ") + cudaGetErrorString(e)); return -1; }
     }
     ctx->launches += 2;
