@@ -50,6 +50,11 @@ __device__ __forceinline__ void tma_bulk_g2s(unsigned dst, const void *src, unsi
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// pull a contiguous range into L2 (no destination): the rows other tiles are about to gather from
+__device__ __forceinline__ void tma_prefetch_l2(const void *src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned phase)
 {
     asm volatile("{\n .reg .pred P1;\n LAB_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
@@ -65,6 +70,64 @@ __device__ __forceinline__ double2 ldg2_here(const double2 *p)
     return v;
 }
 
+// Scheduling fence without instructions: the value x may not be consumed before `dep` has been
+// computed.  Warps issue in order, so the first consumer of a gathered value stalls the warp
+// for the rest of the gather's latency even when independent arithmetic follows in the
+// instruction stream; tying the gathered registers to the result of the element's own-state
+// chain (van Genuchten pows / the overland power) keeps that chain in front of them.
+#ifndef PB_NO_ORDER
+#define PB_AFTER(x, dep) asm volatile("" : "+d"(x) : "d"(dep))
+#else
+#define PB_AFTER(x, dep)
+#endif
+
+// Neighbour gathers pinned at their point of issue (asm volatile keeps its order relative to the
+// other volatile statements, e.g. the dictionary fetches that start the own-state chains): all
+// of a tile's gathers leave at the top of the tile instead of being sunk towards their consumers.
+#ifndef PB_NO_ORDER
+__device__ __forceinline__ double ld_here(const double *p)
+{
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double4 ld4_here(const double4 *p)
+{
+    double4 v;
+    asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    asm volatile("ld.global.v2.f64 {%0, %1}, [%2+16];" : "=d"(v.z), "=d"(v.w) : "l"(p));
+    return v;
+}
+#else
+__device__ __forceinline__ double ld_here(const double *p) { return *p; }
+__device__ __forceinline__ double4 ld4_here(const double4 *p) { return *p; }
+#endif
+// Per-lane asynchronous gathers (LDGSTS): global -> this warp's gather buffer in shared memory,
+// no registers held while they are in flight; completion per thread (cp.async.wait_group).
+__device__ __forceinline__ void cp_async16(unsigned dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(unsigned dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <bool GH> __device__ __forceinline__ const double *p_surf(const DevMesh &m, const double *y, int i)
+{
+    return (!GH || i < m.nown) ? y + i : m.gel + (size_t)(i - m.nown) * m.gs;
+}
+template <bool GH> __device__ __forceinline__ const double *p_gw(const DevMesh &m, const double *y, int i)
+{
+    return (!GH || i < m.nown) ? y + m.o_gw + i : m.gel + (size_t)(i - m.nown) * m.gs + 1;
+}
+template <bool GH> __device__ __forceinline__ const double *p_fg(const DevMesh &m, const double *y, int i)
+{
+    return (!GH || i < m.nown) ? y + m.o_fg + i : m.gel + (size_t)(i - m.nown) * m.gs + 2;
+}
+
 #define RFC(c, r) (m.rf[(size_t)(c) * m.nrs + (r)])
 #define RIC(c, r) (m.ri[(size_t)(c) * m.nrs + (r)])
 #define FOC(c, i) (m.forc[(size_t)(c) * m.nes + (i)])   /* bc columns only (rare path) */
@@ -77,25 +140,25 @@ __device__ __forceinline__ double max0(double v) { return (v >= 0.0) ? v : 0.0; 
 // the rank's own unknowns inside y; the rest are ghosts whose values arrived
 // with the halo exchange as records {surf, gw[, fbr_gw]} / {stage, gw}.
 // Single-GPU: nown == ne, rown == nr, the ghost branch is never taken.
-__device__ __forceinline__ double y_surf(const DevMesh &m, const double *__restrict__ y, int i)
+template <bool GH> __device__ __forceinline__ double y_surf(const DevMesh &m, const double *__restrict__ y, int i)
 {
-    return (i < m.nown) ? y[i] : m.gel[(size_t)(i - m.nown) * m.gs];
+    return (!GH || i < m.nown) ? y[i] : m.gel[(size_t)(i - m.nown) * m.gs];
 }
-__device__ __forceinline__ double y_gw(const DevMesh &m, const double *__restrict__ y, int i)
+template <bool GH> __device__ __forceinline__ double y_gw(const DevMesh &m, const double *__restrict__ y, int i)
 {
-    return (i < m.nown) ? y[m.o_gw + i] : m.gel[(size_t)(i - m.nown) * m.gs + 1];
+    return (!GH || i < m.nown) ? y[m.o_gw + i] : m.gel[(size_t)(i - m.nown) * m.gs + 1];
 }
-__device__ __forceinline__ double y_fg(const DevMesh &m, const double *__restrict__ y, int i)
+template <bool GH> __device__ __forceinline__ double y_fg(const DevMesh &m, const double *__restrict__ y, int i)
 {
-    return (i < m.nown) ? y[m.o_fg + i] : m.gel[(size_t)(i - m.nown) * m.gs + 2];
+    return (!GH || i < m.nown) ? y[m.o_fg + i] : m.gel[(size_t)(i - m.nown) * m.gs + 2];
 }
-__device__ __forceinline__ double y_stage(const DevMesh &m, const double *__restrict__ y, int r)
+template <bool GH> __device__ __forceinline__ double y_stage(const DevMesh &m, const double *__restrict__ y, int r)
 {
-    return (r < m.rown) ? y[m.o_stg + r] : m.gri[(size_t)(r - m.rown) * 2];
+    return (!GH || r < m.rown) ? y[m.o_stg + r] : m.gri[(size_t)(r - m.rown) * 2];
 }
-__device__ __forceinline__ double y_rgw(const DevMesh &m, const double *__restrict__ y, int r)
+template <bool GH> __device__ __forceinline__ double y_rgw(const DevMesh &m, const double *__restrict__ y, int r)
 {
-    return (r < m.rown) ? y[m.o_rgw + r] : m.gri[(size_t)(r - m.rown) * 2 + 1];
+    return (!GH || r < m.rown) ? y[m.o_rgw + r] : m.gri[(size_t)(r - m.rown) * 2 + 1];
 }
 
 // a / b for a finite b > 0.  IEEE gives 0/b = 0 with the sign of a, i.e. a
@@ -283,11 +346,11 @@ struct Bank {
     double surfh, gw, zmax, zmin, effk;
 };
 
-__device__ __forceinline__ Bank load_bank(const DevMesh &m, const double *__restrict__ y, int e)
+template <bool GH> __device__ __forceinline__ Bank load_bank(const DevMesh &m, const double *__restrict__ y, int e)
 {
     Bank b;
-    b.surfh = surf_h(max0(y_surf(m, y, e)));
-    b.gw = max0(y_gw(m, y, e));
+    b.surfh = surf_h(max0(y_surf<GH>(m, y, e)));
+    b.gw = max0(y_gw<GH>(m, y, e));
     b.zmax = TSC(TS_ZMAX, e);
     b.zmin = TSC(TS_ZMIN, e);
     b.effk = eff_kh_elem(m, e, b.gw);
@@ -356,17 +419,17 @@ __device__ __forceinline__ double sub_elem_to_river(const Bank &b, double zbed, 
 // ---------------------------------------------------------------------------
 // river part of k_pre: RiverFlow() parallel loop, src/river_flow.c:10-86
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void river_fluxes(const DevMesh &m, const double *__restrict__ y, int r)
+template <bool GH> __device__ __forceinline__ void river_fluxes(const DevMesh &m, const double *__restrict__ y, int r)
 {
-    const double stage = max0(y_stage(m, y, r));
-    const double rgw = max0(y_rgw(m, y, r));
+    const double stage = max0(y_stage<GH>(m, y, r));
+    const double rgw = max0(y_rgw<GH>(m, y, r));
     const int down = RIC(PB_RI_DOWN, r);
     const int ord = RIC(PB_RI_INTRPL_ORD, r);
     const double zbed = RFC(PB_R_ZBED, r), rzmin = RFC(PB_R_ZMIN, r), rzmax = RFC(PB_R_ZMAX, r);
     const double len = RFC(PB_R_SHP_LENGTH, r), coeff = RFC(PB_R_SHP_COEFF, r);
     const double rough = RFC(PB_R_ROUGH, r);
-    const Bank L = load_bank(m, y, RIC(PB_RI_LEFTELE, r));
-    const Bank R = load_bank(m, y, RIC(PB_RI_RIGHTELE, r));
+    const Bank L = load_bank<GH>(m, y, RIC(PB_RI_LEFTELE, r));
+    const Bank R = load_bank<GH>(m, y, RIC(PB_RI_RIGHTELE, r));
     double rf_up = 0.0, rf_down, rf_down_a2a;
 
     // the previous call's bank overland fluxes stay visible to Infil (H2)
@@ -396,8 +459,8 @@ __device__ __forceinline__ void river_fluxes(const DevMesh &m, const double *__r
             rf_up += flux;
         }
         // ChanFlowRiverToRiver, river_flow.c:255-298
-        const double stage_d = max0(y_stage(m, y, d));
-        const double rgw_d = max0(y_rgw(m, y, d));
+        const double stage_d = max0(y_stage<GH>(m, y, d));
+        const double rgw_d = max0(y_rgw<GH>(m, y, d));
         const int ord_d = RIC(PB_RI_INTRPL_ORD, d);
         const double len_d = RFC(PB_R_SHP_LENGTH, d), coeff_d = RFC(PB_R_SHP_COEFF, d);
         {
@@ -420,8 +483,8 @@ __device__ __forceinline__ void river_fluxes(const DevMesh &m, const double *__r
         }
         // SubFlowRiverToRiver, river_flow.c:300-329 (_ARITH_)
         {
-            const Bank DL = load_bank(m, y, RIC(PB_RI_LEFTELE, d));
-            const Bank DR = load_bank(m, y, RIC(PB_RI_RIGHTELE, d));
+            const Bank DL = load_bank<GH>(m, y, RIC(PB_RI_LEFTELE, d));
+            const Bank DR = load_bank<GH>(m, y, RIC(PB_RI_RIGHTELE, d));
             double effk = 0.5 * (L.effk + R.effk);
             double effk_nabr = 0.5 * (DL.effk + DR.effk);
             double total_h = rgw + rzmin;
@@ -594,7 +657,7 @@ __device__ __forceinline__ void vg_kr_psi_a(Arith<FAST> &A, double satn, double 
 }
 
 // returns false (nothing written) when FAST arithmetic left its domain
-template <bool FAST>
+template <bool FAST, bool GH>
 __device__ __forceinline__ bool elem_pre(const DevMesh &m, const double *__restrict__ y, int i,
                                          const double *st, unsigned bar, unsigned phase, bool ys)
 {
@@ -615,18 +678,28 @@ __device__ __forceinline__ bool elem_pre(const DevMesh &m, const double *__restr
         }
         cid = nbs[3 * PB_TILE + (i & 31)];
     }
+#ifdef PB_FAKE_GATHER
+    nn[0] = nn[1] = nn[2] = i;
+#endif
     const double2 *crow = reinterpret_cast<const double2 *>(m.cls + (size_t)cid * CC_STRIDE);
     const double2 c_mach = __ldg(crow + CC_KMACH / 2);      // {kmach, areafv}
     const double c_ksath = __ldg(m.cls + (size_t)cid * CC_STRIDE + CC_KSATH);
     double ysn[3], zmaxn[3];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-        ysn[j] = y_surf(m, y, nn[j]);
-        zmaxn[j] = m.snb[nn[j]].y;
+        ysn[j] = ld_here(p_surf<GH>(m, y, nn[j]));
+#ifndef PB_PRE_ZMAX_SNB
+        // neighbour's zmax out of its tile's column of the static table: that tile's slab is being
+        // fetched by some CTA at about the same time, so the line is in L2 (and the static
+        // neighbour records are not read by this kernel at all)
+        zmaxn[j] = ld_here(&TSC(TS_ZMAX, nn[j]));
+#else
+        zmaxn[j] = ld_here(&m.snb[nn[j]].y);
+#endif
     }
     const double *sy = st + (TS_PRE1 - TS_PRE0) * PB_TILE;
-    const double surfh = surf_h_a<FAST>(A, max0(ys ? sy[0] : y_surf(m, y, i)));
-    const double gw = max0(ys ? sy[PB_TILE] : y_gw(m, y, i));
+    const double surfh = surf_h_a<FAST>(A, max0(ys ? sy[0] : y_surf<GH>(m, y, i)));
+    const double gw = max0(ys ? sy[PB_TILE] : y_gw<GH>(m, y, i));
     const double effkh = eff_kh_a<FAST>(A, EC(TS_DEPTH), EC(TS_DMAC), c_mach.x, c_mach.y, c_ksath, gw);
     // pow(avg_h, 0.6666667) of OverLandFlow (lat_flow.c:270): AvgHsurf (lat_flow.c:175-203)
     // returns the depth above DEPRSTG of the UPWIND element, so the power is a
@@ -635,6 +708,8 @@ __device__ __forceinline__ bool elem_pre(const DevMesh &m, const double *__restr
     // while the neighbour gathers are in flight.
     const double hd = (surfh > PB_DEPRSTG) ? 1.0 * (surfh - PB_DEPRSTG) : 0.0;
     const double p23 = A.powp(hd, 0.6666667);
+#pragma unroll
+    for (int j = 0; j < 3; j++) { PB_AFTER(ysn[j], p23); PB_AFTER(zmaxn[j], p23); }
     double sf = 0.0;
     if (m.surf_mode == PB_DIFF_WAVE) {
         const double zmax = EC(TS_ZMAX);
@@ -653,7 +728,7 @@ __device__ __forceinline__ bool elem_pre(const DevMesh &m, const double *__restr
                     else h[j] = FOC(PB_F_BC0 + j, i);
                 } else if (code[j] < 0) {
                     const int r = (-code[j] - 2) >> 2;
-                    const double stage = max0(y_stage(m, y, r));
+                    const double stage = max0(y_stage<GH>(m, y, r));
                     h[j] = (stage > RFC(PB_R_SHP_DEPTH, r)) ? RFC(PB_R_ZBED, r) + stage : RFC(PB_R_ZMAX, r);
                 }
             }
@@ -668,14 +743,23 @@ __device__ __forceinline__ bool elem_pre(const DevMesh &m, const double *__restr
 #undef EC
 }
 
-template <int DUMMY>
+template <bool GH>
 __device__ __noinline__ void elem_pre_exact(const DevMesh *gm, const double *__restrict__ y, int i,
                                             const double *st, unsigned bar, unsigned phase, bool ys)
 {
     const DevMesh &m = *gm;
-    elem_pre<false>(m, y, i, st, bar, phase, ys);
+    elem_pre<false, GH>(m, y, i, st, bar, phase, ys);
     if (m.slow_count) atomicAdd(m.slow_count, 1ULL);
 }
+
+// per-warp gather buffer of k_main: per edge [4][32] x 16 B + [32] x 8 B (+ [32] x 8 B fbr)
+#ifndef PB_GATHER_ASYNC
+#define PB_GATHER_ASYNC 0
+#endif
+template <bool FBR> struct MainGather {
+    static constexpr int EDGE = 2048 + 256 + (FBR ? 256 : 0);
+    static constexpr int WARP = PB_GATHER_ASYNC ? 3 * EDGE + 256 : 0;    // + one scratch double per lane
+};
 
 // ---------------------------------------------------------------------------
 // element part of k_main
@@ -683,11 +767,14 @@ __device__ __noinline__ void elem_pre_exact(const DevMesh *gm, const double *__r
 // FAST: every division / pow goes through Arith<true> (fdiv.cuh) and the
 // function returns false, without having written anything, when one of them
 // left the fast-path domain; the caller then runs the FAST = false version.
-template <bool FBR, bool FAST>
+template <bool FBR, bool FAST, bool GH>
 __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__restrict__ y,
                                           double *__restrict__ dy, int i, const double *st,
-                                          const double *f, unsigned bar, unsigned phase, int ys)
+                                          const double *f, unsigned bar, unsigned phase, int ys,
+                                          unsigned char *gb)
 {
+    // gb: this warp's gather buffer (FAST): per edge [4][32] 16-byte chunks {dnb, snb} of the
+    // neighbour + [32] gw (+ [32] fbr_gw), filled by per-lane cp.async at the top of the tile
     // st / f: this lane's column 0 of the stage's slabs (static slots TS_MAIN0.., hot
     // forcing columns), filled by the bulk copies issued STAGES tiles ago in k_main; behind
     // them the tile's own state columns (ys bit 0: gw [, fbr_gw], bit 1: unsat [, fbr_unsat]
@@ -712,23 +799,48 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
     const double c_rzd = __ldg(m.cls + (size_t)cid * CC_STRIDE + CC_RZD);
     double4 dn[3], sn[3];     // {surfh, effkh, sf, p23} and {zmin, zmax, rough, zbed} of the neighbours
     double gwn[3];
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-        dn[j] = m.dnb[nn[j]];
-        sn[j] = m.snb[nn[j]];
-        gwn[j] = max0(y_gw(m, y, nn[j]));
-    }
     double fgn[3] = {0.0, 0.0, 0.0};
     int cidn[3] = {0, 0, 0};
-    if (FBR && FAST) {      // bedrock: the neighbours' deep groundwater and geology class
+    constexpr int GBE = MainGather<FBR>::EDGE;      // bytes per edge in the gather buffer
+    constexpr bool GA = FAST && (PB_GATHER_ASYNC != 0);
+#ifdef PB_FAKE_GATHER      // timing experiment only (wrong results): every gather hits the element itself
+    nn[0] = nn[1] = nn[2] = i;
+#endif
+    if (GA) {
+        // neighbour gathers straight into shared memory; they are collected below, after the
+        // element's own-state chains (van Genuchten), which need none of them
+        const unsigned g0 = smem_u32(gb) + (i & 31) * 16;
 #pragma unroll
         for (int j = 0; j < 3; j++) {
-            fgn[j] = max0(y_fg(m, y, nn[j]));
-            cidn[j] = m.cid[nn[j]];
+            const char *pd = reinterpret_cast<const char *>(m.dnb + nn[j]);
+            const char *ps = reinterpret_cast<const char *>(m.snb + nn[j]);
+            const unsigned g = g0 + j * GBE;
+            cp_async16(g, pd);
+            cp_async16(g + 512, pd + 16);
+            cp_async16(g + 1024, ps);
+            cp_async16(g + 1536, ps + 16);
+            cp_async8(smem_u32(gb) + j * GBE + 2048 + (i & 31) * 8, p_gw<GH>(m, y, nn[j]));
+            if (FBR) {
+                cp_async8(smem_u32(gb) + j * GBE + 2304 + (i & 31) * 8, p_fg<GH>(m, y, nn[j]));
+                cidn[j] = m.cid[nn[j]];
+            }
+        }
+        cp_async_commit();
+    } else {
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            dn[j] = m.dnb[nn[j]];
+            sn[j] = m.snb[nn[j]];
+            gwn[j] = max0(y_gw<GH>(m, y, nn[j]));
+            if (FBR && FAST) {
+                fgn[j] = max0(y_fg<GH>(m, y, nn[j]));
+                cidn[j] = m.cid[nn[j]];
+            }
         }
     }
     const double *sy = f + 4 * PB_TILE;
-    const double4 own = *reinterpret_cast<const double4 *>(sy - (i & 31) + (FBR ? 4 : 2) * PB_TILE + 4 * (i & 31));
+    const double4 own = PB_GATHER_ASYNC ? m.dnb[i]
+                                        : *reinterpret_cast<const double4 *>(sy - (i & 31) + (FBR ? 4 : 2) * PB_TILE + 4 * (i & 31));
     // ode.c:25-49
     const double unsat = max0((ys & 2) ? sy[1 * PB_TILE] : y[m.o_unsat + i]);
     const double gw = max0((ys & 1) ? sy[0] : y[m.o_gw + i]);
@@ -793,6 +905,29 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
         vg_kr_psi_a<FAST>(A, sv, c_g0.x, r_galpha, c_g0.y, c_g1.x, c_g1.y, kr, ps);
         g_kr = full ? 1.0 : kr;
         g_psi = (ps > PB_PSIMIN) ? ps : PB_PSIMIN;
+    }
+
+    if (GA) {
+        // collect the gathers (each lane reads what it copied itself); the wait takes the result
+        // of the own-state chains as an operand so that it cannot be scheduled ahead of them
+        {
+            // (a volatile shared store of that result right in front of the wait: ptxas keeps
+            // memory operations in order around the wait, and the store needs the chains' result)
+            const double dep = FBR ? satkfunc + g_kr + psi_u : satkfunc + psi_u;
+            asm volatile("st.volatile.shared.f64 [%0], %1;\n\tcp.async.wait_group 0;"
+                         ::"r"(smem_u32(gb) + 3 * GBE + (i & 31) * 8), "d"(dep) : "memory");
+        }
+        const unsigned char *g0 = gb + (i & 31) * 16;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const unsigned char *g = g0 + j * GBE;
+            const double2 a = *reinterpret_cast<const double2 *>(g), b = *reinterpret_cast<const double2 *>(g + 512);
+            const double2 c = *reinterpret_cast<const double2 *>(g + 1024), d = *reinterpret_cast<const double2 *>(g + 1536);
+            dn[j] = make_double4(a.x, a.y, b.x, b.y);
+            sn[j] = make_double4(c.x, c.y, d.x, d.y);
+            gwn[j] = max0(*reinterpret_cast<const double *>(gb + j * GBE + 2048 + (i & 31) * 8));
+            if (FBR) fgn[j] = max0(*reinterpret_cast<const double *>(gb + j * GBE + 2304 + (i & 31) * 8));
+        }
     }
 
     // LateralFlow, lat_flow.c:17-51.  The element-to-element formulas run for all
@@ -1051,7 +1186,7 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
                     const int r = (-code[j] - 2) >> 2;
                     const int l = RIC(PB_RI_LEFTELE, r);
                     const int n = (l == i) ? RIC(PB_RI_RIGHTELE, r) : l;
-                    const double fg_n = max0(y_fg(m, y, n));
+                    const double fg_n = max0(y_fg<GH>(m, y, n));
                     double diff_h = (fg + zbed) - (fg_n + m.snb[n].w);
                     double avgh = avg_h(diff_h, fg, fg_n);
                     double grad_h = div_any(diff_h, m.fbr_dist[r]);
@@ -1135,7 +1270,7 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
                     dist = m.fbr_dist[r];
                 }
                 // FbrFlowElemToElem, lat_flow.c:374-390
-                const double fg_n = max0(y_fg(m, y, n));
+                const double fg_n = max0(y_fg<GH>(m, y, n));
                 double diff_h = (fg + zbed) - (fg_n + m.snb[n].w);
                 double avgh = avg_h(diff_h, fg, fg_n);
                 double grad_h = A.divr(diff_h, dist);
@@ -1199,13 +1334,13 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
 }
 
 // the rare elements whose arithmetic left the fast-path domain: plain `/` and pow()
-template <bool FBR>
+template <bool FBR, bool GH>
 __device__ __noinline__ void elem_main_exact(const DevMesh *gm, const double *__restrict__ y,
                                              double *__restrict__ dy, int i, const double *st,
                                              const double *f, unsigned bar, unsigned phase, int ys)
 {
     const DevMesh &m = *gm;
-    elem_main<FBR, false>(m, y, dy, i, st, f, bar, phase, ys);
+    elem_main<FBR, false, GH>(m, y, dy, i, st, f, bar, phase, ys, nullptr);
     if (m.slow_count) atomicAdd(m.slow_count, 1ULL);
 }
 
@@ -1272,7 +1407,7 @@ __device__ __forceinline__ void river_main(const DevMesh &m, double *__restrict_
 #define PB_MAIN_MINB_FBR 2
 #endif
 #ifndef PB_MAIN_WARPS_FBR
-#define PB_MAIN_WARPS_FBR 10   // fbr: 10 warps x 2 CTAs at 96 registers: 175.3 us (8 / 7 / 6 warps: 178.8 / 191 / 195 us)
+#define PB_MAIN_WARPS_FBR 8    // fbr: 8 warps x 2 CTAs at 128 registers (10 x 2 at 96 spills: +4 us)
 #endif
 
 #ifndef PB_RING_GROUP
@@ -1311,20 +1446,27 @@ template <int STAGES, int STAGE_BYTES> struct Ring {
     }
     __device__ __forceinline__ unsigned bar(int s) const { return bar0 + 8 * s; }
     __device__ __forceinline__ unsigned char *stage(int s) const { return base + (size_t)s * STAGE_BYTES; }
-    static constexpr int smem_bytes() { return STAGES * STAGE_BYTES + 12 * STAGES + 16; }
+    // behind the control words: up to 8 copy descriptors of a stage (lane c issues copy c)
+    __host__ __device__ static constexpr int desc_off() { return (STAGES * STAGE_BYTES + 12 * STAGES + 16 + 31) / 32 * 32; }
+    __host__ __device__ static constexpr int smem_bytes() { return desc_off() + 8 * 32; }
 };
+// One bulk copy of a stage: src = base + tile * stride (bytes), dst = stage + off; kind 1 = L2 prefetch only
+struct __align__(16) StageCopy { unsigned long long base; unsigned stride, off, bytes, kind, pad0, pad1; };
 
 template <bool FBR> struct MainCfg {
     static constexpr int NC = (FBR ? TS_FBR1 : TS_MAIN1) - TS_MAIN0;
     // static slab | hot forcing columns | own state {gw, unsat[, fbr_gw, fbr_unsat]} | own dynamic record
     static constexpr int SBS = NC * PB_TILE * 8, SBF = 4 * PB_TILE * 8;
-    static constexpr int NY = FBR ? 4 : 2, SBY = NY * PB_TILE * 8, SBD = PB_TILE * 32;
+    // (with asynchronous gathers the own dynamic record is fetched with them: shared memory is short)
+    static constexpr int NY = FBR ? 4 : 2, SBY = NY * PB_TILE * 8, SBD = PB_GATHER_ASYNC ? 0 : PB_TILE * 32;
     static constexpr int SB = SBS + SBF + SBY + SBD;
     static constexpr int STAGES = FBR ? PB_MAIN_STAGES_FBR : PB_MAIN_STAGES;
     static constexpr int MINB = FBR ? PB_MAIN_MINB_FBR : PB_MAIN_MINB;
     static constexpr int WARPS = FBR ? PB_MAIN_WARPS_FBR : PB_RHS_WARPS;
     static constexpr int THREADS = WARPS * 32;
     typedef Ring<STAGES, SB> ring_t;
+    static constexpr int RING_BYTES = (ring_t::smem_bytes() + 127) / 128 * 128;
+    static constexpr int SMEM = RING_BYTES + WARPS * MainGather<FBR>::WARP;
 };
 struct PreCfg {
     static constexpr int NC = TS_PRE1 - TS_PRE0;
@@ -1333,7 +1475,8 @@ struct PreCfg {
     typedef Ring<PB_PRE_STAGES, SB> ring_t;
 };
 
-static __global__ void __launch_bounds__(PB_PRE_THREADS, PB_PRE_MINB)
+template <bool GH>     // GH: the local mesh has ghost entities (partitioned run)
+__global__ void __launch_bounds__(PB_PRE_THREADS, PB_PRE_MINB)
 k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r, const HaloWait hw, int ys)
 {
     constexpr int SBS = PreCfg::SBS;
@@ -1395,7 +1538,7 @@ k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r, c
         if (g >= e_end) break;
         if (g < r_end) {
             const int r = (int)g * PB_TILE + lane;
-            if (r < m.nr) river_fluxes(m, y, r);
+            if (r < m.nr) river_fluxes<GH>(m, y, r);
             continue;
         }
         const int k = q - qe0, s = k % PB_PRE_STAGES, n = k / PB_PRE_STAGES;
@@ -1405,17 +1548,30 @@ k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r, c
         const double *st = reinterpret_cast<const double *>(ring.stage(s)) + lane;
         if (i < m.ne) {
             const bool tys = (g - r_end) < ntile_own;
-            if (!elem_pre<true>(m, y, i, st, ring.bar(s), phase, tys))
-                elem_pre_exact<0>(m.self, y, i, st, ring.bar(s), phase, tys);
+            if (!elem_pre<true, GH>(m, y, i, st, ring.bar(s), phase, tys))
+                elem_pre_exact<GH>(m.self, y, i, st, ring.bar(s), phase, tys);
         } else {
             mbar_wait(ring.bar(s), phase);
         }
         __syncwarp();           // every lane is done with the stage: hand it to the tile STAGES tickets ahead
-        if (lane == 0) { ring.release(s, n); request(q + PB_PRE_STAGES, true, true); }
+        if (lane == 0) ring.release(s, n);
+        const long long tn = item(q + PB_PRE_STAGES) - r_end;
+        if (tn < ntile_e) {
+            // lane 0 the static slab, lanes 1 and 2 the own surf / gw columns of a tile of owned elements
+            const bool own = tn < ntile_own;
+            if (lane == 0) mbar_expect_tx(ring.bar(s), SBS + (own ? 2 * PB_TILE * 8 : 0));
+            __syncwarp();
+            if (lane < (own ? 3 : 1)) {
+                const double *src = (lane == 0) ? m.es + ((size_t)tn * TS_NCOL + TS_PRE0) * PB_TILE
+                                                : y + (lane == 1 ? 0 : m.o_gw) + (size_t)tn * PB_TILE;
+                const unsigned off = (lane == 0) ? 0 : SBS + (lane - 1) * PB_TILE * 8;
+                tma_bulk_g2s(smem_u32(ring.stage(s)) + off, src, (lane == 0) ? SBS : PB_TILE * 8, ring.bar(s));
+            }
+        }
     }
 }
 
-template <bool FBR>
+template <bool FBR, bool GH>
 __global__ void __launch_bounds__(MainCfg<FBR>::THREADS, MainCfg<FBR>::MINB)
 k_main(const DevMesh m, const double *__restrict__ y, double *__restrict__ dy, int ntile_e, int ntile_r, int ys)
 {
@@ -1459,10 +1615,41 @@ k_main(const DevMesh m, const double *__restrict__ y, double *__restrict__ dy, i
                     if (ys & 1) tma_bulk_g2s(smem_u32(sp + 2 * PB_TILE * 8), y + m.o_fg + tile * PB_TILE, PB_TILE * 8, ring.bar(s));
                     if (ys & 2) tma_bulk_g2s(smem_u32(sp + 3 * PB_TILE * 8), y + m.o_fu + tile * PB_TILE, PB_TILE * 8, ring.bar(s));
                 }
-                tma_bulk_g2s(smem_u32(sp + SBY), m.dnb + tile * PB_TILE, SBD, ring.bar(s));
+                if (SBD) tma_bulk_g2s(smem_u32(sp + SBY), m.dnb + tile * PB_TILE, SBD, ring.bar(s));
+#ifndef PB_NO_SNB_PREFETCH
+                // the static neighbour records of this tile's elements are gathered by the tiles
+                // around it, which are in flight on other SMs now: have them in L2
+                tma_prefetch_l2(m.snb + tile * PB_TILE, PB_TILE * 32);
+#endif
             }
         }
     };
+    // In the loop below a stage is re-armed by the whole warp: lane c issues copy c of the table
+    // (one address computation per lane instead of one copy after the other on lane 0)
+    StageCopy *desc = reinterpret_cast<StageCopy *>(smem + MainCfg<FBR>::ring_t::desc_off());
+    int ncopy = 0;
+    unsigned total_bytes = SBS + SBF + dyn_bytes;
+    {
+        auto add = [&](const void *base, unsigned stride, unsigned off, unsigned bytes, unsigned kind) {
+            if (threadIdx.x == 0) {
+                StageCopy c;
+                c.base = (unsigned long long)base; c.stride = stride; c.off = off;
+                c.bytes = bytes; c.kind = kind; c.pad0 = c.pad1 = 0;
+                desc[ncopy] = c;
+            }
+            ncopy++;
+        };
+        add(m.es + (size_t)TS_MAIN0 * PB_TILE, TS_NCOL * PB_TILE * 8, 0, SBS, 0);
+        add(m.ft, 4 * PB_TILE * 8, SBS, SBF, 0);
+        if (ys & 1) add(y + m.o_gw, PB_TILE * 8, SBS + SBF, PB_TILE * 8, 0);
+        if (ys & 2) add(y + m.o_unsat, PB_TILE * 8, SBS + SBF + PB_TILE * 8, PB_TILE * 8, 0);
+        if (FBR && (ys & 1)) add(y + m.o_fg, PB_TILE * 8, SBS + SBF + 2 * PB_TILE * 8, PB_TILE * 8, 0);
+        if (FBR && (ys & 2)) add(y + m.o_fu, PB_TILE * 8, SBS + SBF + 3 * PB_TILE * 8, PB_TILE * 8, 0);
+        if (SBD) add(m.dnb, PB_TILE * 32, SBS + SBF + SBY, SBD, 0);
+#ifndef PB_NO_SNB_PREFETCH
+        add(m.snb, PB_TILE * 32, 0, PB_TILE * 32, 1);
+#endif
+    }
     if (lane == 0)
         for (int k = warp; k < STAGES; k += MainCfg<FBR>::WARPS) request(qe0 + k, true, false);
     // the static slabs above do not depend on k_pre; everything below does (no-op when the
@@ -1470,6 +1657,7 @@ k_main(const DevMesh m, const double *__restrict__ y, double *__restrict__ dy, i
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (lane == 0)
         for (int k = warp; k < STAGES; k += MainCfg<FBR>::WARPS) request(qe0 + k, false, true);
+    __syncthreads();        // the descriptor table is visible to every warp
     const long long r_end = (long long)gr * PB_RING_GROUP, e_end = r_end + ntile_e;
     for (;;) {
         const int q = ring.take(lane);
@@ -1487,13 +1675,26 @@ k_main(const DevMesh m, const double *__restrict__ y, double *__restrict__ dy, i
         const double *st = reinterpret_cast<const double *>(ring.stage(s)) + lane;
         const double *f = reinterpret_cast<const double *>(ring.stage(s) + SBS) + lane;
         if (i < m.nown) {
-            if (!elem_main<FBR, true>(m, y, dy, i, st, f, ring.bar(s), phase, ys))
-                elem_main_exact<FBR>(m.self, y, dy, i, st, f, ring.bar(s), phase, ys);
+            if (!elem_main<FBR, true, GH>(m, y, dy, i, st, f, ring.bar(s), phase, ys,
+                                      smem + MainCfg<FBR>::RING_BYTES + warp * MainGather<FBR>::WARP))
+                elem_main_exact<FBR, GH>(m.self, y, dy, i, st, f, ring.bar(s), phase, ys);
         } else {
             mbar_wait(ring.bar(s), phase);
         }
-        __syncwarp();
-        if (lane == 0) { ring.release(s, n); request(q + STAGES, true, true); }
+        __syncwarp();           // every lane is done with the stage: hand it to the tile STAGES tickets ahead
+        if (lane == 0) ring.release(s, n);
+        const long long kk = item(q + STAGES) - r_end;
+        if (kk < ntile_e) {
+            const unsigned tile = (unsigned)(ntile_e - 1 - (int)kk);
+            if (lane == 0) mbar_expect_tx(ring.bar(s), total_bytes);
+            __syncwarp();
+            if (lane < ncopy) {
+                const StageCopy d = desc[lane];
+                const void *src = reinterpret_cast<const void *>(d.base + (unsigned long long)tile * d.stride);
+                if (d.kind == 0) tma_bulk_g2s(smem_u32(ring.stage(s)) + d.off, src, d.bytes, ring.bar(s));
+                else tma_prefetch_l2(src, d.bytes);
+            }
+        }
     }
 }
 

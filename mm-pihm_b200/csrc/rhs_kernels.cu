@@ -15,17 +15,20 @@ int rhs_configure(pihm_b200_ctx *ctx, int sms)
 {
     const DevMesh &dm = ctx->dm;
     const int pre_smem = PreCfg::ring_t::smem_bytes();
-    const int main_smem = dm.fbr ? MainCfg<true>::ring_t::smem_bytes() : MainCfg<false>::ring_t::smem_bytes();
+    const int main_smem = dm.fbr ? MainCfg<true>::SMEM : MainCfg<false>::SMEM;
     int bpre = 0, bmain = 0;
-    cudaError_t e = cudaFuncSetAttribute(k_pre, cudaFuncAttributeMaxDynamicSharedMemorySize, pre_smem);
+    // GH = ghost entities present (a partition): the variant without them skips the owned /
+    // ghost distinction in every state access
+    const bool gh = (dm.nown != dm.ne) || (dm.rown != dm.nr);
+    const void *kp = gh ? (const void *)k_pre<true> : (const void *)k_pre<false>;
+    const void *km = dm.fbr ? (gh ? (const void *)k_main<true, true> : (const void *)k_main<true, false>)
+                            : (gh ? (const void *)k_main<false, true> : (const void *)k_main<false, false>);
+    cudaError_t e = cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, pre_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(km, cudaFuncAttributeMaxDynamicSharedMemorySize, main_smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpre, kp, PB_PRE_THREADS, pre_smem);
     if (e == cudaSuccess)
-        e = dm.fbr ? cudaFuncSetAttribute(k_main<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, main_smem)
-                   : cudaFuncSetAttribute(k_main<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, main_smem);
-    if (e == cudaSuccess)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpre, k_pre, PB_PRE_THREADS, pre_smem);
-    if (e == cudaSuccess)
-        e = dm.fbr ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bmain, k_main<true>, MainCfg<true>::THREADS, main_smem)
-                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bmain, k_main<false>, MainCfg<false>::THREADS, main_smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bmain, km, dm.fbr ? MainCfg<true>::THREADS : MainCfg<false>::THREADS,
+                                                          main_smem);
     if (e != cudaSuccess || bpre < 1 || bmain < 1) {
         set_error(std::string("pihm_b200_create: RHS kernel configuration failed: ") + cudaGetErrorString(e));
         return -1;
@@ -125,7 +128,9 @@ int rhs_launch(pihm_b200_ctx *ctx, const double *y, double *dy, bool replay)
     // own-state columns of a tile by bulk copy: needs 16-byte alignment of each block inside y
     int ys = 0;
     if (ctx->ystage && ((uintptr_t)y & 15) == 0) ys = 1 | ((dm.nown % 2 == 0) ? 2 : 0);
-    k_pre<<<gpre, PB_PRE_THREADS, ctx->pre_smem, ctx->s()>>>(dm, y, te, tr, hw, ys & 1);
+    const bool gh = (dm.nown != dm.ne) || (dm.rown != dm.nr);
+    if (gh) k_pre<true><<<gpre, PB_PRE_THREADS, ctx->pre_smem, ctx->s()>>>(dm, y, te, tr, hw, ys & 1);
+    else k_pre<false><<<gpre, PB_PRE_THREADS, ctx->pre_smem, ctx->s()>>>(dm, y, te, tr, hw, ys & 1);
     {
         // k_main right behind k_pre with programmatic stream serialization (PDL): its launch
         // latency and prologue overlap k_pre's tail
@@ -139,8 +144,11 @@ int rhs_launch(pihm_b200_ctx *ctx, const double *y, double *dy, bool replay)
         at[0].val.programmaticStreamSerializationAllowed = ctx->pdl ? 1 : 0;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        const cudaError_t e = dm.fbr ? cudaLaunchKernelEx(&cfg, k_main<true>, dm, y, dy, te_own, tr_own, ys)
-                                     : cudaLaunchKernelEx(&cfg, k_main<false>, dm, y, dy, te_own, tr_own, ys);
+        const cudaError_t e =
+            dm.fbr ? (gh ? cudaLaunchKernelEx(&cfg, k_main<true, true>, dm, y, dy, te_own, tr_own, ys)
+                         : cudaLaunchKernelEx(&cfg, k_main<true, false>, dm, y, dy, te_own, tr_own, ys))
+                   : (gh ? cudaLaunchKernelEx(&cfg, k_main<false, true>, dm, y, dy, te_own, tr_own, ys)
+                         : cudaLaunchKernelEx(&cfg, k_main<false, false>, dm, y, dy, te_own, tr_own, ys));
         if (e != cudaSuccess) { set_error(std::string("k_main launch: ") + cudaGetErrorString(e)); return -1; }
     }
     ctx->launches += 2;
