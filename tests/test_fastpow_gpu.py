@@ -1,5 +1,7 @@
 """pow_pos() (csrc/fastpow.cuh), the inlined pow of the RHS kernels, against
-libdevice pow(): bitwise on the fast path, and identical through the fallback."""
+libdevice pow(): on the fast path bitwise in the bit-for-bit build (RHS_RELAX=0) and, in the
+default build (plain-double u^3 c(u^2) term of the logarithm, PB_RELAX & 8), equal in all but a
+few results per thousand and never more than one ulp apart; identical through the fallback."""
 import numpy as np
 import pytest
 
@@ -17,7 +19,7 @@ def run(x, y):
     return fast, ref
 
 
-def test_domain_of_the_rhs_bitwise():
+def test_domain_of_the_rhs_one_ulp():
     rng = np.random.default_rng(0)
     n = 1 << 20
     # saturations, 1 - s^m, (1/s)^m - 1, ponding depths; van Genuchten / Manning exponents
@@ -26,7 +28,11 @@ def test_domain_of_the_rhs_bitwise():
     y = np.concatenate([rng.uniform(1.0, 10.0, n // 4), rng.uniform(0.05, 1.0, n // 4),
                         rng.uniform(0.1, 1.0, n // 4), np.full(n // 4, 0.6666667)])
     fast, ref = run(x, y)
-    assert np.array_equal(fast, ref), f"{(fast != ref).sum()} of {n} differ, max rel {np.abs(fast / ref - 1).max():.2e}"
+    differ = fast != ref
+    ulp = np.abs(fast - ref) / np.spacing(np.abs(ref))
+    print(f"pow_pos vs libdevice pow: {differ.sum()} of {n} differ ({differ.mean():.2e}), max {ulp.max():.0f} ulp")
+    assert ulp.max() <= 1.0, f"max {ulp.max()} ulp, max rel {np.abs(fast / ref - 1).max():.2e}"
+    assert differ.mean() <= 5e-3, f"{differ.sum()} of {n} differ"
 
 
 def test_edge_cases_take_the_fallback():
