@@ -1,17 +1,28 @@
 // cvode_b200.cu -- variable-order BDF + Newton + scaled GMRES(maxl) with all
 // vector work on the device.
 //
-// This is a from-scratch statement of the algorithm the reference reaches
-// through SetCVodeParam()/SolveCVode() (src/ode.c:340-498): CVODE 2.9.0's
-// BDF/Newton stepper (cvode/src/cvode/cvode.c), its CVSPGMR glue
-// (cvode_spgmr.c, cvode_spils.c) and the generic SPGMR solver
-// (cvode/src/sundials/sundials_spgmr.c, sundials_iterative.c), restricted to
-// what MM-PIHM configures: CV_BDF, CV_NEWTON, scalar tolerances, PREC_NONE,
-// modified Gram-Schmidt, no restarts, difference-quotient J*v, tstop mode,
-// stability-limit detection on.  The control flow (every branch, counter and
-// heuristic constant) follows the reference so that step sequences agree; the
-// N_V* calls are replaced by the fused kernels of cvode_kernels.cuh and the
-// host only synchronises where CVODE branches on a norm.
+// The algorithm is the one the reference reaches through SetCVodeParam()/SolveCVode()
+// (src/ode.c:340-498): CVODE 2.9.0's BDF/Newton stepper (cvode/src/cvode/cvode.c), its
+// CVSPGMR glue (cvode_spgmr.c, cvode_spils.c) and the generic SPGMR solver
+// (cvode/src/sundials/sundials_spgmr.c, sundials_iterative.c), restricted to what MM-PIHM
+// configures: CV_BDF, CV_NEWTON, scalar tolerances, PREC_NONE, modified Gram-Schmidt, no
+// restarts, difference-quotient J*v, tstop mode, stability-limit detection on.
+//
+// What is new here is the device side: the N_V* calls are replaced by the fused kernels of
+// cvode_kernels.cuh, scalars stay on the device, the host only synchronises where CVODE
+// branches on a norm.  The HOST control flow is a restatement of CVODE's: every branch,
+// counter and heuristic constant follows the reference so that step sequences agree bit for
+// bit (tests/test_dropin_gpu.py), and the scalar routines cvSLdet (stability-limit detection,
+// cvode.c:3335-3602), cvSetBDF / cvSetTqBDF (cvode.c:2400-2531) and cvAdjustOrder /
+// cvIncreaseBDF / cvDecreaseBDF (cvode.c:2106-2241) follow cvode.c statement by statement.
+// That code is derived from SUNDIALS:
+//
+//   Copyright (c) 2002-2016, Lawrence Livermore National Security.
+//   Produced at the Lawrence Livermore National Laboratory.
+//   Written by A.C. Hindmarsh, D.R. Reynolds, R. Serban, C.S. Woodward, S.D. Cohen,
+//   A.G. Taylor, S. Peles, L.E. Banks, and D. Shumaker.  UCRL-CODE-155951 (CVODE).
+//   All rights reserved.  BSD 3-clause license: see THIRD_PARTY_NOTICES.md at the
+//   repository root for the full text, which applies to those portions.
 #include <algorithm>
 #include <atomic>
 #include <cfloat>
