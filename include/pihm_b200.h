@@ -192,6 +192,17 @@ int             pihm_b200_comm_unique_id(void *out128);
 int             pihm_b200_comm_init(pihm_b200_ctx *ctx, int rank, int nranks,
                                     const void *id128);
 int64_t         pihm_b200_num_state_var_global(const pihm_b200_ctx *ctx);
+/* pihm_b200_comm_init fails (all ranks, the set-up is collective) when the peer-memory halo
+ * exchange cannot be mapped; PIHM_B200_NO_P2P=1 selects NCCL send/recv + ncclAllReduce instead,
+ * PIHM_B200_P2P_OPTIONAL=1 allows the silent fallback.  pihm_b200_comm_paths reports what runs:
+ * out[0] = 1 halo over peer memory inside the first RHS kernel (0: NCCL send/recv),
+ * out[1] = 1 the ranks share one process (pihm_b200_comm_init_local). */
+int             pihm_b200_comm_paths(const pihm_b200_ctx *ctx, int32_t *out2);
+/* Ranks that live in ONE process (ctxs[r] = rank r, one context per rank on one or several
+ * devices with peer access; one host thread per rank drives its integrator): the same
+ * peer-memory halo exchange and in-kernel all-reduce, wired with plain pointers -- no NCCL.
+ * pihm_b200_set_halo first; create the integrators of ALL ranks before the first solve. */
+int             pihm_b200_comm_init_local(pihm_b200_ctx **ctxs, int nranks);
 /* transport-free access to the exchange (single-process emulation of several
  * ranks on one GPU, used by the tests): packed send records of y, and the
  * ghost records of this context */

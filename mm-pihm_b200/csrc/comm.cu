@@ -7,6 +7,7 @@
 #include <dlfcn.h>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <vector>
 #include "common.cuh"
 
@@ -83,6 +84,7 @@ int comm_halo_exchange(pihm_b200_ctx *ctx)
 int comm_allreduce(pihm_b200_ctx *ctx, double *dev_ptr, int count, int op)
 {
     if (ctx->nranks <= 1) return 0;
+    if (!ctx->comm) { set_error("all-reduce without a communicator (same-process rank group: no NCCL)"); return -1; }
     Nccl &n = nccl();
     const int nop = (op == 0) ? ncclSum : (op == 1 ? ncclMin : ncclMax);
     return check(n.AllReduce(dev_ptr, dev_ptr, (size_t)count, ncclFloat64, nop, ctx->comm, ctx->s()), "ncclAllReduce");
@@ -97,28 +99,34 @@ int comm_share_buffer(pihm_b200_ctx *ctx, void *local, void **peers)
     Nccl &n = nccl();
     if (ctx->nranks <= 1 || !ctx->comm || !n.AllGather) return -1;
     const int R = ctx->nranks;
+    // A local failure must not leave the collective sequence: every rank goes through the
+    // all-gather and the agreement all-reduce, and a rank that failed votes "no".  The staging
+    // area is the context's reduction scratch (red_blocks + 64 doubles >= (R + 1) handles).
     cudaIpcMemHandle_t mine;
-    int good = (cudaIpcGetMemHandle(&mine, local) == cudaSuccess) ? 1 : 0;
-    unsigned char *d_h = nullptr;
+    std::memset(&mine, 0, sizeof(mine));
+    int good = (local && cudaIpcGetMemHandle(&mine, local) == cudaSuccess) ? 1 : 0;
+    static_assert(sizeof(cudaIpcMemHandle_t) * (PB_MAX_RANKS_H + 1) <= sizeof(double) * 64 + 8 * 64, "staging area");
+    unsigned char *d_h = reinterpret_cast<unsigned char *>(ctx->d_red);
     std::vector<cudaIpcMemHandle_t> all(R);
-    if (cudaMalloc((void **)&d_h, sizeof(mine) * (R + 1)) != cudaSuccess) return -1;
     cudaMemcpyAsync(d_h + sizeof(mine) * R, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->s());
     int rc = n.AllGather(d_h + sizeof(mine) * R, d_h, sizeof(mine), /*ncclInt8*/ 0, ctx->comm, ctx->s());
     cudaMemcpyAsync(all.data(), d_h, sizeof(mine) * R, cudaMemcpyDeviceToHost, ctx->s());
     if (cudaStreamSynchronize(ctx->s()) != cudaSuccess || rc != 0) good = 0;
+    for (int r = 0; r < R; r++) peers[r] = nullptr;
     for (int r = 0; r < R && good; r++) {
         if (r == ctx->rank) { peers[r] = local; continue; }
-        if (cudaIpcOpenMemHandle(&peers[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) good = 0;
+        if (cudaIpcOpenMemHandle(&peers[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { peers[r] = nullptr; good = 0; }
     }
     cudaGetLastError();
     // agree: every rank must have every mapping, otherwise nobody uses them
-    double v = (double)good, *d = reinterpret_cast<double *>(d_h);
+    double v = (double)good, *d = ctx->d_red;
     cudaMemcpyAsync(d, &v, sizeof(double), cudaMemcpyHostToDevice, ctx->s());
     n.AllReduce(d, d, 1, ncclFloat64, ncclMin, ctx->comm, ctx->s());
     cudaMemcpyAsync(&v, d, sizeof(double), cudaMemcpyDeviceToHost, ctx->s());
     cudaStreamSynchronize(ctx->s());
-    cudaFree(d_h);
-    return (v > 0.5) ? 0 : -1;
+    if (v > 0.5) return 0;
+    comm_unshare_buffer(ctx, peers);        // somebody failed: close what this rank had opened
+    return -1;
 }
 
 void comm_unshare_buffer(pihm_b200_ctx *ctx, void **peers)
@@ -130,25 +138,36 @@ void comm_unshare_buffer(pihm_b200_ctx *ctx, void **peers)
 // Peer-memory halo exchange: every rank allocates [2 parities][ghost element records | ghost
 // river records] + arrival flags, maps it into all ranks, and learns from each neighbour where
 // its own records go in the neighbour's buffer (one grouped ncclSend/ncclRecv of 3 doubles).
-// Collective over all ranks; on any failure everybody keeps the NCCL send/recv path.
-int comm_setup_halo_p2p(pihm_b200_ctx *ctx)
+// Collective over all ranks; a rank with a local failure stays in the sequence and votes "no",
+// and then nobody uses the mappings.
+static long long halo_stride(const pihm_b200_ctx *ctx)
 {
-    Nccl &n = nccl();
-    if (ctx->nranks <= 1 || ctx->nranks > PB_MAX_RANKS_H || !ctx->comm) return -1;
-    const int nn = (int)ctx->nbr_rank.size();
-    const int gs = ctx->dm.gs;
     const long long ng = ctx->dm.ne - ctx->dm.nown, nrg = ctx->dm.nr - ctx->dm.rown;
-    const long long stride = ((gs * ng + 2 * nrg + 3) / 4) * 4 + 4;
-    int good = (nn <= PB_MAX_NBR) ? 1 : 0;
+    return ((ctx->dm.gs * ng + 2 * nrg + 3) / 4) * 4 + 4;
+}
+// local allocations: the buffer itself, the CTA counter of the put, the two parity views of the mesh
+static int halo_alloc(pihm_b200_ctx *ctx)
+{
+    const long long stride = halo_stride(ctx);
     const size_t bytes = sizeof(double) * (size_t)(2 * stride + 2 * PB_MAX_RANKS_H);
+    int good = 1;
     if (cudaMalloc((void **)&ctx->d_hx, bytes) != cudaSuccess) { ctx->d_hx = nullptr; good = 0; }
     else cudaMemset(ctx->d_hx, 0, bytes);
-    if (!ctx->d_hcount && cudaMalloc((void **)&ctx->d_hcount, sizeof(unsigned int)) == cudaSuccess)
-        cudaMemset(ctx->d_hcount, 0, sizeof(unsigned int));
-    if (comm_share_buffer(ctx, ctx->d_hx, ctx->hx_peer) != 0) good = 0;
-    // tell every neighbour where its records land here: {stride, element offset, river offset}
-    double *d_x = nullptr;
-    std::vector<double> mine(3 * (size_t)std::max(nn, 1)), theirs(3 * (size_t)std::max(nn, 1), 0.0);
+    if (!ctx->d_hcount) {
+        if (cudaMalloc((void **)&ctx->d_hcount, sizeof(unsigned int)) == cudaSuccess) cudaMemset(ctx->d_hcount, 0, sizeof(unsigned int));
+        else { ctx->d_hcount = nullptr; good = 0; }
+    }
+    for (int p = 0; p < 2; p++)
+        if (!ctx->d_dm_par[p] && cudaMalloc((void **)&ctx->d_dm_par[p], sizeof(DevMesh)) != cudaSuccess) { ctx->d_dm_par[p] = nullptr; good = 0; }
+    cudaGetLastError();
+    return good;
+}
+// where neighbour k's records land in THIS rank's buffer: {stride, element offset, river offset}
+static void halo_my_layout(const pihm_b200_ctx *ctx, std::vector<double> &mine)
+{
+    const int nn = (int)ctx->nbr_rank.size(), gs = ctx->dm.gs;
+    const long long ng = ctx->dm.ne - ctx->dm.nown, stride = halo_stride(ctx);
+    mine.assign(3 * (size_t)std::max(nn, 1), 0.0);
     long long roff_e = 0, roff_r = 0;
     for (int k = 0; k < nn; k++) {
         mine[3 * k] = (double)stride;
@@ -157,29 +176,12 @@ int comm_setup_halo_p2p(pihm_b200_ctx *ctx)
         roff_e += ctx->recv_e_cnt[k];
         roff_r += ctx->recv_r_cnt[k];
     }
-    if (cudaMalloc((void **)&d_x, sizeof(double) * 6 * (size_t)std::max(nn, 1)) != cudaSuccess) d_x = nullptr;
-    if (!d_x) {     // stay collective: the neighbours are waiting in their group call
-        set_error("halo p2p setup: allocation failed");
-        return -1;
-    }
-    cudaMemcpyAsync(d_x, mine.data(), sizeof(double) * 3 * nn, cudaMemcpyHostToDevice, ctx->s());
-    n.GroupStart();
-    for (int k = 0; k < nn; k++) {
-        n.Send(d_x + 3 * k, 3, ncclFloat64, ctx->nbr_rank[k], ctx->comm, ctx->s());
-        n.Recv(d_x + 3 * nn + 3 * k, 3, ncclFloat64, ctx->nbr_rank[k], ctx->comm, ctx->s());
-    }
-    if (n.GroupEnd() != 0) good = 0;
-    cudaMemcpyAsync(theirs.data(), d_x + 3 * nn, sizeof(double) * 3 * nn, cudaMemcpyDeviceToHost, ctx->s());
-    if (cudaStreamSynchronize(ctx->s()) != cudaSuccess) good = 0;
-    // agree
-    double v = (double)good;
-    cudaMemcpyAsync(d_x, &v, sizeof(double), cudaMemcpyHostToDevice, ctx->s());
-    n.AllReduce(d_x, d_x, 1, ncclFloat64, ncclMin, ctx->comm, ctx->s());
-    cudaMemcpyAsync(&v, d_x, sizeof(double), cudaMemcpyDeviceToHost, ctx->s());
-    cudaStreamSynchronize(ctx->s());
-    cudaFree(d_x);
-    cudaGetLastError();
-    if (v < 0.5) return -1;
+}
+// everything agreed: theirs[3k..] = where this rank's records land in neighbour k's buffer
+static void halo_finish(pihm_b200_ctx *ctx, const std::vector<double> &theirs)
+{
+    const int nn = (int)ctx->nbr_rank.size(), gs = ctx->dm.gs;
+    const long long ng = ctx->dm.ne - ctx->dm.nown, stride = halo_stride(ctx);
     HaloPeers &hp = ctx->hpeers;
     hp.nn = nn;
     hp.myrank = ctx->rank;
@@ -197,17 +199,93 @@ int comm_setup_halo_p2p(pihm_b200_ctx *ctx)
         DevMesh dm = ctx->dm;
         dm.gel = ctx->d_hx + p * stride;
         dm.gri = ctx->d_hx + p * stride + gs * ng;
-        if (cudaMalloc((void **)&ctx->d_dm_par[p], sizeof(DevMesh)) != cudaSuccess) return -1;
         dm.self = ctx->d_dm_par[p];
         cudaMemcpy(ctx->d_dm_par[p], &dm, sizeof(DevMesh), cudaMemcpyHostToDevice);
     }
     ctx->halo_p2p = 1;
+}
+static void halo_release(pihm_b200_ctx *ctx)
+{
+    if (ctx->d_hx) { cudaFree(ctx->d_hx); ctx->d_hx = nullptr; }
+    for (int p = 0; p < 2; p++) if (ctx->d_dm_par[p]) { cudaFree(ctx->d_dm_par[p]); ctx->d_dm_par[p] = nullptr; }
+}
+
+int comm_setup_halo_p2p(pihm_b200_ctx *ctx)
+{
+    Nccl &n = nccl();
+    if (ctx->nranks <= 1 || ctx->nranks > PB_MAX_RANKS_H || !ctx->comm) return -1;
+    const int nn = (int)ctx->nbr_rank.size();
+    int good = (nn <= PB_MAX_NBR) ? 1 : 0;
+    if (!halo_alloc(ctx)) good = 0;
+    const int shared = (comm_share_buffer(ctx, ctx->d_hx, ctx->hx_peer) == 0);
+    if (!shared) good = 0;
+    // tell every neighbour where its records land here; staging in the reduction scratch (no
+    // allocation that could fail between the collectives)
+    std::vector<double> mine, theirs(3 * (size_t)std::max(nn, 1), 0.0);
+    halo_my_layout(ctx, mine);
+    double *d_x = ctx->d_red;
+    const bool fits = 6 * (size_t)std::max(nn, 1) <= 64 + (size_t)ctx->red_blocks;
+    if (!fits) good = 0;
+    if (fits) cudaMemcpyAsync(d_x, mine.data(), sizeof(double) * 3 * nn, cudaMemcpyHostToDevice, ctx->s());
+    n.GroupStart();
+    for (int k = 0; k < nn && fits; k++) {
+        n.Send(d_x + 3 * k, 3, ncclFloat64, ctx->nbr_rank[k], ctx->comm, ctx->s());
+        n.Recv(d_x + 3 * nn + 3 * k, 3, ncclFloat64, ctx->nbr_rank[k], ctx->comm, ctx->s());
+    }
+    if (n.GroupEnd() != 0) good = 0;
+    if (fits) cudaMemcpyAsync(theirs.data(), d_x + 3 * nn, sizeof(double) * 3 * nn, cudaMemcpyDeviceToHost, ctx->s());
+    if (cudaStreamSynchronize(ctx->s()) != cudaSuccess) good = 0;
+    // agree
+    double v = (double)good;
+    cudaMemcpyAsync(d_x, &v, sizeof(double), cudaMemcpyHostToDevice, ctx->s());
+    n.AllReduce(d_x, d_x, 1, ncclFloat64, ncclMin, ctx->comm, ctx->s());
+    cudaMemcpyAsync(&v, d_x, sizeof(double), cudaMemcpyDeviceToHost, ctx->s());
+    cudaStreamSynchronize(ctx->s());
+    cudaGetLastError();
+    if (v < 0.5) {      // somebody failed: nobody uses peer memory; undo the local part
+        if (shared) comm_unshare_buffer(ctx, ctx->hx_peer);
+        halo_release(ctx);
+        return -1;
+    }
+    halo_finish(ctx, theirs);
+    return 0;
+}
+
+// The same wiring for ranks that live in ONE process (one context per rank, on one or several
+// devices): buffers are exchanged as plain pointers, no NCCL, no IPC.  Used by the single-GPU
+// tests of the peer-memory halo exchange / in-kernel all-reduce, and by a threaded driver.
+int comm_setup_halo_local(pihm_b200_ctx **ctxs, int n)
+{
+    for (int r = 0; r < n; r++) {
+        cudaSetDevice(ctxs[r]->device);
+        if ((int)ctxs[r]->nbr_rank.size() > PB_MAX_NBR || !halo_alloc(ctxs[r])) {
+            for (int q = 0; q <= r; q++) halo_release(ctxs[q]);
+            set_error("comm_init_local: halo buffers");
+            return -1;
+        }
+    }
+    for (int r = 0; r < n; r++) {
+        pihm_b200_ctx *ctx = ctxs[r];
+        for (int q = 0; q < n; q++) ctx->hx_peer[q] = ctxs[q]->d_hx;
+        const int nn = (int)ctx->nbr_rank.size();
+        std::vector<double> theirs(3 * (size_t)std::max(nn, 1), 0.0), lay;
+        for (int k = 0; k < nn; k++) {
+            const pihm_b200_ctx *o = ctxs[ctx->nbr_rank[k]];
+            halo_my_layout(o, lay);
+            int ko = -1;
+            for (size_t j = 0; j < o->nbr_rank.size(); j++) if (o->nbr_rank[j] == r) ko = (int)j;
+            if (ko < 0) { set_error("comm_init_local: neighbour relation is not symmetric"); return -1; }
+            for (int c = 0; c < 3; c++) theirs[3 * k + c] = lay[3 * ko + c];
+        }
+        cudaSetDevice(ctx->device);
+        halo_finish(ctx, theirs);
+    }
     return 0;
 }
 
 void comm_destroy(pihm_b200_ctx *ctx)
 {
-    if (ctx->halo_p2p) { comm_unshare_buffer(ctx, ctx->hx_peer); ctx->halo_p2p = 0; }
+    if (ctx->halo_p2p) { if (!ctx->lgroup) comm_unshare_buffer(ctx, ctx->hx_peer); ctx->halo_p2p = 0; }
     if (ctx->d_hx) { cudaFree(ctx->d_hx); ctx->d_hx = nullptr; }
     if (ctx->d_hcount) { cudaFree(ctx->d_hcount); ctx->d_hcount = nullptr; }
     for (int p = 0; p < 2; p++) if (ctx->d_dm_par[p]) { cudaFree(ctx->d_dm_par[p]); ctx->d_dm_par[p] = nullptr; }
@@ -253,8 +331,74 @@ int pihm_b200_comm_init(pihm_b200_ctx *ctx, int rank, int nranks, const void *id
     PB_CUDA(cudaMemcpyAsync(&v, d, sizeof(double), cudaMemcpyDeviceToHost, ctx->s()));
     PB_CUDA(cudaStreamSynchronize(ctx->s()));
     ctx->nsv_global = (long long)(v + 0.5);
-    // neighbours' ghost buffers over NVLink peer memory (falls back to ncclSend/ncclRecv)
-    if (!(std::getenv("PIHM_B200_NO_P2P") && std::atoi(std::getenv("PIHM_B200_NO_P2P")))) pb::comm_setup_halo_p2p(ctx);
+    // neighbours' ghost buffers over NVLink peer memory.  PIHM_B200_NO_P2P=1 asks for the NCCL
+    // send/recv path instead; without it a failed mapping is an error (all ranks see it: the
+    // set-up is collective), unless PIHM_B200_P2P_OPTIONAL=1 allows the silent fallback.
+    const bool no_p2p = std::getenv("PIHM_B200_NO_P2P") && std::atoi(std::getenv("PIHM_B200_NO_P2P"));
+    if (!no_p2p && pb::comm_setup_halo_p2p(ctx) != 0) {
+        const bool optional = std::getenv("PIHM_B200_P2P_OPTIONAL") && std::atoi(std::getenv("PIHM_B200_P2P_OPTIONAL"));
+        if (!optional) {
+            pb::set_error("comm_init: the peer-memory halo exchange could not be set up (CUDA IPC / peer access); "
+                          "set PIHM_B200_NO_P2P=1 to run over NCCL send/recv");
+            return -1;
+        }
+    }
+    return 0;
+}
+
+// Ranks of ONE process (ctxs[r] = rank r; any mix of devices with peer access): peer-memory halo
+// exchange and in-kernel all-reduce wired with plain pointers, no NCCL.  Create the integrators
+// (pihm_b200_cvode_create) of ALL ranks before the first solve: each one registers its exchange
+// buffer with the group.
+int pihm_b200_comm_init_local(pihm_b200_ctx **ctxs, int nranks)
+{
+    if (!ctxs || nranks < 1 || nranks > PB_MAX_RANKS_H) { pb::set_error("comm_init_local: bad argument"); return -1; }
+    auto g = std::make_shared<pb::LocalGroup>();
+    g->n = nranks;
+    long long nsv = 0;
+    for (int r = 0; r < nranks; r++) {
+        if (!ctxs[r] || ctxs[r]->comm || ctxs[r]->lgroup) { pb::set_error("comm_init_local: context already in a group"); return -1; }
+        nsv += ctxs[r]->nsv;
+        g->ctx[r] = ctxs[r];
+    }
+    for (int r = 0; r < nranks; r++)
+        for (int q = 0; q < nranks; q++)
+            if (ctxs[r]->device != ctxs[q]->device) {
+                cudaSetDevice(ctxs[r]->device);
+                cudaDeviceEnablePeerAccess(ctxs[q]->device, 0);
+                cudaGetLastError();         // already enabled is fine
+            }
+    for (int r = 0; r < nranks; r++) {
+        ctxs[r]->rank = r;
+        ctxs[r]->nranks = nranks;
+        ctxs[r]->nsv_global = nsv;
+        ctxs[r]->lgroup = g;
+        // Ranks that SHARE a device wait for each other inside kernels (halo flags in k_pre, tickets
+        // in the reduction kernels), so a waiting kernel must leave room for its peers' kernels: the
+        // k_pre grids of all OTHER ranks together put at most one CTA on an SM (a k_main CTA of the
+        // rank they wait for still fits beside it), and no kernel is launched ahead of its
+        // predecessor's end (no PDL: a dependent grid parked on the SMs could keep a peer's kernel
+        // off them).  Host calls that synchronise the device (cudaMalloc / cudaFree) must not be
+        // issued while a peer's RHS is in flight: allocate before the first evaluation.
+        int share = 0, sms = 1;
+        for (int q = 0; q < nranks; q++) share += (ctxs[q]->device == ctxs[r]->device);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctxs[r]->device);
+        if (share > 1) {
+            ctxs[r]->pdl = 0;
+            ctxs[r]->pre_grid = std::max(1, std::min(ctxs[r]->pre_grid, sms / (share - 1)));
+            ctxs[r]->main_grid = std::max(1, ctxs[r]->main_grid / share);
+        }
+    }
+    if (nranks == 1) return 0;
+    return pb::comm_setup_halo_local(ctxs, nranks);
+}
+
+// which transport the partitioned run uses: out[0] halo (1 peer memory inside k_pre, 0 NCCL send/recv)
+int pihm_b200_comm_paths(const pihm_b200_ctx *ctx, int32_t *out)
+{
+    if (!ctx || !out) return -1;
+    out[0] = ctx->halo_p2p;
+    out[1] = ctx->lgroup ? 1 : 0;
     return 0;
 }
 

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
 #include <string>
 #include <vector>
 #include "pihm_b200.h"
@@ -123,7 +124,15 @@ struct HaloWait {
 }  // namespace pb
 
 struct pihm_b200_ctx;
+struct pihm_b200_cvode;
 namespace pb {
+// ranks that live in one process (pihm_b200_comm_init_local): exchange buffers as plain pointers
+struct LocalGroup {
+    int n = 0;
+    pihm_b200_ctx *ctx[8] = {};
+    double *xbuf[8] = {};            // integrator exchange buffers (cvode_b200.cu), by rank
+    double **peer_tab[8] = {};       // each integrator's device table of those
+};
 // comm.cu: NCCL (dlopen'ed) halo exchange and scalar all-reduce
 int comm_halo_exchange(pihm_b200_ctx *ctx);
 int comm_allreduce(pihm_b200_ctx *ctx, double *dev_ptr, int count, int op /*0 sum, 1 min, 2 max*/);
@@ -131,6 +140,7 @@ void comm_destroy(pihm_b200_ctx *ctx);
 int comm_share_buffer(pihm_b200_ctx *ctx, void *local, void **peers /*[nranks]*/);
 void comm_unshare_buffer(pihm_b200_ctx *ctx, void **peers);
 int comm_setup_halo_p2p(pihm_b200_ctx *ctx);
+int comm_setup_halo_local(pihm_b200_ctx **ctxs, int n);
 }  // namespace pb
 
 namespace pb {
@@ -193,6 +203,7 @@ struct pihm_b200_ctx {
     int nse = 0, nsr = 0;
     // peer-memory halo exchange (comm.cu: comm_setup_halo_p2p)
     int halo_p2p = 0;
+    int ntile_int = 0;                 // leading element tiles that read no ghost in k_pre (interior of the partition)
     double *d_hx = nullptr;            // [2][gel | gri] + flags, mapped into the neighbours
     long long hx_stride = 0;           // doubles per parity copy
     void *hx_peer[8] = {};             // all ranks' buffers mapped here (PB_MAX_RANKS_H)
@@ -201,6 +212,7 @@ struct pihm_b200_ctx {
     unsigned int *d_hcount = nullptr;
     long long halo_seq = 0;
     void *comm = nullptr;              // ncclComm_t
+    std::shared_ptr<pb::LocalGroup> lgroup;   // same-process rank group (no NCCL)
     int rank = 0, nranks = 1;
     long long nsv_global = 0;
     // staging for host <-> device vectors

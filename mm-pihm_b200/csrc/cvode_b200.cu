@@ -1242,10 +1242,28 @@ pihm_b200_cvode *pihm_b200_cvode_create(pihm_b200_ctx *ctx)
             cudaMemsetAsync(cv->d_xbuf, 0, sizeof(double) * PB_XB_DOUBLES, ctx->s());
             cudaStreamSynchronize(ctx->s());
         }
-        if (comm_share_buffer(ctx, got ? (void *)cv->d_xbuf : nullptr, cv->h_peer) == 0 && got) {
+        if (ctx->lgroup) {
+            // ranks of one process: register with the group and refresh every registered table
+            // (complete once the integrators of all ranks exist -- before the first solve)
+            pb::LocalGroup &g = *ctx->lgroup;
+            if (got) {
+                g.xbuf[ctx->rank] = cv->d_xbuf;
+                g.peer_tab[ctx->rank] = cv->d_peer;
+                for (int r = 0; r < g.n; r++)
+                    if (g.peer_tab[r]) cudaMemcpy(g.peer_tab[r], g.xbuf, sizeof(double *) * PB_MAX_RANKS, cudaMemcpyHostToDevice);
+                cv->rb.peer = cv->d_peer;
+                cv->p2p = true;
+            }
+        } else if (comm_share_buffer(ctx, got ? (void *)cv->d_xbuf : nullptr, cv->h_peer) == 0 && got) {
             cudaMemcpy(cv->d_peer, cv->h_peer, sizeof(double *) * PB_MAX_RANKS, cudaMemcpyHostToDevice);
             cv->rb.peer = cv->d_peer;
             cv->p2p = true;
+        }
+        if (!cv->p2p && (ctx->lgroup || ctx->halo_p2p)) {
+            // the halo runs over peer memory, so the scalars must too (or the caller asked for NCCL for both)
+            set_error("cvode_create: the exchange buffers of the in-kernel all-reduce could not be shared");
+            pihm_b200_cvode_destroy(cv);
+            return nullptr;
         }
     }
     if (ctx->nranks > 1 && !cv->p2p) {
@@ -1314,7 +1332,11 @@ void pihm_b200_cvode_destroy(pihm_b200_cvode *cv)
                      cv->tempv, cv->ftemp, cv->V[0], cv->V[1], cv->V[2], cv->V[3], cv->V[4], cv->V[5],
                      cv->vtemp, cv->ytemp, cv->d_part, cv->d_sc};
     for (double *p : all) if (p) cudaFree(p);
-    if (cv->p2p) comm_unshare_buffer(cv->ctx, cv->h_peer);
+    if (cv->p2p && !cv->ctx->lgroup) comm_unshare_buffer(cv->ctx, cv->h_peer);
+    if (cv->ctx->lgroup && cv->ctx->lgroup->xbuf[cv->ctx->rank] == cv->d_xbuf) {
+        cv->ctx->lgroup->xbuf[cv->ctx->rank] = nullptr;
+        cv->ctx->lgroup->peer_tab[cv->ctx->rank] = nullptr;
+    }
     if (cv->d_xbuf) cudaFree(cv->d_xbuf);
     if (cv->d_peer) cudaFree(cv->d_peer);
     if (cv->d_counter) cudaFree(cv->d_counter);

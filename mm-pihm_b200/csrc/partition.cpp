@@ -5,8 +5,8 @@
 // segment, river <-> downstream segment), so the mesh shards with
 // one halo exchange per RHS evaluation.
 //
-// Partition p owns a contiguous chunk of the locality ordering (reorder.h) and
-// every river segment whose left-bank element it owns.  Its LOCAL mesh is again
+// Partition p owns a contiguous chunk of the locality ordering (reorder.h), listed as
+// [interior | boundary] (see below), and every river segment whose left-bank element it owns.  Its LOCAL mesh is again
 // a plain pihm_b200_mesh (same column tables, local 1-based numbering):
 //     elements = [ owned | ghosts grouped by owner rank ]
 //     rivers   = [ owned | ghosts grouped by owner rank ]
@@ -88,10 +88,22 @@ pihm_b200_partition *pihm_b200_partition_create(const pihm_b200_mesh *m, int npa
     std::vector<std::map<int, std::vector<int>>> need_e(nparts), need_rv(nparts);
     for (int p = 0; p < nparts; p++) {
         pihm_b200_partition::Part &pt = P->parts[p];
-        pt.elems = owned_e[p]; pt.nown_e = (int)owned_e[p].size();
-        pt.rivs = owned_r[p]; pt.nown_r = (int)owned_r[p].size();
         std::vector<char> mine(ne, 0);
         for (int e : owned_e[p]) mine[e] = 1;
+        // Owned elements in the order [interior | boundary], each in locality order: an interior
+        // element reads no ghost in the first RHS kernel (all three neighbours and every adjacent
+        // river are owned), so that kernel works on the interior tiles while the halo records of
+        // this evaluation are still on their way and waits for them only before the rest.
+        std::stable_partition(owned_e[p].begin(), owned_e[p].end(), [&](int e) {
+            for (int j = 0; j < 3; j++) {
+                const int n = EI(PB_EI_NABR0 + j, e);
+                if (n > 0 && !mine[n - 1]) return false;
+                if (n < 0 && P->owner_r[-n - 1] != p) return false;
+            }
+            return true;
+        });
+        pt.elems = owned_e[p]; pt.nown_e = (int)owned_e[p].size();
+        pt.rivs = owned_r[p]; pt.nown_r = (int)owned_r[p].size();
         std::set<int> G;
         std::vector<int> ring1, tmp;
         // two rings of edge neighbours

@@ -34,16 +34,31 @@ static int vec_blocks(const pihm_b200_ctx *ctx, long long n)
     const long long cap = (long long)ctx->red_blocks;     // SMs x 4 resident CTAs
     return (int)std::max<long long>(1, std::min(b, cap));
 }
+// N_VDotProd / N_VMaxNorm / N_VWrmsNorm / N_VMin of the stand-alone N_Vector (nvector_b200.cu).
+// On a partitioned context the vectors hold the owned unknowns only: the raw sum / max / min is
+// all-reduced over the ranks (NCCL) and the WRMS norm divides by the GLOBAL length, so every
+// rank of an external CVODE sees the same bits and takes the same branches.
 template <int OP, int POST>
 static double reduce_sync(pihm_b200_ctx *ctx, long long n, const double *x, const double *y)
 {
     const int g = vec_blocks(ctx, n);
     unsigned int *counter = (unsigned int *)(ctx->d_nan + 2);
     double *part = ctx->d_red + 64;
-    k_reduce<OP, POST><<<g, PB_VEC_THREADS, 0, ctx->s()>>>(n, x, y, part, counter, ctx->d_red, ctx->h_red);
+    if (ctx->nranks <= 1) {
+        k_reduce<OP, POST><<<g, PB_VEC_THREADS, 0, ctx->s()>>>(n, x, y, part, counter, ctx->d_red, ctx->h_red);
+        ctx->launches++;
+        cudaStreamSynchronize(ctx->s());
+        return ctx->h_red[0];
+    }
+    k_reduce<OP, 0><<<g, PB_VEC_THREADS, 0, ctx->s()>>>(n, x, y, part, counter, ctx->d_red, nullptr);
     ctx->launches++;
+    const int op = (OP == RD_MIN) ? 1 : (OP == RD_MAXABS ? 2 : 0);
+    if (pb::comm_allreduce(ctx, ctx->d_red, 1, op) != 0) return std::nan("");
+    double v = 0.0;
+    cudaMemcpyAsync(&v, ctx->d_red, sizeof(double), cudaMemcpyDeviceToHost, ctx->s());
     cudaStreamSynchronize(ctx->s());
-    return ctx->h_red[0];
+    if (POST == 1) v = std::sqrt(v / (double)ctx->nsv_global);
+    return v;
 }
 
 }  // namespace pb
@@ -246,6 +261,18 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
             bct[(size_t)j * nes + i] = EI(PB_EI_BC0 + j, e);
             fbct[(size_t)j * nes + i] = EI(PB_EI_FBRBC0 + j, e);
         }
+    }
+    // leading tiles whose elements read no ghost in k_pre (all neighbours and adjacent rivers owned):
+    // the partitioner lists the owned elements as [interior | boundary] (partition.cpp)
+    {
+        int first_dep = nown_elem;
+        for (int i = 0; i < nown_elem && first_dep == nown_elem; i++)
+            for (int j = 0; j < 3; j++) {
+                const int code = nb[(size_t)j * nes + i];
+                if (code >= nown_elem) first_dep = i;
+                else if (code <= -2 && ((-code - 2) >> 2) >= nown_riv) first_dep = i;
+            }
+        ctx->ntile_int = first_dep / 32;
     }
     // the neighbour codes and the class id ride in the tile slab as int32 [4][32] (pseudo-columns TS_NB0/1)
     for (int t = 0; t < ntile; t++) {

@@ -1475,42 +1475,96 @@ struct PreCfg {
     typedef Ring<PB_PRE_STAGES, SB> ring_t;
 };
 
+// Halo exchange over peer memory, folded into k_pre (partitioned run).  At its start the grid
+// stores this rank's boundary states straight into the neighbours' ghost buffers (NVLink
+// stores) as records in their ghost order -- elements {surf, gw[, fbr_gw]}, rivers {stage, gw}
+// -- and the last CTA to finish raises this rank's arrival flag in each of them.  The CTAs then
+// work on the INTERIOR element tiles (the partitioner lists the owned elements as [interior |
+// boundary]: an interior tile reads no ghost) and only before the first river / boundary / ghost
+// tile does a warp wait for the flags of this rank's neighbours.  Two parity copies of the ghost
+// buffers alternate per RHS: a neighbour can start the exchange of RHS n+2 only after this rank
+// has sent n+1, i.e. after it has finished reading the copy of RHS n.
+struct HaloPut {
+    int nse, nsr;                     // records to send: elements, rivers
+    const int *send_e, *send_r;       // local owned indices, grouped by neighbour (hp.e_ptr / r_ptr)
+    HaloPeers hp;
+    int par;                          // parity copy of this exchange
+    double seq;                       // its sequence number (the flag value)
+    unsigned int *counter;            // CTAs that have finished their stores
+};
+
+__device__ __forceinline__ void halo_put(const DevMesh &m, const double *__restrict__ y, const HaloPut &h)
+{
+    const HaloPeers &hp = h.hp;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < h.nse + h.nsr; k += gridDim.x * blockDim.x) {
+        if (k < h.nse) {
+            int kk = 0;
+            while (kk + 1 < hp.nn && k >= hp.e_ptr[kk + 1]) kk++;
+            const int i = h.send_e[k];
+            double *dst = hp.base[kk] + h.par * hp.pstride[kk] + hp.gel_off[kk] + (size_t)(k - hp.e_ptr[kk]) * m.gs;
+            dst[0] = y[i];
+            dst[1] = y[m.o_gw + i];
+            if (m.gs == 3) dst[2] = y[m.o_fg + i];
+        } else {
+            const int kr = k - h.nse;
+            int kk = 0;
+            while (kk + 1 < hp.nn && kr >= hp.r_ptr[kk + 1]) kk++;
+            const int r = h.send_r[kr];
+            double *dst = hp.base[kk] + h.par * hp.pstride[kk] + hp.gri_off[kk] + (size_t)(kr - hp.r_ptr[kk]) * 2;
+            dst[0] = y[m.o_stg + r];
+            dst[1] = y[m.o_rgw + r];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(h.counter, 1u) == gridDim.x - 1) {
+            *h.counter = 0u;
+            __threadfence_system();
+            for (int kk = 0; kk < hp.nn; kk++) {
+                volatile double *f = hp.base[kk] + hp.flag_off[kk] + h.par * PB_MAX_RANKS_H + hp.myrank;
+                *f = h.seq;
+            }
+        }
+    }
+}
+
 template <bool GH>     // GH: the local mesh has ghost entities (partitioned run)
 __global__ void __launch_bounds__(PB_PRE_THREADS, PB_PRE_MINB)
-k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r, const HaloWait hw, int ys)
+k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r, int ntile_int, const HaloWait hw,
+      const HaloPut hput, int ys)
 {
     constexpr int SBS = PreCfg::SBS;
     // programmatic dependent launch: k_main's CTAs may become resident as this kernel's CTAs
     // retire and run their prologue (ring set-up, first slab requests); they wait for the
     // completion of this grid (griddepcontrol.wait) before they touch what it writes
     asm volatile("griddepcontrol.launch_dependents;");
-    if (hw.nn > 0) {        // partitioned run: the neighbours' halo records of this RHS have arrived
-        if ((int)threadIdx.x < hw.nn) {
-            long long spins = 0;
-            while (hw.flags[hw.rank[threadIdx.x]] != hw.seq)
-                if (++spins > (1LL << 31)) { atomicOr(m.nan_flag, 2); break; }   // lost neighbour: flag, do not hang
-            __threadfence_system();
-        }
-        __syncthreads();
-    }
     extern __shared__ __align__(128) unsigned char smem[];
     PreCfg::ring_t ring(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = gridDim.x, b = blockIdx.x;
-    const int gr = (ntile_r + PB_RING_GROUP - 1) / PB_RING_GROUP;         // river groups
-    const int qe0 = (gr > b) ? (gr - b + G - 1) / G * PB_RING_GROUP : 0; // first element ticket of this CTA
-    ring.init();
-    auto item = [&](int q) {    // tile index in [river groups | element tiles]
-        return ((long long)(q / PB_RING_GROUP) * G + b) * PB_RING_GROUP + q % PB_RING_GROUP;
+    // Work items of the grid, taken by ticket (ticket q of CTA b = item q * G + b):
+    //   without a peer-memory halo   [ river tiles | element tiles ]       (the slow river tiles first)
+    //   with one                     [ interior element tiles | river tiles | other element tiles ]
+    const int E_int = (GH && hw.nn > 0) ? min(ntile_int, ntile_e) : 0;
+    const int R = ntile_r;
+    const int qr0 = (E_int > b) ? (E_int - b + G - 1) / G : 0;          // this CTA's river tickets: [qr0, qr1)
+    const int qr1 = (E_int + R > b) ? (E_int + R - b + G - 1) / G : 0;
+    const int nrq = qr1 - qr0;
+    auto q_of_k = [&](int k) { return (k < qr0) ? k : k + nrq; };       // k-th element ticket of this CTA
+    auto tile_of_q = [&](int q) {       // element tile of an element ticket (>= ntile_e: past the end)
+        const long long g = (long long)q * G + b;
+        return (g < E_int) ? g : g - R;
     };
-    // request the tile of element ticket q (no-op past the end): the static slab does not depend
-    // on the previous kernel (prologue), the own surf / gw columns of a tile of owned elements do
-    // (after the dependency wait; the arrival travels with this part)
+    ring.init();
+    // request the tile of the k-th element ticket (no-op past the end): the static slab does not
+    // depend on the previous kernel (prologue), the own surf / gw columns of a tile of owned
+    // elements do (after the dependency wait; the arrival travels with this part)
     const int ntile_own = ys ? m.nown / PB_TILE : 0;        // tiles whose 32 elements all live in y
-    auto request = [&](int q, bool stat, bool dyn) {
-        const long long tile = item(q) - (long long)gr * PB_RING_GROUP;
+    auto request = [&](int k, bool stat, bool dyn) {
+        const long long tile = tile_of_q(q_of_k(k));
         if (tile < ntile_e) {
-            const int s = (q - qe0) % PB_PRE_STAGES;
+            const int s = k % PB_PRE_STAGES;
             if (stat) {
                 mbar_expect_tx_only(ring.bar(s), SBS);
                 tma_bulk_g2s(smem_u32(ring.stage(s)), m.es + ((size_t)tile * TS_NCOL + TS_PRE0) * PB_TILE, SBS, ring.bar(s));
@@ -1527,27 +1581,41 @@ k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r, c
         }
     };
     if (lane == 0)
-        for (int k = warp; k < PB_PRE_STAGES; k += PB_PRE_WARPS) request(qe0 + k, true, false);
+        for (int k = warp; k < PB_PRE_STAGES; k += PB_PRE_WARPS) request(k, true, false);
     asm volatile("griddepcontrol.wait;" ::: "memory");      // y comes from the previous kernel of the stream
+    if (GH && hput.hp.nn > 0) halo_put(m, y, hput);
     if (lane == 0)
-        for (int k = warp; k < PB_PRE_STAGES; k += PB_PRE_WARPS) request(qe0 + k, false, true);
-    const long long r_end = (long long)gr * PB_RING_GROUP, e_end = r_end + ntile_e;
+        for (int k = warp; k < PB_PRE_STAGES; k += PB_PRE_WARPS) request(k, false, true);
+    const long long g_end = (long long)ntile_e + R;
+    bool halo_seen = !(GH && hw.nn > 0);
     for (;;) {
         const int q = ring.take(lane);
-        const long long g = item(q);
-        if (g >= e_end) break;
-        if (g < r_end) {
-            const int r = (int)g * PB_TILE + lane;
+        const long long g = (long long)q * G + b;
+        if (g >= g_end) break;
+        if (GH && !halo_seen && g >= E_int) {
+            // the neighbours' halo records of this RHS have arrived (one lane per neighbour)
+            if (lane < hw.nn) {
+                long long spins = 0;
+                while (hw.flags[hw.rank[lane]] != hw.seq)
+                    if (++spins > (1LL << 31)) { atomicOr(m.nan_flag, 2); break; }   // lost neighbour: flag, do not hang
+                __threadfence_system();
+            }
+            __syncwarp();
+            halo_seen = true;
+        }
+        if (g >= E_int && g < E_int + R) {
+            const int r = (int)(g - E_int) * PB_TILE + lane;
             if (r < m.nr) river_fluxes<GH>(m, y, r);
             continue;
         }
-        const int k = q - qe0, s = k % PB_PRE_STAGES, n = k / PB_PRE_STAGES;
+        const long long tile = (g < E_int) ? g : g - R;
+        const int k = q - min(max(q - qr0, 0), nrq), s = k % PB_PRE_STAGES, n = k / PB_PRE_STAGES;
         const unsigned phase = (unsigned)n & 1u;
         ring.acquire(s, n);
-        const int i = (int)(g - r_end) * PB_TILE + lane;
+        const int i = (int)tile * PB_TILE + lane;
         const double *st = reinterpret_cast<const double *>(ring.stage(s)) + lane;
         if (i < m.ne) {
-            const bool tys = (g - r_end) < ntile_own;
+            const bool tys = tile < ntile_own;
             if (!elem_pre<true, GH>(m, y, i, st, ring.bar(s), phase, tys))
                 elem_pre_exact<GH>(m.self, y, i, st, ring.bar(s), phase, tys);
         } else {
@@ -1555,7 +1623,7 @@ k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r, c
         }
         __syncwarp();           // every lane is done with the stage: hand it to the tile STAGES tickets ahead
         if (lane == 0) ring.release(s, n);
-        const long long tn = item(q + PB_PRE_STAGES) - r_end;
+        const long long tn = tile_of_q(q_of_k(k + PB_PRE_STAGES));
         if (tn < ntile_e) {
             // lane 0 the static slab, lanes 1 and 2 the own surf / gw columns of a tile of owned elements
             const bool own = tn < ntile_own;
@@ -1732,50 +1800,6 @@ k_halo_pack(const DevMesh m, const double *__restrict__ y, int nse, const int *_
         const int r = send_r[k - nse];
         buf_r[(size_t)(k - nse) * 2] = y[m.o_stg + r];
         buf_r[(size_t)(k - nse) * 2 + 1] = y[m.o_rgw + r];
-    }
-}
-
-// Halo exchange over peer memory: the records go straight into the neighbours' ghost buffers
-// (NVLink stores), then the last block to finish raises this rank's arrival flag in each of
-// them.  k_pre of the neighbour waits for the flags of its neighbours (HaloWait).  Two parity
-// copies of the ghost buffers alternate per RHS: a neighbour can start the exchange of RHS n+2
-// only after this rank has sent n+1, i.e. after it has finished reading the copy of RHS n.
-static __global__ void __launch_bounds__(256)
-k_halo_put(const DevMesh m, const double *__restrict__ y, int nse, const int *__restrict__ send_e,
-           int nsr, const int *__restrict__ send_r, const HaloPeers hp, int par, double seq,
-           unsigned int *counter)
-{
-    asm volatile("griddepcontrol.launch_dependents;");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < nse) {
-        int kk = 0;
-        while (kk + 1 < hp.nn && k >= hp.e_ptr[kk + 1]) kk++;
-        const int i = send_e[k];
-        double *dst = hp.base[kk] + par * hp.pstride[kk] + hp.gel_off[kk] + (size_t)(k - hp.e_ptr[kk]) * m.gs;
-        dst[0] = y[i];
-        dst[1] = y[m.o_gw + i];
-        if (m.gs == 3) dst[2] = y[m.o_fg + i];
-    } else if (k < nse + nsr) {
-        const int kr = k - nse;
-        int kk = 0;
-        while (kk + 1 < hp.nn && kr >= hp.r_ptr[kk + 1]) kk++;
-        const int r = send_r[kr];
-        double *dst = hp.base[kk] + par * hp.pstride[kk] + hp.gri_off[kk] + (size_t)(kr - hp.r_ptr[kk]) * 2;
-        dst[0] = y[m.o_stg + r];
-        dst[1] = y[m.o_rgw + r];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (atomicAdd(counter, 1u) == gridDim.x - 1) {
-            *counter = 0u;
-            __threadfence_system();
-            for (int kk = 0; kk < hp.nn; kk++) {
-                volatile double *f = hp.base[kk] + hp.flag_off[kk] + par * PB_MAX_RANKS_H + hp.myrank;
-                *f = seq;
-            }
-        }
     }
 }
 

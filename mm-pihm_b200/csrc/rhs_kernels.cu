@@ -80,6 +80,7 @@ int rhs_launch(pihm_b200_ctx *ctx, const double *y, double *dy, bool replay)
 {
     DevMesh dm = ctx->dm;
     HaloWait hw{};
+    HaloPut hput{};
     if (replay) {
         if (ctx->nranks > 1 && ctx->halo_p2p) {     // the ghost records of the last exchange
             const int par = (int)(ctx->halo_seq & 1);
@@ -92,16 +93,16 @@ int rhs_launch(pihm_b200_ctx *ctx, const double *y, double *dy, bool replay)
         dm.self = ctx->d_dm_rec;
         PB_CUDA(cudaMemcpyAsync(ctx->d_dm_rec, &dm, sizeof(DevMesh), cudaMemcpyHostToDevice, ctx->s()));
     } else if (ctx->nranks > 1 && ctx->halo_p2p) {
-        // halo exchange over peer memory: stores into the neighbours' ghost buffers + arrival flags
+        // halo exchange over peer memory, inside k_pre: stores into the neighbours' ghost buffers +
+        // arrival flags at the start of the kernel, the wait before its first non-interior tile
         const long long seq = ++ctx->halo_seq;
         const int par = (int)(seq & 1);
-        const int n = ctx->nse + ctx->nsr;
-        if (ctx->hpeers.nn > 0) {
-            k_halo_put<<<std::max(1, (n + 255) / 256), 256, 0, ctx->s()>>>(dm, y, ctx->nse, ctx->d_send_e_idx, ctx->nsr,
-                                                                            ctx->d_send_r_idx, ctx->hpeers, par,
-                                                                            (double)seq, ctx->d_hcount);
-            ctx->launches++;
-        }
+        hput.nse = ctx->nse; hput.nsr = ctx->nsr;
+        hput.send_e = ctx->d_send_e_idx; hput.send_r = ctx->d_send_r_idx;
+        hput.hp = ctx->hpeers;
+        hput.par = par;
+        hput.seq = (double)seq;
+        hput.counter = ctx->d_hcount;
         dm.gel = ctx->d_hx + par * ctx->hx_stride;
         dm.gri = dm.gel + (size_t)dm.gs * (dm.ne - dm.nown);
         dm.self = ctx->d_dm_par[par];
@@ -129,8 +130,8 @@ int rhs_launch(pihm_b200_ctx *ctx, const double *y, double *dy, bool replay)
     int ys = 0;
     if (ctx->ystage && ((uintptr_t)y & 15) == 0) ys = 1 | ((dm.nown % 2 == 0) ? 2 : 0);
     const bool gh = (dm.nown != dm.ne) || (dm.rown != dm.nr);
-    if (gh) k_pre<true><<<gpre, PB_PRE_THREADS, ctx->pre_smem, ctx->s()>>>(dm, y, te, tr, hw, ys & 1);
-    else k_pre<false><<<gpre, PB_PRE_THREADS, ctx->pre_smem, ctx->s()>>>(dm, y, te, tr, hw, ys & 1);
+    if (gh) k_pre<true><<<gpre, PB_PRE_THREADS, ctx->pre_smem, ctx->s()>>>(dm, y, te, tr, ctx->ntile_int, hw, hput, ys & 1);
+    else k_pre<false><<<gpre, PB_PRE_THREADS, ctx->pre_smem, ctx->s()>>>(dm, y, te, tr, te, hw, hput, ys & 1);
     {
         // k_main right behind k_pre with programmatic stream serialization (PDL): its launch
         // latency and prologue overlap k_pre's tail

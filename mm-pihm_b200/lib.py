@@ -88,6 +88,8 @@ _SIGS = {
     "pihm_b200_comm_unique_id": (C.c_int, [C.c_void_p]),
     "pihm_b200_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "pihm_b200_num_state_var_global": (C.c_int64, [C.c_void_p]),
+    "pihm_b200_comm_paths": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pihm_b200_comm_init_local": (C.c_int, [C.c_void_p, C.c_int]),
     "pihm_b200_halo_pack_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pihm_b200_set_ghosts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pihm_b200_num_state_var": (C.c_int64, [C.c_void_p]),
@@ -280,6 +282,18 @@ class Model:
     def comm_init(self, rank: int, nranks: int, unique_id: bytes):
         buf = C.create_string_buffer(unique_id, 128)
         _check(self.L, self.L.pihm_b200_comm_init(self.h, rank, nranks, buf), "comm_init")
+
+    @staticmethod
+    def comm_init_local(models):
+        """ranks of one process (models[r] = rank r): peer-memory halo + in-kernel all-reduce, no NCCL"""
+        L = models[0].L
+        arr = (C.c_void_p * len(models))(*[m.h for m in models])
+        _check(L, L.pihm_b200_comm_init_local(arr, len(models)), "comm_init_local")
+
+    def comm_paths(self) -> dict:
+        out = np.zeros(2, np.int32)
+        _check(self.L, self.L.pihm_b200_comm_paths(self.h, _ptr(out)), "comm_paths")
+        return {"halo": "p2p" if out[0] else "nccl", "same_process": bool(out[1])}
 
     @property
     def nsv_global(self) -> int:

@@ -1,0 +1,142 @@
+"""The multi-GPU data path on ONE GPU: ranks of a same-process group (pihm_b200_comm_init_local), one
+context + stream + host thread per rank on device 0, buffers shared by plain pointer.  Executes what a
+real N-GPU run executes -- the halo put at the head of k_pre (stores into the neighbours' ghost
+buffers + arrival flags), interior tiles before the flag wait, the in-kernel ticketed all-reduce of
+every integrator norm -- and compares with the unpartitioned run:
+  * RHS: bit for bit (two calls: the second one sees the first one's river-edge flows);
+  * integrator: all ranks take the same control flow (identical counters), state in lock step with the
+    single-GPU run (the reduction order differs, so not bitwise).
+SURVEY 8(e); VERDICT r1 'make the peer-memory halo and ticketed all-reduce testable on one GPU'."""
+import threading
+
+import numpy as np
+import pytest
+
+import mm_pihm_b200  # noqa: F401
+from mm_pihm_b200 import lib, partition as PT, watershed as W
+
+pytestmark = pytest.mark.gpu
+
+
+def run_ranks(fn, n):
+    """fn(rank) on one host thread per rank (ctypes releases the GIL inside the library)"""
+    out, err = [None] * n, [None] * n
+
+    def body(r):
+        try:
+            out[r] = fn(r)
+        except BaseException as e:      # noqa: BLE001
+            err[r] = e
+    th = [threading.Thread(target=body, args=(r,)) for r in range(n)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(300)
+    assert not any(t.is_alive() for t in th), "a rank hangs"
+    for e in err:
+        if e is not None:
+            raise e
+    return out
+
+
+def make_group(tb, nparts):
+    parts = PT.partition(tb, nparts)
+    models = [lib.Model(p) for p in parts]
+    lib.Model.comm_init_local(models)
+    for m in models:
+        assert m.comm_paths() == {"halo": "p2p", "same_process": True}
+        assert m.nsv_global == (5 if tb["fbr"] else 3) * tb["nelem"] + 2 * tb["nriver"]
+    return parts, models
+
+
+@pytest.mark.parametrize("fbr", [False, True])
+@pytest.mark.parametrize("nparts", [2, 3])
+def test_peer_memory_halo_rhs_bitwise(fbr, nparts):
+    tb = W.make_named("10k", fbr=fbr, dirichlet_edges=True)
+    ne, nr = tb["nelem"], tb["nriver"]
+    y = W.wet_state(tb, seed=4)
+    forc = W.storm_forcing(tb, 3 * 3600.0, ws0_surf=np.maximum(y[:ne], 0))
+    single = lib.Model(tb, reorder=1)
+    single.set_forcing(forc, np.zeros(nr))
+    ref = [single.ODE(0.0, y), single.ODE(0.0, y)]
+    single.close()
+    parts, models = make_group(tb, nparts)
+    # every allocation before the first evaluation: cudaMalloc / cudaFree synchronise the device, and a
+    # rank's k_pre in flight waits for its neighbours' (ranks on separate GPUs have no such coupling)
+    yvs, dvs = [], []
+    for m, p in zip(models, parts):
+        m.set_forcing(forc[:, p["elem_gid"]], np.zeros(p["nriver"]))
+        yvs.append(m.N_VNew(y[p["state_idx"]])); dvs.append(m.N_VNew())
+
+    def rank(r):
+        m, yv, dv = models[r], yvs[r], dvs[r]
+        outs = []
+        for _ in range(6):              # both parity copies of the ghost buffers, several times
+            m.ode_dev(0.0, yv, dv)
+            outs.append(dv.download())
+        assert m.check_nan() == 0       # also: no 'lost neighbour' flag
+        return outs
+
+    outs = run_ranks(rank, nparts)
+    for call in range(6):
+        dy = np.empty_like(y)
+        for p, o in zip(parts, outs):
+            dy[p["state_idx"]] = o[call]
+        want = ref[min(call, 1)]
+        assert np.array_equal(dy, want), f"call {call}: {np.abs(dy - want).max():.3e}"
+    for m in models:
+        m.close()
+
+
+@pytest.mark.parametrize("fbr", [False, True])
+def test_peer_memory_integrator_lockstep(fbr):
+    nparts, nsteps = 2, 20
+    tb = W.make_named("10k", fbr=fbr, dirichlet_edges=True)
+    ne, nr = tb["nelem"], tb["nriver"]
+    single = lib.Model(tb, reorder=1)
+    cv1 = lib.Cvode(single)
+    y1 = single.N_VNew(tb["y0"])
+    cv1.SetCVodeParam(y1)
+    for k in range(nsteps):
+        if k % 15 == 0:
+            single.set_forcing(W.storm_forcing(tb, 2 * 3600.0 + k * 60.0), np.zeros(nr))
+        single.Summary(y1)
+        cv1.SolveCVode((k + 1) * 60.0, y1)
+    s1, yr = cv1.stats(), y1.download()
+    cv1.close(); single.close()
+
+    parts, models = make_group(tb, nparts)
+    cvs = [lib.Cvode(m) for m in models]        # all integrators exist before the first solve
+    yvs = []
+    for m, p, cv in zip(models, parts, cvs):
+        yvs.append(m.N_VNew(tb["y0"][p["state_idx"]]))
+        m.set_stale_ovlflow(np.zeros((3, p["nelem"])))
+        m.set_forcing_col(W.F_WS0SURF, np.zeros(p["nelem"]))
+
+    def rank(r):
+        m, p, cv, yv = models[r], parts[r], cvs[r], yvs[r]
+        cv.SetCVodeParam(yv)
+        for k in range(nsteps):
+            if k % 15 == 0:
+                f = W.storm_forcing(tb, 2 * 3600.0 + k * 60.0)
+                m.set_forcing(f[:, p["elem_gid"]], np.zeros(p["nriver"]))
+            m.Summary(yv)
+            cv.SolveCVode((k + 1) * 60.0, yv)
+        st = cv.stats()
+        return yv.download(), (st["nst"], st["nfe"], st["nli"], st["nni"])
+
+    outs = run_ranks(rank, nparts)
+    assert len({o[1] for o in outs}) == 1, f"ranks took different control flow: {[o[1] for o in outs]}"
+    ym = np.empty_like(yr)
+    for p, o in zip(parts, outs):
+        ym[p["state_idx"]] = o[0]
+    unit = 1e-3 * np.abs(yr) + 1e-4
+    err = (np.abs(ym - yr) / unit).max()
+    nst = outs[0][1][0]
+    print(f"[local group] {nparts} ranks on one GPU vs 1 context after {nsteps} steps: {err:.3e} x (reltol|y|+abstol), "
+          f"nst {nst}/{s1['nst']}")
+    assert err <= 30.0 and abs(nst - s1["nst"]) <= 0.25 * s1["nst"]
+    for cv in cvs:
+        cv.close()
+    for m in models:
+        m.close()
