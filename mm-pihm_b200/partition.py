@@ -76,7 +76,8 @@ def partition(tables: dict, nparts: int, parts=None) -> list:
                  stepsize=tables["stepsize"], elem_f64=ef, elem_i32=ei, riv_f64=rf, riv_i32=ri,
                  nown_elem=no, nown_riv=ro, elem_gid=eg, riv_gid=rg[:rl], nbr_rank=nbr[:nn],
                  send_e_ptr=sep, send_e_idx=sei[:nse], recv_e_cnt=rec[:nn],
-                 send_r_ptr=srp, send_r_idx=sri[:nsr], recv_r_cnt=rrc[:nn], part=p, nparts=nparts)
+                 send_r_ptr=srp, send_r_idx=sri[:nsr], recv_r_cnt=rrc[:nn], part=p, nparts=nparts,
+                 _ne_glob=int(tables["nelem"]), _nr_glob=int(tables["nriver"]))
         d["state_idx"] = state_index(no, ro, fbr, eg, d["riv_gid"], tables["nelem"], tables["nriver"])
         # element-wise helper arrays of the global tables restricted to this part
         for key in ("xc", "yc"):
@@ -101,3 +102,23 @@ def local_state(part: dict, y_global: np.ndarray, extended: bool = False) -> np.
 
 def _glob(part, what):
     return part["_ne_glob"] if what == "ne" else part["_nr_glob"]
+
+
+def owned_in_local(part: dict) -> np.ndarray:
+    """positions of the owned unknowns inside the state vector of the whole local mesh (owned + ghosts)"""
+    return state_index(part["nown_elem"], part["nown_riv"], bool(part["fbr"]), np.arange(part["nelem"]),
+                       np.arange(part["nriver"]), part["nelem"], part["nriver"])
+
+
+def ghost_records(part: dict, y_global: np.ndarray):
+    """the ghost records a halo exchange would deliver, {surf, gw[, fbr_gw]} per ghost element and
+    {stage, gw} per ghost river in local (= receive) order, taken from a global state vector"""
+    ne, nr, fbr = _glob(part, "ne"), _glob(part, "nr"), bool(part["fbr"])
+    ge = np.asarray(part["elem_gid"][part["nown_elem"]:], np.int64)
+    gr = np.asarray(part["riv_gid"][part["nown_riv"]:], np.int64)
+    cols = [y_global[ge], y_global[2 * ne + ge]]
+    if fbr:
+        cols.append(y_global[4 * ne + 2 * nr + ge])
+    erec = np.ascontiguousarray(np.stack(cols, axis=1)).ravel()
+    rrec = np.ascontiguousarray(np.stack([y_global[3 * ne + gr], y_global[3 * ne + nr + gr]], axis=1)).ravel()
+    return erec, rrec

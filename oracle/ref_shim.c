@@ -565,6 +565,18 @@ void ref_set_cvode_param(void)
     H.cvode_ready = 1;
 }
 
+/* the AdjCVodeMaxStep controller parameters of ctrl_struct (read_para.c); tables mode leaves them 0 */
+void ref_set_maxstep_ctrl(double stmin, double nncfn, double nnimax,
+    double nnimin, double decr, double incr)
+{
+    H.pihm->ctrl.stmin = stmin;
+    H.pihm->ctrl.nncfn = nncfn;
+    H.pihm->ctrl.nnimax = nnimax;
+    H.pihm->ctrl.nnimin = nnimin;
+    H.pihm->ctrl.decr = decr;
+    H.pihm->ctrl.incr = incr;
+}
+
 void ref_set_max_step(double hmax)
 {
     H.pihm->ctrl.maxstep = hmax;

@@ -71,6 +71,7 @@ class RefModel:
                                   C.c_double, C.c_void_p, C.c_void_p]
         L.ref_ode.argtypes = [C.c_double, C.c_void_p, C.c_void_p]
         L.ref_set_max_step.argtypes = [C.c_double]
+        L.ref_set_maxstep_ctrl.argtypes = [C.c_double] * 6
         L.ref_create_from_tables.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
         self.fbr = bool(L.ref_is_fbr())
         assert self.fbr == fbr
@@ -269,6 +270,10 @@ class RefModel:
     # -- integrator ------------------------------------------------------------
     def set_cvode_param(self):
         self.lib.ref_set_cvode_param()
+
+    def set_maxstep_ctrl(self, stmin=1.0, nncfn=0.0, nnimax=3.0, nnimin=1.0, decr=1.2, incr=1.2):
+        """the AdjCVodeMaxStep parameters (ctrl_struct; the reference reads them from the .para file)"""
+        self.lib.ref_set_maxstep_ctrl(stmin, nncfn, nnimax, nnimin, decr, incr)
 
     def set_max_step(self, h):
         self.lib.ref_set_max_step(float(h))

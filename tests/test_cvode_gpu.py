@@ -128,6 +128,47 @@ def test_reinit_and_max_step_controller():
     cv.close(); model.close()
 
 
+@pytest.mark.parametrize("ctl", [dict(stmin=1.0, nncfn=0.0, nnimax=3.0, nnimin=1.0, decr=1.2, incr=1.2),
+                                 dict(stmin=5.0, nncfn=0.0, nnimax=1.5, nnimin=1.2, decr=1.5, incr=1.1)])
+def test_adj_cvode_max_step_vs_reference(ctl):
+    """AdjCVodeMaxStep (src/ode.c:500-560) against the reference's own controller: ref_model_step(adj_max_step=1)
+    calls the unmodified function after every model step; in the lock-step phase of the 2400-triangle run
+    (identical counters) the two maxstep sequences must be identical, value for value.  The second parameter
+    set makes the controller move in both directions."""
+    import reflib
+    if not reflib.available(False):
+        pytest.skip("oracle/_ref not present")
+    tb = W.make_named("small", dirichlet_edges=True)
+    ne, nr = tb["nelem"], tb["nriver"]
+    ref = reflib.RefModel(fbr=False).create_from_tables(tb)
+    ref.set_maxstep_ctrl(**ctl)
+    ref.init_state(tb["y0"]); ref.set_ovlflow(np.zeros((3, ne))); ref.set_cvode_param()
+    model = lib.Model(tb, reorder=1)
+    cv = lib.Cvode(model)
+    y = model.N_VNew(tb["y0"])
+    cv.SetCVodeParam(y, **ctl)
+    seq = []
+    for k in range(15):
+        if k % 15 == 0:
+            f = W.storm_forcing(tb, k * 60.0)
+            model.set_forcing(f, np.zeros(nr))
+        fr = f.copy(); fr[W.F_WS0SURF] = ref.get_ws()[:ne]
+        ref.set_forcing(fr, np.zeros(nr))
+        ref.model_step(k, adj_max_step=True)
+        model.Summary(y)
+        cv.SolveCVode((k + 1) * 60.0, y)
+        hmax = cv.AdjCVodeMaxStep()
+        sr, sg = ref.stats(), cv.stats()
+        assert [sg[q] for q in ("nst", "nni", "ncfn", "nfe")] == [sr[q] for q in ("nst", "nni", "ncfn", "nfe")], \
+            f"step {k}: counters left lock step"
+        assert hmax == ref.ctrl()["maxstep"], f"step {k}: maxstep {hmax} vs reference {ref.ctrl()['maxstep']}"
+        seq.append(hmax)
+    print("maxstep sequence:", seq)
+    if ctl["nnimax"] < 3.0:
+        assert min(seq) < 60.0, "the controller never moved"
+    ref.close(); cv.close(); model.close()
+
+
 def test_100k_lockstep_with_live_reference():
     """BASELINE config[1]: synthetic 100k-triangle watershed with river network on 1 B200,
     RHS + CVODE correctness against the reference run on the same box (oracle/_ref)."""

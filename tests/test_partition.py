@@ -63,6 +63,16 @@ def test_local_meshes_reproduce_global_rhs(fbr, nparts):
         ol = oraclelib.OracleModel(p)
         ol.set_forcing(forc[:, p["elem_gid"]], np.zeros(rl))
         own = PT.state_index(p["nown_elem"], p["nown_riv"], fbr, np.arange(nl), np.arange(rl), nl, rl)
+        # the helpers of the GPU tests: whole-local-mesh state, owned positions in it, ghost records
+        assert np.array_equal(PT.local_state(p, y, extended=True), y[idx])
+        assert np.array_equal(PT.owned_in_local(p), own)
+        assert np.array_equal(PT.local_state(p, y, extended=True)[own], PT.local_state(p, y))
+        ge, gr = PT.ghost_records(p, y)
+        gs = 3 if fbr else 2
+        no_, ro_ = p["nown_elem"], p["nown_riv"]
+        assert np.array_equal(ge.reshape(-1, gs)[:, 0], y[idx][no_:nl])
+        assert np.array_equal(ge.reshape(-1, gs)[:, 1], y[idx][2 * nl + no_:3 * nl])
+        assert np.array_equal(gr.reshape(-1, 2)[:, 0], y[idx][3 * nl + ro_:3 * nl + rl])
         assert np.array_equal(ol.ode(y[idx])[own], dy1[p["state_idx"]])
         assert np.array_equal(ol.ode(y[idx])[own], dy2[p["state_idx"]])   # stale river-edge flows carried locally
         # Summary()/MassBalance() of the owned elements from the local fluxes = the global ones

@@ -76,6 +76,8 @@ def test_rhs_vs_oracle_variants(fbr, modes, riv_order):
                           riv_mode=modes[1], riv_order=riv_order, trib_every=8)
     ne, nr = tb["nelem"], tb["nriver"]
     tb["elem_i32"][W.EI_BC2, 0] = -1
+    if fbr:     # FbrBoundFluxElem's Neumann branch (lat_flow.c:392-424): a prescribed bedrock flux on the same edge
+        tb["elem_i32"][W.EI_FBRBC2, 0] = -1
     tb["riv_i32"][W.RI_BCTYPE, 3] = 1
     tb["riv_i32"][W.RI_BCTYPE, 5] = -1
     rng = np.random.default_rng(riv_order + 10 * fbr)
@@ -86,6 +88,8 @@ def test_rhs_vs_oracle_variants(fbr, modes, riv_order):
         y = W.wet_state(tb, seed=outlet + 20)
         forc = W.storm_forcing(tb, 3 * 3600.0, ws0_surf=np.maximum(y[:ne], 0))
         forc[W.F_BC2, 0] = 1e-5
+        if fbr:
+            forc[W.F_FBRBC2, 0] = 3e-6
         rivbc = rng.uniform(0.0, 1e-3, nr)
         rivbc[3] = tb["riv_f64"][W.R_ZBED, 3] - 0.3
         rivbc[23] = tb["riv_f64"][W.R_ZBED, 23] - 0.4 if outlet == -1 else 2e-3
@@ -183,6 +187,58 @@ def test_rhs_100k_vs_oracle(fbr):
     c = _oracle_case(tb, om, y, forc, np.zeros(tb["nriver"]), np.zeros((3, ne)))
     worst, exact = check_case(model, tb, c, "100k")
     print(f"100k fbr={fbr}: max rel err {worst:.2e}; bit-exact fraction {exact:.4f}")
+    model.close()
+
+
+@pytest.mark.parametrize("fbr", [False, True])
+def test_rhs_1m_vs_oracle(fbr):
+    """BASELINE configs [2] and [3]: the 1M-triangle benchmark mesh (pihm and pihm-fbr) against the oracle
+    port on two seeded states."""
+    tb = W.make_named("1M", fbr=fbr)
+    ne, nr = tb["nelem"], tb["nriver"]
+    om = oraclelib.OracleModel(tb)
+    model = lib.Model(tb, reorder=1)
+    worst = 0.0
+    for seed in (11, 12):
+        y = W.wet_state(tb, seed=seed)
+        forc = W.storm_forcing(tb, 3 * 3600.0, ws0_surf=np.maximum(y[:ne], 0))
+        c = _oracle_case(tb, om, y, forc, np.zeros(nr), np.zeros((3, ne)))
+        w, exact = check_case(model, tb, c, f"1M fbr={fbr} seed {seed}")
+        worst = max(worst, w)
+        print(f"1M fbr={fbr} seed {seed}: max rel err {w:.2e}; bit-exact fraction {exact:.4f}; "
+              f"slow-path elements {model.slow_path_count()}")
+    assert worst <= RTOL
+    model.close()
+
+
+def test_rhs_8m_partition_vs_oracle():
+    """BASELINE config[4]: one rank's share of the 8M-triangle mesh split over 8 GPUs (1M owned triangles +
+    two rings of ghosts), ghost records as the halo exchange delivers them, against the oracle port run on
+    the same local mesh (owned + ghosts as a plain mesh: its owned components are those of the global RHS)."""
+    from mm_pihm_b200 import partition as PT
+    tb = W.make_named("8M")
+    ne, nr = tb["nelem"], tb["nriver"]
+    y = W.wet_state(tb, seed=5)
+    part = PT.partition(tb, 8, parts=[3])[0]
+    forc = W.storm_forcing(tb, 3 * 3600.0, ws0_surf=np.maximum(y[:ne], 0))[:, part["elem_gid"]]
+    del tb
+    nl, rl = part["nelem"], part["nriver"]
+    own = PT.owned_in_local(part)
+    yl = PT.local_state(part, y, extended=True)
+    om = oraclelib.OracleModel(part)
+    c = _oracle_case(part, om, yl, forc, np.zeros(rl), np.zeros((3, nl)))
+    scale = dy_scale(part, forc, c["xflux"], c["rivflow"])[own]
+    model = lib.Model(part)
+    model.set_forcing(forc, np.zeros(rl))
+    model.set_ghosts(*PT.ghost_records(part, y))
+    yv = model.N_VNew(PT.local_state(part, y)); dv = model.N_VNew()
+    model.ode_dev(0.0, yv, dv)
+    dy = dv.download()
+    assert model.check_nan() == 0
+    err = rel_err(dy, c["dy"][own], scale)
+    print(f"8M/8 partition ({part['nown_elem']} owned + {nl - part['nown_elem']} ghost elements): max rel err "
+          f"{err.max():.2e}; bit-exact fraction {np.mean(dy == c['dy'][own]):.4f}")
+    assert err.max() <= RTOL, f"rel err {err.max():.3e} at {err.argmax()}"
     model.close()
 
 
