@@ -61,6 +61,19 @@ def forcing_at(tb, k):
     return W.storm_forcing(tb, T0 + k * STEP)
 
 
+def workload_config(size, fbr, ne_glob, nr_glob, world):
+    """the `config` object -- identical in both arms (the driver compares them)"""
+    txt = (f"pihm{'-fbr' if fbr else ''} synthetic {size}-triangle watershed ({ne_glob} elements, {nr_glob} river "
+           f"segments), 60 s model steps (SolveCVode + Summary/MassBalance) in the rain pulse (t0 = 2 h), "
+           f"reltol 1e-3 abstol 1e-4")
+    if world > 1:
+        txt += (f"; weak scaling: 1M triangles per GPU, mesh partitioned over {world} GPUs; "
+                f"value = sim-days/s x (triangles / 1M)")
+    return {"workload": txt, "nelem": ne_glob, "nriver": nr_glob,
+            "nsv": (5 if fbr else 3) * ne_glob + 2 * nr_glob, "parallelism": f"mesh-partition x{world}",
+            "l2": "RHS working set 376 B x nelem and 21 state-sized vectors exceed the 126 MB L2"}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
@@ -168,6 +181,8 @@ def run_ours(args):
     y = model.N_VNew(y0)
     tb["y0"] = y0
     K, Wu = args.steps, args.warmup
+    model.set_diagnostics(True)     # Summary() + MassBalance() on the device after every step (update.c:3-160)
+    paths = model.comm_paths() if world > 1 else {"halo": None}
 
     def barrier():
         if world > 1:
@@ -185,6 +200,7 @@ def run_ours(args):
         y.upload(tb["y0"])
         model.set_stale_ovlflow(np.zeros((3, ne)))
         model.set_forcing(forcing_at(tb, 0), np.zeros(nr))
+        model.set_ws0(y)                # after the forcing table: its ws0.surf column is a placeholder
         cv.SetCVodeParam(y)
 
     # forcing tables of every LSM step (15 model steps) the run crosses, generated before any
@@ -199,8 +215,9 @@ def run_ours(args):
                 model.set_forcing_col(c, host_forc[c])
         elif k % 15 == 0:
             model.set_forcing(forc_host[k], rivbc0)
-        model.Summary(y)
+            model.Summary(y)            # the table's ws0.surf column is a placeholder: ws0.surf = y[SURF] again
         cv.SolveCVode((k + 1) * STEP, y)
+        model.SummaryMB(y, STEP)        # like the reference's step (pihm.c:53-57): mass balance, ws0 <- y
         if e2e:
             model.L.pihm_b200_vec_download(y.h, host_y.ctypes.data)
 
@@ -260,14 +277,38 @@ def run_ours(args):
     ev1.record(stream)
     barrier()
     rhs_ms = max_over_ranks(ev0.elapsed_time(ev1)) / nrep
+
+    # ---- the same kernels in situ: events around every RHS evaluation the integrator issues, and the
+    # host time spent at its synchronisation points (a few steps; not part of the timed regions above)
+    reset()
+    for k in range(2):
+        step(k)
+    cv.profile(True)
+    nprof = min(K, 10)
+    for k in range(2, 2 + nprof):
+        step(k)
+    pf = cv.get_profile()
+    cv.profile(False)
+    rhs_ms_in_situ = max_over_ranks(pf["rhs_ms"] / max(pf["rhs_evals"], 1))
+    host_wait_ms = max_over_ranks(pf["host_wait_ms"] / nprof)
     peak, peak_src = measured_peak()
-    achieved = B_RHS[fbr] * model.nown_elem / (rhs_ms * 1e-3) / 1e9      # per GPU
+    nown_elem, nsv_local = model.nown_elem, model.nsv
+    achieved = B_RHS[fbr] * nown_elem / (rhs_ms * 1e-3) / 1e9      # per GPU
     if world > 1:
         tot = torch.tensor([float(rhs_evals), float(l1 - l0)], dtype=torch.float64, device="cuda")
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
         rhs_evals = int(tot[0].item())
+    cv.close(); model.close()
+    del cv, model, y, yd
+    # ---- strong scaling side figure: the 8M-triangle mesh of BASELINE config[4] on these N GPUs
+    strong = None
+    if not args.no_strong and not fbr:
+        if world == 8 and size == "8M":
+            strong = {"mesh": "8M", "ms_per_step": ms / K, "ms_per_rhs_eval": ms / max(rhs_evals, 1),
+                      "rhs_evals_per_step": rhs_evals / K, "rhs_ms": rhs_ms, "steps": K, "same_as": "main run"}
+        else:
+            strong = strong_scaling_leg(args, rank, world, local, stream, barrier, max_over_ranks)
     if rank != 0:
-        cv.close(); model.close()
         dist.destroy_process_group()
         return
 
@@ -276,36 +317,92 @@ def run_ours(args):
         "value": value, "unit": "sim-days/s", "n_gpus": world, "steps": K, "warmup": Wu,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"pihm{'-fbr' if fbr else ''} synthetic {size}-triangle watershed "
-                               f"({ne_glob} elements, {nr_glob} river segments), 60 s model steps in the rain pulse "
-                               f"(t0 = 2 h), reltol 1e-3 abstol 1e-4"
-                               + (f"; mesh partitioned over {world} GPUs (1M triangles each), halo exchange per RHS "
-                                  f"and scalar all-reduce per norm over NVLink peer memory inside our kernels (NCCL: setup, "
-                                  f"fallback); value = sim-days/s x (triangles / 1M)"
-                                  if world > 1 else ""),
-                   "nelem": ne_glob, "nriver": nr_glob, "nsv": model.nsv_global if world > 1 else model.nsv,
-                   "reorder": args.reorder, "parallelism": f"mesh-partition x{world}",
-                   "l2": "RHS working set 376 B x nelem and 21 state-sized vectors exceed the 126 MB L2"},
+        "config": workload_config(size, fbr, ne_glob, nr_glob, world),
         "rhs_evals_per_s": rhs_evals / (ms * 1e-3), "rhs_evals": rhs_evals, "cvode_steps": nst,
-        "rhs_ms": rhs_ms,
+        "ms_per_rhs_eval": ms / max(rhs_evals, 1),      # whole step / evaluations: RHS + vector kernels + host
+        "rhs_ms": rhs_ms,                               # k_pre + k_main, back to back (30 calls, same input)
+        "rhs_ms_in_situ": rhs_ms_in_situ,               # the same pair inside the integrator (event to event)
+        "host_wait_ms_per_step": host_wait_ms,          # host time at the integrator's synchronisation points
+        "halo_path": paths["halo"], "allreduce_path": paths["halo"],     # p2p: inside our kernels over NVLink peer memory
+        "strong_scaling_8M": strong,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": RHS_TRAFFIC_BYTES.get((size, fbr)),
                      "kernel": "k_pre + k_main (one RHS evaluation, per GPU)",
                      "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": B_RHS[fbr] * model.nown_elem,
+                     "algorithmic_bytes_per_launch": B_RHS[fbr] * nown_elem,
+                     "frac_in_situ": B_RHS[fbr] * nown_elem / (rhs_ms_in_situ * 1e-3) / 1e9 / peak,
                      "traffic_source": "profiles/r01g_rhs_1M_ncu_summary.md (pihm) / r01d (fbr): ncu --set full, dram read+write"},
         "fp64": fp64_side(size, fbr, rhs_ms, clk),
         "e2e": {"value": e2e_value, "unit": "sim-days/s", "ms_per_step": ms_e2e / K,
-                "h2d_bytes_per_step": 3 * 8 * ne, "d2h_bytes_per_step": 8 * model.nsv},
+                "h2d_bytes_per_step": 3 * 8 * ne, "d2h_bytes_per_step": 8 * nsv_local},
         "gpu_launches": int(l1 - l0),
         "clocks": clk,
     }
     if not args.no_cpu and world == 1:
         out["cpu_baseline"] = cpu_reference(tb, fbr, steps=args.cpu_steps, warmup=Wu)
     print(json.dumps(out))
-    cv.close(); model.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def strong_scaling_leg(args, rank, world, local, stream, barrier, max_over_ranks, steps=6, warmup=3):
+    """BASELINE config[4] / north_star '>= 6x on 8 B200 for an 8M-triangle mesh': the SAME 8M mesh on the N GPUs of
+    this run (N = 1: unpartitioned), a few model steps of the same storm; ms per step and per RHS evaluation."""
+    import torch
+    import torch.distributed as dist
+    from mm_pihm_b200 import lib, partition as PT
+    tb = W.make_named("8M")
+    nr = tb["nriver"]
+    if world > 1:
+        part = PT.partition(tb, world, parts=[rank])[0]
+        y0 = tb["y0"][part["state_idx"]]
+        tb = part
+        model = lib.Model(tb, device=local)
+        uid = [lib.Model.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        model.comm_init(rank, world, uid[0])
+    else:
+        y0 = tb["y0"]
+        model = lib.Model(tb, device=local, reorder=args.reorder)
+    ne, nr = tb["nelem"], tb["nriver"]
+    model.set_stream(stream.cuda_stream)
+    model.set_diagnostics(True)
+    cv = lib.Cvode(model)
+    y = model.N_VNew(y0)
+    model.set_stale_ovlflow(np.zeros((3, ne)))
+    model.set_forcing(forcing_at(tb, 0), np.zeros(nr))
+    model.set_ws0(y)
+    cv.SetCVodeParam(y)
+
+    def step(k):
+        cv.SolveCVode((k + 1) * STEP, y)
+        model.SummaryMB(y, STEP)
+    for k in range(warmup):
+        step(k)
+    st0 = cv.stats()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for k in range(warmup, warmup + steps):
+        step(k)
+    ev1.record(stream)
+    barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    st1 = cv.stats()
+    evals = (st1["nfe"] + st1["nfeLS"]) - (st0["nfe"] + st0["nfeLS"])
+    yd = model.N_VNew()
+    for _ in range(3):
+        model.ode_dev(0.0, y, yd)
+    barrier()
+    ev0.record(stream)
+    for _ in range(20):
+        model.ode_dev(0.0, y, yd)
+    ev1.record(stream)
+    barrier()
+    rhs_ms = max_over_ranks(ev0.elapsed_time(ev1)) / 20
+    cv.close(); model.close()
+    return {"mesh": "8M", "ms_per_step": ms / steps, "ms_per_rhs_eval": ms / max(evals, 1),
+            "rhs_evals_per_step": evals / steps, "rhs_ms": rhs_ms, "steps": steps, "warmup": warmup}
 
 
 # --------------------------------------------------------------------------- reference / CPU baseline
@@ -352,19 +449,19 @@ def run_reference(args):
     tb = W.make_named(size, fbr=fbr)
     steps = min(args.steps, args.ref_max_steps)
     cb = cpu_reference(tb, fbr, steps=steps, warmup=args.warmup)
+    # same scaling of the metric as our arm: sim-days/s x (triangles / 1M) when the job carries N x 1M triangles
+    scale = tb["nelem"] / 1.0e6 if args.gpus > 1 else 1.0
     out = {
         "impl": "reference",
         "metric": "simulated days/wall-sec at 1M triangles; RHS evals/s and achieved HBM GB/s",
-        "value": cb["value"] * (tb["nelem"] / 1.0e6 if args.gpus > 1 else 1.0), "unit": "sim-days/s",
+        "value": cb["value"] * scale, "unit": "sim-days/s",
         "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"pihm{'-fbr' if fbr else ''} synthetic {args.size}-triangle watershed "
-                               f"({tb['nelem']} elements, {tb['nriver']} river segments), 60 s model steps in "
-                               f"the rain pulse (t0 = 2 h), reltol 1e-3 abstol 1e-4"},
+        "config": workload_config(size, fbr, tb["nelem"], tb["nriver"], args.gpus),
         "rhs_evals_per_s": cb["rhs_evals_per_s"],
         "cpu_baseline": cb,
-        "e2e": {"value": cb["value"], "unit": "sim-days/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": cb["value"] * scale, "unit": "sim-days/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out))
 
@@ -379,6 +476,7 @@ def main():
     ap.add_argument("--fbr", action="store_true")
     ap.add_argument("--reorder", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-strong", action="store_true", help="skip the 8M strong-scaling side figure")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--ref-max-steps", type=int, default=30)
     args = ap.parse_args()

@@ -466,6 +466,12 @@ int             pihm_b200_spgmr_solve(pihm_b200_cvode *cv, double tn,
                                       const pihm_b200_vec *weight,
                                       const pihm_b200_vec *ycur,
                                       const pihm_b200_vec *fcur);
+/* In-situ profile of the integrator (no reference counterpart; bench.py): CUDA events around each
+ * RHS evaluation it issues and the host time spent at its synchronisation points.  on = 1 clears
+ * the accumulators.  out5 = {ms inside cvode_solve, ms of host waiting, number of host
+ * synchronisations, ms of RHS kernels event to event, RHS evaluations timed}. */
+int             pihm_b200_cvode_profile(pihm_b200_cvode *cv, int on);
+int             pihm_b200_cvode_get_profile(pihm_b200_cvode *cv, double *out5);
 /* AdjCVodeMaxStep (ode.c:500-560) on the integrator's own counters */
 typedef struct pihm_b200_maxstep_ctrl {
     double          maxstep, stepsize, stmin, nncfn, nnimax, nnimin, decr, incr;

@@ -89,6 +89,7 @@ struct DevMesh {
     const int *ri;       // [PB_RI_NCOL][nrs]  LEFT/RIGHT = internal element idx
     const double *rivbc; // [nrs]
     const double *fbr_dist;  // [nrs] nabrdist(left bank) + nabrdist(right bank)
+    const double *dist_cold; // [3][nes] nabrdist (boundary edges / exact path; the tiles carry 1 / nabrdist)
     const int *up_ptr;   // [nr+1] CSR of upstream segments, ascending index
     const int *up_idx;
     double *rivflow;     // [11][nrs]
@@ -147,6 +148,7 @@ namespace pb {
 // rhs_kernels.cu: the RHS kernels live in their own translation unit (own -fmad setting)
 int rhs_configure(pihm_b200_ctx *ctx, int sms);
 int rhs_class_rcp(pihm_b200_ctx *ctx);
+int rhs_tile_rcp(pihm_b200_ctx *ctx);
 int rhs_halo_pack(pihm_b200_ctx *ctx, const double *y);
 int rhs_launch(pihm_b200_ctx *ctx, const double *y, double *dy, bool replay);
 }  // namespace pb
@@ -184,6 +186,7 @@ struct pihm_b200_ctx {
     std::vector<int> iperm;            // reference element -> internal element
     std::vector<int> riv_left_edge, riv_right_edge;   // edge slot of each bank
     // device allocations
+    double *d_dist_cold = nullptr;
     double *d_es = nullptr, *d_ft = nullptr, *d_forc = nullptr, *d_rf = nullptr, *d_rivbc = nullptr;
     double4 *d_snb = nullptr, *d_dnb = nullptr;
     double *d_cls = nullptr;

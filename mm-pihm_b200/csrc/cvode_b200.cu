@@ -1315,7 +1315,7 @@ void pihm_b200_cvode_destroy(pihm_b200_cvode *cv)
     pb::note_free(cv->ctx, cv->zn[0]);  // the vectors go away: keep the last RHS input if it is one of them
     pb::note_free(cv->ctx, cv->ytemp);
     cudaStreamSynchronize(cv->ctx->s());
-    if (cv->prof) {
+    if (cv->prof && getenv("PIHM_B200_PROFILE")) {
         double rhs_ms = 0.0;
         for (size_t i = 0; i + 1 < cv->prof_used; i += 2) {
             float ms = 0.f;
@@ -1326,8 +1326,9 @@ void pihm_b200_cvode_destroy(pihm_b200_cvode *cv)
                         "rhs(in situ) %.3f ms over %zu evals (%.1f us each)  launches %lld\n",
                 cv->prof_solve_ns * 1e-6, cv->prof_wait_ns * 1e-6, cv->prof_nsync, rhs_ms, cv->prof_used / 2,
                 cv->prof_used ? rhs_ms * 2e3 / cv->prof_used : 0.0, (long long)cv->ctx->launches);
-        for (cudaEvent_t e : cv->prof_ev) cudaEventDestroy(e);
     }
+    for (cudaEvent_t e : cv->prof_ev) cudaEventDestroy(e);
+    cv->prof_ev.clear();
     double *all[] = {cv->zn[0], cv->zn[1], cv->zn[2], cv->zn[3], cv->zn[4], cv->zn[5], cv->ewt, cv->acor,
                      cv->tempv, cv->ftemp, cv->V[0], cv->V[1], cv->V[2], cv->V[3], cv->V[4], cv->V[5],
                      cv->vtemp, cv->ytemp, cv->d_part, cv->d_sc};
@@ -1480,6 +1481,42 @@ int pihm_b200_cvode_get_stats(const pihm_b200_cvode *cv, pihm_b200_cvode_stats *
     st->nor = cv->nor; st->nsetups = cv->nsetups;
     st->qlast = cv->qu; st->qcur = cv->next_q;
     st->hlast = cv->hu; st->hcur = cv->next_h; st->tcur = cv->tn;
+    return 0;
+}
+
+// In-situ profile (bench.py): CUDA events around every RHS evaluation the integrator issues and the
+// host time spent waiting at its synchronisation points.  Switching it on clears the accumulators.
+int pihm_b200_cvode_profile(pihm_b200_cvode *cv, int on)
+{
+    if (!cv) return -1;
+    cudaStreamSynchronize(cv->ctx->s());
+    if (on && cv->prof_ev.empty()) {
+        cv->prof_ev.resize(16384);
+        for (cudaEvent_t &ev : cv->prof_ev)
+            if (cudaEventCreate(&ev) != cudaSuccess) { set_error("cvode_profile: cudaEventCreate"); return -1; }
+    }
+    cv->prof = on != 0;
+    if (on) { cv->prof_used = 0; cv->prof_nsync = 0; cv->prof_wait_ns = 0; cv->prof_solve_ns = 0; }
+    return 0;
+}
+
+// out[0] ms inside pihm_b200_cvode_solve, out[1] ms of host waiting in out[2] synchronisations,
+// out[3] ms of RHS kernels (k_pre + k_main, event to event) over out[4] timed evaluations
+int pihm_b200_cvode_get_profile(pihm_b200_cvode *cv, double *out5)
+{
+    if (!cv || !out5) return -1;
+    cudaStreamSynchronize(cv->ctx->s());
+    double rhs_ms = 0.0;
+    for (size_t i = 0; i + 1 < cv->prof_used; i += 2) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, cv->prof_ev[i], cv->prof_ev[i + 1]);
+        rhs_ms += ms;
+    }
+    out5[0] = cv->prof_solve_ns * 1e-6;
+    out5[1] = cv->prof_wait_ns * 1e-6;
+    out5[2] = (double)cv->prof_nsync;
+    out5[3] = rhs_ms;
+    out5[4] = (double)(cv->prof_used / 2);
     return 0;
 }
 

@@ -338,6 +338,7 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
         ctx->d_snb = ctx->d_dnb + nes;
         if (cudaMemcpy(ctx->d_snb, snb.data(), sizeof(double4) * nes, cudaMemcpyHostToDevice) != cudaSuccess) rc = -1;
     }
+    zalloc((void **)&ctx->d_dist_cold, sizeof(double) * 3 * nes);
     zalloc((void **)&ctx->d_rivflow, sizeof(double) * PIHM_B200_NUM_RIVFLX * nrs);
     zalloc((void **)&ctx->d_stale, sizeof(double) * 2 * nrs);
     zalloc((void **)&ctx->d_nan, sizeof(int) * 4);
@@ -361,9 +362,11 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
     }
     dm.es = ctx->d_es; dm.ft = ctx->d_ft; dm.snb = ctx->d_snb; dm.dnb = ctx->d_dnb; dm.cls = ctx->d_cls; dm.cid = ctx->d_cid; dm.bct = ctx->d_bct; dm.fbct = ctx->d_fbct;
     dm.forc = ctx->d_forc; dm.rf = ctx->d_rf; dm.ri = ctx->d_ri; dm.rivbc = ctx->d_rivbc;
+    dm.dist_cold = ctx->d_dist_cold;
     dm.fbr_dist = ctx->d_fbr_dist; dm.up_ptr = ctx->d_up_ptr; dm.up_idx = ctx->d_up_idx;
     dm.rivflow = ctx->d_rivflow; dm.s2c_stale = ctx->d_stale;
-    if (pb::rhs_class_rcp(ctx) != 0) {      // reciprocals of the dictionary's divisors and of DEPRSTG / dt
+    if (pb::rhs_tile_rcp(ctx) != 0 ||       // reciprocals of the element areas and neighbour distances
+        pb::rhs_class_rcp(ctx) != 0) {      // reciprocals of the dictionary's divisors and of DEPRSTG / dt
         set_error("pihm_b200_create: class dictionary set-up failed");
         pihm_b200_destroy(ctx);
         return nullptr;
@@ -431,7 +434,7 @@ void pihm_b200_destroy(pihm_b200_ctx *ctx)
     if (ctx->l2_on) cudaCtxResetPersistingL2Cache();   // hand the set-aside lines back
     pihm_b200_vec_free(ctx->y_tmp);
     pihm_b200_vec_free(ctx->yd_tmp);
-    void *dev[] = {ctx->d_es, ctx->d_ft, ctx->d_dnb, ctx->d_cls, ctx->d_cid, ctx->d_forc, ctx->d_rf, ctx->d_rivbc, ctx->d_fbr_dist,
+    void *dev[] = {ctx->d_dist_cold, ctx->d_es, ctx->d_ft, ctx->d_dnb, ctx->d_cls, ctx->d_cid, ctx->d_forc, ctx->d_rf, ctx->d_rivbc, ctx->d_fbr_dist,
                    ctx->d_bct, ctx->d_fbct, ctx->d_ri, ctx->d_up_ptr, ctx->d_up_idx,
                    ctx->d_rivflow, ctx->d_stale, ctx->d_xflux, ctx->d_nan, ctx->d_perm,
                    ctx->d_iperm, ctx->d_stage, ctx->d_red, ctx->d_gel, ctx->d_gri, ctx->d_send_e, ctx->d_send_r,

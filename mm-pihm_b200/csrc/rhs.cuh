@@ -573,7 +573,13 @@ template <bool FAST>
 __device__ __forceinline__ double surf_h_a(Arith<FAST> &A, double surfeqv)
 {
     if (!FAST) return surf_h(surfeqv);
-    const double lo = A.sqrtp(2.0 * PB_DEPRSTG * ((surfeqv > 0.0) ? surfeqv : 0.0));
+    // the root is needed only for 0 < surfeqv <= DEPRSTG / 2 (sqrt(0) = 0): when no lane of the warp
+    // is in that range -- ponded or dry ground -- the whole warp skips it (same bits either way)
+    double lo = 0.0;
+#ifdef PB_SQRT_VOTE       // (measured: with mixed states the vote costs more than the skipped roots give)
+    if (__any_sync(__activemask(), surfeqv > 0.0 && surfeqv <= 0.5 * PB_DEPRSTG))
+#endif
+        lo = A.sqrtp(2.0 * PB_DEPRSTG * ((surfeqv > 0.0) ? surfeqv : 0.0));
     const double hi = PB_DEPRSTG + (surfeqv - 0.5 * PB_DEPRSTG);
     return (surfeqv < 0.0) ? 0.0 : ((surfeqv <= 0.5 * PB_DEPRSTG) ? lo : hi);
 }
@@ -707,7 +713,7 @@ __device__ __forceinline__ bool elem_pre(const DevMesh &m, const double *__restr
     // the element's own state only: placed ahead of the friction slope, its FP64 chain runs
     // while the neighbour gathers are in flight.
     const double hd = (surfh > PB_DEPRSTG) ? 1.0 * (surfh - PB_DEPRSTG) : 0.0;
-    const double p23 = A.powp(hd, 0.6666667);
+    const double p23 = A.pow23(hd);
 #pragma unroll
     for (int j = 0; j < 3; j++) { PB_AFTER(ysn[j], p23); PB_AFTER(zmaxn[j], p23); }
     double sf = 0.0;
@@ -780,6 +786,7 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
     // them the tile's own state columns (ys bit 0: gw [, fbr_gw], bit 1: unsat [, fbr_unsat]
     // arrived with the stage; otherwise they are read from y) and its own dynamic records
 #define EC(c) st[((c) - TS_MAIN0) * PB_TILE]
+#define DISTC(j) m.dist_cold[(size_t)(j) * m.nes + i]
     Arith<FAST> A;
     mbar_wait(bar, phase);      // static + forcing slabs have landed
     // ---- loads: neighbour codes, then all gathers (unconditional) ---------------
@@ -851,7 +858,9 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
     const double depth = EC(TS_DEPTH), dinf = EC(TS_DINF);
     const double rough = c_por.y;
     const double pcpdrp = f[0 * PB_TILE];
-    const double r_area = A.rcp(area);
+    // (FAST: the refined reciprocals of the static divisors come with the tile; a NaN marks one outside
+    // the fast division's domain and sends the element to the exact path)
+    const double r_area = FAST ? EC(TS_RAREA) : 0.0;
 
     // EtExtract (non-Noah), hydrol.c:51-87
     double edir_surf = 0.0, edir_unsat = 0.0, edir_gw = 0.0, ett_unsat = 0.0, ett_gw = 0.0;
@@ -941,8 +950,10 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
 #pragma unroll
         for (int j = 0; j < 3; j++) {
             const double edge = EC(TS_EDGE0 + j);
-            const double dist = (code[j] >= 0) ? EC(TS_NABRDIST0 + j) : 1.0;
-            const double r_dist = A.rcp(dist);
+            const double r_dist = FAST ? EC(TS_RDIST0 + j) : 0.0;
+            // the distance itself: exact path only (and the fast one of a build without PB_RELAX & 1)
+            const double dist = (!FAST || !(PB_RELAX & 1)) ? ((code[j] >= 0) ? DISTC(j) : 1.0) : 1.0;
+            if (FAST) A.ok = A.ok && (r_dist == r_dist);
             if (FBR && FAST) {
                 // FbrFlowElemToElem, lat_flow.c:374-390 (an edge without an element behind it
                 // sees the element itself: zero; boundary and river edges are patched below)
@@ -973,14 +984,22 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
             }
             const double avg_rough = 0.5 * (rough + sn[j].z);
             p[j] = (diff_h > 0.0) ? own.w : dn[j].w;   // pow(avgh, 0.6666667) of the upwind element (k_pre)
+#if PB_RELAX & 64
+            den[j] = FAST ? A.rsqrt_times_rcp(avg_sf, avg_rough) : A.sqrtr(avg_sf) * avg_rough;   // FAST: 1 / den
+#else
             den[j] = A.sqrtr(avg_sf) * avg_rough;
+#endif
             num[j] = avgh * edge;                     // crossa; crossa * p * grad left to right (lat_flow.c:270)
             ovl_infil[j] = grad_h;                    // parked: grad_h of the overland flux
         }
         // OverLandFlow, lat_flow.c:267-271
 #pragma unroll
         for (int j = 0; j < 3; j++) {
+#if PB_RELAX & 64
+            ovl[j] = FAST ? num[j] * p[j] * ovl_infil[j] * den[j] : A.divr(num[j] * p[j] * ovl_infil[j], den[j]);
+#else
             ovl[j] = A.divr(num[j] * p[j] * ovl_infil[j], den[j]);
+#endif
             ovl_infil[j] = ovl[j];
         }
     }
@@ -997,7 +1016,7 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
                     const double head = FOC(PB_F_BC0 + j, i);
                     double diff_h = gw + zmin - head;
                     double avgh = avg_h(diff_h, gw, head - zmin);
-                    double grad_h = div_pos(diff_h, EC(TS_NABRDIST0 + j));
+                    double grad_h = div_pos(diff_h, DISTC(j));
                     sub[j] = effkh * grad_h * avgh * EC(TS_EDGE0 + j);
                 } else {
                     sub[j] = -FOC(PB_F_BC0 + j, i);
@@ -1176,7 +1195,7 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
                         const double head = FOC(PB_F_FBRBC0 + j, i);
                         double diff_h = fg + zbed - head;
                         double avgh = avg_h(diff_h, fg, head - zbed);
-                        double grad_h = div_pos(diff_h, EC(TS_NABRDIST0 + j));
+                        double grad_h = div_pos(diff_h, DISTC(j));
                         fbrflow[j] = gksath * grad_h * avgh * EC(TS_EDGE0 + j);
                     } else {
                         fbrflow[j] = -FOC(PB_F_FBRBC0 + j, i);
@@ -1251,7 +1270,7 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
                     const double head = FOC(PB_F_FBRBC0 + j, i);
                     double diff_h = fg + zbed - head;
                     double avgh = avg_h(diff_h, fg, head - zbed);
-                    double grad_h = div_pos(diff_h, EC(TS_NABRDIST0 + j));
+                    double grad_h = div_pos(diff_h, DISTC(j));
                     fbrflow[j] = gksath * grad_h * avgh * EC(TS_EDGE0 + j);
                 } else {
                     fbrflow[j] = -FOC(PB_F_FBRBC0 + j, i);
@@ -1261,7 +1280,7 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
                 double dist;
                 if (code[j] >= 0) {
                     n = code[j];
-                    dist = EC(TS_NABRDIST0 + j);
+                    dist = DISTC(j);
                 } else {
                     // neighbour across the river, lat_flow.c:85-100
                     const int r = (-code[j] - 2) >> 2;
@@ -1331,6 +1350,7 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
     }
     return true;
 #undef EC
+#undef DISTC
 }
 
 // the rare elements whose arithmetic left the fast-path domain: plain `/` and pow()
@@ -1763,6 +1783,23 @@ k_main(const DevMesh m, const double *__restrict__ y, double *__restrict__ dy, i
                 else tma_prefetch_l2(src, d.bytes);
             }
         }
+    }
+}
+
+// One-off: the tiles' RAREA / RDIST* slots.  The packer left the neighbour distances in RDIST*: they move to
+// the cold table, and the slot gets the refined reciprocal (of 1.0 on an edge without an element behind it:
+// LateralFlow's straight-line block sees the element itself there), NaN outside Arith<true>::rcp's domain.
+static __global__ void k_tile_rcp(double *es, double *dist_cold, int nes)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nes) return;
+    double *tile = es + (size_t)(i >> 5) * TS_NCOL * PB_TILE + (i & 31);
+    const int *nbs = reinterpret_cast<const int *>(es + ((size_t)(i >> 5) * TS_NCOL + TS_NB0) * PB_TILE);
+    tile[TS_RAREA * PB_TILE] = rcp_or_nan(tile[TS_AREA * PB_TILE]);
+    for (int j = 0; j < 3; j++) {
+        const double d = tile[(TS_RDIST0 + j) * PB_TILE];
+        dist_cold[(size_t)j * nes + i] = d;
+        tile[(TS_RDIST0 + j) * PB_TILE] = rcp_or_nan((nbs[j * PB_TILE + (i & 31)] >= 0) ? d : 1.0);
     }
 }
 

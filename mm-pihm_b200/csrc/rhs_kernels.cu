@@ -59,6 +59,14 @@ int rhs_class_rcp(pihm_b200_ctx *ctx)
     return 0;
 }
 
+// RAREA / RDIST* slots of the tiles and the cold distance table (k_tile_rcp)
+int rhs_tile_rcp(pihm_b200_ctx *ctx)
+{
+    const int nes = ctx->dm.nes;
+    k_tile_rcp<<<(nes + 255) / 256, 256>>>(ctx->d_es, ctx->d_dist_cold, nes);
+    return (cudaDeviceSynchronize() == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : -1;
+}
+
 // the packed send records of a state vector (NCCL transport / single-process emulation)
 int rhs_halo_pack(pihm_b200_ctx *ctx, const double *y)
 {

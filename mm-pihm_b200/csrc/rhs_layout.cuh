@@ -30,7 +30,10 @@ namespace pb {
 enum {   // k_pre reads [TS_PRE0, TS_PRE1), k_main [TS_MAIN0, TS_MAIN1 / TS_FBR1)
     TS_NABRX0 = 0, TS_NABRX1, TS_NABRX2, TS_NABRY0, TS_NABRY1, TS_NABRY2,
     TS_ZMAX, TS_DEPTH, TS_DMAC, TS_NB0, TS_NB1,     // NB0/NB1: int32 [4][32] = 3 neighbour codes + class id
-    TS_AREA, TS_DINF, TS_ZMIN, TS_EDGE0, TS_EDGE1, TS_EDGE2, TS_NABRDIST0, TS_NABRDIST1, TS_NABRDIST2,
+    // RAREA / RDIST*: refined reciprocals of the area and of the three neighbour distances (1.0 on an edge
+    // without an element behind it), filled on the device at create time (k_tile_rcp); the distances
+    // themselves are needed on boundary edges and by the exact path only: cold table DevMesh::dist_cold
+    TS_AREA, TS_RAREA, TS_DINF, TS_ZMIN, TS_EDGE0, TS_EDGE1, TS_EDGE2, TS_RDIST0, TS_RDIST1, TS_RDIST2,
     TS_ZBED, TS_GDEPTH,
     TS_NCOL,
     TS_PRE0 = TS_NABRX0, TS_PRE1 = TS_AREA, TS_MAIN0 = TS_ZMAX, TS_MAIN1 = TS_ZBED, TS_FBR1 = TS_NCOL
@@ -52,8 +55,8 @@ __host__ __device__ inline int tile_slot_of(int abi_col)
         case PB_E_AREA: return TS_AREA;  case PB_E_ZMIN: return TS_ZMIN;  case PB_E_ZMAX: return TS_ZMAX;
         case PB_E_ZBED: return TS_ZBED;
         case PB_E_EDGE0: return TS_EDGE0; case PB_E_EDGE1: return TS_EDGE1; case PB_E_EDGE2: return TS_EDGE2;
-        case PB_E_NABRDIST0: return TS_NABRDIST0; case PB_E_NABRDIST1: return TS_NABRDIST1;
-        case PB_E_NABRDIST2: return TS_NABRDIST2;
+        case PB_E_NABRDIST0: return TS_RDIST0; case PB_E_NABRDIST1: return TS_RDIST1;    // the packer stores the
+        case PB_E_NABRDIST2: return TS_RDIST2;      // distance; k_tile_rcp moves it to dist_cold and leaves 1 / d
         case PB_E_NABRX0: return TS_NABRX0; case PB_E_NABRX1: return TS_NABRX1; case PB_E_NABRX2: return TS_NABRX2;
         case PB_E_NABRY0: return TS_NABRY0; case PB_E_NABRY1: return TS_NABRY1; case PB_E_NABRY2: return TS_NABRY2;
         case PB_E_DEPTH: return TS_DEPTH; case PB_E_DINF: return TS_DINF; case PB_E_DMAC: return TS_DMAC;

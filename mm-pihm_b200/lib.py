@@ -149,6 +149,8 @@ _SIGS = {
     "pihm_b200_spgmr_solve": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pihm_b200_adj_cvode_max_step": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pihm_b200_cvode_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "pihm_b200_cvode_get_profile": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 # include/pihm_b200_sundials.h
 _SUNDIALS_SIGS = {
@@ -494,6 +496,14 @@ class Cvode:
     def AdjCVodeMaxStep(self):
         _check(self.L, self.L.pihm_b200_adj_cvode_max_step(self.h, C.byref(self.ctrl)), "adj_max_step")
         return self.ctrl.maxstep
+
+    def profile(self, on: bool = True):
+        _check(self.L, self.L.pihm_b200_cvode_profile(self.h, int(on)), "cvode_profile")
+
+    def get_profile(self) -> dict:
+        out = np.zeros(5)
+        _check(self.L, self.L.pihm_b200_cvode_get_profile(self.h, _ptr(out)), "cvode_get_profile")
+        return dict(solve_ms=out[0], host_wait_ms=out[1], host_syncs=int(out[2]), rhs_ms=out[3], rhs_evals=int(out[4]))
 
     def stats(self) -> dict:
         st = CvodeStats()
