@@ -216,6 +216,16 @@ __device__ __forceinline__ double avg_h(double diff, double hsub, double hnabr)
     return a;
 }
 
+// AvgH for heads that are already clamped at zero (max0): the inner tests are no-ops then
+__device__ __forceinline__ double avg_h_nn(double diff, double hsub, double hnabr)
+{
+#ifdef PB_AVGH_GENERIC
+    return avg_h(diff, hsub, hnabr);
+#else
+    return (diff > 0.0) ? hsub : hnabr;
+#endif
+}
+
 // DhByDl, src/lat_flow.c:227-234
 __device__ __forceinline__ double dh_by_dl(const double *l1, const double *l2, const double *h)
 {
@@ -960,13 +970,13 @@ __device__ __forceinline__ bool elem_main(const DevMesh &m, const double *__rest
                 const double gksath = __ldg(m.cls + (size_t)cid * CC_STRIDE + CC_GKSATH);
                 const double gk_n = __ldg(m.cls + (size_t)cidn[j] * CC_STRIDE + CC_GKSATH);
                 const double dfh = (fg + EC(TS_ZBED)) - (fgn[j] + sn[j].w);
-                fbrflow[j] = 0.5 * (gksath + gk_n) * A.divr(dfh, dist, r_dist) * avg_h(dfh, fg, fgn[j]) * edge;
+                fbrflow[j] = 0.5 * (gksath + gk_n) * A.divr(dfh, dist, r_dist) * avg_h_nn(dfh, fg, fgn[j]) * edge;
             }
             const double gw_n = gwn[j], surfh_n = dn[j].x;
             const double zmin_n = sn[j].x, zmax_n = sn[j].y;
             // SubFlowElemToElem, lat_flow.c:273-298
             double diff_h = (gw + zmin) - (gw_n + zmin_n);
-            double avgh = avg_h(diff_h, gw, gw_n);
+            double avgh = avg_h_nn(diff_h, gw, gw_n);
             double grad_h = A.divr(diff_h, dist, r_dist);
             double avg_ksat = 0.5 * (effkh + dn[j].y);
             sub[j] = avg_ksat * grad_h * avgh * edge;
@@ -1427,7 +1437,7 @@ __device__ __forceinline__ void river_main(const DevMesh &m, double *__restrict_
 #define PB_MAIN_MINB_FBR 2
 #endif
 #ifndef PB_MAIN_WARPS_FBR
-#define PB_MAIN_WARPS_FBR 8    // fbr: 8 warps x 2 CTAs at 128 registers (10 x 2 at 96 spills: +4 us)
+#define PB_MAIN_WARPS_FBR 10   // fbr: 10 warps x 2 CTAs at 96 registers (8 x 2 at 128: 134.6 -> 130.3 us at 1M, r02q)
 #endif
 
 #ifndef PB_RING_GROUP

@@ -13,7 +13,7 @@ tb = W.make_named(size)
 ne, nr = tb["nelem"], tb["nriver"]
 m = lib.Model(tb, reorder=1)
 cv = lib.Cvode(m)
-y = m.N_VNew(tb["y0"])
+y = m.N_VNew(tb["y0"] * (1.0 + float(os.environ.get("PERTURB", "0"))))
 if mode != "old":
     m.set_diagnostics(True)
 m.set_stale_ovlflow(np.zeros((3, ne)))
