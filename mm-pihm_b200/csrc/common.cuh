@@ -89,6 +89,8 @@ struct DevMesh {
     const int *ri;       // [PB_RI_NCOL][nrs]  LEFT/RIGHT = internal element idx
     const double *rivbc; // [nrs]
     const double *fbr_dist;  // [nrs] nabrdist(left bank) + nabrdist(right bank)
+    const int *riv_tile_order;   // [ceil(nr / 32)] river tiles, those that read no ghost state first (partitions)
+    int ntile_rc;                //   ... and how many of them there are
     const double *dist_cold; // [3][nes] nabrdist (boundary edges / exact path; the tiles carry 1 / nabrdist)
     const int *up_ptr;   // [nr+1] CSR of upstream segments, ascending index
     const int *up_idx;
@@ -187,6 +189,7 @@ struct pihm_b200_ctx {
     std::vector<int> riv_left_edge, riv_right_edge;   // edge slot of each bank
     // device allocations
     double *d_dist_cold = nullptr;
+    int *d_riv_tile_order = nullptr;
     double *d_es = nullptr, *d_ft = nullptr, *d_forc = nullptr, *d_rf = nullptr, *d_rivbc = nullptr;
     double4 *d_snb = nullptr, *d_dnb = nullptr;
     double *d_cls = nullptr;

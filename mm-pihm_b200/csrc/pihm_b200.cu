@@ -274,6 +274,8 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
             }
         ctx->ntile_int = first_dep / 32;
     }
+    // leading element tiles above: the strict rule for pihm-fbr also wants both banks of an adjacent river owned
+    // (FbrFlow across the river, lat_flow.c:85-100) -- k_main does not use the split, k_pre reads the stage only.
     // the neighbour codes and the class id ride in the tile slab as int32 [4][32] (pseudo-columns TS_NB0/1)
     for (int t = 0; t < ntile; t++) {
         int *dst = reinterpret_cast<int *>(&es[((size_t)t * TS_NCOL + TS_NB0) * 32]);
@@ -312,7 +314,29 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
         }
     }
 
+    // river tiles (32 segments) in the order k_pre takes them: first those that read owned state only --
+    // the segment, both banks, the downstream segment and its banks (river_flow.c:10-86) -- then the rest
+    std::vector<int> riv_tile_order;
+    int ntile_rc = 0;
+    {
+        const int ntr = (nr + 31) / 32;
+        std::vector<char> ghosty(ntr, 0);
+        auto ghost_elem = [&](int e_ref) { return iperm[e_ref - 1] >= nown_elem; };   // 1-based reference index
+        for (int r = 0; r < nr; r++) {
+            bool g = r >= nown_riv || ghost_elem(RI(PB_RI_LEFTELE, r)) || ghost_elem(RI(PB_RI_RIGHTELE, r));
+            const int d = RI(PB_RI_DOWN, r);
+            if (d > 0)
+                g = g || (d - 1) >= nown_riv || ghost_elem(RI(PB_RI_LEFTELE, d - 1)) || ghost_elem(RI(PB_RI_RIGHTELE, d - 1));
+            if (g) ghosty[r >> 5] = 1;
+        }
+        for (int t = 0; t < ntr; t++) if (!ghosty[t]) riv_tile_order.push_back(t);
+        ntile_rc = (int)riv_tile_order.size();
+        for (int t = 0; t < ntr; t++) if (ghosty[t]) riv_tile_order.push_back(t);
+        if (riv_tile_order.empty()) riv_tile_order.push_back(0);
+    }
+
     int rc = 0;
+    rc |= upload(&ctx->d_riv_tile_order, riv_tile_order);
     rc |= upload(&ctx->d_es, es);
     rc |= upload(&ctx->d_cls, cls);
     rc |= upload(&ctx->d_cid, cid);
@@ -363,6 +387,7 @@ pihm_b200_ctx *pihm_b200_create_part(const pihm_b200_mesh *mesh, int device, int
     dm.es = ctx->d_es; dm.ft = ctx->d_ft; dm.snb = ctx->d_snb; dm.dnb = ctx->d_dnb; dm.cls = ctx->d_cls; dm.cid = ctx->d_cid; dm.bct = ctx->d_bct; dm.fbct = ctx->d_fbct;
     dm.forc = ctx->d_forc; dm.rf = ctx->d_rf; dm.ri = ctx->d_ri; dm.rivbc = ctx->d_rivbc;
     dm.dist_cold = ctx->d_dist_cold;
+    dm.riv_tile_order = ctx->d_riv_tile_order; dm.ntile_rc = ntile_rc;
     dm.fbr_dist = ctx->d_fbr_dist; dm.up_ptr = ctx->d_up_ptr; dm.up_idx = ctx->d_up_idx;
     dm.rivflow = ctx->d_rivflow; dm.s2c_stale = ctx->d_stale;
     if (pb::rhs_tile_rcp(ctx) != 0 ||       // reciprocals of the element areas and neighbour distances
@@ -434,7 +459,7 @@ void pihm_b200_destroy(pihm_b200_ctx *ctx)
     if (ctx->l2_on) cudaCtxResetPersistingL2Cache();   // hand the set-aside lines back
     pihm_b200_vec_free(ctx->y_tmp);
     pihm_b200_vec_free(ctx->yd_tmp);
-    void *dev[] = {ctx->d_dist_cold, ctx->d_es, ctx->d_ft, ctx->d_dnb, ctx->d_cls, ctx->d_cid, ctx->d_forc, ctx->d_rf, ctx->d_rivbc, ctx->d_fbr_dist,
+    void *dev[] = {ctx->d_riv_tile_order, ctx->d_dist_cold, ctx->d_es, ctx->d_ft, ctx->d_dnb, ctx->d_cls, ctx->d_cid, ctx->d_forc, ctx->d_rf, ctx->d_rivbc, ctx->d_fbr_dist,
                    ctx->d_bct, ctx->d_fbct, ctx->d_ri, ctx->d_up_ptr, ctx->d_up_idx,
                    ctx->d_rivflow, ctx->d_stale, ctx->d_xflux, ctx->d_nan, ctx->d_perm,
                    ctx->d_iperm, ctx->d_stage, ctx->d_red, ctx->d_gel, ctx->d_gri, ctx->d_send_e, ctx->d_send_r,

@@ -1574,17 +1574,25 @@ k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r, i
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = gridDim.x, b = blockIdx.x;
     // Work items of the grid, taken by ticket (ticket q of CTA b = item q * G + b):
-    //   without a peer-memory halo   [ river tiles | element tiles ]       (the slow river tiles first)
-    //   with one                     [ interior element tiles | river tiles | other element tiles ]
-    const int E_int = (GH && hw.nn > 0) ? min(ntile_int, ntile_e) : 0;
+    //   [ clean river tiles | interior element tiles | other river tiles | other element tiles ]
+    // "clean" / "interior": the tile reads no ghost state (pihm_b200_create_part classifies them; the
+    // partitioner lists the owned elements as [interior | boundary], the river tiles are taken through
+    // m.riv_tile_order, clean ones first).  With a peer-memory halo the first two sections run while the
+    // neighbours' records are still on their way; without one there is nothing to wait for and the order
+    // is simply [ river tiles | element tiles ] (the slow river tiles first).
+    const bool halo = GH && hw.nn > 0;
     const int R = ntile_r;
-    const int qr0 = (E_int > b) ? (E_int - b + G - 1) / G : 0;          // this CTA's river tickets: [qr0, qr1)
-    const int qr1 = (E_int + R > b) ? (E_int + R - b + G - 1) / G : 0;
-    const int nrq = qr1 - qr0;
-    auto q_of_k = [&](int k) { return (k < qr0) ? k : k + nrq; };       // k-th element ticket of this CTA
+    const int Rc = halo ? min(m.ntile_rc, R) : R;
+    const int E_int = halo ? min(ntile_int, ntile_e) : 0;
+    const int E_nog = GH ? min(ntile_int, ntile_e) : ntile_e;      // leading tiles served by the ghost-free code
+    const long long B1 = (long long)Rc + E_int, B2 = B1 + (R - Rc);     // sections: [0,Rc) [Rc,B1) [B1,B2) [B2, R + ntile_e)
+    auto first_q = [&](long long B) { return (B > b) ? (int)((B - b + G - 1) / G) : 0; };   // first ticket with item >= B
+    const int qa0 = first_q(Rc), qa1 = first_q(B1), qb0 = first_q(B2);
+    const int na = qa1 - qa0;                                       // element tickets of the interior section
+    auto q_of_k = [&](int k) { return (k < na) ? k + qa0 : k - na + qb0; };     // k-th element ticket of this CTA
     auto tile_of_q = [&](int q) {       // element tile of an element ticket (>= ntile_e: past the end)
         const long long g = (long long)q * G + b;
-        return (g < E_int) ? g : g - R;
+        return (g < B1) ? g - Rc : g - B2 + E_int;
     };
     ring.init();
     // request the tile of the k-th element ticket (no-op past the end): the static slab does not
@@ -1617,12 +1625,12 @@ k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r, i
     if (lane == 0)
         for (int k = warp; k < PB_PRE_STAGES; k += PB_PRE_WARPS) request(k, false, true);
     const long long g_end = (long long)ntile_e + R;
-    bool halo_seen = !(GH && hw.nn > 0);
+    bool halo_seen = !halo;
     for (;;) {
         const int q = ring.take(lane);
         const long long g = (long long)q * G + b;
         if (g >= g_end) break;
-        if (GH && !halo_seen && g >= E_int) {
+        if (GH && !halo_seen && g >= B1) {
             // the neighbours' halo records of this RHS have arrived (one lane per neighbour)
             if (lane < hw.nn) {
                 long long spins = 0;
@@ -1633,21 +1641,27 @@ k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r, i
             __syncwarp();
             halo_seen = true;
         }
-        if (g >= E_int && g < E_int + R) {
-            const int r = (int)(g - E_int) * PB_TILE + lane;
-            if (r < m.nr) river_fluxes<GH>(m, y, r);
+        if (g < Rc || (g >= B1 && g < B2)) {
+            const int t = (int)((g < Rc) ? g : g - B1 + Rc);
+            const int r = (GH ? m.riv_tile_order[t] : t) * PB_TILE + lane;
+            if (r < m.nr) {
+                if (GH && t >= m.ntile_rc) river_fluxes<GH>(m, y, r);
+                else river_fluxes<false>(m, y, r);          // a clean tile reads owned state only
+            }
             continue;
         }
-        const long long tile = (g < E_int) ? g : g - R;
-        const int k = q - min(max(q - qr0, 0), nrq), s = k % PB_PRE_STAGES, n = k / PB_PRE_STAGES;
+        const long long tile = (g < B1) ? g - Rc : g - B2 + E_int;
+        const int k = (q < qa1) ? q - qa0 : q - qb0 + na, s = k % PB_PRE_STAGES, n = k / PB_PRE_STAGES;
         const unsigned phase = (unsigned)n & 1u;
         ring.acquire(s, n);
         const int i = (int)tile * PB_TILE + lane;
         const double *st = reinterpret_cast<const double *>(ring.stage(s)) + lane;
         if (i < m.ne) {
             const bool tys = tile < ntile_own;
-            if (!elem_pre<true, GH>(m, y, i, st, ring.bar(s), phase, tys))
-                elem_pre_exact<GH>(m.self, y, i, st, ring.bar(s), phase, tys);
+            // (a tile of the interior reads no ghost: the variant without the owned / ghost distinction)
+            const bool done = (GH && tile >= E_nog) ? elem_pre<true, GH>(m, y, i, st, ring.bar(s), phase, tys)
+                                                    : elem_pre<true, false>(m, y, i, st, ring.bar(s), phase, tys);
+            if (!done) elem_pre_exact<GH>(m.self, y, i, st, ring.bar(s), phase, tys);
         } else {
             mbar_wait(ring.bar(s), phase);
         }

@@ -118,6 +118,10 @@ int rhs_launch(pihm_b200_ctx *ctx, const double *y, double *dy, bool replay)
         hw.nn = ctx->hpeers.nn;
         for (int k = 0; k < hw.nn; k++) hw.rank[k] = ctx->nbr_rank[k];
         hw.seq = (double)seq;
+        // timing experiments only (wrong results): bit 0 drops the flag wait, bit 1 the put
+        static const int dbg = std::getenv("PIHM_B200_HALO_DEBUG") ? std::atoi(std::getenv("PIHM_B200_HALO_DEBUG")) : 0;
+        if (dbg & 1) hw.nn = 0;
+        if (dbg & 2) hput.hp.nn = 0;
     } else if (ctx->nranks > 1) {
         // one-ring(+) halo exchange of neighbour and river states before the RHS
         const int n = ctx->nse + ctx->nsr;
@@ -138,8 +142,25 @@ int rhs_launch(pihm_b200_ctx *ctx, const double *y, double *dy, bool replay)
     int ys = 0;
     if (ctx->ystage && ((uintptr_t)y & 15) == 0) ys = 1 | ((dm.nown % 2 == 0) ? 2 : 0);
     const bool gh = (dm.nown != dm.ne) || (dm.rown != dm.nr);
-    if (gh) k_pre<true><<<gpre, PB_PRE_THREADS, ctx->pre_smem, ctx->s()>>>(dm, y, te, tr, ctx->ntile_int, hw, hput, ys & 1);
-    else k_pre<false><<<gpre, PB_PRE_THREADS, ctx->pre_smem, ctx->s()>>>(dm, y, te, tr, te, hw, hput, ys & 1);
+    {
+        // k_pre too is launched with programmatic stream serialization: its prologue (ring set-up, the
+        // first static-slab requests) depends on nothing the predecessor writes and overlaps its tail;
+        // everything else comes after griddepcontrol.wait
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(gpre);
+        cfg.blockDim = dim3(PB_PRE_THREADS);
+        cfg.dynamicSmemBytes = ctx->pre_smem;
+        cfg.stream = ctx->s();
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = (ctx->pdl && !std::getenv("PIHM_B200_PRE_NO_PDL")) ? 1 : 0;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        const int ys1 = ys & 1;
+        const cudaError_t e = gh ? cudaLaunchKernelEx(&cfg, k_pre<true>, dm, y, te, tr, ctx->ntile_int, hw, hput, ys1)
+                                 : cudaLaunchKernelEx(&cfg, k_pre<false>, dm, y, te, tr, te, hw, hput, ys1);
+        if (e != cudaSuccess) { set_error(std::string("k_pre launch: ") + cudaGetErrorString(e)); return -1; }
+    }
     {
         // k_main right behind k_pre with programmatic stream serialization (PDL): its launch
         // latency and prologue overlap k_pre's tail
