@@ -35,10 +35,10 @@ STEP = 60.0
 B_RHS = {False: 376.0, True: 476.0}     # algorithmic bytes / element / RHS
 # dram__bytes_read.sum + dram__bytes_write.sum of one RHS (k_pre + k_main) from the committed
 # ncu --set full capture (profiles/); None where no capture exists
-RHS_TRAFFIC_BYTES = {("1M", False): 418.8e6, ("1M", True): 460.3e6}
+RHS_TRAFFIC_BYTES = {("1M", False): 384.7e6, ("1M", True): 437.4e6}
 # FP64 side figure: 2 x DFMA + DADD + DMUL thread instructions of k_pre + k_main from the same kind
-# of capture (profiles/r01i_rhs_1M_ncu_summary.md): 295.2 + 782.7 MFLOP per RHS at 1M triangles
-RHS_FP64_FLOP = {("1M", False): 1.078e9}
+# of capture (profiles/r02_rhs_1M_ncu_summary.md): 179 + 581 MFLOP per RHS at 1M triangles (pihm), 179 + 1069 (fbr)
+RHS_FP64_FLOP = {("1M", False): 0.760e9, ("1M", True): 1.248e9}
 FP64_LANES_PER_SM = 64      # sm__sass_thread_inst_executed_op_dfma_pred_on peak_sustained per SM and cycle
 
 
@@ -54,7 +54,7 @@ def fp64_side(size, fbr, rhs_ms, clk):
     peak = nsm * FP64_LANES_PER_SM * 2 * mhz * 1e6 / 1e12
     ach = flop / (rhs_ms * 1e-3) / 1e12
     return {"flop_per_rhs": flop, "achieved_tflops": ach, "peak_tflops": peak, "frac": ach / peak,
-            "source": "profiles/r01i_rhs_1M_ncu_summary.md (2 x DFMA + DADD + DMUL thread instructions)"}
+            "source": "profiles/r02_rhs_1M_ncu_summary.md (2 x DFMA + DADD + DMUL thread instructions)"}
 
 
 def forcing_at(tb, k):
@@ -291,6 +291,13 @@ def run_ours(args):
     cv.profile(False)
     rhs_ms_in_situ = max_over_ranks(pf["rhs_ms"] / max(pf["rhs_evals"], 1))
     host_wait_ms = max_over_ranks(pf["host_wait_ms"] / nprof)
+    # ---- N_Vector / integrator kernels in situ: a pair of CUDA events around every vector kernel of a few
+    # more model steps (programmatic serialization off meanwhile), true bytes read + written per launch
+    cv.profile(2)
+    for k in range(2 + nprof, 2 + nprof + min(K, 5)):
+        step(k)
+    kp = cv.get_kernel_profile()
+    cv.profile(False)
     peak, peak_src = measured_peak()
     nown_elem, nsv_local = model.nown_elem, model.nsv
     achieved = B_RHS[fbr] * nown_elem / (rhs_ms * 1e-3) / 1e9      # per GPU
@@ -331,8 +338,19 @@ def run_ours(args):
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": B_RHS[fbr] * nown_elem,
                      "frac_in_situ": B_RHS[fbr] * nown_elem / (rhs_ms_in_situ * 1e-3) / 1e9 / peak,
-                     "traffic_source": "profiles/r01g_rhs_1M_ncu_summary.md (pihm) / r01d (fbr): ncu --set full, dram read+write"},
+                     "traffic_source": "profiles/r02_rhs_1M_ncu_summary.md: ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of k_pre + k_main"},
         "fp64": fp64_side(size, fbr, rhs_ms, clk),
+        # per fused vector kernel of the integrator, in situ on rank 0: algorithmic bytes (vector passes x 8 N)
+        # / event-to-event time / the same measured peak; short kernels (2-3 passes of 24 MB) carry their launch
+        # latency and reduction tail in the denominator
+        "vector_roofline": {
+            "peak": peak, "unit": "GB/s",
+            "kernels": {nm: {"launches": v["launches"], "us": 1e3 * v["ms"] / max(v["launches"], 1),
+                             "gbs": v["bytes"] / max(v["ms"], 1e-9) / 1e6,
+                             "frac": v["bytes"] / max(v["ms"], 1e-9) / 1e6 / peak} for nm, v in kp.items()},
+            "all": {"gbs": sum(v["bytes"] for v in kp.values()) / max(sum(v["ms"] for v in kp.values()), 1e-9) / 1e6,
+                    "frac": sum(v["bytes"] for v in kp.values()) / max(sum(v["ms"] for v in kp.values()), 1e-9) / 1e6 / peak},
+        },
         "e2e": {"value": e2e_value, "unit": "sim-days/s", "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": 3 * 8 * ne, "d2h_bytes_per_step": 8 * nsv_local},
         "gpu_launches": int(l1 - l0),

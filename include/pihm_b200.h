@@ -472,6 +472,11 @@ int             pihm_b200_spgmr_solve(pihm_b200_cvode *cv, double tn,
  * synchronisations, ms of RHS kernels event to event, RHS evaluations timed}. */
 int             pihm_b200_cvode_profile(pihm_b200_cvode *cv, int on);
 int             pihm_b200_cvode_get_profile(pihm_b200_cvode *cv, double *out5);
+/* on = 2 in pihm_b200_cvode_profile also brackets every vector kernel of the integrator with CUDA events
+ * (programmatic serialization off while it lasts).  Per kernel that ran: name (24 bytes each), summed
+ * event-to-event ms, bytes read + written (vector passes x 8 N) and launches; returns the entry count. */
+int             pihm_b200_cvode_get_kernel_profile(pihm_b200_cvode *cv, int cap,
+                    char *names, double *ms, double *bytes, int64_t *launches);
 /* AdjCVodeMaxStep (ode.c:500-560) on the integrator's own counters */
 typedef struct pihm_b200_maxstep_ctrl {
     double          maxstep, stepsize, stmin, nncfn, nnimax, nnimin, decr, incr;

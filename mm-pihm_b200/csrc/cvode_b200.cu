@@ -197,6 +197,54 @@ struct pihm_b200_cvode {
     // N_VWrmsNorm = SUNRsqrt(sum / N)  (nvector_serial.c:685)
     double wrms(int slot) const { const double v = h_sc[slot] / n_global; return (v <= 0.0) ? 0.0 : std::sqrt(v); }
 
+    // ---- per-kernel in-situ profile (pihm_b200_cvode_profile(cv, 2); bench.py's vector_roofline) ----
+    // Every vector kernel launch is bracketed by a pair of CUDA events (PDL off so the pair sees the
+    // kernel alone) and booked under its kernel id together with the bytes it reads and writes
+    // (vector passes x 8 N).  Off by default: one branch per launch.
+    enum KId { K_EWT = 0, K_PREDICT, K_RESCALE, K_NEWTON_RES, K_KRYLOV_A, K_KRYLOV_B, K_KRYLOV_C, K_MGS_STEP,
+               K_MGS_CHAIN, K_SPGMR_FINAL, K_NEWTON_UPDATE, K_WSQ, K_COMPLETE, K_ETA, K_DKY, K_SCALE, K_COPY,
+               K_AXPY, K_DOT, K_NKERN };
+    struct KAcc { double ms = 0.0, bytes = 0.0; long long n = 0; } kacc[K_NKERN];
+    struct KPend { int id; double bytes; cudaEvent_t a, b; };
+    std::vector<KPend> kpend;
+    std::vector<cudaEvent_t> kfree;
+    bool kprof = false;
+    cudaEvent_t kev()
+    {
+        if (kfree.empty()) { cudaEvent_t e; cudaEventCreate(&e); return e; }
+        cudaEvent_t e = kfree.back(); kfree.pop_back(); return e;
+    }
+    void kflush()
+    {
+        cudaStreamSynchronize(s());
+        for (const KPend &k : kpend) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, k.a, k.b) == cudaSuccess) { kacc[k.id].ms += ms; kacc[k.id].bytes += k.bytes; kacc[k.id].n++; }
+            kfree.push_back(k.a); kfree.push_back(k.b);
+        }
+        kpend.clear();
+    }
+    void kbegin(int id, double passes)
+    {
+        if (kpend.size() >= 2048) kflush();
+        KPend k{id, passes * 8.0 * (double)N, kev(), kev()};
+        cudaEventRecord(k.a, s());
+        kpend.push_back(k);
+    }
+    void kend() { cudaEventRecord(kpend.back().b, s()); }
+    // launch of a vector kernel: kernel id + vector passes (N doubles read or written) for the profile
+    template <typename... ExpTypes, typename... ActTypes>
+    void LK(int id, double passes, void (*kernel)(ExpTypes...), ActTypes &&... args)
+    {
+        if (!kprof) {
+            launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, kernel, std::forward<ActTypes>(args)...);
+            return;
+        }
+        kbegin(id, passes);
+        launch_pdl(s(), 0, blocks, PB_VEC_THREADS, kernel, std::forward<ActTypes>(args)...);
+        kend();
+    }
+
     // ---- thin launch helpers -------------------------------------------------
     void rhs(const double *yin, double *ydot)
     {
@@ -217,23 +265,23 @@ struct pihm_b200_cvode {
     ZnPtrs znp() const { ZnPtrs p; for (int j = 0; j < 6; j++) p.z[j] = zn[j]; return p; }
     void scale_inplace(double c, double *v)
     {
-        launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_elementwise<EW_SCALE>, N, c, v, nullptr, v);
+        LK(K_SCALE, 2, k_elementwise<EW_SCALE>, N, c, v, nullptr, v);
         count();
     }
     void copy(const double *src, double *dst)
     {
         clobber(dst);
-        launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_elementwise<EW_COPY>, N, 0.0, src, nullptr, dst);
+        LK(K_COPY, 2, k_elementwise<EW_COPY>, N, 0.0, src, nullptr, dst);
         count();
     }
     void axpy(double a, const double *x, double *yv)     // Vaxpy: y += a*x
     {
-        launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_linearsum_alias<LS_GENERAL>, N, a, x, 1.0, yv, yv);
+        LK(K_AXPY, 3, k_linearsum_alias<LS_GENERAL>, N, a, x, 1.0, yv, yv);
         count();
     }
     void launch_ewt()                                    // efun + tolsf norm (cvode.c:1349,1376)
     {
-        launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_ewt, N, reltol, abstol, zn[0], ewt, R());
+        LK(K_EWT, 2, k_ewt, N, reltol, abstol, zn[0], ewt, R());
         count();
         red(SC_EWT_MIN, 1, 1);
         red(SC_EWT_NRM);
@@ -270,7 +318,7 @@ void pihm_b200_cvode::cvRescale()
     Coef6 f{};
     double factor = eta;
     for (int j = 1; j <= q; j++) { f.c[j] = factor; factor *= eta; }
-    launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_rescale, N, q, znp(), f);
+    LK(K_RESCALE, 2.0 * q, k_rescale, N, q, znp(), f);
     count();
     h = hscale * eta;
     next_h = h;
@@ -286,7 +334,7 @@ void pihm_b200_cvode::cvPredict()
         if ((tn - tstop) * h > 0.0) tn = tstop;
     }
     clobber(zn[0]);
-    launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_predict<1>, N, q, znp());
+    LK(K_PREDICT, 2.0 * q + 1, k_predict<1>, N, q, znp());
     count();
 }
 
@@ -295,7 +343,7 @@ void pihm_b200_cvode::cvRestore(double saved_t)
 {
     tn = saved_t;
     clobber(zn[0]);
-    launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_predict<-1>, N, q, znp());
+    LK(K_PREDICT, 2.0 * q + 1, k_predict<-1>, N, q, znp());
     count();
 }
 
@@ -322,7 +370,7 @@ void pihm_b200_cvode::cvAdjustOrder(int deltaq)
         }
         A1 = (-alpha0 - alpha1) / prod;
         // zn[L] = A1 * zn[indx_acor]
-        launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_elementwise<EW_SCALE>, N, A1, zn[indx_acor], nullptr, zn[L]);
+        LK(K_SCALE, 2, k_elementwise<EW_SCALE>, N, A1, zn[indx_acor], nullptr, zn[L]);
         count();
         for (int j = 2; j <= q; j++) axpy(l[j], zn[L], zn[j]);
     } else if (deltaq == -1) {
@@ -437,15 +485,15 @@ int pihm_b200_cvode::spgmrSolve(bool *b_is_zero)
             const int l_plus_1 = lk + 1;
             krydim = l_plus_1;
             // A-tilde V[l]: right scaling, DQ J*v, I - gamma J, left scaling, first MGS dot
-            launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_krylov_a, N, cnorm, V[lk], ewt, vtemp, R());
+            LK(K_KRYLOV_A, 4, k_krylov_a, N, cnorm, V[lk], ewt, vtemp, R());
             red(SC_VNRM);
             clobber(ytemp);
-            launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_krylov_b, N, n_global, d_sc, vtemp, y, ytemp);
+            LK(K_KRYLOV_B, 3, k_krylov_b, N, n_global, d_sc, vtemp, y, ytemp);
             count(2);
             rhs(ytemp, V[l_plus_1]);     // Jv = f(tn, y + sig*v)   (cvode_spils.c:687)
             nfes++;
             njtimes++;
-            launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_krylov_c, N, n_global, gamma, d_sc, vtemp, ftemp, ewt,
+            LK(K_KRYLOV_C, 6, k_krylov_c, N, n_global, gamma, d_sc, vtemp, ftemp, ewt,
                                                             V[0], V[l_plus_1], R());
             count();
             red(SC_VK2);
@@ -462,17 +510,19 @@ int pihm_b200_cvode::spgmrSolve(bool *b_is_zero)
                 int nsteps = l_plus_1, per = chain_per_thread;
                 double *vk = V[l_plus_1];
                 void *args[] = {&n_, &nsteps, &kp, &vk, &r, &per};
+                if (kprof) kbegin(K_MGS_CHAIN, 2.0 + 2.0 * l_plus_1 - 1.0);
                 if (cudaLaunchCooperativeKernel((void *)k_mgs_chain, dim3(blocks), dim3(PB_VEC_THREADS), args,
                                                 chain_smem, s()) != cudaSuccess) {
                     set_error(std::string("k_mgs_chain launch: ") + cudaGetErrorString(cudaGetLastError()));
                     return -1;
                 }
+                if (kprof) kend();
                 count();
             } else
             for (int i = 0; i < l_plus_1; i++) {
                 const double *vnext = (i + 1 < l_plus_1) ? V[i + 1] : V[l_plus_1];
                 const int slot_next = (i + 1 < l_plus_1) ? SC_H0 + i + 1 : SC_NEW2;
-                launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_mgs_step, N, d_sc, SC_H0 + i, V[i], vnext,
+                LK(K_MGS_STEP, (vnext == V[l_plus_1]) ? 3 : 4, k_mgs_step, N, d_sc, SC_H0 + i, V[i], vnext,
                                                                 V[l_plus_1], slot_next, R());
                 count();
                 red(slot_next);
@@ -486,7 +536,7 @@ int pihm_b200_cvode::spgmrSolve(bool *b_is_zero)
                 // re-orthogonalisation branch (sundials_iterative.c:73-88); rare
                 double new_norm_2 = 0.0;
                 for (int i = 0; i < l_plus_1; i++) {
-                    launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_reduce<RD_DOT, 0>, 
+                    LK(K_DOT, 2, k_reduce<RD_DOT, 0>, 
                         N, V[i], V[l_plus_1], d_part, d_counter, d_sc + SC_TMP, h_sc_map + SC_TMP);
                     count();
                     red_nccl(SC_TMP);
@@ -601,10 +651,10 @@ int pihm_b200_cvode::cvNewtonIteration()
     for (;;) {
         clobber(y);
         if (m == 0)
-            launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_newton_res<true>, N, rl1, gamma, zn[0], zn[1], ftemp, ewt,
+            LK(K_NEWTON_RES, 8, k_newton_res<true>, N, rl1, gamma, zn[0], zn[1], ftemp, ewt,
                                                                    acor, y, tempv, V[0], R());
         else
-            launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_newton_res<false>, N, rl1, gamma, zn[0], zn[1], ftemp, ewt,
+            LK(K_NEWTON_RES, 6, k_newton_res<false>, N, rl1, gamma, zn[0], zn[1], ftemp, ewt,
                                                                     acor, y, tempv, V[0], R());
         count();
         red(SC_BSUM);
@@ -622,9 +672,9 @@ int pihm_b200_cvode::cvNewtonIteration()
         if (bnorm <= deltar) {
             // x = b (first iteration) or x = 0
             if (mnewt > 0)
-                launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_newton_update<true>, N, tempv, ewt, zn[0], acor, y, R());
+                LK(K_NEWTON_UPDATE, 5, k_newton_update<true>, N, tempv, ewt, zn[0], acor, y, R());
             else
-                launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_newton_update<false>, N, tempv, ewt, zn[0], acor, y, R());
+                LK(K_NEWTON_UPDATE, 6, k_newton_update<false>, N, tempv, ewt, zn[0], acor, y, R());
             count();
             retval = 0;
         } else {
@@ -633,12 +683,12 @@ int pihm_b200_cvode::cvNewtonIteration()
             retval = spgmrSolve(&zero);
             if (retval == 0) {
                 if (zero || krydim_last == 0) {
-                    launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_newton_update<true>, N, tempv, ewt, zn[0], acor, y, R());
+                    LK(K_NEWTON_UPDATE, 5, k_newton_update<true>, N, tempv, ewt, zn[0], acor, y, R());
                 } else {
                     KryPtrs kp{};
                     Coef6 c{};
                     for (int k = 0; k < krydim_last; k++) { kp.v[k] = V[k]; c.c[k] = yg[k]; }
-                    launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_spgmr_final, N, krydim_last, kp, c, ewt, zn[0], acor, y, R());
+                    LK(K_SPGMR_FINAL, krydim_last + 5.0, k_spgmr_final, N, krydim_last, kp, c, ewt, zn[0], acor, y, R());
                 }
                 count();
             }
@@ -656,7 +706,7 @@ int pihm_b200_cvode::cvNewtonIteration()
             if (m == 0) {
                 acnrm = del;
             } else {
-                launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_wsq, N, acor, nullptr, ewt, SC_ACNRM, -1, R());
+                LK(K_WSQ, 2, k_wsq, N, acor, nullptr, ewt, SC_ACNRM, -1, R());
                 count();
                 red(SC_ACNRM);
                 sync_spin();
@@ -739,7 +789,7 @@ int pihm_b200_cvode::cvDoErrorTest(int *nflagPtr, double saved_t, int *nefPtr, d
     nscon = 0;
     rhs(zn[0], tempv);
     nfe++;
-    launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_elementwise<EW_SCALE>, N, h, tempv, nullptr, zn[1]);
+    LK(K_SCALE, 2, k_elementwise<EW_SCALE>, N, h, tempv, nullptr, zn[1]);
     count();
     return TRY_AGAIN;
 }
@@ -764,7 +814,7 @@ void pihm_b200_cvode::cvCompleteStep()
         indx_acor = qmax;
     }
     clobber(zn[0]);
-    launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_complete, N, q, znp(), lc, acor, save);
+    LK(K_COMPLETE, 2.0 * (q + 1) + 1 + (save ? 1 : 0), k_complete, N, q, znp(), lc, acor, save);
     count();
 }
 
@@ -829,7 +879,7 @@ void pihm_b200_cvode::cvPrepareNextStep(double dsm)
     etaqm1 = 0.0;
     etaqp1 = 0.0;
     if (do_m1 || do_p1) {
-        launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_eta, N, do_m1, do_p1, cquot, zn[q], zn[qmax], acor, ewt, R());
+        LK(K_ETA, 1.0 + (do_m1 ? 1 : 0) + (do_p1 ? 2 : 0), k_eta, N, do_m1, do_p1, cquot, zn[q], zn[qmax], acor, ewt, R());
         count();
         red(SC_ETA_M1, 2);
         sync_spin();
@@ -854,7 +904,7 @@ void pihm_b200_cvode::cvBDFStab()
             for (int i = 5; i >= 2; i--) ssdat[i][k] = ssdat[i - 1][k];
         int factorial = 1;
         for (int i = 1; i <= q - 1; i++) factorial *= i;
-        launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_wsq, N, zn[q], zn[q - 1], ewt, SC_STAB1, SC_STAB2, R());
+        LK(K_WSQ, 3, k_wsq, N, zn[q], zn[q - 1], ewt, SC_STAB1, SC_STAB2, R());
         count();
         red(SC_STAB1, 2);
         sync_spin();
@@ -1067,7 +1117,7 @@ int pihm_b200_cvode::getDky(double t, double *dky)
     if ((t - tp) * (t - tn1) > 0.0) return CV_BAD_T;
     const double sv = (t - tn) / h;
     clobber(dky);
-    launch_pdl(s(), ctx->pdl, blocks, PB_VEC_THREADS, k_dky, N, q, sv, znp(), dky);
+    LK(K_DKY, q + 2.0, k_dky, N, q, sv, znp(), dky);
     count();
     return CV_SUCCESS;
 }
@@ -1329,6 +1379,8 @@ void pihm_b200_cvode_destroy(pihm_b200_cvode *cv)
     }
     for (cudaEvent_t e : cv->prof_ev) cudaEventDestroy(e);
     cv->prof_ev.clear();
+    for (const auto &k : cv->kpend) { cudaEventDestroy(k.a); cudaEventDestroy(k.b); }
+    for (cudaEvent_t e : cv->kfree) cudaEventDestroy(e);
     double *all[] = {cv->zn[0], cv->zn[1], cv->zn[2], cv->zn[3], cv->zn[4], cv->zn[5], cv->ewt, cv->acor,
                      cv->tempv, cv->ftemp, cv->V[0], cv->V[1], cv->V[2], cv->V[3], cv->V[4], cv->V[5],
                      cv->vtemp, cv->ytemp, cv->d_part, cv->d_sc};
@@ -1497,7 +1549,34 @@ int pihm_b200_cvode_profile(pihm_b200_cvode *cv, int on)
     }
     cv->prof = on != 0;
     if (on) { cv->prof_used = 0; cv->prof_nsync = 0; cv->prof_wait_ns = 0; cv->prof_solve_ns = 0; }
+    // on == 2: also a pair of events around every vector kernel (pihm_b200_cvode_get_kernel_profile)
+    if (cv->kprof) cv->kflush();
+    cv->kprof = on == 2;
+    if (cv->kprof) for (auto &k : cv->kacc) k = pihm_b200_cvode::KAcc();
     return 0;
+}
+
+// Per-kernel in-situ figures since pihm_b200_cvode_profile(cv, 2): for each vector kernel of the integrator
+// that ran, its name (24 bytes, NUL-terminated), the summed event-to-event time, the bytes it read and
+// wrote (vector passes x 8 N, the algorithmic traffic) and the number of launches.  Returns the number
+// of entries written (<= cap).
+int pihm_b200_cvode_get_kernel_profile(pihm_b200_cvode *cv, int cap, char *names, double *ms, double *bytes,
+                                       int64_t *launches)
+{
+    if (!cv || !names || !ms || !bytes || !launches) return -1;
+    static const char *const nm[pihm_b200_cvode::K_NKERN] = {
+        "k_ewt", "k_predict", "k_rescale", "k_newton_res", "k_krylov_a", "k_krylov_b", "k_krylov_c", "k_mgs_step",
+        "k_mgs_chain", "k_spgmr_final", "k_newton_update", "k_wsq", "k_complete", "k_eta", "k_dky",
+        "k_elementwise<scale>", "k_elementwise<copy>", "k_linearsum<axpy>", "k_reduce<dot>"};
+    cv->kflush();
+    int n = 0;
+    for (int k = 0; k < pihm_b200_cvode::K_NKERN && n < cap; k++) {
+        if (cv->kacc[k].n == 0) continue;
+        std::snprintf(names + 24 * n, 24, "%s", nm[k]);
+        ms[n] = cv->kacc[k].ms; bytes[n] = cv->kacc[k].bytes; launches[n] = cv->kacc[k].n;
+        n++;
+    }
+    return n;
 }
 
 // out[0] ms inside pihm_b200_cvode_solve, out[1] ms of host waiting in out[2] synchronisations,

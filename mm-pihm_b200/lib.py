@@ -151,6 +151,8 @@ _SIGS = {
     "pihm_b200_adj_cvode_max_step": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pihm_b200_cvode_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "pihm_b200_cvode_get_profile": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pihm_b200_cvode_get_kernel_profile": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                     C.c_void_p]),
 }
 # include/pihm_b200_sundials.h
 _SUNDIALS_SIGS = {
@@ -497,8 +499,24 @@ class Cvode:
         _check(self.L, self.L.pihm_b200_adj_cvode_max_step(self.h, C.byref(self.ctrl)), "adj_max_step")
         return self.ctrl.maxstep
 
-    def profile(self, on: bool = True):
+    def profile(self, on=True):
+        """on = 2: also CUDA events around every vector kernel (get_kernel_profile)"""
         _check(self.L, self.L.pihm_b200_cvode_profile(self.h, int(on)), "cvode_profile")
+
+    def get_kernel_profile(self) -> dict:
+        """{kernel: dict(ms, bytes, launches)} since profile(2): event-to-event time and algorithmic bytes"""
+        cap = 32
+        names = C.create_string_buffer(24 * cap)
+        ms, by = np.zeros(cap), np.zeros(cap)
+        n_l = np.zeros(cap, dtype=np.int64)
+        n = self.L.pihm_b200_cvode_get_kernel_profile(self.h, cap, names, _ptr(ms), _ptr(by), _ptr(n_l))
+        if n < 0:
+            raise RuntimeError("cvode_get_kernel_profile failed")
+        out = {}
+        for k in range(n):
+            nm = names.raw[24 * k:24 * (k + 1)].split(b"\0")[0].decode()
+            out[nm] = dict(ms=float(ms[k]), bytes=float(by[k]), launches=int(n_l[k]))
+        return out
 
     def get_profile(self) -> dict:
         out = np.zeros(5)
