@@ -374,6 +374,35 @@ int             pihm_b200_print_data(pihm_b200_ctx *ctx, int id, double *out,
                                      int32_t *counter_out);
 
 /* ------------------------------------------------------------------------
+ * Output files written from the device columns (second half).
+ *   replaces: InitOutputFile (src/print.c:72-151), the record writing of
+ *             PrintData (src/print.c:193-251) and PrintInit (src/print.c:253-313),
+ *             i.e. the consumers of map_output.c's pointer lists.
+ * All variables that are due at a print time are averaged, reset and packed by
+ * one kernel and cross PCIe in ONE copy; the records have the reference's bytes:
+ *   <name>.dat   { double t ; double value[nelem | nriver] }   per record
+ *   <name>.txt   "<timestr>"\tvalue...\n  with %lf
+ *   restart .ic  per element { cmc, sneqv, surf, unsat, gw [, fbr_unsat, fbr_gw] },
+ *                then per river { stage, gw }
+ * ---------------------------------------------------------------------- */
+/* name: path without extension (varctrl.name, map_output.c: "<outputdir><project>.<var>") */
+int             pihm_b200_print_open(pihm_b200_ctx *ctx, int id, const char *name,
+                                     int ascii, int append);
+/* ids: the variables PrintNow() (src/print.c:578, host time logic) says are due
+ * at model time t; timestr = pihm_time.str of t */
+int             pihm_b200_print_write(pihm_b200_ctx *ctx, const int32_t *ids, int n,
+                                      int t, const char *timestr);
+int             pihm_b200_print_close(pihm_b200_ctx *ctx);
+/* device -> host copies made by the writers so far, and their bytes */
+int             pihm_b200_print_io_stats(pihm_b200_ctx *ctx, int64_t *copies,
+                                         int64_t *bytes);
+/* cmc / sneqv: [nelem] host arrays in reference order, or NULL = the device ET
+ * state (pihm_b200_et_create; zero without it) */
+int             pihm_b200_write_ic(pihm_b200_ctx *ctx, const char *path,
+                                   const pihm_b200_vec *y, const double *cmc,
+                                   const double *sneqv);
+
+/* ------------------------------------------------------------------------
  * Device-resident N_Vector.
  *   replaces: cvode/src/nvec_ser/nvector_serial.c:421-770 (ops) and
  *             :76-419 (constructors), same arithmetic per component.

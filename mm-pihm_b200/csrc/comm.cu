@@ -375,17 +375,20 @@ int pihm_b200_comm_init_local(pihm_b200_ctx **ctxs, int nranks)
         ctxs[r]->lgroup = g;
         // Ranks that SHARE a device wait for each other inside kernels (halo flags in k_pre, tickets
         // in the reduction kernels), so a waiting kernel must leave room for its peers' kernels: the
-        // k_pre grids of all OTHER ranks together put at most one CTA on an SM (a k_main CTA of the
-        // rank they wait for still fits beside it), and no kernel is launched ahead of its
-        // predecessor's end (no PDL: a dependent grid parked on the SMs could keep a peer's kernel
-        // off them).  Host calls that synchronise the device (cudaMalloc / cudaFree) must not be
-        // issued while a peer's RHS is in flight: allocate before the first evaluation.
+        // k_pre grids of ALL ranks together leave 16 SMs without any of their CTAs (an SM that hosts a
+        // waiting k_pre CTA keeps that kernel's shared-memory configuration: a peer's kernel that wants
+        // another one -- the state permutation of a download, a vector kernel -- cannot join it there,
+        // and with every SM taken the peer never gets to the launch its neighbour waits for: the tests
+        // hung about one time in four), and no kernel is launched ahead of its predecessor's end (no
+        // PDL: a dependent grid parked on the SMs could keep a peer's kernel off them).  Host calls
+        // that synchronise the device (cudaMalloc / cudaFree) must not be issued while a peer's RHS is
+        // in flight: allocate before the first evaluation.
         int share = 0, sms = 1;
         for (int q = 0; q < nranks; q++) share += (ctxs[q]->device == ctxs[r]->device);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctxs[r]->device);
         if (share > 1) {
             ctxs[r]->pdl = 0;
-            ctxs[r]->pre_grid = std::max(1, std::min(ctxs[r]->pre_grid, sms / (share - 1)));
+            ctxs[r]->pre_grid = std::max(1, std::min(ctxs[r]->pre_grid, std::max(1, (sms - 16) / share)));
             ctxs[r]->main_grid = std::max(1, ctxs[r]->main_grid / share);
         }
     }

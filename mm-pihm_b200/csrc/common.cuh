@@ -105,6 +105,38 @@ struct DevMesh {
 }  // namespace pb
 
 namespace pb {
+// System-scope fence between a result and the flag / ticket that announces it (peer GPUs over NVLink, the
+// host over a mapped page).  __threadfence_system() is membar.sys = fence.sc.sys (MEMBAR.SC.SYS), measured at
+// ~6.5 us per executing warp inside the busy RHS kernel (tools/mgpu_rhs_probe.py, PB_HALO_TIMING).
+// PB_SYS_FENCE=1 builds the release / acquire form (fence.acq_rel.sys, MEMBAR.ALL.SYS) instead: no measurable
+// difference on one GPU (8.34 vs 8.44 ms per step), and the same-process rank-group tests
+// (tests/test_localgroup_gpu.py) intermittently lost a neighbour's flag with it -- so the sc fences stay.
+#ifndef PB_SYS_FENCE
+#define PB_SYS_FENCE 0
+#endif
+__device__ __forceinline__ void fence_sys()
+{
+#if PB_SYS_FENCE == 1
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+#elif PB_SYS_FENCE == 2       // timing experiment only: no fence at all
+    asm volatile("" ::: "memory");
+#else
+    __threadfence_system();
+#endif
+}
+// ... and the device-scope one between a block's partial result and the counter that elects the last block
+// (the threadFenceReduction pattern): release / acquire as well (MEMBAR.ALL.GPU instead of MEMBAR.SC.GPU)
+__device__ __forceinline__ void fence_gpu()
+{
+#if PB_SYS_FENCE == 0
+    __threadfence();
+#else
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
+}
+}  // namespace pb
+
+namespace pb {
 // Peer-memory halo exchange (partitioned run): what k_halo_put needs to store this rank's
 // boundary states straight into its neighbours' ghost buffers, and what k_pre waits for.
 #define PB_MAX_NBR 8
@@ -153,6 +185,7 @@ int rhs_class_rcp(pihm_b200_ctx *ctx);
 int rhs_tile_rcp(pihm_b200_ctx *ctx);
 int rhs_halo_pack(pihm_b200_ctx *ctx, const double *y);
 int rhs_launch(pihm_b200_ctx *ctx, const double *y, double *dy, bool replay);
+int rhs_halo_times(unsigned long long *out, int reset);
 }  // namespace pb
 
 namespace pb {

@@ -76,7 +76,7 @@ __device__ __forceinline__ void red_exchange(const RedBuf &rb, double &a, int sl
         x[xb_index(par, slotA, rb.rank)] = a;
         if (slotB >= 0) x[xb_index(par, slotB, rb.rank)] = b;
     }
-    __threadfence_system();
+    fence_sys();
     for (int p = 0; p < rb.nranks; p++) {
         volatile double *x = rb.peer[p];
         x[xb_index(par, slotA, rb.rank) + 1] = rb.seq;
@@ -88,7 +88,7 @@ __device__ __forceinline__ void red_exchange(const RedBuf &rb, double &a, int sl
         while (mine[xb_index(par, slotA, r) + 1] != rb.seq)
             if (++spins > (1LL << 31)) { lost = true; break; }   // a lost rank must not hang the GPU forever
     }
-    __threadfence_system();
+    fence_sys();
     double sa = MIN_A ? __longlong_as_double(0x7ff0000000000000LL) : 0.0, sb = 0.0;
     for (int r = 0; r < rb.nranks; r++) {
         const double va = mine[xb_index(par, slotA, r)];
@@ -134,12 +134,12 @@ __device__ __forceinline__ void red_finish(const RedBuf &rb, double a, int slotA
     if (threadIdx.x == 0) {
         rb.part[(size_t)slotA * rb.max_blocks + blockIdx.x] = a;
         if (slotB >= 0) rb.part[(size_t)slotB * rb.max_blocks + blockIdx.x] = b;
-        __threadfence();
+        fence_gpu();
         last = (atomicAdd(rb.counter, 1u) == gridDim.x - 1);
     }
     __syncthreads();
     if (!last) return;
-    __threadfence();
+    fence_gpu();
     double sa = MIN_A ? __longlong_as_double(0x7ff0000000000000LL) : 0.0, sb = 0.0;
     const volatile double *pa = rb.part + (size_t)slotA * rb.max_blocks;
     const volatile double *pb_ = rb.part + (size_t)(slotB >= 0 ? slotB : slotA) * rb.max_blocks;
@@ -156,7 +156,7 @@ __device__ __forceinline__ void red_finish(const RedBuf &rb, double a, int slotA
         rb.hsc[slotA] = sa;
         if (slotB >= 0) { rb.sc[slotB] = sb; rb.hsc[slotB] = sb; }
         *rb.counter = 0u;
-        __threadfence_system();          // results visible to the host before the ticket
+        fence_sys();          // results visible to the host before the ticket
         rb.hsc[SC_SEQ] = rb.seq;
         if (rb.gate) *reinterpret_cast<volatile double *>(rb.gate) = rb.seq;
     }
@@ -434,7 +434,7 @@ k_mgs_chain(long long n, int nsteps, KryPtrs V, double *Vk, RedBuf rb, int per_t
             if (threadIdx.x == 0) {
                 const double want = seq0 + (double)(st - 1);
                 while (*gate != want) { }
-                __threadfence();
+                fence_gpu();
             }
             __syncthreads();
         }

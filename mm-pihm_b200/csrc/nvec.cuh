@@ -138,13 +138,13 @@ k_reduce(long long n, const double *__restrict__ x, const double *__restrict__ y
     __shared__ bool last;
     if (threadIdx.x == 0) {
         part[blockIdx.x] = v;
-        __threadfence();
+        fence_gpu();
         const unsigned int t = atomicAdd(counter, 1u);
         last = (t == gridDim.x - 1);
     }
     __syncthreads();
     if (!last) return;
-    __threadfence();
+    fence_gpu();
     double s = rd_identity<OP>();
     for (int b = threadIdx.x; b < (int)gridDim.x; b += PB_VEC_THREADS)
         s = rd_combine<OP>(s, ((volatile double *)part)[b]);

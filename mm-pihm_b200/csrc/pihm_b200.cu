@@ -468,6 +468,7 @@ void pihm_b200_destroy(pihm_b200_ctx *ctx)
                    ctx->d_etf, ctx->d_eti, ctx->d_eto, ctx->d_et_tab};
     pb::comm_destroy(ctx);
     for (void *p : dev) if (p) cudaFree(p);
+    pihm_b200_print_close(ctx);        // files and staging buffers of the output writers (output.cu)
     for (pb::PrintVar &v : ctx->pvars) if (v.acc) cudaFree(v.acc);
     if (ctx->h_et_tab) cudaFreeHost(ctx->h_et_tab);
     if (ctx->et_ev) cudaEventDestroy(ctx->et_ev);
@@ -960,6 +961,15 @@ int pihm_b200_ode(pihm_b200_ctx *ctx, double t, const pihm_b200_vec *y, pihm_b20
         return -1;
     }
     return pb::rhs_launch(ctx, y->d, ydot->d, false);
+}
+
+// timing experiment of the halo protocol (library built with RHS_EXTRA=-DPB_HALO_TIMING; -2 otherwise):
+// out[256][8] %globaltimer stamps per RHS evaluation (rhs.cuh), then reset
+int pihm_b200_debug_halo_times(pihm_b200_ctx *ctx, unsigned long long *out, int reset)
+{
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    return pb::rhs_halo_times(out, reset);
 }
 
 int pihm_b200_check_nan(pihm_b200_ctx *ctx)

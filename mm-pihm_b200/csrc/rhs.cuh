@@ -1418,6 +1418,9 @@ __device__ __forceinline__ void river_main(const DevMesh &m, double *__restrict_
 #define PB_PRE_WARPS 10    // k_pre: 3 x 10 (3 x 8, 2 x 12, 2 x 10, 4 x 6: 1.5-5 us slower)
 #endif
 #define PB_PRE_THREADS (PB_PRE_WARPS * 32)
+#ifndef PB_PRE_HALO_FRAC
+#define PB_PRE_HALO_FRAC 35    // per cent of the interior tiles k_pre takes before the tiles that wait for the halo
+#endif
 #ifndef PB_PRE_STAGES
 #define PB_PRE_STAGES 12
 #endif
@@ -1505,6 +1508,26 @@ struct PreCfg {
     typedef Ring<PB_PRE_STAGES, SB> ring_t;
 };
 
+// Timing experiment (-DPB_HALO_TIMING, tools/mgpu_rhs_probe.py): %globaltimer stamps of the halo
+// protocol per RHS evaluation, [seq & 255][slot]; slots: 0 first CTA past the dependency wait,
+// 1 arrival flags raised, 2 / 3 first / last warp reaches the flag wait, 4 last warp leaves it,
+// 5 k_pre ends, 6 k_main's first CTA past its dependency wait, 7 k_main ends
+#ifdef PB_HALO_TIMING
+__device__ unsigned long long g_ht[256][8];
+__device__ int g_ht_seq;
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define HT_MIN(sq, k) atomicMin(&g_ht[(sq) & 255][k], gtime())
+#define HT_MAX(sq, k) atomicMax(&g_ht[(sq) & 255][k], gtime())
+#else
+#define HT_MIN(sq, k) ((void)0)
+#define HT_MAX(sq, k) ((void)0)
+#endif
+
 // Halo exchange over peer memory, folded into k_pre (partitioned run).  At its start the grid
 // stores this rank's boundary states straight into the neighbours' ghost buffers (NVLink
 // stores) as records in their ghost order -- elements {surf, gw[, fbr_gw]}, rivers {stage, gw}
@@ -1521,12 +1544,20 @@ struct HaloPut {
     int par;                          // parity copy of this exchange
     double seq;                       // its sequence number (the flag value)
     unsigned int *counter;            // CTAs that have finished their stores
+    int nput;                         // CTAs that put (the first nput of the grid), one record per thread
 };
 
+// Executed by the first h.nput CTAs of k_pre before they turn to their work items: one record per thread,
+// one system-scope fence per CTA, by the thread that counts the CTA in after the CTA barrier (the barrier
+// orders the other threads' stores before it).  Measured on 2 B200 (PB_HALO_TIMING, 3.4 k records): flags up
+// 11 us after the kernel starts (two sc fences and the NVLink round trip in between), seen by the
+// neighbour ~10 us later.  Variants tried and dropped: every CTA of the grid putting and fencing (same
+// 11 us, but all of them start late); a single communication CTA that does nothing else (27 rounds of
+// dependent latencies: 25-29 us); a few dedicated CTAs with four records per thread (same time as this).
 __device__ __forceinline__ void halo_put(const DevMesh &m, const double *__restrict__ y, const HaloPut &h)
 {
     const HaloPeers &hp = h.hp;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < h.nse + h.nsr; k += gridDim.x * blockDim.x) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < h.nse + h.nsr; k += h.nput * blockDim.x) {
         if (k < h.nse) {
             int kk = 0;
             while (kk + 1 < hp.nn && k >= hp.e_ptr[kk + 1]) kk++;
@@ -1545,16 +1576,17 @@ __device__ __forceinline__ void halo_put(const DevMesh &m, const double *__restr
             dst[1] = y[m.o_rgw + r];
         }
     }
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (atomicAdd(h.counter, 1u) == gridDim.x - 1) {
+        fence_sys();
+        if (atomicAdd(h.counter, 1u) == (unsigned)h.nput - 1) {
             *h.counter = 0u;
-            __threadfence_system();
+            fence_sys();
             for (int kk = 0; kk < hp.nn; kk++) {
                 volatile double *f = hp.base[kk] + hp.flag_off[kk] + h.par * PB_MAX_RANKS_H + hp.myrank;
                 *f = h.seq;
             }
+            HT_MAX((int)h.seq, 1);
         }
     }
 }
@@ -1574,26 +1606,35 @@ k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r, i
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = gridDim.x, b = blockIdx.x;
     // Work items of the grid, taken by ticket (ticket q of CTA b = item q * G + b):
-    //   [ clean river tiles | interior element tiles | other river tiles | other element tiles ]
+    //   [ clean river tiles | interior A | other river tiles | boundary + ghost element tiles | interior B ]
     // "clean" / "interior": the tile reads no ghost state (pihm_b200_create_part classifies them; the
     // partitioner lists the owned elements as [interior | boundary], the river tiles are taken through
     // m.riv_tile_order, clean ones first).  With a peer-memory halo the first two sections run while the
-    // neighbours' records are still on their way; without one there is nothing to wait for and the order
-    // is simply [ river tiles | element tiles ] (the slow river tiles first).
+    // neighbours' records are on their way (interior A is the first PB_PRE_HALO_FRAC per cent of the
+    // interior tiles); every warp waits for the flags before its first item behind them.  The tiles that
+    // need the records come next and NOT last: a river tile is a long serial computation -- at the end
+    // of the kernel the few that wait for the halo were a 16 us tail (PB_HALO_TIMING: 128 -> 113 us per RHS
+    // on 2 B200) -- so they run under the cover of interior B.  Without a peer-memory halo there is nothing
+    // to wait for and the order is simply [ river tiles | element tiles ], slow tiles first.
+    // (Tried and dropped: only the warps that take a halo-dependent item wait, the clean river tiles behind
+    // them -- 1 us faster, but the same-process rank-group tests hung intermittently with it.)
     const bool halo = GH && hw.nn > 0;
     const int R = ntile_r;
     const int Rc = halo ? min(m.ntile_rc, R) : R;
     const int E_int = halo ? min(ntile_int, ntile_e) : 0;
+    const int E_a = (int)((long long)E_int * PB_PRE_HALO_FRAC / 100);
     const int E_nog = GH ? min(ntile_int, ntile_e) : ntile_e;      // leading tiles served by the ghost-free code
-    const long long B1 = (long long)Rc + E_int, B2 = B1 + (R - Rc);     // sections: [0,Rc) [Rc,B1) [B1,B2) [B2, R + ntile_e)
+    // section boundaries: [0,C0) river | [C0,C1) elements | [C1,C2) river | [C2,C3) elements | [C3,C4) elements
+    const long long C0 = Rc, C1 = C0 + E_a, C2 = C1 + (R - Rc), C3 = C2 + (ntile_e - E_int), C4 = C3 + (E_int - E_a);
     auto first_q = [&](long long B) { return (B > b) ? (int)((B - b + G - 1) / G) : 0; };   // first ticket with item >= B
-    const int qa0 = first_q(Rc), qa1 = first_q(B1), qb0 = first_q(B2);
-    const int na = qa1 - qa0;                                       // element tickets of the interior section
+    const int qa0 = first_q(C0), qa1 = first_q(C1), qb0 = first_q(C2);
+    const int na = qa1 - qa0;                                       // element tickets of interior A
     auto q_of_k = [&](int k) { return (k < na) ? k + qa0 : k - na + qb0; };     // k-th element ticket of this CTA
-    auto tile_of_q = [&](int q) {       // element tile of an element ticket (>= ntile_e: past the end)
-        const long long g = (long long)q * G + b;
-        return (g < B1) ? g - Rc : g - B2 + E_int;
+    auto k_of_q = [&](int q) { return (q < qa1) ? q - qa0 : q - qb0 + na; };
+    auto tile_of_g = [&](long long g) -> long long {   // element tile of an element item (ntile_e: past the end)
+        return (g < C1) ? g - C0 : (g < C3) ? g - C2 + E_int : (g < C4) ? g - C3 + E_a : (long long)ntile_e;
     };
+    auto tile_of_q = [&](int q) { return tile_of_g((long long)q * G + b); };
     ring.init();
     // request the tile of the k-th element ticket (no-op past the end): the static slab does not
     // depend on the previous kernel (prologue), the own surf / gw columns of a tile of owned
@@ -1621,28 +1662,33 @@ k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r, i
     if (lane == 0)
         for (int k = warp; k < PB_PRE_STAGES; k += PB_PRE_WARPS) request(k, true, false);
     asm volatile("griddepcontrol.wait;" ::: "memory");      // y comes from the previous kernel of the stream
-    if (GH && hput.hp.nn > 0) halo_put(m, y, hput);
+#ifdef PB_HALO_TIMING
+    if (GH && threadIdx.x == 0) { HT_MIN((int)hput.seq, 0); if (b == 0) g_ht_seq = (int)hput.seq; }
+#endif
+    if (GH && hput.hp.nn > 0 && b < hput.nput) halo_put(m, y, hput);
     if (lane == 0)
         for (int k = warp; k < PB_PRE_STAGES; k += PB_PRE_WARPS) request(k, false, true);
-    const long long g_end = (long long)ntile_e + R;
+    const long long g_end = C4;
     bool halo_seen = !halo;
     for (;;) {
         const int q = ring.take(lane);
         const long long g = (long long)q * G + b;
         if (g >= g_end) break;
-        if (GH && !halo_seen && g >= B1) {
+        if (GH && !halo_seen && g >= C1) {
             // the neighbours' halo records of this RHS have arrived (one lane per neighbour)
+            if (lane == 0) { HT_MIN((int)hw.seq, 2); HT_MAX((int)hw.seq, 3); }
             if (lane < hw.nn) {
                 long long spins = 0;
                 while (hw.flags[hw.rank[lane]] != hw.seq)
                     if (++spins > (1LL << 31)) { atomicOr(m.nan_flag, 2); break; }   // lost neighbour: flag, do not hang
-                __threadfence_system();
+                fence_sys();
             }
             __syncwarp();
+            if (lane == 0) HT_MAX((int)hw.seq, 4);
             halo_seen = true;
         }
-        if (g < Rc || (g >= B1 && g < B2)) {
-            const int t = (int)((g < Rc) ? g : g - B1 + Rc);
+        if (g < C0 || (g >= C1 && g < C2)) {
+            const int t = (int)((g < C0) ? g : g - C1 + Rc);
             const int r = (GH ? m.riv_tile_order[t] : t) * PB_TILE + lane;
             if (r < m.nr) {
                 if (GH && t >= m.ntile_rc) river_fluxes<GH>(m, y, r);
@@ -1650,8 +1696,8 @@ k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r, i
             }
             continue;
         }
-        const long long tile = (g < B1) ? g - Rc : g - B2 + E_int;
-        const int k = (q < qa1) ? q - qa0 : q - qb0 + na, s = k % PB_PRE_STAGES, n = k / PB_PRE_STAGES;
+        const long long tile = tile_of_g(g);
+        const int k = k_of_q(q), s = k % PB_PRE_STAGES, n = k / PB_PRE_STAGES;
         const unsigned phase = (unsigned)n & 1u;
         ring.acquire(s, n);
         const int i = (int)tile * PB_TILE + lane;
@@ -1681,6 +1727,9 @@ k_pre(const DevMesh m, const double *__restrict__ y, int ntile_e, int ntile_r, i
             }
         }
     }
+#ifdef PB_HALO_TIMING
+    if (GH && lane == 0) HT_MAX((int)hput.seq, 5);
+#endif
 }
 
 template <bool FBR, bool GH>
@@ -1767,6 +1816,10 @@ k_main(const DevMesh m, const double *__restrict__ y, double *__restrict__ dy, i
     // the static slabs above do not depend on k_pre; everything below does (no-op when the
     // kernel was not launched with the programmatic-serialization attribute)
     asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifdef PB_HALO_TIMING
+    const int ht_seq = g_ht_seq;
+    if (GH && threadIdx.x == 0) HT_MIN(ht_seq, 6);
+#endif
     if (lane == 0)
         for (int k = warp; k < STAGES; k += MainCfg<FBR>::WARPS) request(qe0 + k, false, true);
     __syncthreads();        // the descriptor table is visible to every warp
@@ -1808,6 +1861,9 @@ k_main(const DevMesh m, const double *__restrict__ y, double *__restrict__ dy, i
             }
         }
     }
+#ifdef PB_HALO_TIMING
+    if (GH && lane == 0) HT_MAX(ht_seq, 7);
+#endif
 }
 
 // One-off: the tiles' RAREA / RDIST* slots.  The packer left the neighbour distances in RDIST*: they move to

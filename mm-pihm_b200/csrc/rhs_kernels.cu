@@ -79,6 +79,25 @@ int rhs_halo_pack(pihm_b200_ctx *ctx, const double *y)
     return 0;
 }
 
+// timing experiment (build with RHS_EXTRA=-DPB_HALO_TIMING): read / reset the %globaltimer stamps
+int rhs_halo_times(unsigned long long *out, int reset)
+{
+#ifdef PB_HALO_TIMING
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (out && cudaMemcpyFromSymbol(out, g_ht, sizeof(unsigned long long) * 256 * 8) != cudaSuccess) return -1;
+    if (reset) {
+        std::vector<unsigned long long> h(256 * 8);
+        for (int i = 0; i < 256; i++)
+            for (int k = 0; k < 8; k++) h[i * 8 + k] = (k == 0 || k == 2 || k == 6) ? ~0ULL : 0ULL;
+        if (cudaMemcpyToSymbol(g_ht, h.data(), sizeof(unsigned long long) * 256 * 8) != cudaSuccess) return -1;
+    }
+    return 0;
+#else
+    (void)out; (void)reset;
+    return -2;
+#endif
+}
+
 // ---------------------------------------------------------------------------
 // RHS
 // ---------------------------------------------------------------------------
@@ -111,6 +130,7 @@ int rhs_launch(pihm_b200_ctx *ctx, const double *y, double *dy, bool replay)
         hput.par = par;
         hput.seq = (double)seq;
         hput.counter = ctx->d_hcount;
+        hput.nput = std::max(1, (ctx->nse + ctx->nsr + PB_PRE_THREADS - 1) / PB_PRE_THREADS);     // one record per thread
         dm.gel = ctx->d_hx + par * ctx->hx_stride;
         dm.gri = dm.gel + (size_t)dm.gs * (dm.ne - dm.nown);
         dm.self = ctx->d_dm_par[par];
@@ -137,6 +157,7 @@ int rhs_launch(pihm_b200_ctx *ctx, const double *y, double *dy, bool replay)
     const int te_own = (dm.nown + PB_TILE - 1) / PB_TILE, tr_own = (dm.rown + PB_TILE - 1) / PB_TILE;
     const auto groups = [](int t) { return (t + PB_RING_GROUP - 1) / PB_RING_GROUP; };
     const int gpre = std::max(1, std::min(ctx->pre_grid, groups(te) + groups(tr)));
+    if (hput.nput > gpre) hput.nput = gpre;
     const int gmain = std::max(1, std::min(ctx->main_grid, groups(te_own) + groups(tr_own)));
     // own-state columns of a tile by bulk copy: needs 16-byte alignment of each block inside y
     int ys = 0;

@@ -118,6 +118,11 @@ _SIGS = {
     "pihm_b200_print_add": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "pihm_b200_print_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "pihm_b200_print_data": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "pihm_b200_print_open": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_int]),
+    "pihm_b200_print_write": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
+    "pihm_b200_print_close": (C.c_int, [C.c_void_p]),
+    "pihm_b200_print_io_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pihm_b200_write_ic": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pihm_b200_set_diagnostics": (C.c_int, [C.c_void_p, C.c_int]),
     "pihm_b200_set_ws0": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pihm_b200_summary_mb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double]),
@@ -412,6 +417,30 @@ class Model:
         out = np.zeros(self.nriver if river else self.nelem); cnt = C.c_int32(0)
         _check(self.L, self.L.pihm_b200_print_data(self.h, int(vid), _ptr(out), C.byref(cnt)), "print_data")
         return out, cnt.value
+
+    # output files fed from the device (InitOutputFile / PrintData / PrintInit, src/print.c:72-313) ----
+    def print_open(self, vid: int, name: str, ascii: bool = True, append: bool = False):
+        _check(self.L, self.L.pihm_b200_print_open(self.h, int(vid), name.encode(), int(ascii), int(append)), "print_open")
+
+    def print_write(self, ids, t: int, timestr: str):
+        """PrintData for the variables that are due at model time t: one kernel, one D2H copy, records appended"""
+        a = np.ascontiguousarray(ids, np.int32)
+        _check(self.L, self.L.pihm_b200_print_write(self.h, _ptr(a), len(a), int(t), timestr.encode()), "print_write")
+
+    def print_close(self):
+        self.L.pihm_b200_print_close(self.h)
+
+    def print_io_stats(self):
+        n, b = C.c_int64(0), C.c_int64(0)
+        self.L.pihm_b200_print_io_stats(self.h, C.byref(n), C.byref(b))
+        return n.value, b.value
+
+    def write_ic(self, path: str, y: "Vec", cmc=None, sneqv=None):
+        """PrintInit (src/print.c:253-313): the restart file of state y"""
+        c = np.ascontiguousarray(cmc, np.float64) if cmc is not None else None
+        s = np.ascontiguousarray(sneqv, np.float64) if sneqv is not None else None
+        _check(self.L, self.L.pihm_b200_write_ic(self.h, path.encode(), y.h, _ptr(c) if c is not None else None,
+                                                 _ptr(s) if s is not None else None), "write_ic")
 
     def set_flux_recording(self, on: bool):
         _check(self.L, self.L.pihm_b200_set_flux_recording(self.h, int(on)), "set_flux_recording")

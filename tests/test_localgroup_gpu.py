@@ -6,13 +6,25 @@ every integrator norm -- and compares with the unpartitioned run:
   * RHS: bit for bit (two calls: the second one sees the first one's river-edge flows);
   * integrator: all ranks take the same control flow (identical counters), state in lock step with the
     single-GPU run (the reduction order differs, so not bitwise).
-SURVEY 8(e); VERDICT r1 'make the peer-memory halo and ticketed all-reduce testable on one GPU'."""
+SURVEY 8(e); VERDICT r1 'make the peer-memory halo and ticketed all-reduce testable on one GPU'.
+
+Each case runs in a process of its own with a time limit and is repeated (up to 4 attempts) when it does not
+come back: the kernels of the emulated ranks wait for each other ON ONE GPU, i.e. they need the hardware to run
+kernels of different streams side by side, which CUDA does not promise -- now and then (measured: one run of
+this file in six with the round-1 kernels as well as with the present ones) a rank's kernel is not dispatched
+while its neighbours' kernels spin, and the group stalls.  Ranks on GPUs of their own (the real multi-GPU run,
+tests/test_multigpu_gpu.py::test_nccl_partitioned_run, bench.py --gpus N) have no such coupling.  A wrong
+result (an assertion of the case) fails at once and is never retried."""
+import os
+import subprocess
+import sys
 import threading
 
 import numpy as np
 import pytest
 
-import mm_pihm_b200  # noqa: F401
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))     # run as a script (run_isolated)
+import mm_pihm_b200  # noqa: E402,F401
 from mm_pihm_b200 import lib, partition as PT, watershed as W
 
 pytestmark = pytest.mark.gpu
@@ -49,9 +61,33 @@ def make_group(tb, nparts):
     return parts, models
 
 
+def run_isolated(case, *args, limit=60, attempts=4):
+    """the case in a fresh process; a stall (no return within `limit` s) is retried, a failure is not"""
+    cmd = [sys.executable, os.path.abspath(__file__), case] + [str(a) for a in args]
+    for k in range(attempts):
+        try:
+            p = subprocess.run(cmd, capture_output=True, text=True, timeout=limit)
+        except subprocess.TimeoutExpired:
+            print(f"[local group] {case}{args}: attempt {k + 1} stalled (co-scheduling of the emulated ranks)")
+            continue
+        sys.stdout.write(p.stdout)
+        assert p.returncode == 0, f"{case}{args} failed:\n{p.stdout[-3000:]}\n{p.stderr[-3000:]}"
+        return
+    raise AssertionError(f"{case}{args}: stalled in {attempts} attempts")
+
+
 @pytest.mark.parametrize("fbr", [False, True])
 @pytest.mark.parametrize("nparts", [2, 3])
 def test_peer_memory_halo_rhs_bitwise(fbr, nparts):
+    run_isolated("halo", int(fbr), nparts)
+
+
+@pytest.mark.parametrize("fbr", [False, True])
+def test_peer_memory_integrator_lockstep(fbr):
+    run_isolated("lockstep", int(fbr), limit=90)
+
+
+def case_halo_rhs_bitwise(fbr, nparts):
     tb = W.make_named("10k", fbr=fbr, dirichlet_edges=True)
     ne, nr = tb["nelem"], tb["nriver"]
     y = W.wet_state(tb, seed=4)
@@ -88,8 +124,7 @@ def test_peer_memory_halo_rhs_bitwise(fbr, nparts):
         m.close()
 
 
-@pytest.mark.parametrize("fbr", [False, True])
-def test_peer_memory_integrator_lockstep(fbr):
+def case_integrator_lockstep(fbr):
     nparts, nsteps = 2, 20
     tb = W.make_named("10k", fbr=fbr, dirichlet_edges=True)
     ne, nr = tb["nelem"], tb["nriver"]
@@ -140,3 +175,10 @@ def test_peer_memory_integrator_lockstep(fbr):
         cv.close()
     for m in models:
         m.close()
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "halo":
+        case_halo_rhs_bitwise(bool(int(sys.argv[2])), int(sys.argv[3]))
+    else:
+        case_integrator_lockstep(bool(int(sys.argv[2])))
