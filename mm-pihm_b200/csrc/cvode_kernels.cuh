@@ -61,16 +61,58 @@ struct RedBuf {
 #define PB_XB_DOUBLES (2 * SC_COUNT * PB_MAX_RANKS * 2)
 __device__ __forceinline__ int xb_index(int par, int slot, int r) { return ((par * SC_COUNT + slot) * PB_MAX_RANKS + r) * 2; }
 
-// All-reduce of the finishing thread's raw sums over the ranks, inside the reduction kernel:
-// the value and then (after a system-scope fence) the kernel's ticket are stored straight into
-// every rank's exchange buffer over NVLink; the thread then waits for the ticket of every rank
-// in its own buffer and combines the values in rank order, so all ranks hold the same bits.
-// Consecutive tickets alternate between two copies of the buffer: a rank can be at most one
-// reduction ahead of the slowest one, so a value is never overwritten before it has been read.
+// All-reduce of the finishing thread's raw sums over the ranks, inside the reduction kernel: the thread stores
+// {value, ticket} straight into every rank's exchange buffer over NVLink, waits for the pair of every rank in
+// its own buffer and combines the values in rank order, so all ranks hold the same bits.  Consecutive tickets
+// alternate between two copies of the buffer: a rank can be at most one reduction ahead of the slowest one,
+// so a value is never overwritten before it has been read.
+// {value, ticket} travel as ONE naturally aligned 16-byte store / load: the pair arrives (or not) as a whole, so
+// it validates itself and the exchange needs no fence between a value and its ticket (PB_RED_PAIR = 0: the
+// protocol of round 1 -- values, system-scope fence, tickets, wait, fence -- whose two fences cost ~5 us each)
+#ifndef PB_RED_PAIR
+#define PB_RED_PAIR 1
+#endif
+__device__ __forceinline__ void st_pair(double *p, double v, double t)
+{
+    asm volatile("st.volatile.global.v2.f64 [%0], {%1, %2};" ::"l"(__cvta_generic_to_global(p)), "d"(v), "d"(t) : "memory");
+}
+__device__ __forceinline__ void ld_pair(const double *p, double &v, double &t)
+{
+    asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(v), "=d"(t) : "l"(__cvta_generic_to_global(p)) : "memory");
+}
+
 template <bool MIN_A>
 __device__ __forceinline__ void red_exchange(const RedBuf &rb, double &a, int slotA, double &b, int slotB)
 {
     const int par = (int)((long long)rb.seq & 1);
+#if PB_RED_PAIR
+    for (int p = 0; p < rb.nranks; p++) {
+        double *x = rb.peer[p];
+        st_pair(x + xb_index(par, slotA, rb.rank), a, rb.seq);
+        if (slotB >= 0) st_pair(x + xb_index(par, slotB, rb.rank), b, rb.seq);
+    }
+    const double *mine = rb.peer[rb.rank];
+    bool lost = false;
+    double sa = MIN_A ? __longlong_as_double(0x7ff0000000000000LL) : 0.0, sb = 0.0;
+    for (int r = 0; r < rb.nranks; r++) {       // rank order: every rank adds the same values in the same order
+        double va = 0.0, vb = 0.0, tk = 0.0;
+        long long spins = 0;
+        for (;;) {
+            ld_pair(mine + xb_index(par, slotA, r), va, tk);
+            if (tk == rb.seq) break;
+            if (++spins > (1LL << 31)) { lost = true; break; }   // a lost rank must not hang the GPU forever
+        }
+        if (slotB >= 0 && !lost) {
+            for (;;) {
+                ld_pair(mine + xb_index(par, slotB, r), vb, tk);
+                if (tk == rb.seq) break;
+                if (++spins > (1LL << 31)) { lost = true; break; }
+            }
+        }
+        sa = MIN_A ? ((va < sa) ? va : sa) : sa + va;
+        sb += vb;
+    }
+#else
     for (int p = 0; p < rb.nranks; p++) {
         volatile double *x = rb.peer[p];
         x[xb_index(par, slotA, rb.rank)] = a;
@@ -95,6 +137,7 @@ __device__ __forceinline__ void red_exchange(const RedBuf &rb, double &a, int sl
         sa = MIN_A ? ((va < sa) ? va : sa) : sa + va;
         if (slotB >= 0) sb += mine[xb_index(par, slotB, r)];
     }
+#endif
     // a rank that never arrived: poison the result so that the integrator stops (NaN norm)
     a = lost ? __longlong_as_double(0x7ff8000000000000LL) : sa;
     b = lost ? __longlong_as_double(0x7ff8000000000000LL) : sb;
