@@ -314,7 +314,7 @@ def run_ours(args):
             strong = {"mesh": "8M", "ms_per_step": ms / K, "ms_per_rhs_eval": ms / max(rhs_evals, 1),
                       "rhs_evals_per_step": rhs_evals / K, "rhs_ms": rhs_ms, "steps": K, "same_as": "main run"}
         else:
-            strong = strong_scaling_leg(args, rank, world, local, stream, barrier, max_over_ranks)
+            strong = strong_scaling_leg(args, rank, world, local, stream, barrier, max_over_ranks, steps=K, warmup=Wu)
     if rank != 0:
         dist.destroy_process_group()
         return
@@ -365,7 +365,8 @@ def run_ours(args):
 
 def strong_scaling_leg(args, rank, world, local, stream, barrier, max_over_ranks, steps=6, warmup=3):
     """BASELINE config[4] / north_star '>= 6x on 8 B200 for an 8M-triangle mesh': the SAME 8M mesh on the N GPUs of
-    this run (N = 1: unpartitioned), a few model steps of the same storm; ms per step and per RHS evaluation."""
+    this run (N = 1: unpartitioned), the same model steps of the same storm as the main run (so that the line of
+    N = 1 and the main line of N = 8 divide into the strong-scaling factor); ms per step and per RHS evaluation."""
     import torch
     import torch.distributed as dist
     from mm_pihm_b200 import lib, partition as PT
@@ -392,7 +393,12 @@ def strong_scaling_leg(args, rank, world, local, stream, barrier, max_over_ranks
     model.set_ws0(y)
     cv.SetCVodeParam(y)
 
+    forc_host = {k: forcing_at(tb, k) for k in range(0, warmup + steps + 15, 15)}
+
     def step(k):
+        if k % 15 == 0 and k > 0:
+            model.set_forcing(forc_host[k], np.zeros(nr))
+            model.Summary(y)
         cv.SolveCVode((k + 1) * STEP, y)
         model.SummaryMB(y, STEP)
     for k in range(warmup):

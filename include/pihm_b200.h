@@ -3,9 +3,10 @@
  *
  * Everything here is plain C: pointers, sizes and opaque handles.  No torch,
  * no C++ types.  A PIHM driver written in C links this library and keeps its
- * own elem_struct/river_struct arrays; the packing stub that turns those AoS
- * arrays into the column tables below is shown in INTEGRATION.md (and is what
- * oracle/ref_shim.c does for the tests).
+ * own elem_struct/river_struct arrays; glue/pihm_b200_glue.c is the translation
+ * unit that replaces src/ode.c in the pihm / pihm-fbr drivers: it packs those
+ * AoS arrays into the column tables below and defines ODE / SetCVodeParam /
+ * SolveCVode / AdjCVodeMaxStep / NumStateVar on top of this ABI.
  *
  * Each entry point cites the reference interface it replaces
  * (paths relative to the MM-PIHM tree).

@@ -76,3 +76,16 @@ def rel_err(a, ref, scale=None):
     den = np.abs(ref) if scale is None else np.maximum(np.abs(ref), scale)
     den = np.where(den == 0.0, 1.0, den)
     return np.abs(a - ref) / den
+
+
+def record(name, **values):
+    """append a measured figure (parity multiple, worst error ...) to gpurun_out/parity_record.jsonl so that
+    the numbers the tolerance tests observed are kept next to the pass / fail verdict (copied to profiles/)"""
+    import json
+    try:
+        d = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity_record.jsonl"), "a") as f:
+            f.write(json.dumps({"test": name, **{k: (float(v) if hasattr(v, "__float__") else v) for k, v in values.items()}}) + "\n")
+    except OSError:
+        pass

@@ -16,7 +16,7 @@ be expected beyond the lock-step phase; work counters must stay within 25 % at t
 import numpy as np
 import pytest
 
-from helpers import golden_tables, load_golden
+from helpers import golden_tables, load_golden, record
 import mm_pihm_b200  # noqa: F401
 from mm_pihm_b200 import lib, watershed as W
 
@@ -32,6 +32,7 @@ def check_state(y, yref, tag, ypert=None, lockstep=False):
     self_sens = (np.abs(ypert - yref) / unit).max() if ypert is not None else float("nan")
     print(f"{tag}: max err {worst:.3e} x (reltol|y|+abstol); reference's own 1e-15 sensitivity {self_sens:.3e}")
     lim = MULT_LOCKSTEP if lockstep else MULT
+    record("trajectory " + tag, multiple_of_reltol_y_plus_abstol=worst, reference_self_sensitivity=self_sens, bound=lim)
     assert worst <= lim, f"{tag}: state error {worst:.3e} x (reltol|y|+abstol) at {np.argmax(err)}"
     return worst
 
@@ -199,6 +200,8 @@ def test_100k_lockstep_with_live_reference():
     err = (np.abs(yg - yr) / unit).max()
     print(f"100k: {nsteps} model steps, err {err:.3e} x (reltol|y|+abstol); nst {sg['nst']}/{sr['nst']} "
           f"nfe {sg['nfe']}/{sr['nfe']} nli {sg['nli']}/{sr['nli']}")
+    record("100k live reference, 12 model steps", multiple_of_reltol_y_plus_abstol=err, bound=MULT,
+           nst=int(sg["nst"]), nst_reference=int(sr["nst"]))
     assert err <= MULT
     assert abs(sg["nst"] - sr["nst"]) <= 0.25 * sr["nst"]
     ref.close(); cv.close(); model.close()

@@ -12,6 +12,7 @@ import glob
 import os
 import shutil
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -63,6 +64,10 @@ def compare(ref_out, our_out, label):
             rel = float(np.abs(a - b).max() / scale)
             worst_flux = max(worst_flux, rel)
             assert rel <= 1e-6, f"{label} {name}: {rel:.3g} of the column's magnitude"
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import record
+    record("unchanged driver, input/example, 3 simulated hours: " + label, files=len(files),
+           states_multiple_of_reltol_y_plus_abstol=worst_state, bound=10.0, fluxes_rel_to_column_magnitude=worst_flux)
     print(f"[{label}] {len(files)} output files: states within {worst_state:.3g} x (reltol|y|+abstol), "
           f"fluxes within {worst_flux:.3g} of their magnitude")
     return worst_state, worst_flux

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oraclelib
-from helpers import dy_scale, golden_cases, golden_tables, load_golden, rel_err
+from helpers import dy_scale, golden_cases, golden_tables, load_golden, record, rel_err
 import mm_pihm_b200  # noqa: F401
 from mm_pihm_b200 import lib, watershed as W
 
@@ -187,6 +187,7 @@ def test_rhs_100k_vs_oracle(fbr):
     c = _oracle_case(tb, om, y, forc, np.zeros(tb["nriver"]), np.zeros((3, ne)))
     worst, exact = check_case(model, tb, c, "100k")
     print(f"100k fbr={fbr}: max rel err {worst:.2e}; bit-exact fraction {exact:.4f}")
+    record(f"RHS vs oracle, 100k fbr={fbr}", max_rel_err=worst, bit_exact_fraction=exact, bound=RTOL)
     model.close()
 
 
@@ -207,6 +208,7 @@ def test_rhs_1m_vs_oracle(fbr):
         worst = max(worst, w)
         print(f"1M fbr={fbr} seed {seed}: max rel err {w:.2e}; bit-exact fraction {exact:.4f}; "
               f"slow-path elements {model.slow_path_count()}")
+    record(f"RHS vs oracle, 1M fbr={fbr}", max_rel_err=worst, bound=RTOL)
     assert worst <= RTOL
     model.close()
 
@@ -238,6 +240,7 @@ def test_rhs_8m_partition_vs_oracle():
     err = rel_err(dy, c["dy"][own], scale)
     print(f"8M/8 partition ({part['nown_elem']} owned + {nl - part['nown_elem']} ghost elements): max rel err "
           f"{err.max():.2e}; bit-exact fraction {np.mean(dy == c['dy'][own]):.4f}")
+    record("RHS vs oracle, one rank's share of the 8M mesh", max_rel_err=err.max(), bound=RTOL)
     assert err.max() <= RTOL, f"rel err {err.max():.3e} at {err.argmax()}"
     model.close()
 
