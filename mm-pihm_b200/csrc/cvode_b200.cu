@@ -75,6 +75,7 @@ inline double rsqrt_s(double x) { return (x <= 0.0) ? 0.0 : std::sqrt(x); }
 // Every integrator kernel is launched with programmatic stream serialization (PDL): it may
 // become resident while its predecessor drains; all of them start with pdl_enter()
 // (cvode_kernels.cuh: launch_dependents + wait), so nothing is read or written early.
+static thread_local cudaError_t g_launch_error = cudaSuccess;
 template <typename... ExpTypes, typename... ActTypes>
 static inline void launch_pdl(cudaStream_t st, int pdl, int grid, int block, void (*kernel)(ExpTypes...),
                               ActTypes &&... args)
@@ -88,7 +89,8 @@ static inline void launch_pdl(cudaStream_t st, int pdl, int grid, int block, voi
     at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kernel, std::forward<ActTypes>(args)...);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, std::forward<ActTypes>(args)...);
+    if (e != cudaSuccess && g_launch_error == cudaSuccess) g_launch_error = e;     // first failure wins; solve() reports it
 }
 
 struct pihm_b200_cvode {
@@ -133,7 +135,7 @@ struct pihm_b200_cvode {
     void count(int k = 1) { ctx->launches += k; }
     // Multi-GPU: kernels leave rank-local partial sums in d_sc; red() all-reduces
     // the slots in stream order and sync() then fetches the global values.
-    double *h_sc_map = nullptr;          // mapped mirror the kernels write (single GPU: == h_sc)
+    double *h_sc_map = nullptr;          // mapped page the kernels write: [SC_COUNT] pairs {value, ticket}
     // p2p: the fused reduction kernels all-reduce their scalars themselves over peer memory
     // (red_exchange, cvode_kernels.cuh) and write the GLOBAL values to the mapped mirror, like
     // on one GPU; otherwise NCCL does it after the kernel.
@@ -145,7 +147,17 @@ struct pihm_b200_cvode {
     {
         if (ctx->nranks > 1 && !p2p)
             cudaMemcpyAsync(h_sc, d_sc, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, ctx->s());
-        cudaStreamSynchronize(ctx->s());
+        note_status(cudaStreamSynchronize(ctx->s()));
+        if (!(ctx->nranks > 1 && !p2p)) sync_spin_();      // the stream has drained: every pair is there
+        else npend = 0;
+    }
+    // a failed launch or a device fault: remember the first one; the step loop stops at its next check
+    cudaError_t dev_error = cudaSuccess;
+    void note_status(cudaError_t e) { if (e != cudaSuccess && dev_error == cudaSuccess) dev_error = e; }
+    bool failed()
+    {
+        if (g_launch_error != cudaSuccess) { note_status(g_launch_error); g_launch_error = cudaSuccess; }
+        return dev_error != cudaSuccess;
     }
     void red(int slot, int n = 1, int op = 0) { if (ctx->nranks > 1 && !p2p) comm_allreduce(ctx, d_sc + slot, n, op); }
     // a plain k_reduce launch (N_Vector kernel, rank-local result): always NCCL
@@ -160,7 +172,22 @@ struct pihm_b200_cvode {
     // that word (~2 us) instead of cudaStreamSynchronize (~15 us); use it only when the last
     // kernel launched was a reduction kernel.
     long long seq_ctr = 0;
-    RedBuf &R() { rb.seq = (double)(++seq_ctr); return rb; }
+    // R(slots): the next ticket; the slots the kernel will produce are noted so that the next host
+    // synchronisation waits for exactly those pairs
+    int pend_slot[2 * SC_COUNT] = {}, npend = 0;
+    double pend_seq[2 * SC_COUNT] = {};
+    void expect(int slot, double seq)
+    {
+        for (int k = 0; k < npend; k++) if (pend_slot[k] == slot) { pend_seq[k] = seq; return; }
+        pend_slot[npend] = slot; pend_seq[npend] = seq; npend++;
+    }
+    RedBuf &R(int slotA, int slotB = -1)
+    {
+        rb.seq = (double)(++seq_ctr);
+        expect(slotA, rb.seq);
+        if (slotB >= 0) expect(slotB, rb.seq);
+        return rb;
+    }
     // PIHM_B200_PROFILE=1: host wait time per sync and in-situ RHS event times, printed at destroy
     bool prof = false;
     long long prof_nsync = 0, prof_wait_ns = 0, prof_solve_ns = 0;
@@ -184,15 +211,24 @@ struct pihm_b200_cvode {
     void sync_spin_()
     {
         if (ctx->nranks > 1 && !p2p) { sync(); return; }
-        volatile double *tk = h_sc_map + SC_SEQ;
-        const double want = (double)seq_ctr;
-        for (long long it = 0; *tk != want; it++) {
-            if ((it & 0xfff) == 0xfff && cudaStreamQuery(ctx->s()) != cudaErrorNotReady) {
-                cudaStreamSynchronize(ctx->s());      // finished (or failed) without the ticket: stop spinning
-                break;
+        // every pair the kernels since the last synchronisation produce: wait for its ticket, take its value
+        for (int k = 0; k < npend; k++) {
+            volatile double *pr = h_sc_map + 2 * pend_slot[k];
+            const double want = pend_seq[k];
+            for (long long it = 0; pr[1] != want; it++) {
+                if ((it & 0xfff) == 0xfff && cudaStreamQuery(ctx->s()) != cudaErrorNotReady) {
+                    // finished (or failed) without the ticket: stop spinning; a ticket that is still missing
+                    // after the stream has drained means the scalar is stale -> fatal, not a branch on garbage
+                    note_status(cudaStreamSynchronize(ctx->s()));
+                    std::atomic_thread_fence(std::memory_order_acquire);
+                    if (pr[1] != want) note_status(cudaErrorUnknown);
+                    break;
+                }
             }
+            std::atomic_thread_fence(std::memory_order_acquire);
+            h_sc[pend_slot[k]] = pr[0];
         }
-        std::atomic_thread_fence(std::memory_order_acquire);
+        npend = 0;
     }
     // N_VWrmsNorm = SUNRsqrt(sum / N)  (nvector_serial.c:685)
     double wrms(int slot) const { const double v = h_sc[slot] / n_global; return (v <= 0.0) ? 0.0 : std::sqrt(v); }
@@ -252,12 +288,12 @@ struct pihm_b200_cvode {
         wrap_b.d = ydot;
         if (prof && prof_used + 2 <= prof_ev.size()) {
             cudaEventRecord(prof_ev[prof_used], s());
-            pihm_b200_ode(ctx, tn, &wrap_a, &wrap_b);
+            if (pihm_b200_ode(ctx, tn, &wrap_a, &wrap_b) != 0) note_status(cudaErrorLaunchFailure);
             cudaEventRecord(prof_ev[prof_used + 1], s());
             prof_used += 2;
             return;
         }
-        pihm_b200_ode(ctx, tn, &wrap_a, &wrap_b);
+        if (pihm_b200_ode(ctx, tn, &wrap_a, &wrap_b) != 0) note_status(cudaErrorLaunchFailure);
     }
     // diagnostics (pihm_b200_set_diagnostics): say so BEFORE a kernel overwrites a vector that
     // can be the input of the last RHS call (zn[0], y, ytemp), see common.cuh note_write
@@ -281,7 +317,7 @@ struct pihm_b200_cvode {
     }
     void launch_ewt()                                    // efun + tolsf norm (cvode.c:1349,1376)
     {
-        LK(K_EWT, 2, k_ewt, N, reltol, abstol, zn[0], ewt, R());
+        LK(K_EWT, 2, k_ewt, N, reltol, abstol, zn[0], ewt, R(SC_EWT_MIN, SC_EWT_NRM));
         count();
         red(SC_EWT_MIN, 1, 1);
         red(SC_EWT_NRM);
@@ -485,7 +521,7 @@ int pihm_b200_cvode::spgmrSolve(bool *b_is_zero)
             const int l_plus_1 = lk + 1;
             krydim = l_plus_1;
             // A-tilde V[l]: right scaling, DQ J*v, I - gamma J, left scaling, first MGS dot
-            LK(K_KRYLOV_A, 4, k_krylov_a, N, cnorm, V[lk], ewt, vtemp, R());
+            LK(K_KRYLOV_A, 4, k_krylov_a, N, cnorm, V[lk], ewt, vtemp, R(SC_VNRM));
             red(SC_VNRM);
             clobber(ytemp);
             LK(K_KRYLOV_B, 3, k_krylov_b, N, n_global, d_sc, vtemp, y, ytemp);
@@ -494,7 +530,7 @@ int pihm_b200_cvode::spgmrSolve(bool *b_is_zero)
             nfes++;
             njtimes++;
             LK(K_KRYLOV_C, 6, k_krylov_c, N, n_global, gamma, d_sc, vtemp, ftemp, ewt,
-                                                            V[0], V[l_plus_1], R());
+                                                            V[0], V[l_plus_1], R(SC_VK2, SC_H0));
             count();
             red(SC_VK2);
             red(SC_H0);
@@ -505,6 +541,8 @@ int pihm_b200_cvode::spgmrSolve(bool *b_is_zero)
                 RedBuf r = rb;
                 r.seq = (double)(seq_ctr + 1);           // one ticket per step
                 r.gate = d_sc + SC_GATE;
+                for (int st = 0; st < l_plus_1; st++)
+                    expect((st == l_plus_1 - 1) ? SC_NEW2 : SC_H0 + st + 1, (double)(seq_ctr + 1 + st));
                 seq_ctr += l_plus_1;
                 long long n_ = N;
                 int nsteps = l_plus_1, per = chain_per_thread;
@@ -523,7 +561,7 @@ int pihm_b200_cvode::spgmrSolve(bool *b_is_zero)
                 const double *vnext = (i + 1 < l_plus_1) ? V[i + 1] : V[l_plus_1];
                 const int slot_next = (i + 1 < l_plus_1) ? SC_H0 + i + 1 : SC_NEW2;
                 LK(K_MGS_STEP, (vnext == V[l_plus_1]) ? 3 : 4, k_mgs_step, N, d_sc, SC_H0 + i, V[i], vnext,
-                                                                V[l_plus_1], slot_next, R());
+                                                                V[l_plus_1], slot_next, R(slot_next));
                 count();
                 red(slot_next);
             }
@@ -537,10 +575,11 @@ int pihm_b200_cvode::spgmrSolve(bool *b_is_zero)
                 double new_norm_2 = 0.0;
                 for (int i = 0; i < l_plus_1; i++) {
                     LK(K_DOT, 2, k_reduce<RD_DOT, 0>, 
-                        N, V[i], V[l_plus_1], d_part, d_counter, d_sc + SC_TMP, h_sc_map + SC_TMP);
+                        N, V[i], V[l_plus_1], d_part, d_counter, d_sc + SC_TMP, h_sc_map + 2 * SC_TMP);
                     count();
                     red_nccl(SC_TMP);
                     sync();
+                    if (!(ctx->nranks > 1)) h_sc[SC_TMP] = h_sc_map[2 * SC_TMP];      // (partitioned: red_nccl brought it)
                     const double new_product = h_sc[SC_TMP];
                     temp = 1000.0 * Hes[i][lk];
                     if ((temp + new_product) == temp) continue;
@@ -652,10 +691,10 @@ int pihm_b200_cvode::cvNewtonIteration()
         clobber(y);
         if (m == 0)
             LK(K_NEWTON_RES, 8, k_newton_res<true>, N, rl1, gamma, zn[0], zn[1], ftemp, ewt,
-                                                                   acor, y, tempv, V[0], R());
+                                                                   acor, y, tempv, V[0], R(SC_BSUM));
         else
             LK(K_NEWTON_RES, 6, k_newton_res<false>, N, rl1, gamma, zn[0], zn[1], ftemp, ewt,
-                                                                    acor, y, tempv, V[0], R());
+                                                                    acor, y, tempv, V[0], R(SC_BSUM));
         count();
         red(SC_BSUM);
         sync_spin();
@@ -672,9 +711,9 @@ int pihm_b200_cvode::cvNewtonIteration()
         if (bnorm <= deltar) {
             // x = b (first iteration) or x = 0
             if (mnewt > 0)
-                LK(K_NEWTON_UPDATE, 5, k_newton_update<true>, N, tempv, ewt, zn[0], acor, y, R());
+                LK(K_NEWTON_UPDATE, 5, k_newton_update<true>, N, tempv, ewt, zn[0], acor, y, R(SC_DEL));
             else
-                LK(K_NEWTON_UPDATE, 6, k_newton_update<false>, N, tempv, ewt, zn[0], acor, y, R());
+                LK(K_NEWTON_UPDATE, 6, k_newton_update<false>, N, tempv, ewt, zn[0], acor, y, R(SC_DEL));
             count();
             retval = 0;
         } else {
@@ -683,12 +722,12 @@ int pihm_b200_cvode::cvNewtonIteration()
             retval = spgmrSolve(&zero);
             if (retval == 0) {
                 if (zero || krydim_last == 0) {
-                    LK(K_NEWTON_UPDATE, 5, k_newton_update<true>, N, tempv, ewt, zn[0], acor, y, R());
+                    LK(K_NEWTON_UPDATE, 5, k_newton_update<true>, N, tempv, ewt, zn[0], acor, y, R(SC_DEL));
                 } else {
                     KryPtrs kp{};
                     Coef6 c{};
                     for (int k = 0; k < krydim_last; k++) { kp.v[k] = V[k]; c.c[k] = yg[k]; }
-                    LK(K_SPGMR_FINAL, krydim_last + 5.0, k_spgmr_final, N, krydim_last, kp, c, ewt, zn[0], acor, y, R());
+                    LK(K_SPGMR_FINAL, krydim_last + 5.0, k_spgmr_final, N, krydim_last, kp, c, ewt, zn[0], acor, y, R(SC_DEL));
                 }
                 count();
             }
@@ -706,7 +745,7 @@ int pihm_b200_cvode::cvNewtonIteration()
             if (m == 0) {
                 acnrm = del;
             } else {
-                LK(K_WSQ, 2, k_wsq, N, acor, nullptr, ewt, SC_ACNRM, -1, R());
+                LK(K_WSQ, 2, k_wsq, N, acor, nullptr, ewt, SC_ACNRM, -1, R(SC_ACNRM));
                 count();
                 red(SC_ACNRM);
                 sync_spin();
@@ -879,7 +918,7 @@ void pihm_b200_cvode::cvPrepareNextStep(double dsm)
     etaqm1 = 0.0;
     etaqp1 = 0.0;
     if (do_m1 || do_p1) {
-        LK(K_ETA, 1.0 + (do_m1 ? 1 : 0) + (do_p1 ? 2 : 0), k_eta, N, do_m1, do_p1, cquot, zn[q], zn[qmax], acor, ewt, R());
+        LK(K_ETA, 1.0 + (do_m1 ? 1 : 0) + (do_p1 ? 2 : 0), k_eta, N, do_m1, do_p1, cquot, zn[q], zn[qmax], acor, ewt, R(SC_ETA_M1, SC_ETA_P1));
         count();
         red(SC_ETA_M1, 2);
         sync_spin();
@@ -904,7 +943,7 @@ void pihm_b200_cvode::cvBDFStab()
             for (int i = 5; i >= 2; i--) ssdat[i][k] = ssdat[i - 1][k];
         int factorial = 1;
         for (int i = 1; i <= q - 1; i++) factorial *= i;
-        LK(K_WSQ, 3, k_wsq, N, zn[q], zn[q - 1], ewt, SC_STAB1, SC_STAB2, R());
+        LK(K_WSQ, 3, k_wsq, N, zn[q], zn[q - 1], ewt, SC_STAB1, SC_STAB2, R(SC_STAB1, SC_STAB2));
         count();
         red(SC_STAB1, 2);
         sync_spin();
@@ -1196,7 +1235,13 @@ int pihm_b200_cvode::solve(double tout, double *yout, double *tret)
         }
         if (tn + h == tn) nhnil++;
 
-        const int kflag = cvStep();
+        int kflag = cvStep();
+        if (failed()) {
+            set_error(std::string("device error inside the integrator: ") + cudaGetErrorString(dev_error));
+            dev_error = cudaSuccess;
+            tretlast = *tret = tn;
+            return CV_RHSFUNC_FAIL;
+        }
         if (kflag != CV_SUCCESS) {
             istate = kflag;
             set_error("cvStep failed with flag " + std::to_string(kflag) + " at t = " + std::to_string(tn) +
@@ -1260,7 +1305,8 @@ pihm_b200_cvode *pihm_b200_cvode_create(pihm_b200_ctx *ctx)
     ok = ok && cudaMalloc((void **)&cv->d_part, sizeof(double) * SC_COUNT * ctx->red_blocks) == cudaSuccess;
     ok = ok && cudaMalloc((void **)&cv->d_sc, sizeof(double) * SC_COUNT) == cudaSuccess;
     ok = ok && cudaMalloc((void **)&cv->d_counter, sizeof(unsigned int) * 4) == cudaSuccess;
-    ok = ok && cudaHostAlloc((void **)&cv->h_sc, sizeof(double) * SC_COUNT, cudaHostAllocMapped) == cudaSuccess;
+    ok = ok && cudaHostAlloc((void **)&cv->h_sc_map, sizeof(double) * 2 * SC_COUNT, cudaHostAllocMapped) == cudaSuccess;
+    ok = ok && cudaHostAlloc((void **)&cv->h_sc, sizeof(double) * SC_COUNT, cudaHostAllocDefault) == cudaSuccess;
     if (!ok) {
         set_error(std::string("cvode_create: allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
         pihm_b200_cvode_destroy(cv);
@@ -1269,10 +1315,10 @@ pihm_b200_cvode *pihm_b200_cvode_create(pihm_b200_ctx *ctx)
     cudaMemsetAsync(cv->d_sc, 0, sizeof(double) * SC_COUNT, ctx->s());
     cudaMemsetAsync(cv->d_counter, 0, sizeof(unsigned int) * 4, ctx->s());
     std::memset(cv->h_sc, 0, sizeof(double) * SC_COUNT);
+    std::memset(cv->h_sc_map, 0, sizeof(double) * 2 * SC_COUNT);
     cv->rb.part = cv->d_part;
     cv->rb.counter = cv->d_counter;
     cv->rb.sc = cv->d_sc;
-    cv->h_sc_map = cv->h_sc;
     cv->rb.hsc = cv->h_sc_map;
     if (const char *e = getenv("PIHM_B200_PROFILE")) {
         cv->prof = atoi(e) != 0;
@@ -1316,18 +1362,8 @@ pihm_b200_cvode *pihm_b200_cvode_create(pihm_b200_ctx *ctx)
             return nullptr;
         }
     }
-    if (ctx->nranks > 1 && !cv->p2p) {
-        // kernels keep writing their (rank-local) values to the mapped mirror; the host
-        // reads a separate pinned copy that sync() fills after the all-reduces
-        double *pinned = nullptr;
-        if (cudaHostAlloc((void **)&pinned, sizeof(double) * SC_COUNT, cudaHostAllocDefault) != cudaSuccess) {
-            set_error("cvode_create: pinned scalar buffer");
-            pihm_b200_cvode_destroy(cv);
-            return nullptr;
-        }
-        std::memset(pinned, 0, sizeof(double) * SC_COUNT);
-        cv->h_sc = pinned;
-    }
+    // (partitioned run without peer memory: the kernels' rank-local values go to the mapped pairs and are
+    // ignored; the host reads h_sc, which sync() fills from d_sc after the NCCL all-reduces)
     cv->rb.max_blocks = ctx->red_blocks;
     {
         // k_mgs_chain: every CTA must be resident and a thread's elements of one vector must fit
@@ -1459,7 +1495,7 @@ int pihm_b200_spgmr_solve(pihm_b200_cvode *cv, double tn, double gamma, double t
     {
         cv->clobber(cv->V[0]);
         launch_pdl(cv->s(), cv->ctx->pdl, cv->blocks, PB_VEC_THREADS, k_lsolve_head, cv->N, (const double *)b->d,
-                   (const double *)weight->d, cv->V[0], cv->R());
+                   (const double *)weight->d, cv->V[0], cv->R(SC_BSUM));
         cv->count();
         cv->red(SC_BSUM);
         cv->sync_spin();

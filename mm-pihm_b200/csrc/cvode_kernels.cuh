@@ -46,9 +46,9 @@ struct RedBuf {
     double *part;            // [SC_COUNT][max_blocks]
     unsigned int *counter;
     double *sc;              // device scalars
-    volatile double *hsc;    // mapped host mirror
+    volatile double *hsc;    // mapped host mirror: [SC_COUNT] pairs {value, ticket}
     int max_blocks;
-    double seq;              // ticket written to hsc[SC_SEQ] after the results
+    double seq;              // ticket of this reduction kernel (travels with each result)
     // partitioned run: the exchange buffer of every rank, mapped into this one (comm_share_buffer);
     // null = single GPU, or the scalars are all-reduced by NCCL after the kernel
     double *const *peer;
@@ -195,13 +195,15 @@ __device__ __forceinline__ void red_finish(const RedBuf &rb, double a, int slotA
     if (slotB >= 0) sb = red_block<false>(sb);
     if (threadIdx.x == 0) {
         if (rb.peer) red_exchange<MIN_A>(rb, sa, slotA, sb, slotB);
+        // to the host: {value, ticket} of each slot as ONE 16-byte store into the mapped page -- the pair
+        // validates itself (the host polls the ticket word of every slot it is about to read), so no
+        // system-scope fence sits between the results and their announcement, i.e. in the kernel's tail
+        double *hp = const_cast<double *>(rb.hsc);
         rb.sc[slotA] = sa;
-        rb.hsc[slotA] = sa;
-        if (slotB >= 0) { rb.sc[slotB] = sb; rb.hsc[slotB] = sb; }
+        st_pair(hp + 2 * slotA, sa, rb.seq);
+        if (slotB >= 0) { rb.sc[slotB] = sb; st_pair(hp + 2 * slotB, sb, rb.seq); }
         *rb.counter = 0u;
-        fence_sys();          // results visible to the host before the ticket
-        rb.hsc[SC_SEQ] = rb.seq;
-        if (rb.gate) *reinterpret_cast<volatile double *>(rb.gate) = rb.seq;
+        if (rb.gate) { fence_gpu(); *reinterpret_cast<volatile double *>(rb.gate) = rb.seq; }
     }
 }
 

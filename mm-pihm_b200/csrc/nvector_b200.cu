@@ -101,8 +101,11 @@ pihm_b200_vec *N_VPihmB200_Device(N_Vector v) { return v ? D(v) : nullptr; }
 int PihmB200_ODE(realtype t, N_Vector y, N_Vector ydot, void *user_data)
 {
     pihm_b200_ctx *ctx = (pihm_b200_ctx *)user_data;
-    pihm_b200_ode(ctx, t, D(y), D(ydot));
-    return 0;     // ODE() always returns 0 (src/ode.c:299)
+    // ODE() itself always returns 0 (src/ode.c:299) and exits on a NaN (CheckDy, :302-311).  Here a failed
+    // launch is an unrecoverable RHS error for CVODE (< 0, cvode.c:2683-2684); NaNs raise the context's flag
+    // on the device -- the caller asks pihm_b200_check_nan(ctx) after CVode() returns (the flag costs a
+    // device -> host copy, which does not belong between two kernels of the integrator).
+    return (pihm_b200_ode(ctx, t, D(y), D(ydot)) != 0) ? -1 : 0;
 }
 
 }  // extern "C"
