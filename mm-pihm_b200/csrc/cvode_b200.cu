@@ -116,6 +116,12 @@ struct pihm_b200_cvode {
     int q = 1, qprime = 1, qu = 0, L = 2, qwait = 2, qmax = BDF_Q_MAX, next_q = 0, nscon = 0;
     int mnewt = 0, maxcor = NLS_MAXCOR, maxnef = MXNEF, maxncf = MXNCF, indx_acor = 0;
     bool tstopset = false, sldeton = true, initialised = false, ewt_pending = false;
+    bool resc_pending = false;           // cvRescale factors waiting for the next k_predict
+    Coef6 resc_f{};
+    // cvCompleteStep fused with the next step's error weights and the norms of cvPrepareNextStep / cvBDFStab
+    // (k_complete_norms; PIHM_B200_FOLD=0: the separate k_ewt / k_eta / k_wsq launches)
+    bool fold = true, ewt_ready = false, fold_m1 = false, fold_p1 = false, fold_stab = false;
+    double *ewt_next = nullptr;
     long long nst = 0, nfe = 0, ncfn = 0, netf = 0, nni = 0, nsetups = 0, nhnil = 0, nor = 0;
     long long mxstep = 500, mxhnil = MXHNIL_DEFAULT;
     // CVSPGMR state
@@ -354,8 +360,15 @@ void pihm_b200_cvode::cvRescale()
     Coef6 f{};
     double factor = eta;
     for (int j = 1; j <= q; j++) { f.c[j] = factor; factor *= eta; }
+    // (folding this into the k_predict that always follows was built and measured: the fused variant spills
+    // and takes 56 us against 19 + 19 us for the two launches -- PB_FUSE_RESCALE)
+#ifdef PB_FUSE_RESCALE
+    resc_f = f;
+    resc_pending = true;
+#else
     LK(K_RESCALE, 2.0 * q, k_rescale, N, q, znp(), f);
     count();
+#endif
     h = hscale * eta;
     next_h = h;
     hscale = h;
@@ -370,7 +383,9 @@ void pihm_b200_cvode::cvPredict()
         if ((tn - tstop) * h > 0.0) tn = tstop;
     }
     clobber(zn[0]);
-    LK(K_PREDICT, 2.0 * q + 1, k_predict<1>, N, q, znp());
+    if (resc_pending) LK(K_PREDICT, 2.0 * q + 2, k_predict<1, true>, N, q, znp(), resc_f);
+    else LK(K_PREDICT, 2.0 * q + 1, k_predict<1, false>, N, q, znp(), Coef6{});
+    resc_pending = false;
     count();
 }
 
@@ -379,7 +394,7 @@ void pihm_b200_cvode::cvRestore(double saved_t)
 {
     tn = saved_t;
     clobber(zn[0]);
-    LK(K_PREDICT, 2.0 * q + 1, k_predict<-1>, N, q, znp());
+    LK(K_PREDICT, 2.0 * q + 1, k_predict<-1, false>, N, q, znp(), Coef6{});
     count();
 }
 
@@ -853,8 +868,36 @@ void pihm_b200_cvode::cvCompleteStep()
         indx_acor = qmax;
     }
     clobber(zn[0]);
-    LK(K_COMPLETE, 2.0 * (q + 1) + 1 + (save ? 1 : 0), k_complete, N, q, znp(), lc, acor, save);
+    if (!fold) {
+        LK(K_COMPLETE, 2.0 * (q + 1) + 1 + (save ? 1 : 0), k_complete, N, q, znp(), lc, acor, save);
+        count();
+        return;
+    }
+    // what cvPrepareNextStep (cvode.c:3029-3059) and cvBDFStab (:3249-3297) will ask for, decided here with the
+    // conditions they apply (etamax, qwait after its decrement above, q, saved_tq5, sldeton)
+    const bool need_eta = (etamax != 1.0) && (qwait == 0);
+    fold_m1 = need_eta && (q > 1);
+    fold_p1 = need_eta && (q != qmax) && (saved_tq5 != 0.0);
+    fold_stab = sldeton && (q >= 3);
+    CompleteNorms cn{};
+    cn.reltol = reltol; cn.abstol = abstol;
+    cn.cquot = fold_p1 ? (tq[5] / saved_tq5) * rpowerI(h / tau[2], L) : 0.0;
+    cn.ewt_next = ewt_next; cn.ewt = ewt; cn.znmax = zn[qmax];
+    cn.do_zq = (fold_m1 || fold_stab) ? 1 : 0;
+    cn.do_zqm1 = fold_stab ? 1 : 0;
+    cn.do_p1 = fold_p1 ? 1 : 0;
+    RedBuf &r = R(SC_EWT_MIN, SC_EWT_NRM);
+    if (cn.do_zq) expect(SC_STAB1, r.seq);
+    if (cn.do_zqm1) expect(SC_STAB2, r.seq);
+    if (cn.do_p1) expect(SC_ETA_P1, r.seq);
+    LK(K_COMPLETE, 2.0 * (q + 1) + 2 + (save ? 1 : 0) + ((cn.do_zq || cn.do_p1) ? 1 : 0) + (cn.do_p1 ? 1 : 0),
+       k_complete_norms, N, q, znp(), lc, acor, save, cn, r);
     count();
+    red(SC_EWT_MIN, 1, 1);
+    red(SC_EWT_NRM);
+    if (cn.do_zq) red(SC_STAB1, cn.do_zqm1 ? 2 : 1);
+    if (cn.do_p1) red(SC_ETA_P1);
+    ewt_ready = true;
 }
 
 // cvode.c:3067-3082
@@ -917,7 +960,19 @@ void pihm_b200_cvode::cvPrepareNextStep(double dsm)
     if (do_p1) cquot = (tq[5] / saved_tq5) * rpowerI(h / tau[2], L);
     etaqm1 = 0.0;
     etaqp1 = 0.0;
-    if (do_m1 || do_p1) {
+    if (fold && (do_m1 || do_p1)) {
+        // produced by k_complete_norms (cvCompleteStep decided with the same conditions)
+        sync_spin();
+        h_sc[SC_ETA_M1] = h_sc[SC_STAB1];
+        if (do_m1) {
+            const double ddn = wrms(SC_ETA_M1) * tq[1];
+            etaqm1 = 1.0 / (rpowerR(BIAS1 * ddn, 1.0 / q) + ADDON);
+        }
+        if (do_p1) {
+            const double dup = wrms(SC_ETA_P1) * tq[3];
+            etaqp1 = 1.0 / (rpowerR(BIAS3 * dup, 1.0 / (L + 1)) + ADDON);
+        }
+    } else if (do_m1 || do_p1) {
         LK(K_ETA, 1.0 + (do_m1 ? 1 : 0) + (do_p1 ? 2 : 0), k_eta, N, do_m1, do_p1, cquot, zn[q], zn[qmax], acor, ewt, R(SC_ETA_M1, SC_ETA_P1));
         count();
         red(SC_ETA_M1, 2);
@@ -943,10 +998,12 @@ void pihm_b200_cvode::cvBDFStab()
             for (int i = 5; i >= 2; i--) ssdat[i][k] = ssdat[i - 1][k];
         int factorial = 1;
         for (int i = 1; i <= q - 1; i++) factorial *= i;
-        LK(K_WSQ, 3, k_wsq, N, zn[q], zn[q - 1], ewt, SC_STAB1, SC_STAB2, R(SC_STAB1, SC_STAB2));
-        count();
-        red(SC_STAB1, 2);
-        sync_spin();
+        if (!fold) {
+            LK(K_WSQ, 3, k_wsq, N, zn[q], zn[q - 1], ewt, SC_STAB1, SC_STAB2, R(SC_STAB1, SC_STAB2));
+            count();
+            red(SC_STAB1, 2);
+        }
+        sync_spin();                     // (fold: the two sums come from k_complete_norms)
         const double sq = factorial * q * (q + 1) * acnrm / std::max(tq[5], TINY);
         const double sqm1 = factorial * q * wrms(SC_STAB1);
         const double sqm2 = factorial * wrms(SC_STAB2);
@@ -1220,7 +1277,11 @@ int pihm_b200_cvode::solve(double tout, double *yout, double *tret)
     for (;;) {
         next_h = h;
         next_q = q;
-        if (nst > 0) launch_ewt();       // checked at the first sync inside the step
+        if (nst > 0) {                   // efun; checked at the first sync inside the step
+            if (fold && ewt_ready) { std::swap(ewt, ewt_next); ewt_pending = true; }    // written by k_complete_norms
+            else launch_ewt();
+            ewt_ready = false;
+        }
         if ((mxstep > 0) && (nstloc >= mxstep)) {
             set_error("mxstep steps taken before reaching tout");
             istate = CV_TOO_MUCH_WORK;
@@ -1296,7 +1357,7 @@ pihm_b200_cvode *pihm_b200_cvode_create(pihm_b200_ctx *ctx)
     const size_t bytes = sizeof(double) * ((size_t)std::max<long long>(cv->N, 1) + PB_VEC_PAD);
     double **all[] = {&cv->zn[0], &cv->zn[1], &cv->zn[2], &cv->zn[3], &cv->zn[4], &cv->zn[5], &cv->ewt,
                       &cv->acor, &cv->tempv, &cv->ftemp, &cv->V[0], &cv->V[1], &cv->V[2], &cv->V[3],
-                      &cv->V[4], &cv->V[5], &cv->vtemp, &cv->ytemp};
+                      &cv->V[4], &cv->V[5], &cv->vtemp, &cv->ytemp, &cv->ewt_next};
     bool ok = true;
     for (double **p : all) {
         if (cudaMalloc((void **)p, bytes) != cudaSuccess) { ok = false; break; }
@@ -1327,6 +1388,7 @@ pihm_b200_cvode *pihm_b200_cvode_create(pihm_b200_ctx *ctx)
             for (cudaEvent_t &ev : cv->prof_ev) cudaEventCreate(&ev);
         }
     }
+    if (const char *e = getenv("PIHM_B200_FOLD")) cv->fold = atoi(e) != 0;
     cv->rb.peer = nullptr;
     cv->rb.nranks = ctx->nranks;
     cv->rb.rank = ctx->rank;
@@ -1419,7 +1481,7 @@ void pihm_b200_cvode_destroy(pihm_b200_cvode *cv)
     for (cudaEvent_t e : cv->kfree) cudaEventDestroy(e);
     double *all[] = {cv->zn[0], cv->zn[1], cv->zn[2], cv->zn[3], cv->zn[4], cv->zn[5], cv->ewt, cv->acor,
                      cv->tempv, cv->ftemp, cv->V[0], cv->V[1], cv->V[2], cv->V[3], cv->V[4], cv->V[5],
-                     cv->vtemp, cv->ytemp, cv->d_part, cv->d_sc};
+                     cv->vtemp, cv->ytemp, cv->ewt_next, cv->d_part, cv->d_sc};
     for (double *p : all) if (p) cudaFree(p);
     if (cv->p2p && !cv->ctx->lgroup) comm_unshare_buffer(cv->ctx, cv->h_peer);
     if (cv->ctx->lgroup && cv->ctx->lgroup->xbuf[cv->ctx->rank] == cv->d_xbuf) {
@@ -1463,6 +1525,8 @@ int pihm_b200_cvode_init(pihm_b200_cvode *cv, const pihm_b200_cvode_param *p, do
     cv->nli = cv->ncfl = cv->nfes = cv->njtimes = 0;
     cv->tstopset = false;
     cv->ewt_pending = false;
+    cv->ewt_ready = false;
+    cv->resc_pending = false;
     cv->initialised = true;
     // ODE() hidden state restarts like a fresh model only when the caller says so;
     // SetCVodeParam itself does not touch elem.wf (src/ode.c:340-431)

@@ -207,6 +207,58 @@ __device__ __forceinline__ void red_finish(const RedBuf &rb, double a, int slotA
     }
 }
 
+// the same for up to NV sums of one kernel (slot[k] < 0: not wanted; value 0 may be a minimum): per value the
+// block tree, the partials, the last block's sum in index order -- each value goes through exactly the
+// operations red_finish would apply to it, so a sum does not depend on which kernel produced it
+template <int NV, bool MIN_0>
+__device__ __forceinline__ void red_finish_n(const RedBuf &rb, double (&v)[NV], const int (&slot)[NV])
+{
+#pragma unroll
+    for (int k = 0; k < NV; k++)
+        if (slot[k] >= 0) v[k] = (MIN_0 && k == 0) ? red_block<true>(v[k]) : red_block<false>(v[k]);
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; k++)
+            if (slot[k] >= 0) rb.part[(size_t)slot[k] * rb.max_blocks + blockIdx.x] = v[k];
+        fence_gpu();
+        last = (atomicAdd(rb.counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    fence_gpu();
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        if (slot[k] < 0) continue;
+        const bool is_min = MIN_0 && k == 0;
+        double sa = is_min ? __longlong_as_double(0x7ff0000000000000LL) : 0.0;
+        const volatile double *pa = rb.part + (size_t)slot[k] * rb.max_blocks;
+        for (int j = threadIdx.x; j < (int)gridDim.x; j += PB_VEC_THREADS) {
+            const double va = pa[j];
+            sa = is_min ? ((va < sa) ? va : sa) : sa + va;
+        }
+        v[k] = is_min ? red_block<true>(sa) : red_block<false>(sa);
+    }
+    if (threadIdx.x == 0) {
+        if (rb.peer) {
+            // one exchange per value (they share the kernel's ticket; the buffer is indexed by slot)
+#pragma unroll
+            for (int k = 0; k < NV; k++) {
+                if (slot[k] < 0) continue;
+                double dummy = 0.0;
+                if (MIN_0 && k == 0) red_exchange<true>(rb, v[k], slot[k], dummy, -1);
+                else red_exchange<false>(rb, v[k], slot[k], dummy, -1);
+            }
+        }
+        double *hp = const_cast<double *>(rb.hsc);
+#pragma unroll
+        for (int k = 0; k < NV; k++)
+            if (slot[k] >= 0) { rb.sc[slot[k]] = v[k]; st_pair(hp + 2 * slot[k], v[k], rb.seq); }
+        *rb.counter = 0u;
+        if (rb.gate) { fence_gpu(); *reinterpret_cast<volatile double *>(rb.gate) = rb.seq; }
+    }
+}
+
 #define PB_GRID_STRIDE(i, n)                                                  \
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x,      \
                    stride_ = (long long)gridDim.x * blockDim.x;               \
@@ -259,12 +311,16 @@ k_ewt(long long n, double reltol, double abstol, const double *__restrict__ y,
 }
 
 struct ZnPtrs { double *z[6]; };
+struct Coef6 { double c[6]; };
 
 // cvPredict (cvode.c:2285-2287) / cvRestore (:2887-2889): the q(q+1)/2 in-place
 // N_VLinearSum(1, zn[j-1], +-1, zn[j], zn[j-1]) per component, in registers
-template <int SIGN>
-__global__ void __launch_bounds__(PB_VEC_THREADS, PB_VB_MINB)
-k_predict(long long n, int q, ZnPtrs zn)
+// RESC: the cvRescale that precedes the prediction (cvode.c:2257-2260, zn[j] *= eta^j with the factors
+// from the host) is applied to the loaded values first -- the same products the separate k_rescale
+// launch stored and this kernel read back
+template <int SIGN, bool RESC>
+__global__ void __launch_bounds__(PB_VEC_THREADS, RESC ? 3 : PB_VB_MINB)
+k_predict(long long n, int q, ZnPtrs zn, Coef6 f)
 {
     pdl_enter();
     // two grid-stride steps at a time: all loads of both before the first in-place store
@@ -277,6 +333,10 @@ k_predict(long long n, int q, ZnPtrs zn)
             if (i < n) {
 #pragma unroll
                 for (int j = 0; j < 6; j++) if (j <= q) z[u][j] = zn.z[j][i];
+                if (SIGN > 0 && RESC) {
+#pragma unroll
+                    for (int j = 1; j < 6; j++) if (j <= q) z[u][j] = f.c[j] * z[u][j];
+                }
             }
         }
 #pragma unroll
@@ -289,12 +349,11 @@ k_predict(long long n, int q, ZnPtrs zn)
                         if (j <= q && j >= k) z[u][j - 1] = (SIGN > 0) ? z[u][j - 1] + z[u][j] : z[u][j - 1] - z[u][j];
 #pragma unroll
                 for (int j = 0; j < 5; j++) if (j < q) zn.z[j][i] = z[u][j];
+                if (SIGN > 0 && RESC) zn.z[q][i] = z[u][q];      // rescaled, otherwise untouched by the prediction
             }
         }
     }
 }
-
-struct Coef6 { double c[6]; };
 
 // cvRescale (cvode.c:2257-2260): zn[j] *= eta^j, j = 1..q (factors from the host)
 static __global__ void __launch_bounds__(PB_VEC_THREADS)
@@ -647,6 +706,79 @@ k_complete(long long n, int q, ZnPtrs zn, Coef6 l, const double *__restrict__ ac
             }
         }
     }
+}
+
+// cvCompleteStep fused with everything the rest of the step reads from the vectors it has just written:
+//   * the NEXT step's error weights from the new zn[0] (cvEwtSetSS, cvode.c:4081-4090) into a second buffer
+//     (this step's k_eta / stability norms still need the old ones; the host swaps the pointers at the top
+//     of the next step) with min(reltol |y| + abstol) and the tolsf norm sum (zn0 * ewt_next)^2 (cvode.c:1376),
+//   * sum (zn[q] * ewt)^2 (cvComputeEtaqm1 cvode.c:3097 and cvBDFStab :3267), sum (zn[q-1] * ewt)^2 (:3268),
+//   * sum ((acor - cquot zn[qmax]) * ewt)^2 (cvComputeEtaqp1 :3118-3119),
+// each with the operations and the per-thread summation order of k_ewt / k_wsq / k_eta, whose launches (and
+// the host synchronisations behind two of them) it replaces.
+struct CompleteNorms {
+    double reltol, abstol, cquot;
+    double *ewt_next;
+    const double *ewt, *znmax;
+    int do_zq, do_zqm1, do_p1;
+};
+static __global__ void __launch_bounds__(PB_VEC_THREADS, 3)
+k_complete_norms(long long n, int q, ZnPtrs zn, Coef6 l, const double *__restrict__ acor, double *save,
+                 CompleteNorms cn, RedBuf rb)
+{
+    pdl_enter();
+    double acc[5] = {__longlong_as_double(0x7ff0000000000000LL), 0.0, 0.0, 0.0, 0.0};
+    const double mc = -cn.cquot;
+    const bool any_w = cn.do_zq || cn.do_zqm1 || cn.do_p1;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x,
+                   stride_ = (long long)gridDim.x * blockDim.x; i0 < n; i0 += 2 * stride_) {
+        double z[2][6], a[2], w[2] = {0.0, 0.0}, zm[2] = {0.0, 0.0};
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const long long i = i0 + u * stride_;
+            if (i < n) {
+                a[u] = acor[i];
+#pragma unroll
+                for (int j = 0; j < 6; j++) if (j <= q) z[u][j] = zn.z[j][i];
+                if (any_w) w[u] = cn.ewt[i];
+                if (cn.do_p1) zm[u] = cn.znmax[i];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const long long i = i0 + u * stride_;
+            if (i < n) {
+                double zq = 0.0, zqm1 = 0.0;
+#pragma unroll
+                for (int j = 0; j < 6; j++)
+                    if (j <= q) {
+                        const double v = z[u][j] + l.c[j] * a[u];
+                        zn.z[j][i] = v;
+                        z[u][j] = v;
+                        if (j == q) zq = v;
+                        if (j == q - 1) zqm1 = v;
+                    }
+                if (save) save[i] = a[u];
+                {
+                    const double yi = z[u][0];
+                    double t = fabs(yi);
+                    t = cn.reltol * t;
+                    t = t + cn.abstol;
+                    acc[0] = (t < acc[0]) ? t : acc[0];
+                    const double wn = 1.0 / t;
+                    cn.ewt_next[i] = wn;
+                    const double p = yi * wn;
+                    acc[1] += p * p;
+                }
+                if (cn.do_zq) { const double p = zq * w[u]; acc[2] += p * p; }
+                if (cn.do_zqm1) { const double r = zqm1 * w[u]; acc[3] += r * r; }
+                if (cn.do_p1) { const double t = mc * zm[u] + a[u]; const double p = t * w[u]; acc[4] += p * p; }
+            }
+        }
+    }
+    const int slot[5] = {SC_EWT_MIN, SC_EWT_NRM, cn.do_zq ? SC_STAB1 : -1, cn.do_zqm1 ? SC_STAB2 : -1,
+                         cn.do_p1 ? SC_ETA_P1 : -1};
+    red_finish_n<5, true>(rb, acc, slot);
 }
 
 // cvComputeEtaqm1 / cvComputeEtaqp1 norms (cvode.c:3097, :3118-3119):
