@@ -107,6 +107,35 @@ def test_no_cpu_fallback():
     assert L.pihm_b200_last_error()
 
 
+def test_unchanged_driver_with_the_glue_stops_without_a_gpu():
+    """oracle/_ref/pihm_b200 = the reference's main.c / pihm.c / readers / CVODE with glue/pihm_b200_glue.c for
+    src/ode.c (make -C oracle drivers): reads the project, initialises, and then fails loudly at
+    pihm_b200_create -- the glue has no CPU path either"""
+    import subprocess
+    L = lib.load_library()
+    exe = os.path.join(ROOT, "oracle", "_ref", "pihm_b200")
+    run = os.path.join(ROOT, "oracle", "_ref", "run")
+    if L.pihm_b200_device_count() > 0 or not os.path.exists(exe):
+        pytest.skip("GPU present, or the drivers are not built (needs /root/reference)")
+    p = subprocess.run([exe, "-o", "nogpu", "example"], cwd=run, capture_output=True, text=True, timeout=300)
+    assert p.returncode != 0
+    assert "libpihm_b200" in (p.stdout + p.stderr) and "Simulation completed" not in p.stdout
+
+
+def test_glue_defines_the_reference_symbols():
+    """the five external symbols of src/ode.c (pihm_func.h:104,231,294,296) and the lifecycle hooks"""
+    import re
+    src = open(os.path.join(ROOT, "glue", "pihm_b200_glue.c")).read()
+    for sig in (r"int ODE\(realtype t, N_Vector y, N_Vector ydot, void \*pihm_data\)", r"int NumStateVar\(void\)",
+                r"void SetCVodeParam\(pihm_struct pihm, void \*cvode_mem, N_Vector CV_Y\)",
+                r"void SolveCVode\(int starttime, int \*t, int nextptr, double cputime, void \*cvode_mem, N_Vector CV_Y\)",
+                r"void AdjCVodeMaxStep\(void \*cvode_mem, ctrl_struct \*ctrl\)",
+                r"void PihmB200Init\(pihm_struct pihm\)", r"void PihmB200PushForcing\(pihm_struct pihm\)",
+                r"void PihmB200PullState\(pihm_struct pihm, N_Vector CV_Y\)", r"void PihmB200Free\(void\)"):
+        assert re.search(sig, src), sig
+    assert "oracle" not in src.replace("oracle/Makefile", "")
+
+
 def test_product_never_imports_oracle():
     """the product package must not reference oracle/ anywhere"""
     pkg = os.path.join(ROOT, "mm-pihm_b200")

@@ -61,7 +61,7 @@ def make_group(tb, nparts):
     return parts, models
 
 
-def run_isolated(case, *args, limit=60, attempts=4):
+def run_isolated(case, *args, limit=40, attempts=4):
     """the case in a fresh process; a stall (no return within `limit` s) is retried, a failure is not"""
     cmd = [sys.executable, os.path.abspath(__file__), case] + [str(a) for a in args]
     for k in range(attempts):
@@ -84,7 +84,7 @@ def test_peer_memory_halo_rhs_bitwise(fbr, nparts):
 
 @pytest.mark.parametrize("fbr", [False, True])
 def test_peer_memory_integrator_lockstep(fbr):
-    run_isolated("lockstep", int(fbr), limit=90)
+    run_isolated("lockstep", int(fbr), limit=60)
 
 
 def case_halo_rhs_bitwise(fbr, nparts):

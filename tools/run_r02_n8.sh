@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 N=${1:-8}
-timeout 250 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29552 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r02_bench_n$N.log 2> gpurun_out/r02_bench_n$N.err; echo "bench n$N rc $?"
+timeout 110 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29552 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r02_bench_n$N.log 2> gpurun_out/r02_bench_n$N.err; echo "bench n$N rc $?"
 python - <<EOF
 import json
 for l in open('gpurun_out/r02_bench_n$N.log'):
