@@ -726,9 +726,9 @@ int pihm_b200_cvode::cvNewtonIteration()
         if (bnorm <= deltar) {
             // x = b (first iteration) or x = 0
             if (mnewt > 0)
-                LK(K_NEWTON_UPDATE, 5, k_newton_update<true>, N, tempv, ewt, zn[0], acor, y, R(SC_DEL));
+                LK(K_NEWTON_UPDATE, 5, k_newton_update<true>, N, tempv, ewt, zn[0], acor, y, R(SC_DEL, SC_ACNRM));
             else
-                LK(K_NEWTON_UPDATE, 6, k_newton_update<false>, N, tempv, ewt, zn[0], acor, y, R(SC_DEL));
+                LK(K_NEWTON_UPDATE, 6, k_newton_update<false>, N, tempv, ewt, zn[0], acor, y, R(SC_DEL, SC_ACNRM));
             count();
             retval = 0;
         } else {
@@ -737,12 +737,12 @@ int pihm_b200_cvode::cvNewtonIteration()
             retval = spgmrSolve(&zero);
             if (retval == 0) {
                 if (zero || krydim_last == 0) {
-                    LK(K_NEWTON_UPDATE, 5, k_newton_update<true>, N, tempv, ewt, zn[0], acor, y, R(SC_DEL));
+                    LK(K_NEWTON_UPDATE, 5, k_newton_update<true>, N, tempv, ewt, zn[0], acor, y, R(SC_DEL, SC_ACNRM));
                 } else {
                     KryPtrs kp{};
                     Coef6 c{};
                     for (int k = 0; k < krydim_last; k++) { kp.v[k] = V[k]; c.c[k] = yg[k]; }
-                    LK(K_SPGMR_FINAL, krydim_last + 5.0, k_spgmr_final, N, krydim_last, kp, c, ewt, zn[0], acor, y, R(SC_DEL));
+                    LK(K_SPGMR_FINAL, krydim_last + 5.0, k_spgmr_final, N, krydim_last, kp, c, ewt, zn[0], acor, y, R(SC_DEL, SC_ACNRM));
                 }
                 count();
             }
@@ -751,7 +751,7 @@ int pihm_b200_cvode::cvNewtonIteration()
         if (retval < 0) return CV_LSOLVE_FAIL;
         if (retval > 0) return CONV_FAIL;      // setupNonNull == FALSE (cvode_spgmr.c:262)
 
-        red(SC_DEL);
+        red(SC_DEL, 2);                  // SC_DEL, SC_ACNRM
         sync_spin();
         del = wrms(SC_DEL);
         if (m > 0) crate = std::max(CRDOWN * crate, del / delp);
@@ -760,11 +760,7 @@ int pihm_b200_cvode::cvNewtonIteration()
             if (m == 0) {
                 acnrm = del;
             } else {
-                LK(K_WSQ, 2, k_wsq, N, acor, nullptr, ewt, SC_ACNRM, -1, R(SC_ACNRM));
-                count();
-                red(SC_ACNRM);
-                sync_spin();
-                acnrm = wrms(SC_ACNRM);
+                acnrm = wrms(SC_ACNRM);  // N_VWrmsNorm(acor, ewt): summed by the update kernel that wrote acor
             }
             return CV_SUCCESS;
         }

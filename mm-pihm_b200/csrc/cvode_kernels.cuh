@@ -582,13 +582,14 @@ k_mgs_chain(long long n, int nsteps, KryPtrs V, double *Vk, RedBuf rb, int per_t
 //   xcor = sum_k yg[k]*V[k]  (Vaxpy chain from 0, sundials_spgmr.c:348-357)
 //   xcor = xcor / ewt ; x = 0 + xcor ; b = x         (:366-378, cvode_spgmr.c:389)
 //   del^2 sum = sum (b*ewt)^2 ; acor += b ; y = zn0 + acor   (cvode.c:2762-2764)
+//   and sum (acor*ewt)^2 of the new acor: acnrm of cvode.c:2779 if the iteration converges (saves k_wsq + a sync)
 static __global__ void __launch_bounds__(PB_VEC_THREADS, PB_VB_MINB)
 k_spgmr_final(long long n, int krydim, KryPtrs V, Coef6 yg, const double *__restrict__ ewt,
               const double *__restrict__ zn0, double *__restrict__ acor, double *__restrict__ y,
               RedBuf rb)
 {
     pdl_enter();
-    double s = 0.0;
+    double s = 0.0, s_ac = 0.0;
     constexpr int VB2 = 2;      // 8 input streams: two steps at a time
     for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x,
                    stride_ = (long long)gridDim.x * blockDim.x; i0 < n; i0 += VB2 * stride_) {
@@ -617,10 +618,12 @@ k_spgmr_final(long long n, int krydim, KryPtrs V, Coef6 yg, const double *__rest
                 const double ac = a0[u] + b;
                 acor[i] = ac;
                 y[i] = z0[u] + ac;
+                const double pa = ac * w;       // N_VWrmsNorm(acor, ewt) of cvode.c:2779, in case this iteration converges
+                s_ac += pa * pa;
             }
         }
     }
-    red_finish<false>(rb, s, SC_DEL, 0.0, -1);
+    red_finish<false>(rb, s, SC_DEL, s_ac, SC_ACNRM);
 }
 
 // Tail of the lsolve hook: the solver part of k_spgmr_final,
@@ -649,16 +652,19 @@ k_newton_update(long long n, const double *__restrict__ bvec, const double *__re
                 RedBuf rb)
 {
     pdl_enter();
-    double s = 0.0;
+    double s = 0.0, s_ac = 0.0;
     PB_GRID_STRIDE(i, n) {
         const double b = ZERO_B ? 0.0 : bvec[i];
-        const double p = b * ewt[i];
+        const double w = ewt[i];
+        const double p = b * w;
         s += p * p;
         const double ac = acor[i] + b;
         acor[i] = ac;
         y[i] = zn0[i] + ac;
+        const double pa = ac * w;           // N_VWrmsNorm(acor, ewt), cvode.c:2779
+        s_ac += pa * pa;
     }
-    red_finish<false>(rb, s, SC_DEL, 0.0, -1);
+    red_finish<false>(rb, s, SC_DEL, s_ac, SC_ACNRM);
 }
 
 // sum (x*w)^2 into one slot; optionally a second vector into a second slot
