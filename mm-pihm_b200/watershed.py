@@ -84,13 +84,14 @@ def _river_eq_wid(order, depth, coeff):
 def make_watershed(nx: int, ny: int, fbr: bool = False, seed: int = 12345,
                    trib_every: int = 25, river: bool = True,
                    surf_mode: int = 2, riv_mode: int = 2, stepsize: float = 60.0,
-                   dirichlet_edges: bool = False, riv_order: int = 1) -> dict:
+                   dirichlet_edges: bool = False, riv_order: int = 1, keep_mesh: bool = False) -> dict:
     """Build the column tables of a synthetic watershed.
 
     Returns a dict: nelem, nriver, fbr, surf_mode, riv_mode, stepsize,
     elem_f64 [E_NCOL, nelem], elem_i32 [EI_NCOL, nelem], riv_f64 [R_NCOL, nriver],
     riv_i32 [RI_NCOL, nriver], y0 (RelaxIc state, block layout), plus `xc`, `yc`
-    element centroids (used for partitioning / reordering)."""
+    element centroids (used for partitioning / reordering).  keep_mesh=True adds `mesh`: the node-level
+    description a .mesh / .att / .riv / .bedrock file set is written from (project_files.py)."""
     rng = np.random.default_rng(seed)
     nnx, nny = nx + 1, ny + 1
     ii, jj = np.meshgrid(np.arange(nnx), np.arange(nny), indexing="xy")   # [nny, nnx]
@@ -147,6 +148,7 @@ def make_watershed(nx: int, ny: int, fbr: bool = False, seed: int = 12345,
     nabr[1::2, 1] = np.where(ci > 0, 2 * (c - 1) + 1, 0)
     nabr[1::2, 2] = 2 * c + 1
 
+    nabr_mesh = nabr.copy() if keep_mesh else None      # as a .mesh file holds it: rivers not marked
     # ---- river network -------------------------------------------------
     segs = []        # (from_node, to_node, left_elem(1b), right_elem(1b), down(1b or code))
     if river and ny >= 2 and nx >= 2:
@@ -280,9 +282,15 @@ def make_watershed(nx: int, ny: int, fbr: bool = False, seed: int = 12345,
         y0 += [0.5 * (ef[E_GDEPTH] - fg), fg]
     y0 = np.concatenate(y0)
 
-    return dict(nelem=ne, nriver=nr, fbr=int(fbr), surf_mode=surf_mode, riv_mode=riv_mode,
-                stepsize=float(stepsize), elem_f64=ef, elem_i32=ei, riv_f64=rf, riv_i32=ri,
-                y0=y0, xc=xc, yc=yc, nx=nx, ny=ny, bc_head=forc_bc)
+    out = dict(nelem=ne, nriver=nr, fbr=int(fbr), surf_mode=surf_mode, riv_mode=riv_mode,
+               stepsize=float(stepsize), elem_f64=ef, elem_i32=ei, riv_f64=rf, riv_i32=ri,
+               y0=y0, xc=xc, yc=yc, nx=nx, ny=ny, bc_head=forc_bc)
+    if keep_mesh:
+        S = np.array(segs, np.int64).reshape(-1, 5)
+        out["mesh"] = dict(node=nodes + 1, nabr=nabr_mesh, x=xf, y=yf, zmin=zmin_n.ravel(), zmax=zmax_n.ravel(),
+                           zbed=zbed_n.ravel(), soil_type=soil_e + 1, lc_type=lc_e + 1,
+                           riv_from=S[:, 0] + 1, riv_to=S[:, 1] + 1, riv_order=riv_order)
+    return out
 
 
 def make_named(name: str, **kw) -> dict:
