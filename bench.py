@@ -61,10 +61,24 @@ def forcing_at(tb, k):
     return W.storm_forcing(tb, T0 + k * STEP)
 
 
-def workload_config(size, fbr, ne_glob, nr_glob, world):
+def span_settings(args):
+    """--span day: one simulated day from the RelaxIc state at t = 0 -- the dry hour before
+    the storm, the 6 h rain pulse, 17 h of recession -- with the first simulated hour as warm-up: 60 + 1380 model
+    steps.  The rain column is the only forcing that changes; it is re-uploaded every LSM step (15 model steps)
+    inside the timed region.  Side legs that would repeat the day (strong scaling, CPU baseline) are off."""
+    global T0
+    if args.span == "day":
+        T0 = 0.0
+        args.warmup, args.steps = 60, 1380
+        args.no_strong = args.no_cpu = True
+
+
+def workload_config(size, fbr, ne_glob, nr_glob, world, span="storm"):
     """the `config` object -- identical in both arms (the driver compares them)"""
+    where = ("in the rain pulse (t0 = 2 h)" if span == "storm" else
+             "of one simulated day (t0 = 0: dry hour, 6 h rain pulse, recession), first simulated hour = warm-up")
     txt = (f"pihm{'-fbr' if fbr else ''} synthetic {size}-triangle watershed ({ne_glob} elements, {nr_glob} river "
-           f"segments), 60 s model steps (SolveCVode + Summary/MassBalance) in the rain pulse (t0 = 2 h), "
+           f"segments), 60 s model steps (SolveCVode + Summary/MassBalance) {where}, "
            f"reltol 1e-3 abstol 1e-4")
     if world > 1:
         txt += (f"; weak scaling: 1M triangles per GPU, mesh partitioned over {world} GPUs; "
@@ -140,6 +154,35 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def e2e_leg(args, torch, model, y, reset, step, forc_host, barrier, max_over_ranks, stream, ev0, ev1, tb):
+    """the same K steps through the C ABI with HOST buffers: every step the three forcing columns come from pinned
+    host memory and the state goes back to it (the drop-in driver's per-step traffic)"""
+    K, Wu = args.steps, args.warmup
+    reset()
+    host_y = torch.empty(model.nsv, dtype=torch.float64).pin_memory().numpy()
+    forc_tabs = {}
+    keys = sorted(forc_host) if forc_host else range(0, Wu + K + 15, 15)
+    base = None
+    for k in keys:
+        if forc_host:
+            tab = forc_host[k]
+        else:               # day span: one table, the rain column rewritten per LSM step
+            base = forcing_at(tb, 0)[:W.F_ETT + 1] if base is None else base
+            tab = base.copy(); tab[W.F_PCPDRP] = W.storm_rain(T0 + k * STEP) * W.storm_modulation(tb)
+        t = torch.from_numpy(np.ascontiguousarray(tab)).pin_memory()
+        forc_tabs[k] = t.numpy()
+        forc_tabs[("keep", k)] = t
+    for k in range(Wu):
+        step(k, e2e=True, host_forc=forc_tabs[(k // 15) * 15], host_y=host_y)
+    barrier()
+    ev0.record(stream)
+    for k in range(Wu, Wu + K):
+        step(k, e2e=True, host_forc=forc_tabs[(k // 15) * 15], host_y=host_y)
+    ev1.record(stream)
+    barrier()
+    return max_over_ranks(ev0.elapsed_time(ev1))
+
+
 # --------------------------------------------------------------------------- ours
 def run_ours(args):
     import torch
@@ -205,7 +248,9 @@ def run_ours(args):
 
     # forcing tables of every LSM step (15 model steps) the run crosses, generated before any
     # timed region: the synthetic generator is numpy on the host and not part of the hot path
-    forc_host = {k: forcing_at(tb, k) for k in range(0, Wu + K + 15, 15)}
+    day = args.span == "day"
+    forc_host = {} if day else {k: forcing_at(tb, k) for k in range(0, Wu + K + 15, 15)}
+    rain_mod = W.storm_modulation(tb) if day else None      # day span: only the rain column changes
     rivbc0 = np.zeros(nr)
 
     def step(k, e2e=False, host_forc=None, host_y=None):
@@ -213,6 +258,9 @@ def run_ours(args):
             # the drop-in driver's per-step traffic: forcing columns in, state out
             for c in (W.F_PCPDRP, W.F_EDIR, W.F_ETT):
                 model.set_forcing_col(c, host_forc[c])
+        elif day:
+            if k % 15 == 0:
+                model.set_forcing_col(W.F_PCPDRP, W.storm_rain(T0 + k * STEP) * rain_mod)
         elif k % 15 == 0:
             model.set_forcing(forc_host[k], rivbc0)
             model.Summary(y)            # the table's ws0.surf column is a placeholder: ws0.surf = y[SURF] again
@@ -245,24 +293,10 @@ def run_ours(args):
     value = (K * STEP / 86400.0) / (ms * 1e-3) * mtri
 
     # ---- end to end through the C ABI with host buffers --------------------------
-    reset()
-    # pinned host buffers, as the contract asks: the C ABI copies straight from / into them
-    host_y = torch.empty(model.nsv, dtype=torch.float64).pin_memory().numpy()
-    forc_tabs = {}
-    for k in range(0, Wu + K + 15, 15):
-        t = torch.from_numpy(forc_host[k]).pin_memory()
-        forc_tabs[k] = t.numpy()
-        forc_tabs[("keep", k)] = t
-    for k in range(Wu):
-        step(k, e2e=True, host_forc=forc_tabs[(k // 15) * 15], host_y=host_y)
-    barrier()
-    ev0.record(stream)
-    for k in range(Wu, Wu + K):
-        step(k, e2e=True, host_forc=forc_tabs[(k // 15) * 15], host_y=host_y)
-    ev1.record(stream)
-    barrier()
-    ms_e2e = max_over_ranks(ev0.elapsed_time(ev1))
-    e2e_value = (K * STEP / 86400.0) / (ms_e2e * 1e-3) * mtri
+    ms_e2e = None
+    if not args.no_e2e:
+        ms_e2e = e2e_leg(args, torch, model, y, reset, step, forc_host, barrier, max_over_ranks, stream, ev0, ev1, tb)
+    e2e_value = (K * STEP / 86400.0) / (ms_e2e * 1e-3) * mtri if ms_e2e else None
 
     # ---- RHS kernels: live CUDA-event duration over back-to-back launches ----------
     yv = y
@@ -324,7 +358,7 @@ def run_ours(args):
         "value": value, "unit": "sim-days/s", "n_gpus": world, "steps": K, "warmup": Wu,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(size, fbr, ne_glob, nr_glob, world),
+        "config": workload_config(size, fbr, ne_glob, nr_glob, world, args.span),
         "rhs_evals_per_s": rhs_evals / (ms * 1e-3), "rhs_evals": rhs_evals, "cvode_steps": nst,
         "ms_per_rhs_eval": ms / max(rhs_evals, 1),      # whole step / evaluations: RHS + vector kernels + host
         "rhs_ms": rhs_ms,                               # k_pre + k_main, back to back (30 calls, same input)
@@ -351,8 +385,8 @@ def run_ours(args):
             "all": {"gbs": sum(v["bytes"] for v in kp.values()) / max(sum(v["ms"] for v in kp.values()), 1e-9) / 1e6,
                     "frac": sum(v["bytes"] for v in kp.values()) / max(sum(v["ms"] for v in kp.values()), 1e-9) / 1e6 / peak},
         },
-        "e2e": {"value": e2e_value, "unit": "sim-days/s", "ms_per_step": ms_e2e / K,
-                "h2d_bytes_per_step": 3 * 8 * ne, "d2h_bytes_per_step": 8 * nsv_local},
+        "e2e": ({"value": e2e_value, "unit": "sim-days/s", "ms_per_step": ms_e2e / K,
+                 "h2d_bytes_per_step": 3 * 8 * ne, "d2h_bytes_per_step": 8 * nsv_local} if ms_e2e else None),
         "gpu_launches": int(l1 - l0),
         "clocks": clk,
     }
@@ -482,7 +516,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(size, fbr, tb["nelem"], tb["nriver"], args.gpus),
+        "config": workload_config(size, fbr, tb["nelem"], tb["nriver"], args.gpus, args.span),
         "rhs_evals_per_s": cb["rhs_evals_per_s"],
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"] * scale, "unit": "sim-days/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -503,7 +537,11 @@ def main():
     ap.add_argument("--no-strong", action="store_true", help="skip the 8M strong-scaling side figure")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--ref-max-steps", type=int, default=30)
+    ap.add_argument("--span", default="storm", choices=["storm", "day"],
+                    help="storm: --steps model steps inside the rain pulse (default); day: one simulated day, see span_settings")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (side runs only: a line without e2e is not a bench line)")
     args = ap.parse_args()
+    span_settings(args)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -298,6 +298,17 @@ def make_named(name: str, **kw) -> dict:
     return make_watershed(nx, ny, **kw)
 
 
+def storm_rain(t: float) -> float:
+    """rain rate (m/s) of the synthetic storm at model time t (s): a 6 h half-sine pulse, 12 mm/h at its peak, every 24 h"""
+    th = (t / 3600.0) % 24.0
+    return 12.0e-3 / 3600.0 * np.sin(np.pi * (th - 1.0) / 6.0) if 1.0 <= th < 7.0 else 0.0
+
+
+def storm_modulation(tables: dict) -> np.ndarray:
+    """spatial factor of the rain rate per element"""
+    return 0.75 + 0.25 * np.sin(2 * np.pi * tables["xc"] / 5000.0)
+
+
 def storm_forcing(tables: dict, t: float, ws0_surf=None) -> np.ndarray:
     """Synthetic forcing table [F_NCOL, nelem] at model time t (s):
     a 6 h rain pulse (12 mm/h peak, spatially modulated) every 24 h and
@@ -305,10 +316,7 @@ def storm_forcing(tables: dict, t: float, ws0_surf=None) -> np.ndarray:
     IntcpSnowEt (src/pihm.c:27-48), which stay host code in the reference."""
     ne = tables["nelem"]
     f = np.zeros((F_NCOL, ne))
-    th = (t / 3600.0) % 24.0
-    rain = 12.0e-3 / 3600.0 * np.sin(np.pi * (th - 1.0) / 6.0) if 1.0 <= th < 7.0 else 0.0
-    mod = 0.75 + 0.25 * np.sin(2 * np.pi * tables["xc"] / 5000.0)
-    f[F_PCPDRP] = rain * mod
+    f[F_PCPDRP] = storm_rain(t) * storm_modulation(tables)
     f[F_EDIR] = 2.0e-8
     f[F_ETT] = 3.0e-8
     if ws0_surf is not None:

@@ -22,6 +22,7 @@ from mm_pihm_b200 import lib, watershed as W
 
 pytestmark = pytest.mark.gpu
 RELTOL, ABSTOL, MULT, MULT_LOCKSTEP = 1e-3, 1e-4, 30.0, 1e-6
+DAY_MULT = 10.0          # 10 x (reltol |y| + abstol) after one simulated day
 STAT_KEYS = ("nst", "nfe", "nni", "ncfn", "netf", "nli", "ncfl", "nfeLS")
 
 
@@ -205,6 +206,51 @@ def test_100k_lockstep_with_live_reference():
     assert err <= MULT
     assert abs(sg["nst"] - sr["nst"]) <= 0.25 * sr["nst"]
     ref.close(); cv.close(); model.close()
+
+
+def test_100k_one_day():
+    """BASELINE.md section 4 / SURVEY 8(d) 'Parity acceptance': the integrated state after ONE SIMULATED DAY (1440
+    model steps: dry hour, 6 h storm, 17 h of recession) of the 100k-triangle watershed against the reference's own
+    run of the same day (tests/golden/day_100k.npz, made by tests/golden/make_day_golden.py from oracle/_ref in the
+    build container -- 1440 reference steps are minutes of CPU, too long for the GPU box).  Bound: DAY_MULT x
+    (reltol |y| + abstol) at the half-day and full-day snapshots; the golden file also holds the reference's own
+    drift when its initial state is perturbed by 1e-15 (recorded next to ours)."""
+    import os
+    from helpers import GOLDEN
+    if not os.path.exists(os.path.join(GOLDEN, "day_100k.npz")):
+        pytest.skip("tests/golden/day_100k.npz not generated")
+    g = load_golden("day_100k.npz")
+    tb = W.make_named("100k")
+    nr = tb["nriver"]
+    model = lib.Model(tb, reorder=1)
+    cv = lib.Cvode(model)
+    y = model.N_VNew(tb["y0"])
+    cv.SetCVodeParam(y)
+    snaps = {int(s): i for i, s in enumerate(g["steps"])}
+    keys = [str(k) for k in g["stat_keys"]]
+    for k in range(int(max(snaps))):
+        if k % 15 == 0:
+            model.set_forcing(W.storm_forcing(tb, k * 60.0), np.zeros(nr))
+        model.Summary(y)
+        cv.SolveCVode((k + 1) * 60.0, y)
+        if k + 1 in snaps:
+            i = snaps[k + 1]
+            yref, ypert = g["y"][i], g["y_pert"][i]
+            unit = RELTOL * np.abs(yref) + ABSTOL
+            err = np.abs(y.download() - yref) / unit
+            sens = np.abs(ypert - yref) / unit
+            st = cv.stats()
+            sref = dict(zip(keys, g["stats"][i]))
+            print(f"100k, {k + 1} model steps: max err {err.max():.3e} x (reltol|y|+abstol) (99.9th percentile "
+                  f"{np.percentile(err, 99.9):.3e}); reference's own 1e-15 sensitivity {sens.max():.3e}; "
+                  f"nst {st['nst']}/{int(sref['nst'])} rhs evals {st['nfe'] + st['nfeLS']}/{int(sref['nfe'] + sref['nfeLS'])}")
+            record(f"100k one simulated day, step {k + 1}", multiple_of_reltol_y_plus_abstol=err.max(),
+                   percentile_99_9=float(np.percentile(err, 99.9)), reference_self_sensitivity=sens.max(), bound=DAY_MULT,
+                   nst=int(st["nst"]), nst_reference=int(sref["nst"]))
+            assert err.max() <= DAY_MULT, f"step {k + 1}: {err.max():.3e} x (reltol|y|+abstol) at {np.argmax(err)}"
+            assert abs(st["nst"] - sref["nst"]) <= 0.25 * sref["nst"]
+    assert model.check_nan() == 0
+    cv.close(); model.close()
 
 
 @pytest.mark.parametrize("fbr", [False, True])
