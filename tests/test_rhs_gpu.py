@@ -295,3 +295,41 @@ def test_rhs_1m_properties():
         q_ij = xf[W.X_SUB0 + j, sel]
         q_ji = xf[W.X_SUB0 + back, n]
         assert np.allclose(q_ij, -q_ji, rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("fbr", [False, True])
+def test_rhs_of_a_randomly_numbered_mesh_is_bitwise_the_same(fbr):
+    """A real .mesh file numbers its triangles in the order its mesh generator left them.  The 100k watershed with
+    its elements renumbered at random (tests/test_reorder.py: the patch ordering brings nine neighbour pairs in ten
+    back into one 128-element patch) must give, element for element, the bits of the structured numbering -- with
+    the locality ordering on and off, first and second call (river-edge flows of the previous call)."""
+    from test_reorder import shuffle_elements
+    tb = W.make_named("100k", fbr=fbr)
+    ne, nr = tb["nelem"], tb["nriver"]
+    sh, new_of_old = shuffle_elements(tb, seed=5)
+    y = W.wet_state(tb, seed=21)
+    forc = W.storm_forcing(tb, 3 * 3600.0, ws0_surf=np.maximum(y[:ne], 0))
+    # state and forcing of the renumbered mesh: element blocks permuted, river blocks as they are
+    old_of_new = np.argsort(new_of_old)
+    ys = y.copy()
+    for b in range(5 if fbr else 3):
+        off = b * ne if b < 3 else 3 * ne + 2 * nr + (b - 3) * ne
+        ys[off:off + ne] = y[off:off + ne][old_of_new]
+    forc_s = forc[:, old_of_new]
+    ref_model = lib.Model(tb, reorder=1)
+    ref_model.set_forcing(forc, np.zeros(nr))
+    want = [ref_model.ODE(0.0, y), ref_model.ODE(0.0, y)]
+    ref_model.close()
+    for reorder in (1, 0):
+        model = lib.Model(sh, reorder=reorder)
+        model.set_forcing(np.ascontiguousarray(forc_s), np.zeros(nr))
+        for call in range(2):
+            dy = model.ODE(0.0, ys)
+            back = dy.copy()
+            for b in range(5 if fbr else 3):
+                off = b * ne if b < 3 else 3 * ne + 2 * nr + (b - 3) * ne
+                back[off:off + ne] = dy[off:off + ne][new_of_old]
+            assert np.array_equal(back, want[call]), \
+                f"reorder={reorder} call {call}: {np.abs(back - want[call]).max():.3e}"
+        assert model.nan_flag == 0
+        model.close()
