@@ -156,10 +156,15 @@ def measured_peak():
 
 def e2e_leg(args, torch, model, y, reset, step, forc_host, barrier, max_over_ranks, stream, ev0, ev1, tb):
     """the same K steps through the C ABI with HOST buffers: every step the three forcing columns come from pinned
-    host memory and the state goes back to it (the drop-in driver's per-step traffic)"""
+    host memory and the state goes back to it (the drop-in driver's per-step traffic).  --e2e sync: the copies sit on
+    the compute stream between two steps (pihm_b200_set_forcing_col, pihm_b200_vec_download); --e2e pipelined: the
+    next step's columns travel while this step computes and the state of this step while the next one does
+    (pihm_b200_forcing_prefetch / _commit, pihm_b200_vec_download_async; the last pull is awaited inside the timed
+    region)."""
     K, Wu = args.steps, args.warmup
+    pipelined = args.e2e == "pipelined"
     reset()
-    host_y = torch.empty(model.nsv, dtype=torch.float64).pin_memory().numpy()
+    host_y = [torch.empty(model.nsv, dtype=torch.float64).pin_memory().numpy() for _ in range(2)]
     forc_tabs = {}
     keys = sorted(forc_host) if forc_host else range(0, Wu + K + 15, 15)
     base = None
@@ -172,12 +177,29 @@ def e2e_leg(args, torch, model, y, reset, step, forc_host, barrier, max_over_ran
         t = torch.from_numpy(np.ascontiguousarray(tab)).pin_memory()
         forc_tabs[k] = t.numpy()
         forc_tabs[("keep", k)] = t
+    cols = (W.F_PCPDRP, W.F_EDIR, W.F_ETT)
+
+    def columns(k):
+        tab = forc_tabs[(k // 15) * 15]
+        return [tab[c] for c in cols]
+
+    def run(k):
+        if pipelined:
+            step(k, e2e="pipelined", host_forc=columns(k + 1), host_y=host_y[k & 1])
+        else:
+            step(k, e2e="sync", host_forc=forc_tabs[(k // 15) * 15], host_y=host_y[0])
+    if pipelined:
+        model.forcing_prefetch(cols, columns(0))
     for k in range(Wu):
-        step(k, e2e=True, host_forc=forc_tabs[(k // 15) * 15], host_y=host_y)
+        run(k)
+    if pipelined:
+        model.transfer_wait()
     barrier()
     ev0.record(stream)
     for k in range(Wu, Wu + K):
-        step(k, e2e=True, host_forc=forc_tabs[(k // 15) * 15], host_y=host_y)
+        run(k)
+    if pipelined:
+        model.transfer_wait()           # the last state has arrived in host memory
     ev1.record(stream)
     barrier()
     return max_over_ranks(ev0.elapsed_time(ev1))
@@ -254,7 +276,10 @@ def run_ours(args):
     rivbc0 = np.zeros(nr)
 
     def step(k, e2e=False, host_forc=None, host_y=None):
-        if e2e:
+        if e2e == "pipelined":
+            model.forcing_commit()      # this step's columns, prefetched under the previous step's kernels
+            model.forcing_prefetch((W.F_PCPDRP, W.F_EDIR, W.F_ETT), host_forc)      # the NEXT step's
+        elif e2e:
             # the drop-in driver's per-step traffic: forcing columns in, state out
             for c in (W.F_PCPDRP, W.F_EDIR, W.F_ETT):
                 model.set_forcing_col(c, host_forc[c])
@@ -266,7 +291,9 @@ def run_ours(args):
             model.Summary(y)            # the table's ws0.surf column is a placeholder: ws0.surf = y[SURF] again
         cv.SolveCVode((k + 1) * STEP, y)
         model.SummaryMB(y, STEP)        # like the reference's step (pihm.c:53-57): mass balance, ws0 <- y
-        if e2e:
+        if e2e == "pipelined":
+            model.download_async(y, host_y)
+        elif e2e:
             model.L.pihm_b200_vec_download(y.h, host_y.ctypes.data)
 
     # ---- device-resident timing ------------------------------------------------
@@ -294,6 +321,8 @@ def run_ours(args):
 
     # ---- end to end through the C ABI with host buffers --------------------------
     ms_e2e = None
+    if args.e2e == "auto":
+        args.e2e = "pipelined" if world == 1 else "sync"
     if not args.no_e2e:
         ms_e2e = e2e_leg(args, torch, model, y, reset, step, forc_host, barrier, max_over_ranks, stream, ev0, ev1, tb)
     e2e_value = (K * STEP / 86400.0) / (ms_e2e * 1e-3) * mtri if ms_e2e else None
@@ -386,7 +415,8 @@ def run_ours(args):
                     "frac": sum(v["bytes"] for v in kp.values()) / max(sum(v["ms"] for v in kp.values()), 1e-9) / 1e6 / peak},
         },
         "e2e": ({"value": e2e_value, "unit": "sim-days/s", "ms_per_step": ms_e2e / K,
-                 "h2d_bytes_per_step": 3 * 8 * ne, "d2h_bytes_per_step": 8 * nsv_local} if ms_e2e else None),
+                 "h2d_bytes_per_step": 3 * 8 * ne, "d2h_bytes_per_step": 8 * nsv_local,
+                 "transfers": args.e2e} if ms_e2e else None),
         "gpu_launches": int(l1 - l0),
         "clocks": clk,
     }
@@ -539,6 +569,10 @@ def main():
     ap.add_argument("--ref-max-steps", type=int, default=30)
     ap.add_argument("--span", default="storm", choices=["storm", "day"],
                     help="storm: --steps model steps inside the rain pulse (default); day: one simulated day, see span_settings")
+    ap.add_argument("--e2e", default="auto", choices=["auto", "sync", "pipelined"],
+                    help="host-buffer leg: copies on the compute stream between two steps (sync), or overlapped with the "
+                         "steps on the library's copy stream (pipelined, csrc/transfer.cu); auto = pipelined on one GPU, "
+                         "sync on a partitioned run (the pipelined calls have only been run on unpartitioned contexts)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (side runs only: a line without e2e is not a bench line)")
     args = ap.parse_args()
     span_settings(args)

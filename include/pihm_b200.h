@@ -416,6 +416,35 @@ void           *pihm_b200_vec_devptr(pihm_b200_vec *v);
 int             pihm_b200_vec_upload(pihm_b200_vec *v, const double *host);
 int             pihm_b200_vec_download(const pihm_b200_vec *v, double *host);
 
+/* ------------------------------------------------------------------------
+ * Pipelined host transfers (csrc/transfer.cu): the PCIe copies of a driver
+ * that pushes forcing columns and pulls the state every model step
+ *  run on a copy stream of the context's
+ * own and overlap the kernels of the step.  Host buffers must be PINNED.
+ *   replaces: nothing in the reference (host arrays are the model state
+ *   there); the synchronous forms are pihm_b200_set_forcing_col and
+ *   pihm_b200_vec_download.
+ * forcing_prefetch: start copying `ncol` forcing columns (ids `cols[k]`,
+ *   values `values_pinned[k][nelem]`, reference order) to the device; returns
+ *   at once.  One prefetch may be outstanding.
+ * forcing_commit: scatter the prefetched columns into the device tables, in
+ *   stream order (after every RHS evaluation issued so far).  No-op when
+ *   nothing was prefetched.
+ * vec_download_async: copy `v` (reference order) into `host_pinned`; the
+ *   copy is ordered behind everything issued so far and overlaps what is
+ *   issued afterwards.  transfer_wait returns when the last such copy has
+ *   arrived.  transfer_release frees the pipeline (call before
+ *   pihm_b200_destroy; nothing to do for a context that never used it).
+ * ---------------------------------------------------------------------- */
+int             pihm_b200_forcing_prefetch(pihm_b200_ctx *ctx, int ncol,
+                                           const int *cols,
+                                           const double *const *values_pinned);
+int             pihm_b200_forcing_commit(pihm_b200_ctx *ctx);
+int             pihm_b200_vec_download_async(const pihm_b200_vec *v,
+                                             double *host_pinned);
+int             pihm_b200_transfer_wait(pihm_b200_ctx *ctx);
+int             pihm_b200_transfer_release(pihm_b200_ctx *ctx);
+
 void            pihm_b200_nv_linearsum(double a, const pihm_b200_vec *x,
                                        double b, const pihm_b200_vec *y,
                                        pihm_b200_vec *z);

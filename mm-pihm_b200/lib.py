@@ -133,6 +133,11 @@ _SIGS = {
     "pihm_b200_vec_devptr": (C.c_void_p, [C.c_void_p]),
     "pihm_b200_vec_upload": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pihm_b200_vec_download": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pihm_b200_forcing_prefetch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "pihm_b200_forcing_commit": (C.c_int, [C.c_void_p]),
+    "pihm_b200_vec_download_async": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pihm_b200_transfer_wait": (C.c_int, [C.c_void_p]),
+    "pihm_b200_transfer_release": (C.c_int, [C.c_void_p]),
     "pihm_b200_nv_linearsum": (None, [C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "pihm_b200_nv_const": (None, [C.c_double, C.c_void_p]),
     "pihm_b200_nv_prod": (None, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -271,8 +276,29 @@ class Model:
     # lifecycle ---------------------------------------------------------------
     def close(self):
         if getattr(self, "h", None):
+            self.L.pihm_b200_transfer_release(self.h)
             self.L.pihm_b200_destroy(self.h)
             self.h = None
+
+    # pipelined host transfers (csrc/transfer.cu); every host array must be pinned and stay alive
+    def forcing_prefetch(self, cols, arrays):
+        """start the upload of forcing columns `cols` (ids) from the pinned arrays `arrays` ([nelem] each)"""
+        n = len(cols)
+        ids = (C.c_int * n)(*[int(c) for c in cols])
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrays])
+        for a in arrays:
+            assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.size == self.nelem
+        _check(self.L, self.L.pihm_b200_forcing_prefetch(self.h, n, ids, ptrs), "forcing_prefetch")
+
+    def forcing_commit(self):
+        _check(self.L, self.L.pihm_b200_forcing_commit(self.h), "forcing_commit")
+
+    def download_async(self, v, host):
+        assert host.dtype == np.float64 and host.flags["C_CONTIGUOUS"] and host.size == self.nsv
+        _check(self.L, self.L.pihm_b200_vec_download_async(v.h, host.ctypes.data), "vec_download_async")
+
+    def transfer_wait(self):
+        _check(self.L, self.L.pihm_b200_transfer_wait(self.h), "transfer_wait")
 
     def __del__(self):
         try:
