@@ -416,7 +416,12 @@ def run_ours(args):
         },
         "e2e": ({"value": e2e_value, "unit": "sim-days/s", "ms_per_step": ms_e2e / K,
                  "h2d_bytes_per_step": 3 * 8 * ne, "d2h_bytes_per_step": 8 * nsv_local,
-                 "transfers": args.e2e} if ms_e2e else None),
+                 "transfers": args.e2e,
+                 "note": ("pipelined: the per-step copies overlap the step's kernels on the library's copy stream; the "
+                          "device-resident leg (`value`) re-uploads the whole 11-column forcing table synchronously "
+                          "at every LSM step (k % 15 == 0: 88 MB), which this leg replaces by its per-step columns"
+                          if args.e2e == "pipelined" else
+                          "sync: the per-step copies sit on the compute stream between two steps")} if ms_e2e else None),
         "gpu_launches": int(l1 - l0),
         "clocks": clk,
     }
