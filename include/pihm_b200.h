@@ -433,8 +433,8 @@ int             pihm_b200_vec_download(const pihm_b200_vec *v, double *host);
  * vec_download_async: copy `v` (reference order) into `host_pinned`; the
  *   copy is ordered behind everything issued so far and overlaps what is
  *   issued afterwards.  transfer_wait returns when the last such copy has
- *   arrived.  transfer_release frees the pipeline (call before
- *   pihm_b200_destroy; nothing to do for a context that never used it).
+ *   arrived.  transfer_release frees the pipeline early (pihm_b200_destroy
+ *   does it as well; nothing to do for a context that never used it).
  * ---------------------------------------------------------------------- */
 int             pihm_b200_forcing_prefetch(pihm_b200_ctx *ctx, int ncol,
                                            const int *cols,

@@ -456,6 +456,7 @@ void pihm_b200_destroy(pihm_b200_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    pihm_b200_transfer_release(ctx);                   // copy stream / staging of the pipelined transfers, if used (transfer.cu)
     if (ctx->l2_on) cudaCtxResetPersistingL2Cache();   // hand the set-aside lines back
     pihm_b200_vec_free(ctx->y_tmp);
     pihm_b200_vec_free(ctx->yd_tmp);

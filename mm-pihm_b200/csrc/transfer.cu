@@ -10,7 +10,8 @@
 //     pihm_b200_forcing_commit scatters them into the tile layout in stream order, i.e. after the last RHS
 //     evaluation (and the Summary replay) that reads the previous values.
 // Host buffers must be pinned (cudaHostAlloc / torch pin_memory): a pageable buffer makes the copy synchronous.
-// The state of a context's pipeline lives here, keyed by the context, so that no other translation unit changes.
+// The state of a context's pipeline lives here, keyed by the context (the context structure of common.cuh stays
+// as it is); pihm_b200_destroy releases it.
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -67,6 +68,14 @@ Pipe *pipe_of(pihm_b200_ctx *ctx)
     return &(g_pipes[ctx] = p);
 }
 
+// ... without creating it (nullptr: the context has no pipeline)
+Pipe *find_pipe(pihm_b200_ctx *ctx)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_pipes.find(ctx);
+    return (it == g_pipes.end()) ? nullptr : &it->second;
+}
+
 int vec_grid(const pihm_b200_ctx *ctx, long long n)
 {
     const long long b = (n + PB_VEC_THREADS - 1) / PB_VEC_THREADS;
@@ -103,9 +112,8 @@ int pihm_b200_vec_download_async(const pihm_b200_vec *v, double *host_pinned)
 int pihm_b200_transfer_wait(pihm_b200_ctx *ctx)
 {
     if (!ctx) { set_error("transfer_wait: bad argument"); return -1; }
-    Pipe *p = pipe_of(ctx);
-    if (!p) return -1;
-    if (p->pull_pending) PB_CUDA(cudaEventSynchronize(p->pulled));
+    Pipe *p = find_pipe(ctx);
+    if (p && p->pull_pending) PB_CUDA(cudaEventSynchronize(p->pulled));
     return 0;
 }
 
@@ -133,9 +141,8 @@ int pihm_b200_forcing_prefetch(pihm_b200_ctx *ctx, int ncol, const int *cols, co
 int pihm_b200_forcing_commit(pihm_b200_ctx *ctx)
 {
     if (!ctx) { set_error("forcing_commit: bad argument"); return -1; }
-    Pipe *p = pipe_of(ctx);
-    if (!p) return -1;
-    if (!p->pref_pending) return 0;
+    Pipe *p = find_pipe(ctx);
+    if (!p || !p->pref_pending) return 0;
     const int ne = ctx->dm.ne;
     PB_CUDA(cudaStreamWaitEvent(ctx->s(), p->fetched, 0));
     for (int k = 0; k < p->ncol; k++) {
@@ -150,8 +157,8 @@ int pihm_b200_forcing_commit(pihm_b200_ctx *ctx)
     return 0;
 }
 
-// frees the copy stream and staging buffers of the context's pipeline; call before pihm_b200_destroy
-// (a context that never used the calls above has nothing to release)
+// frees the copy stream and staging buffers of the context's pipeline (pihm_b200_destroy calls it; a context that
+// never used the calls above has nothing to release)
 int pihm_b200_transfer_release(pihm_b200_ctx *ctx)
 {
     std::lock_guard<std::mutex> lk(g_mu);
