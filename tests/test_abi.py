@@ -85,6 +85,12 @@ def test_null_handles_are_refused():
     assert L.pihm_b200_print_update(None, None, 0, None) < 0
     assert L.pihm_b200_print_data(None, 0, None, None) < 0
     assert L.pihm_b200_spgmr_solve(None, 0.0, 0.0, 0.0, 0, None, None, None, None) < 0
+    # pipelined transfers (csrc/transfer.cu)
+    assert L.pihm_b200_forcing_prefetch(None, 1, None, None) < 0
+    assert L.pihm_b200_forcing_commit(None) < 0
+    assert L.pihm_b200_vec_download_async(None, None) < 0
+    assert L.pihm_b200_transfer_wait(None) < 0
+    assert L.pihm_b200_transfer_release(None) == 0          # nothing to release
 
 
 def test_struct_layouts():
