@@ -289,6 +289,7 @@ class Model:
         for a in arrays:
             assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.size == self.nelem
         _check(self.L, self.L.pihm_b200_forcing_prefetch(self.h, n, ids, ptrs), "forcing_prefetch")
+        self._prefetch_keep = list(arrays)      # the copy reads them until the columns are committed
 
     def forcing_commit(self):
         _check(self.L, self.L.pihm_b200_forcing_commit(self.h), "forcing_commit")
