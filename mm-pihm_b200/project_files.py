@@ -14,6 +14,8 @@ Formats (parser in the reference -> writer here):
   .bedrock  src/fbr/read_bedrock.c:3-82   write_bedrock    fbr bc types / idx zbed per node / 5 print controls
   vegprmt   src/read_lc.c:3-78            write_vegprmt    NUMLC / 15 columns / TOPT_DATA CFACTR_DATA RSMAX_DATA BARE NATURAL
   .meteo    src/read_forc.c:3-79          write_meteo      METEO_TS i WIND_LVL z / 2 header lines / time + 7 values
+  .bc       src/read_bc.c:3-102           write_bc         BC_TS k / 2 header lines / time + head  (one series per Dirichlet edge)
+  .lai      src/read_lai.c:3-110          write_lai        LAI_TS 1 / 2 header lines / time + LAI  (option lai_series)
   .para     src/read_para.c:3-200         write_para       fixed keyword ORDER
   .calib    src/read_calib.c:3-173        write_calib      all multipliers 1 (the class tables already hold calibrated values)
 
@@ -23,10 +25,14 @@ The class tables of watershed.py hold *calibrated* values (what InitSoil derives
 returns them: MINSMC 0 and MAXSMC = porosity, KMACV_RO = kmacv / kinfv, KMACH_RO = kmach / ksath (the two
 products re-round: equal to the table within 1 ulp, everything else bit for bit).
 
-Not written: .lai (every element has lai type 0 = monthly table by land cover, src/forcing.c:248-257, so
-ReadLai opens nothing, src/read_lai.c:13-24), .bc (all bc types 0: ReadBc opens nothing,
-src/read_bc.c:14-33; per-element Dirichlet heads of `dirichlet_edges=True` would need one series per edge),
-.ic (INIT_MODE 0 = RelaxIc), the module files of Noah / BGC / Cycles / RT."""
+Boundary conditions: MM-PIHM's bc type of an edge IS the (1-based) index of a time series of the .bc file, its sign
+the kind (> 0 Dirichlet head, < 0 Neumann flux; src/forcing.c:55-86).  The Dirichlet edges of
+`make_watershed(dirichlet_edges=True)` carry one head per edge, so every such edge gets a constant series of its own
+and the .att / .bedrock columns hold the series indices where the generator's tables hold the flag 1 (the RHS reads
+only the sign).  The bedrock layer's heads (storm_forcing: soil head - 8 m) follow as further series.
+Without `lai_series` every element has lai type 0 = monthly table by land cover (src/forcing.c:248-257) and ReadLai
+opens nothing (src/read_lai.c:13-24).  Not written: .ic (INIT_MODE 0 = RelaxIc), river boundary series, the module
+files of Noah / BGC / Cycles / RT."""
 from __future__ import annotations
 
 import os
@@ -53,11 +59,28 @@ def write_mesh(path: str, mesh: dict) -> None:
             f.write(f"{i + 1}\t{_g(mesh['x'][i])}\t{_g(mesh['y'][i])}\t{_g(mesh['zmin'][i])}\t{_g(mesh['zmax'][i])}\n")
 
 
-def write_att(path: str, tables: dict) -> None:
+def bc_series(tables: dict):
+    """-> (bc index columns [3, ne] for .att, fbr bc index columns [3, ne] for .bedrock, heads of the series).
+    One constant series per Dirichlet edge, soil edges first (element-major), then the bedrock edges."""
+    ei, ne = tables["elem_i32"], tables["nelem"]
+    if np.any(ei[W.EI_BC0:W.EI_FBRBC2 + 1] < 0) or np.any(tables["riv_i32"][W.RI_BCTYPE]):
+        raise ValueError("Neumann edges and river boundary conditions are not written")
+    heads = []
+    soil = np.zeros((3, ne), np.int64)
+    fbr = np.zeros((3, ne), np.int64)
+    for dst, first, off in ((soil, W.EI_BC0, 0.0), (fbr, W.EI_FBRBC0, -8.0)):
+        for i, j in zip(*np.nonzero(ei[first:first + 3].T > 0)):       # element-major
+            heads.append(tables["bc_head"][j, i] + off)
+            dst[j, i] = len(heads)
+    return soil, fbr, heads
+
+
+def write_att(path: str, tables: dict, bc_idx=None, lai_type: int = 0) -> None:
     mesh, ei = tables["mesh"], tables["elem_i32"]
     ne = tables["nelem"]
+    bc = ei[W.EI_BC0:W.EI_BC2 + 1] if bc_idx is None else bc_idx
     cols = [np.arange(1, ne + 1), mesh["soil_type"], np.ones(ne, int), mesh["lc_type"], np.ones(ne, int),
-            np.zeros(ne, int), np.zeros(ne, int), ei[W.EI_BC0], ei[W.EI_BC1], ei[W.EI_BC2]]
+            np.full(ne, lai_type, int), np.zeros(ne, int), bc[0], bc[1], bc[2]]
     with open(path, "w") as f:
         f.write("INDEX\tSOIL\tGEOL\tLC\tMETEO\tLAI\tSS\tBC0\tBC1\tBC2\n")
         np.savetxt(f, np.column_stack(cols), fmt="%d", delimiter="\t")
@@ -113,13 +136,13 @@ def write_geol(path: str) -> None:
         f.write(f"1\t{_g(g['ksatv'])}\t{_g(g['ksath'])}\t{_g(g['porosity'])}\t0\t{_g(g['alpha'])}\t{_g(g['beta'])}\n")
 
 
-def write_bedrock(path: str, tables: dict) -> None:
+def write_bedrock(path: str, tables: dict, fbr_bc_idx=None) -> None:
     mesh, ei = tables["mesh"], tables["elem_i32"]
     ne, nn = tables["nelem"], len(mesh["x"])
+    bc = ei[W.EI_FBRBC0:W.EI_FBRBC2 + 1] if fbr_bc_idx is None else fbr_bc_idx
     with open(path, "w") as f:
         f.write("INDEX\tBC0\tBC1\tBC2\n")
-        np.savetxt(f, np.column_stack([np.arange(1, ne + 1), ei[W.EI_FBRBC0], ei[W.EI_FBRBC1], ei[W.EI_FBRBC2]]),
-                   fmt="%d", delimiter="\t")
+        np.savetxt(f, np.column_stack([np.arange(1, ne + 1), bc[0], bc[1], bc[2]]), fmt="%d", delimiter="\t")
         f.write("INDEX\tZBED\n")
         for i in range(nn):
             f.write(f"{i + 1}\t{_g(mesh['zbed'][i])}\n")
@@ -151,6 +174,25 @@ def write_meteo(path: str, hours: int) -> None:
             sun = 600.0 * max(0.0, np.sin(np.pi * (th - 6.0) / 12.0))
             t = str(START + np.timedelta64(h, "h")).replace("T", " ")
             f.write(f"{t}\t{rain:.8f}\t285.15\t70.0\t2.5\t{sun:.2f}\t300.0\t97000.0\n")
+
+
+def _span(hours: int):
+    """first and last record of a constant series: the run's span with a day to spare on both sides"""
+    fmt = lambda t: str(t).replace("T", " ")     # noqa: E731
+    return fmt(START - np.timedelta64(24, "h")), fmt(START + np.timedelta64(hours + 24, "h"))
+
+
+def write_bc(path: str, heads, hours: int) -> None:
+    t0, t1 = _span(hours)
+    with open(path, "w") as f:
+        for k, h in enumerate(heads):
+            f.write(f"BC_TS\t{k + 1}\nTIME\tHEAD\nTS\tm\n{t0}\t{_g(h)}\n{t1}\t{_g(h)}\n")
+
+
+def write_lai(path: str, hours: int, lai: float = 3.0) -> None:
+    t0, t1 = _span(hours)
+    with open(path, "w") as f:
+        f.write(f"LAI_TS\t1\nTIME\tLAI\nTS\tm2/m2\n{t0}\t{_g(lai)}\n{t1}\t{_g(lai)}\n")
 
 
 PRINT_KEYS = ("SURF", "UNSAT", "GW", "RIVSTG", "RIVGW", "SNOW", "CMC", "INFIL", "RECHARGE", "EC", "ETT", "EDIR",
@@ -192,18 +234,22 @@ def write_calib(path: str) -> None:
         f.write("\nSCENARIO\nPRCP\t1.0\nSFCTMP\t0.0\n")
 
 
-def write_project(tables: dict, rundir: str, name: str = "synth", hours: int = 24, **para) -> str:
+def write_project(tables: dict, rundir: str, name: str = "synth", hours: int = 24, lai_series: bool = False,
+                  **para) -> str:
     """Write input/<name>/<name>.* and input/vegprmt.tbl under rundir (created if missing) from a watershed
     made with keep_mesh=True.  Returns the project directory."""
     if "mesh" not in tables:
         raise ValueError("make_watershed(..., keep_mesh=True) is needed: the files hold nodes, not centroids")
-    if np.any(tables["elem_i32"][W.EI_BC0:W.EI_BC2 + 1]) or np.any(tables["riv_i32"][W.RI_BCTYPE]):
-        raise ValueError("boundary-condition series (.bc) are not written: use dirichlet_edges=False")
+    soil_bc, fbr_bc, heads = bc_series(tables)
     d = os.path.join(rundir, "input", name)
     os.makedirs(d, exist_ok=True)
     p = lambda ext: os.path.join(d, f"{name}.{ext}")     # noqa: E731
     write_mesh(p("mesh"), tables["mesh"])
-    write_att(p("att"), tables)
+    write_att(p("att"), tables, soil_bc, lai_type=1 if lai_series else 0)
+    if heads:
+        write_bc(p("bc"), heads, hours)
+    if lai_series:
+        write_lai(p("lai"), hours)
     write_riv(p("riv"), tables)
     write_soil(p("soil"))
     write_meteo(p("meteo"), hours)
@@ -212,5 +258,5 @@ def write_project(tables: dict, rundir: str, name: str = "synth", hours: int = 2
     write_vegprmt(os.path.join(rundir, "input", "vegprmt.tbl"))
     if tables["fbr"]:
         write_geol(p("geol"))
-        write_bedrock(p("bedrock"), tables)
+        write_bedrock(p("bedrock"), tables, fbr_bc)
     return d

@@ -83,8 +83,67 @@ def test_rhs_of_the_file_built_model_equals_the_table_built_one(tmp_path):
         assert d <= 1e-13 * scale, f"call {call}: {d:.3e} (kmach / kmacv differ in the last place at most)"
 
 
+@pytest.mark.parametrize("fbr", [False, True])
+def test_dirichlet_edges_travel_as_bc_series(tmp_path, fbr):
+    """bc type = index of a series of the .bc file (src/forcing.c:55-86): one constant series per Dirichlet edge.
+    The reference's Initialize() must mark exactly the generator's edges, ApplyBc() must hand every edge the
+    generator's head, and ODE() on the file-built model must equal ODE() on the table-built one."""
+    tb = W.make_watershed(40, 30, fbr=fbr, dirichlet_edges=True, keep_mesh=True)
+    ne, nr = tb["nelem"], tb["nriver"]
+    ref = _open(tmp_path, tb, fbr)
+    got = ref.pack_tables()
+    nrow = got["elem_i32"].shape[0]
+    bc_rows = list(range(W.EI_BC0, W.EI_BC2 + 1)) + (list(range(W.EI_FBRBC0, W.EI_FBRBC2 + 1)) if fbr else [])
+    for r in range(nrow):
+        if r in bc_rows:
+            assert np.array_equal(got["elem_i32"][r] > 0, tb["elem_i32"][r] > 0) and (got["elem_i32"][r] >= 0).all()
+        else:
+            assert np.array_equal(got["elem_i32"][r], tb["elem_i32"][r])
+    nset = int((tb["elem_i32"][bc_rows] > 0).sum())
+    assert nset > 0 and sorted(got["elem_i32"][bc_rows][got["elem_i32"][bc_rows] > 0]) == list(range(1, nset + 1))
+    ref.apply_forcing(0)                                    # ApplyBc at the start time
+    forc, _ = ref.get_forcing()
+    want = W.storm_forcing(tb, 0.0)
+    for j in range(3):
+        sel = tb["elem_i32"][W.EI_BC0 + j] > 0
+        assert np.allclose(forc[W.F_BC0 + j, sel], want[W.F_BC0 + j, sel], rtol=ULP2, atol=0)
+        if fbr:
+            sel = tb["elem_i32"][W.EI_FBRBC0 + j] > 0
+            assert np.allclose(forc[W.F_FBRBC0 + j, sel], want[W.F_FBRBC0 + j, sel], rtol=ULP2, atol=0)
+    # the same right-hand side as the table-built model (which carries the flag 1 where the files carry an index)
+    y = W.wet_state(tb, seed=3)
+    f = W.storm_forcing(tb, 3 * 3600.0, ws0_surf=np.maximum(y[:ne], 0))
+    ref.set_forcing(f, np.zeros(nr)); ref.set_ovlflow(np.zeros((3, ne)))
+    a = ref.ode(y)
+    ref.close()
+    tab = reflib.RefModel(fbr=fbr).create_from_tables(tb)
+    tab.set_forcing(f, np.zeros(nr)); tab.set_ovlflow(np.zeros((3, ne)))
+    b = tab.ode(y)
+    tab.close()
+    assert np.abs(a - b).max() <= 1e-13 * np.abs(b).max()
+
+
+def test_lai_series_is_read(tmp_path):
+    """option lai_series: every element refers to LAI series 1 of the .lai file (src/read_lai.c, forcing.c:242-258)"""
+    if not reflib.available(False):
+        pytest.skip("oracle/_ref not present")
+    tb = W.make_watershed(8, 6, keep_mesh=True)
+    PF.write_project(tb, str(tmp_path), "synth", hours=6, lai_series=True)
+    ref = reflib.RefModel(fbr=False).open_project(str(tmp_path), "synth")
+    assert ref.et_dims()["nlai"] == 1 and ref.et_dims()["nmeteo"] == 1
+    _, eti = ref.pack_et_tables()
+    assert (eti[W.ETI_LAI_TYPE] == 1).all()
+    ref.apply_forcing(0)
+    meteo, lai = ref.et_get_forc()
+    assert lai[0] == 3.0 and meteo[0, 1] == 285.15           # the constant series / SFCTMP of write_meteo
+    ref.close()
+
+
 def test_writer_refuses_what_it_cannot_express(tmp_path):
     with pytest.raises(ValueError):
         PF.write_project(W.make_watershed(8, 6), str(tmp_path))                      # no node-level mesh kept
+    tb = W.make_watershed(8, 6, dirichlet_edges=True, keep_mesh=True)
+    tb["elem_i32"] = tb["elem_i32"].copy()
+    tb["elem_i32"][W.EI_BC1, 3] = -1                                                  # a Neumann edge
     with pytest.raises(ValueError):
-        PF.write_project(W.make_watershed(8, 6, dirichlet_edges=True, keep_mesh=True), str(tmp_path))
+        PF.write_project(tb, str(tmp_path))
